@@ -1,0 +1,138 @@
+"""Generate tests/golden/*.npz by running the UPSTREAM functions themselves.
+
+Run in the build container only (needs /root/reference; the GPU box has no
+copy):   python oracle/gen_golden.py
+
+The upstream repo has no tests or fixtures for this path, so the committed
+fixtures are outputs of its own code on seeded inputs (CPU, torch of this
+image).  They pin the oracle (tests/test_oracle_golden.py) and, on the GPU, the
+CUDA kernels (tests/test_gpu_parity.py).  Seeds follow scripts/train.sh:33
+(1024) plus a per-case offset.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+REF = os.environ.get("DSSMD_REFERENCE", "/root/reference")
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+warnings.filterwarnings("ignore")
+
+from models.UtilsNet.submoudles import build_corr  # noqa: E402
+from models.UtilsNet.stereo_op import disp_warp as disp_warp_stereo_op  # noqa: E402
+from utils.disparity_warper import LRwarp_error, disp_warp  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+SEED = 1024
+
+
+def _np(t):
+    return t.detach().to(torch.float32).contiguous().numpy()
+
+
+def corr_cases():
+    # name, B, C, H, W, D, relu, dtype
+    return [
+        ("tiny", 2, 8, 5, 12, 4, True, torch.float32),
+        ("d_gt_w", 1, 16, 3, 6, 9, False, torch.float32),
+        ("model_like", 1, 128, 4, 24, 24, True, torch.float32),
+        ("ragged", 2, 20, 3, 37, 11, False, torch.float32),
+        ("d41", 1, 64, 2, 56, 41, True, torch.float32),
+        ("bf16", 1, 64, 3, 24, 8, True, torch.bfloat16),
+    ]
+
+
+def gen_corr():
+    out = {}
+    for i, (name, B, C, H, W, D, relu, dt) in enumerate(corr_cases()):
+        torch.manual_seed(SEED + i)
+        L = torch.randn(B, C, H, W)
+        R = torch.randn(B, C, H, W)
+        if relu:
+            L, R = L.relu(), R.relu()
+        g = torch.randn(B, D, H, W)
+        L, R, g = L.to(dt), R.to(dt), g.to(dt)
+        Lr, Rr = L.clone().requires_grad_(True), R.clone().requires_grad_(True)
+        vol = build_corr(Lr, Rr, D)
+        vol.backward(g)
+        assert vol.is_contiguous() and vol.shape == (B, D, H, W) and vol.dtype == dt
+        out.update({f"{name}.L": _np(L), f"{name}.R": _np(R), f"{name}.g": _np(g),
+                    f"{name}.D": np.int32(D), f"{name}.out": _np(vol),
+                    f"{name}.gL": _np(Lr.grad), f"{name}.gR": _np(Rr.grad),
+                    f"{name}.bf16": np.bool_(dt == torch.bfloat16)})
+    np.savez_compressed(os.path.join(OUT, "corr.npz"), **out)
+    print("corr.npz:", len(corr_cases()), "cases")
+
+
+def warp_cases():
+    # name, B, C, H, W, max disparity, padding_mode, smooth image?
+    return [
+        ("border_small", 2, 3, 9, 16, 6.0, "border", False),
+        ("zeros_small", 2, 3, 9, 16, 6.0, "zeros", False),
+        ("border_wide", 1, 3, 12, 40, 17.5, "border", True),
+        ("zeros_wide", 1, 3, 12, 40, 17.5, "zeros", True),
+        ("c1", 1, 1, 5, 7, 3.0, "border", False),
+        ("c5_zero_disp", 1, 5, 6, 10, 0.0, "border", False),
+        ("big_disp", 1, 3, 4, 12, 30.0, "border", False),
+    ]
+
+
+def gen_warp():
+    out = {}
+    for i, (name, B, C, H, W, dmax, pad, smooth) in enumerate(warp_cases()):
+        torch.manual_seed(SEED + 100 + i)
+        img = torch.rand(B, C, H, W)
+        if smooth:
+            img = torch.nn.functional.avg_pool2d(img, 3, 1, 1)
+        disp = torch.rand(B, 1, H, W) * dmax
+        g = torch.randn(B, C, H, W)
+        ir, dr = img.clone().requires_grad_(True), disp.clone().requires_grad_(True)
+        warped, mask = disp_warp(ir, dr, padding_mode=pad)
+        w2, m2 = disp_warp_stereo_op(img, disp, padding_mode=pad)
+        assert torch.equal(w2, warped.detach()) and torch.equal(m2, mask.detach())
+        warped.backward(g)
+        out.update({f"{name}.img": _np(img), f"{name}.disp": _np(disp), f"{name}.g": _np(g),
+                    f"{name}.pad": np.str_(pad), f"{name}.warped": _np(warped), f"{name}.mask": _np(mask),
+                    f"{name}.g_img": _np(ir.grad), f"{name}.g_disp": _np(dr.grad)})
+    np.savez_compressed(os.path.join(OUT, "warp.npz"), **out)
+    print("warp.npz:", len(warp_cases()), "cases")
+
+
+def lrwarp_cases():
+    # name, B, C, H0, W0, H, W
+    return [
+        ("half", 1, 3, 12, 20, 6, 10),
+        ("same", 2, 3, 8, 14, 8, 14),
+        ("quarter", 1, 3, 16, 32, 4, 8),
+        ("eighth", 1, 3, 16, 48, 2, 6),
+        ("non_integer", 1, 3, 10, 21, 7, 9),
+    ]
+
+
+def gen_lrwarp():
+    out = {}
+    for i, (name, B, C, H0, W0, H, W) in enumerate(lrwarp_cases()):
+        torch.manual_seed(SEED + 200 + i)
+        imgL, imgR = torch.rand(B, C, H0, W0), torch.rand(B, C, H0, W0)
+        disp = torch.rand(B, 1, H, W) * (W / 4.0)
+        g = torch.randn(B, C, H, W)
+        lr, rr, dr = (t.clone().requires_grad_(True) for t in (imgL, imgR, disp))
+        err = LRwarp_error(lr, dr, rr)
+        err.backward(g)
+        out.update({f"{name}.imgL": _np(imgL), f"{name}.imgR": _np(imgR), f"{name}.disp": _np(disp),
+                    f"{name}.g": _np(g), f"{name}.err": _np(err), f"{name}.g_imgL": _np(lr.grad),
+                    f"{name}.g_imgR": _np(rr.grad), f"{name}.g_disp": _np(dr.grad)})
+    np.savez_compressed(os.path.join(OUT, "lrwarp.npz"), **out)
+    print("lrwarp.npz:", len(lrwarp_cases()), "cases")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(1)  # fixed reduction order for the fixtures
+    print("torch", torch.__version__, "reference at", REF)
+    gen_corr()
+    gen_warp()
+    gen_lrwarp()

@@ -1,0 +1,102 @@
+"""Pins the CPU oracle against outputs of the upstream functions themselves.
+
+tests/golden/*.npz were produced by oracle/gen_golden.py, which imports
+build_corr / disp_warp / LRwarp_error from the upstream tree and runs them (and
+their autograd backward) on CPU.  The upstream repo has no tests of its own for
+this path, so these fixtures are the pin.
+"""
+import numpy as np
+import pytest
+
+from helpers import TOL_BF16, TOL_F32, load_cases, rel_err
+from oracle import oracle as O
+
+CORR = load_cases("corr")
+WARP = load_cases("warp")
+LRW = load_cases("lrwarp")
+
+
+@pytest.mark.parametrize("name", sorted(CORR))
+def test_corr_forward_backward_matches_reference(name):
+    c = CORR[name]
+    tol = TOL_BF16 if bool(c["bf16"]) else TOL_F32
+    D = int(c["D"])
+    out = O.corr_fwd(c["L"], c["R"], D)
+    assert out.shape == c["out"].shape and out.flags["C_CONTIGUOUS"]
+    assert rel_err(out, c["out"]) <= tol
+    gL, gR = O.corr_bwd(c["g"], c["L"], c["R"])
+    assert rel_err(gL, c["gL"]) <= tol
+    assert rel_err(gR, c["gR"]) <= tol
+
+
+@pytest.mark.parametrize("name", sorted(CORR))
+def test_corr_f64_arbiter_agrees(name):
+    c = CORR[name]
+    if bool(c["bf16"]):
+        pytest.skip("fp64 arbiter is for the fp32 cases")
+    out64 = O.corr_fwd(c["L"].astype(np.float64), c["R"].astype(np.float64), int(c["D"]))
+    assert rel_err(out64, c["out"]) <= TOL_F32
+
+
+@pytest.mark.parametrize("name", sorted(WARP))
+def test_warp_forward_backward_matches_reference(name):
+    c = WARP[name]
+    pad = str(c["pad"])
+    warped, mask, bad = O.warp_fwd(c["img"], c["disp"], pad)
+    assert not bad
+    assert rel_err(warped, c["warped"]) <= TOL_F32
+    assert np.array_equal(mask, c["mask"])  # 0/1 mask must be exact
+    g_img, g_disp = O.warp_bwd(c["g"], c["img"], c["disp"], pad)
+    assert rel_err(g_img, c["g_img"]) <= TOL_F32
+    assert rel_err(g_disp, c["g_disp"]) <= TOL_F32
+
+
+@pytest.mark.parametrize("name", sorted(LRW))
+def test_lrwarp_error_matches_reference(name):
+    c = LRW[name]
+    err = O.lrwarp_error(c["imgL"], c["disp"], c["imgR"])
+    assert err.shape == c["err"].shape
+    assert rel_err(err, c["err"]) <= TOL_F32
+
+
+def test_negative_or_nan_disparity_is_flagged():
+    img = np.random.default_rng(0).random((1, 3, 4, 6), dtype=np.float32)
+    disp = np.ones((1, 1, 4, 6), np.float32)
+    assert not O.warp_fwd(img, disp)[2]
+    d2 = disp.copy(); d2[0, 0, 2, 3] = -0.25
+    assert O.warp_fwd(img, d2)[2]
+    d3 = disp.copy(); d3[0, 0, 1, 1] = np.nan
+    assert O.warp_fwd(img, d3)[2]
+
+
+# ---- invariants of SURVEY.md Appendix B, checked on the oracle ----------------
+def test_corr_invariants():
+    rng = np.random.default_rng(1024)
+    L = rng.standard_normal((2, 8, 3, 6)).astype(np.float32)
+    R = rng.standard_normal((2, 8, 3, 6)).astype(np.float32)
+    out = O.corr_fwd(L, R, 9)
+    assert out.shape == (2, 9, 3, 6)
+    for d in range(9):
+        assert np.all(out[:, d, :, :d] == 0)          # zero left border
+    assert np.all(out[:, 6:] == 0)                    # channels d >= W are zero
+    assert rel_err(out[:, 0], (L * R).mean(1)) <= TOL_F32
+    same = O.corr_fwd(L, L, 3)[:, 0]
+    assert np.all(same >= 0)
+    # shift test: R[..., x] = L[..., x+k]  =>  channel k == mean_c L^2 on x >= k
+    k = 2
+    Rs = np.zeros_like(L); Rs[..., :-k] = L[..., k:]
+    outs = O.corr_fwd(L, Rs, 4)
+    assert rel_err(outs[:, k, :, k:], (L[..., k:] ** 2).mean(1)) <= TOL_F32
+
+
+def test_warp_invariants():
+    rng = np.random.default_rng(7)
+    img = rng.random((2, 3, 10, 24), dtype=np.float32)
+    disp = (rng.random((2, 1, 10, 24), dtype=np.float32) * 5).astype(np.float32)
+    warped, mask, _ = O.warp_fwd(img, disp)
+    assert set(np.unique(mask)) <= {0.0, 1.0}
+    assert np.all(mask[:, :, 0] == 0) and np.all(mask[:, :, -1] == 0)   # first/last rows invalid
+    assert np.all(mask[:, 0] == mask[:, 1]) and np.all(mask[:, 0] == mask[:, 2])
+    # disp = 0 is still a resample, not the identity
+    w0, _, _ = O.warp_fwd(img, np.zeros_like(disp))
+    assert np.abs(w0 - img).max() > 0.05
