@@ -1,0 +1,439 @@
+#!/usr/bin/env python
+"""bench.py -- DSSMD hot path (correlation cost volume + disparity warp) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port)
+
+Metric (BASELINE.json): stereo pairs/s @576x960.  One *step* is one pass of the
+hot path over one batch of synthetic SceneFlow-shaped data per GPU:
+    correlation fwd + bwd on the model's 1/8-resolution features [B,128,72,120], D=24
+    disparity warp fwd + bwd on the full-resolution images        [B,3,576,960]
+with B = 4 stereo pairs per GPU (BASELINE config "batch 32 split across 8 B200";
+weak scaling: every rank owns its own 4 pairs, no data-path collective).
+pairs/s = B * n_gpus / step time.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "stereo_pairs_per_s@576x960"
+UNIT = "pairs/s"
+
+WORKLOADS = {
+    # name: (B per GPU, C, Hf, Wf, D, Himg, Wimg, description)
+    "sceneflow_576x960": dict(B=4, C=128, Hf=72, Wf=120, D=24, H=576, W=960,
+                              desc="cfg5: SceneFlow 540x960 padded to 576x960, max_disp=192 (D=24 at 1/8), 4 pairs/GPU"),
+    "kitti_384x1280": dict(B=16, C=128, Hf=48, Wf=160, D=24, H=384, W=1280,
+                           desc="cfg4: KITTI 384x1280, batch 16"),
+    "train_320x640": dict(B=8, C=128, Hf=40, Wf=80, D=24, H=320, W=640,
+                          desc="cfg3 op shapes: 320x640 crops, batch 8/GPU"),
+    "corr_micro": dict(B=8, C=256, Hf=80, Wf=160, D=41, H=320, W=640,
+                       desc="cfg2: correlation microbench C=256 80x160 D=41 batch 8 (+warp at 320x640)"),
+}
+
+
+def algorithmic_bytes(w, esize=4, cimg=3):
+    """bytes each kernel must move, per launch."""
+    B, C, Hf, Wf, D, H, W = (w[k] for k in ("B", "C", "Hf", "Wf", "D", "H", "W"))
+    feat = B * C * Hf * Wf * esize
+    vol = B * D * Hf * Wf * esize
+    px = B * H * W * 4
+    return {
+        "corr_fwd": 2 * feat + vol,
+        "corr_bwd_gL": vol + 2 * feat,
+        "corr_bwd_gR": vol + 2 * feat,
+        "warp_fwd": px * (cimg + 1 + cimg + cimg),
+        "warp_bwd": px * (cimg + cimg + 1 + cimg + 1),
+    }
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------
+# clocks sampler (pynvml; falls back to one nvidia-smi query)
+# ----------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
+
+    _NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+              0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+              0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def _run(self):
+        n = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
+                try:
+                    r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in self._NAMES.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.01)
+
+    def start(self):
+        if self._nvml is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=1.0)
+        if not self.samples:
+            try:
+                import subprocess
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                a, b = out.strip().split(",")
+                self.samples, self.max_mhz = [int(a)], int(b)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------
+# synthetic data, seeded like upstream scripts/train.sh:33
+# ----------------------------------------------------------------------------------
+def make_set(torch, w, device, seed):
+    g = torch.Generator(device=device).manual_seed(seed)
+    B, C, Hf, Wf, D, H, W = (w[k] for k in ("B", "C", "Hf", "Wf", "D", "H", "W"))
+    s = {}
+    s["L"] = torch.randn((B, C, Hf, Wf), generator=g, device=device).relu_()
+    s["R"] = torch.randn((B, C, Hf, Wf), generator=g, device=device).relu_()
+    s["g_vol"] = torch.randn((B, D, Hf, Wf), generator=g, device=device)
+    img = torch.rand((B, 3, H, W), generator=g, device=device)
+    s["img"] = torch.nn.functional.avg_pool2d(img, 9, 1, 4).contiguous()
+    base = torch.rand((B, 1, H // 32 + 1, W // 32 + 1), generator=g, device=device)
+    disp = torch.nn.functional.interpolate(base, size=(H, W), mode="bilinear", align_corners=True)
+    s["disp"] = (0.5 + disp * (192.0 * W / 960.0 - 0.5)).contiguous()
+    s["g_img"] = torch.randn((B, 3, H, W), generator=g, device=device)
+    # outputs, allocated once (the library never allocates)
+    s["vol"] = torch.empty((B, D, Hf, Wf), device=device)
+    s["gL"], s["gR"] = torch.empty_like(s["L"]), torch.empty_like(s["R"])
+    s["warped"], s["mask"] = torch.empty_like(s["img"]), torch.empty_like(s["img"])
+    s["d_img"], s["d_disp"] = torch.empty_like(s["img"]), torch.empty_like(s["disp"])
+    return s
+
+
+def kernel_calls(torch, lib, _lib, w, s):
+    """The five launches of one step, as closures over the C ABI.  Each launches on
+    torch's current stream (so they can be captured into a CUDA graph)."""
+    B, C, Hf, Wf, D, H, W = (w[k] for k in ("B", "C", "Hf", "Wf", "D", "H", "W"))
+    p = {k: ctypes.c_void_p(t.data_ptr()) for k, t in s.items()}
+    null = ctypes.c_void_p(0)
+    F32, BORDER = 0, 1
+    chk = _lib.check
+    st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    return {
+        "corr_fwd": lambda: chk(lib.dssmd_corr_fwd(p["L"], p["R"], p["vol"], B, C, Hf, Wf, D, F32, st())),
+        "corr_bwd_gL": lambda: chk(lib.dssmd_corr_bwd(p["g_vol"], p["L"], p["R"], p["gL"], null, B, C, Hf, Wf, D, F32, st())),
+        "corr_bwd_gR": lambda: chk(lib.dssmd_corr_bwd(p["g_vol"], p["L"], p["R"], null, p["gR"], B, C, Hf, Wf, D, F32, st())),
+        "warp_fwd": lambda: chk(lib.dssmd_warp_fwd(p["img"], p["disp"], p["warped"], p["mask"], null, B, 3, H, W, BORDER, F32, st())),
+        "warp_bwd": lambda: chk(lib.dssmd_warp_bwd(p["g_img"], p["img"], p["disp"], p["d_img"], p["d_disp"], B, 3, H, W, BORDER, F32, st())),
+    }
+
+
+def capture(torch, fn):
+    """Capture fn() (kernel launches on the current stream) into a CUDA graph."""
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    return g
+
+
+def shard_batch(global_batch: int, world_size: int, rank: int):
+    """[begin, end) of the stereo pairs rank `rank` owns (batch-partitioned, no halo)."""
+    per, extra = divmod(global_batch, world_size)
+    begin = rank * per + min(rank, extra)
+    return begin, begin + per + (1 if rank < extra else 0)
+
+
+# ----------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# ----------------------------------------------------------------------------------
+def cpu_step_factory(w, batch):
+    import numpy as np
+    from oracle import oracle as O
+    rng = np.random.default_rng(1024)
+    B = batch
+    C, Hf, Wf, D, H, W = (w[k] for k in ("C", "Hf", "Wf", "D", "H", "W"))
+    L = np.maximum(rng.standard_normal((B, C, Hf, Wf), dtype=np.float32), 0)
+    R = np.maximum(rng.standard_normal((B, C, Hf, Wf), dtype=np.float32), 0)
+    gv = rng.standard_normal((B, D, Hf, Wf), dtype=np.float32)
+    img = rng.random((B, 3, H, W), dtype=np.float32)
+    disp = (0.5 + rng.random((B, 1, H, W), dtype=np.float32) * (192.0 * W / 960.0 - 0.5)).astype(np.float32)
+    gi = rng.standard_normal((B, 3, H, W), dtype=np.float32)
+
+    def step():
+        O.corr_fwd(L, R, D)
+        O.corr_bwd(gv, L, R)
+        O.warp_fwd(img, disp, "border")
+        O.warp_bwd(gi, img, disp, "border")
+
+    return step, O.num_threads()
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    step, cores = cpu_step_factory(w, w["B"])
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = w["B"] / dt
+    sample = f"{args.steps} steps x one full per-GPU batch (B={w['B']}) of {args.workload}, all four ops, fp32"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": w["desc"], "per_gpu_batch": w["B"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "note": "upstream is pure PyTorch (no compiled code of its own); the C/OpenMP oracle port "
+                                 "of its algorithm is timed on all host cores"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------
+def run_gpu(args, w):
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    distributed = world > 1
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    import dssmd_b200
+    from dssmd_b200 import _lib
+    lib = _lib.lib()
+
+    B = w["B"]
+    nsets = args.sets
+    sets = [make_set(torch, w, device, 1024 + 97 * rank + i) for i in range(nsets)]
+    stream = torch.cuda.current_stream(device)
+    calls = [kernel_calls(torch, lib, _lib, w, s) for s in sets]
+    names = list(calls[0].keys())
+    launches_per_step = len(names)
+    set_bytes = sum(t.numel() * t.element_size() for t in sets[0].values())
+
+    def eager_step(i):
+        c = calls[i % nsets]
+        for n in names:
+            c[n]()
+
+    # One CUDA graph per input set: the step is five short kernels, so replaying a
+    # captured graph keeps the host out of the timed region (launch-bound otherwise).
+    for i in range(nsets):
+        eager_step(i)          # first-touch: module load, cudaFuncSetAttribute
+    torch.cuda.synchronize(device)
+    if args.no_graph:
+        step = eager_step
+    else:
+        graphs = [capture(torch, (lambda i=i: eager_step(i))) for i in range(nsets)]
+        step = lambda i: graphs[i % nsets].replay()
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if distributed:
+            dist.barrier()
+            torch.cuda.synchronize(device)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+
+    # ---- device-resident timing: W warm-up steps, then exactly K timed steps -------
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    if distributed:
+        t = torch.tensor([ms_total], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = B * world / (ms_step * 1e-3)
+
+    # ---- per-kernel durations (CUDA events on the launch stream, rotating inputs) ---
+    peak, peak_src = measured_peak()
+    abytes = algorithmic_bytes(w)
+    kern = {}
+    if rank == 0:
+        rounds = max(args.steps // nsets, 5)
+        reps = rounds * nsets
+        for n in names:
+            def one_round(n=n):
+                for i in range(nsets):
+                    calls[i][n]()
+            kg = None if args.no_graph else capture(torch, one_round)
+            run = one_round if kg is None else kg.replay
+            for _ in range(3):
+                run()
+            torch.cuda.synchronize(device)
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record(stream)
+            for _ in range(rounds):
+                run()
+            k1.record(stream)
+            torch.cuda.synchronize(device)
+            us = k0.elapsed_time(k1) * 1e3 / reps
+            gbs = abytes[n] / (us * 1e-6) / 1e9
+            kern[n] = {"us": round(us, 3), "algorithmic_bytes": abytes[n], "GBps": round(gbs, 1),
+                       "frac_of_peak": round(gbs / peak, 4)}
+    barrier()
+
+    # ---- end-to-end through the public Python API with HOST buffers ---------------------
+    dssmd_b200.set_check_negative_disparity(True)
+    h = {k: sets[0][k].cpu().pin_memory() for k in ("L", "R", "g_vol", "img", "disp", "g_img")}
+    out_keys = ("vol", "gL", "gR", "warped", "mask", "d_img", "d_disp")
+    hout = {k: torch.empty_like(sets[0][k], device="cpu").pin_memory() for k in out_keys}
+    h2d = sum(t.numel() * t.element_size() for t in h.values())
+    d2h = sum(t.numel() * t.element_size() for t in hout.values())
+
+    def e2e_step():
+        d = {k: v.to(device, non_blocking=True) for k, v in h.items()}
+        L, R = d["L"].requires_grad_(True), d["R"].requires_grad_(True)
+        img, disp = d["img"].requires_grad_(True), d["disp"].requires_grad_(True)
+        vol = dssmd_b200.build_corr(L, R, w["D"])
+        vol.backward(d["g_vol"])
+        warped, mask = dssmd_b200.disp_warp(img, disp)
+        warped.backward(d["g_img"])
+        res = {"vol": vol.detach(), "gL": L.grad, "gR": R.grad, "warped": warped.detach(), "mask": mask,
+               "d_img": img.grad, "d_disp": disp.grad}
+        for k in out_keys:
+            hout[k].copy_(res[k], non_blocking=True)
+        torch.cuda.synchronize(device)
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if distributed:
+        t = torch.tensor([e2e_ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = B * world / (e2e_ms * 1e-3)
+
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        dom = max(kern, key=lambda n: kern[n]["us"])
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                    "frac": kern[dom]["frac_of_peak"], "traffic": None, "peak_source": peak_src,
+                    "share_of_step": round(kern[dom]["us"] / sum(k["us"] for k in kern.values()), 3)}
+        # CPU baseline: oracle port, bounded sample (one per-GPU batch, best of 2)
+        cpu = None
+        if not args.no_cpu_baseline:
+            stepf, cores = cpu_step_factory(w, B)
+            stepf()
+            best = 1e30
+            for _ in range(2):
+                t0 = time.perf_counter(); stepf(); best = min(best, time.perf_counter() - t0)
+            cpu = {"value": B / best, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"one per-GPU batch (B={B}) of {args.workload}, all four ops, best of 2 after 1 warm-up"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "desc": w["desc"], "per_gpu_batch": B, "global_batch": B * world,
+                       "corr": [B, w["C"], w["Hf"], w["Wf"], w["D"]], "warp": [B, 3, w["H"], w["W"]],
+                       "ops": names, "parallelism": f"batch-sharded x{world}, no data-path collective",
+                       "l2": f"inputs/outputs rotate over {nsets} sets of {set_bytes/1e6:.0f} MB each (> 126 MB L2)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "path": "dssmd_b200.build_corr/.backward + disp_warp/.backward on pinned host tensors"},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline, "kernels": kern, "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="dssmd_b200", choices=["dssmd_b200", "reference"])
+    ap.add_argument("--workload", default="sceneflow_576x960", choices=sorted(WORKLOADS))
+    ap.add_argument("--sets", type=int, default=4, help="input/output sets rotated through to defeat L2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, w)
+    return run_gpu(args, w)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

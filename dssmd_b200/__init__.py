@@ -1,0 +1,19 @@
+"""dssmd_b200 -- B200-native correlation cost volume + disparity warp for DSSMD.
+
+Host-side mirror of the upstream interface (same names, arguments, return
+values and error behaviour) over a C-ABI library of hand-written sm_100a CUDA
+kernels.  No CPU fallback, no Triton, no multi-backend dispatch.
+"""
+from .cost_volume import CostVolume
+from .disparity_warper import LRwarp_error, disp_warp, meshgrid, normalize_coords, read_pfm
+from .functional import resize_bilinear, set_check_negative_disparity
+from .install import install, uninstall
+from .stereo_op import print_tensor_shape
+from .submoudles import build_corr
+
+__all__ = [
+    "build_corr", "CostVolume", "disp_warp", "LRwarp_error", "normalize_coords", "meshgrid",
+    "read_pfm", "print_tensor_shape", "resize_bilinear", "set_check_negative_disparity",
+    "install", "uninstall",
+]
+__version__ = "0.1.0"

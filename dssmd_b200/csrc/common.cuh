@@ -1,0 +1,62 @@
+// common.cuh -- shared device/host helpers for libdssmd_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/dssmd_b200.h"
+
+namespace dssmd {
+
+// ---- thread-local error string (dssmd_last_error) ---------------------------
+void set_error(const char *fmt, ...);
+int fail(int code, const char *fmt, ...);
+int check_launch(const char *what);  // cudaGetLastError -> DSSMD_ERR_CUDA
+
+#define DSSMD_REQUIRE(cond, ...)                                             \
+    do {                                                                     \
+        if (!(cond)) return ::dssmd::fail(DSSMD_ERR_INVALID_ARGUMENT, __VA_ARGS__); \
+    } while (0)
+
+// ---- device properties, cached per device (read-only after first use) ----------
+int sm_count();
+
+// ---- element conversion --------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// 16-byte async global->shared copy; src_bytes == 0 writes zeros (src must still
+// be a valid address).
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// streaming 128-bit global store (outputs are written once, never re-read here)
+__device__ __forceinline__ void st_global_cs(float4 *p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+}  // namespace dssmd

@@ -1,0 +1,528 @@
+// warp.cu -- disparity-guided bilinear warp, forward and backward.
+//
+// Replaces disp_warp (upstream utils/disparity_warper.py:83-106, identical copy at
+// models/UtilsNet/stereo_op.py:41-63) and the backward autograd derives for it.
+// The coordinate arithmetic reproduces the reference's op order exactly
+// (SURVEY.md Appendix A.2): the reference normalises with (W-1)/(H-1) but calls
+// F.grid_sample with align_corners=False, so
+//     t  = x - disp;  gx = 2*(t/(W-1)) - 1;  ix = fma(gx+1, W/2, -0.5)
+//     gy = 2*(y/(H-1)) - 1;                   iy = fma(gy+1, H/2, -0.5)
+// is a 2-D, 4-tap gather whose vertical blend is constant per row.
+// Algorithmic HBM bytes (C image channels, s bytes/elt): forward
+// (C img + 1 disp + C out + C mask)*s per pixel, backward (C g + C img + 1 disp +
+// C g_img + 1 g_disp)*s per pixel.
+#include "common.cuh"
+
+namespace dssmd {
+
+namespace {
+
+// ---- scalar helpers: every op individually rounded, never contracted ----------
+template <typename S> struct Num;
+template <> struct Num<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+    static __device__ __forceinline__ float floor(float a) { return floorf(a); }
+};
+template <> struct Num<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+    static __device__ __forceinline__ double floor(double a) { return ::floor(a); }
+};
+
+// pixel coordinate -> grid_sample source index (reference op order)
+template <typename S>
+__device__ __forceinline__ S unnorm(S pix, int size) {
+    using N = Num<S>;
+    const S g = N::sub(N::mul((S)2, N::div(pix, (S)(size - 1))), (S)1);
+    return N::fma(N::add(g, (S)1), N::div((S)size, (S)2), (S)-0.5);
+}
+
+// One axis of a bilinear tap pair: integer index of the low tap, the two
+// weights, and whether each tap is inside [0, size).
+template <typename S>
+struct Axis {
+    int i0;
+    S w0, w1;      // weights of taps i0 and i0+1
+    bool in0, in1;
+};
+
+template <typename S>
+__device__ __forceinline__ Axis<S> make_axis(S coord, int size) {
+    using N = Num<S>;
+    Axis<S> a;
+    const S f = N::floor(coord);
+    a.w1 = N::sub(coord, f);
+    a.w0 = N::sub((S)1, a.w1);
+    // NaN / huge coordinates: every comparison false -> both taps out of bounds
+    const bool finite = (f >= (S)-2) && (f <= (S)size);
+    a.i0 = finite ? (int)f : -2;
+    a.in0 = finite && a.i0 >= 0 && a.i0 < size;
+    a.in1 = finite && a.i0 + 1 >= 0 && a.i0 + 1 < size;
+    return a;
+}
+
+template <typename S>
+__device__ __forceinline__ S clamp_border(S c, int size) {
+    // ATen clip_coordinates: min(size-1, max(c, 0)); NaN propagates like std::min/max do there
+    return fmin((S)(size - 1), fmax(c, (S)0));
+}
+
+// ---------------------------------------------------------------------------------
+// Forward.  One thread per output pixel column-quad (4 consecutive x) and all C
+// channels: the coordinate work is done once per pixel, not once per channel and
+// per grid_sample call as in the reference.
+//   SUB = false: warped = sample, mask written when non-null      (disp_warp)
+//   SUB = true : out = other - sample, no mask                    (LRwarp_error tail)
+// ---------------------------------------------------------------------------------
+template <typename S, bool SUB>
+__global__ void __launch_bounds__(256) warp_fwd_kernel(const S *__restrict__ img, const S *__restrict__ disp,
+                                                        const S *__restrict__ other, S *__restrict__ out,
+                                                        S *__restrict__ mask, int *neg_flag,
+                                                        int B, int C, int H, int W, int border, int vec) {
+    using N = Num<S>;
+    const int WQ = (W + 3) >> 2;
+    const long long nquads = (long long)B * H * WQ;
+    const long long HW = (long long)H * W;
+    const bool vec_ok = vec != 0;  // W % 4 == 0 and every pointer 16-byte aligned
+    bool bad = false;
+
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nquads;
+         q += (long long)gridDim.x * blockDim.x) {
+        const int xq = (int)(q % WQ);
+        const int y = (int)((q / WQ) % H);
+        const int b = (int)(q / ((long long)WQ * H));
+        const int x0 = xq << 2;
+        const long long rowoff = (long long)y * W;
+
+        // per-row vertical taps
+        const S iy_raw = unnorm<S>((S)y, H);
+        const Axis<S> ym = make_axis<S>(iy_raw, H);                                   // mask: un-clamped
+        const Axis<S> yi = make_axis<S>(border ? clamp_border<S>(iy_raw, H) : iy_raw, H);
+
+        S dv[4];
+        if (vec_ok) {
+            if constexpr (sizeof(S) == 4) {
+                const float4 t = *reinterpret_cast<const float4 *>(disp + (long long)b * HW + rowoff + x0);
+                dv[0] = t.x; dv[1] = t.y; dv[2] = t.z; dv[3] = t.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dv[i] = disp[(long long)b * HW + rowoff + x0 + i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dv[i] = (x0 + i < W) ? disp[(long long)b * HW + rowoff + x0 + i] : (S)0;
+        }
+
+        Axis<S> xi[4];
+        S mv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (!(dv[i] >= (S)0)) bad = true;
+            const S ix_raw = unnorm<S>(N::sub((S)(x0 + i), dv[i]), W);
+            const Axis<S> xm = make_axis<S>(ix_raw, W);
+            // sum of in-bounds weights, reference accumulation order nw, ne, sw, se
+            S m = (S)0;
+            if (xm.in0 && ym.in0) m = N::add(m, N::mul(ym.w0, xm.w0));
+            if (xm.in1 && ym.in0) m = N::add(m, N::mul(ym.w0, xm.w1));
+            if (xm.in0 && ym.in1) m = N::add(m, N::mul(ym.w1, xm.w0));
+            if (xm.in1 && ym.in1) m = N::add(m, N::mul(ym.w1, xm.w1));
+            mv[i] = (m >= (S)0.9999) ? (S)1 : (S)0;
+            xi[i] = make_axis<S>(border ? clamp_border<S>(ix_raw, W) : ix_raw, W);
+        }
+
+        for (int c = 0; c < C; ++c) {
+            const long long plane = ((long long)b * C + c) * HW;
+            const S *p0 = img + plane + (long long)yi.i0 * W;
+            const S *p1 = p0 + W;
+            S v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                S acc = (S)0;
+                const Axis<S> &xa = xi[i];
+                if (xa.in0 && yi.in0) acc = N::fma(p0[xa.i0], N::mul(yi.w0, xa.w0), acc);
+                if (xa.in1 && yi.in0) acc = N::fma(p0[xa.i0 + 1], N::mul(yi.w0, xa.w1), acc);
+                if (xa.in0 && yi.in1) acc = N::fma(p1[xa.i0], N::mul(yi.w1, xa.w0), acc);
+                if (xa.in1 && yi.in1) acc = N::fma(p1[xa.i0 + 1], N::mul(yi.w1, xa.w1), acc);
+                v[i] = acc;
+            }
+            S *o = out + plane + rowoff + x0;
+            if constexpr (SUB) {
+                const S *r = other + plane + rowoff + x0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (x0 + i < W) v[i] = N::sub(r[i], v[i]);
+            }
+            if (vec_ok && sizeof(S) == 4) {
+                st_global_cs(reinterpret_cast<float4 *>(o), make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]));
+                if (!SUB && mask)
+                    st_global_cs(reinterpret_cast<float4 *>(mask + plane + rowoff + x0),
+                                 make_float4((float)mv[0], (float)mv[1], (float)mv[2], (float)mv[3]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (x0 + i < W) {
+                        o[i] = v[i];
+                        if (!SUB && mask) mask[plane + rowoff + x0 + i] = mv[i];
+                    }
+            }
+        }
+    }
+    if (bad && neg_flag) atomicOr(neg_flag, 1);
+}
+
+// ---------------------------------------------------------------------------------
+// Backward.  One block per (b, image row yy).  g_img[b,:,yy,:] only receives
+// contributions from output rows y whose vertical taps {y0, y0+1} include yy
+// (y0 in {y-1, y}), so the block accumulates that one row for a chunk of channels
+// in shared memory and writes it once: no global atomics, every g_img element is
+// written exactly once.  g_disp is a gather and is produced by the block with
+// yy == y while it walks its own output row.
+// ---------------------------------------------------------------------------------
+template <typename S>
+__global__ void __launch_bounds__(256) warp_bwd_kernel(const S *__restrict__ g, const S *__restrict__ img,
+                                                        const S *__restrict__ disp, S *__restrict__ g_img,
+                                                        S *__restrict__ g_disp,
+                                                        int B, int C, int H, int W, int border, int CC) {
+    using N = Num<S>;
+    extern __shared__ unsigned char smem_raw[];
+    S *acc = reinterpret_cast<S *>(smem_raw);  // [CC][W]
+
+    const int yy = blockIdx.x % H;
+    const int b = blockIdx.x / H;
+    const long long HW = (long long)H * W;
+    const S xscale = N::div((S)W, (S)2);       // d ix / d gx
+    const S tscale = N::div((S)2, (S)(W - 1)); // d gx / d t
+
+    for (int c0 = 0; c0 < C; c0 += CC) {
+        const int nc = (C - c0 < CC) ? C - c0 : CC;
+        if (g_img) {
+            for (int i = threadIdx.x; i < nc * W; i += blockDim.x) acc[i] = (S)0;
+        }
+        __syncthreads();
+
+        const int ylo = yy - 2 < 0 ? 0 : yy - 2;
+        const int yhi = yy + 2 > H - 1 ? H - 1 : yy + 2;
+        for (int y = ylo; y <= yhi; ++y) {
+            const S iy_raw = unnorm<S>((S)y, H);
+            const Axis<S> ya = make_axis<S>(border ? clamp_border<S>(iy_raw, H) : iy_raw, H);
+            const bool top = ya.in0 && ya.i0 == yy;        // tap row y0   == yy, weight w0
+            const bool bot = ya.in1 && ya.i0 + 1 == yy;    // tap row y0+1 == yy, weight w1
+            const bool own = (y == yy) && (g_disp != nullptr);
+            if (!((g_img && (top || bot)) || own)) continue;
+            const S wy = top ? ya.w0 : ya.w1;
+
+            for (int x = threadIdx.x; x < W; x += blockDim.x) {
+                const S dv = disp[(long long)b * HW + (long long)y * W + x];
+                S ix = unnorm<S>(N::sub((S)x, dv), W);
+                S gmult = xscale;
+                if (border) {
+                    // clip_coordinates_set_grad: borders count as out of bounds for the gradient
+                    if (ix <= (S)0) { ix = (S)0; gmult = (S)0; }
+                    else if (ix >= (S)(W - 1)) { ix = (S)(W - 1); gmult = (S)0; }
+                }
+                const Axis<S> xa = make_axis<S>(ix, W);
+                S gix = (S)0;
+                for (int c = 0; c < nc; ++c) {
+                    const long long plane = ((long long)b * C + c0 + c) * HW;
+                    const S go = g[plane + (long long)y * W + x];
+                    if (g_img && (top || bot)) {
+                        S *row = acc + c * W;
+                        if (xa.in0) atomicAdd(row + xa.i0, N::mul(go, N::mul(wy, xa.w0)));
+                        if (xa.in1) atomicAdd(row + xa.i0 + 1, N::mul(go, N::mul(wy, xa.w1)));
+                    }
+                    if (own) {
+                        const S *p0 = img + plane + (long long)ya.i0 * W;
+                        const S *p1 = p0 + W;
+                        // d(sample)/d(ix) over in-bounds taps, ATen order nw, ne, sw, se
+                        if (xa.in0 && ya.in0) gix = N::sub(gix, N::mul(N::mul(p0[xa.i0], ya.w0), go));
+                        if (xa.in1 && ya.in0) gix = N::add(gix, N::mul(N::mul(p0[xa.i0 + 1], ya.w0), go));
+                        if (xa.in0 && ya.in1) gix = N::sub(gix, N::mul(N::mul(p1[xa.i0], ya.w1), go));
+                        if (xa.in1 && ya.in1) gix = N::add(gix, N::mul(N::mul(p1[xa.i0 + 1], ya.w1), go));
+                    }
+                }
+                if (own) {
+                    // chain rule: ix <- gx (W/2, 0 where clipped) <- t (2/(W-1)) <- disp (-1)
+                    const S gd = -N::mul(tscale, N::mul(gmult, gix));
+                    S *o = g_disp + (long long)b * HW + (long long)y * W + x;
+                    *o = (c0 == 0) ? gd : N::add(*o, gd);
+                }
+            }
+        }
+        __syncthreads();
+        if (g_img) {
+            for (int i = threadIdx.x; i < nc * W; i += blockDim.x) {
+                const int c = i / W, x = i - c * W;
+                g_img[((long long)b * C + c0 + c) * HW + (long long)yy * W + x] = acc[i];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Bilinear resize, align_corners=False (F.interpolate as called by LRwarp_error,
+// upstream utils/disparity_warper.py:110-113).  Index math follows
+// ATen/native/UpSample.h area_pixel_compute_source_index / guard_index_and_lambda.
+// ---------------------------------------------------------------------------------
+template <typename S>
+struct Src {
+    int i0, i1;
+    S l0, l1;
+};
+
+template <typename S>
+__device__ __forceinline__ Src<S> src_index(int dst, int in_size, int out_size) {
+    using N = Num<S>;
+    Src<S> r;
+    if (in_size == out_size) { r.i0 = r.i1 = dst; r.l0 = (S)1; r.l1 = (S)0; return r; }
+    const S scale = N::div((S)in_size, (S)out_size);
+    S src = N::sub(N::mul(scale, N::add((S)dst, (S)0.5)), (S)0.5);
+    if (src < (S)0) src = (S)0;
+    int k = (int)src;
+    if (k > in_size - 1) k = in_size - 1;
+    S lam = N::sub(src, (S)k);
+    lam = fmin(fmax(lam, (S)0), (S)1);
+    r.i0 = k;
+    r.i1 = k + (k < in_size - 1 ? 1 : 0);
+    r.l1 = lam;
+    r.l0 = N::sub((S)1, lam);
+    return r;
+}
+
+template <typename S>
+__device__ __forceinline__ S resize_at(const S *plane, int Hi, int Wi, const Src<S> &ys, const Src<S> &xs) {
+    using N = Num<S>;
+    const S *r0 = plane + (long long)ys.i0 * Wi, *r1 = plane + (long long)ys.i1 * Wi;
+    const S top = N::add(N::mul(xs.l0, r0[xs.i0]), N::mul(xs.l1, r0[xs.i1]));
+    const S bot = N::add(N::mul(xs.l0, r1[xs.i0]), N::mul(xs.l1, r1[xs.i1]));
+    return N::add(N::mul(ys.l0, top), N::mul(ys.l1, bot));
+}
+
+template <typename S>
+__global__ void __launch_bounds__(256) resize_fwd_kernel(const S *__restrict__ in, S *__restrict__ out,
+                                                          int BC, int Hi, int Wi, int Ho, int Wo) {
+    const long long n = (long long)BC * Ho * Wo;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % Wo);
+        const int y = (int)((i / Wo) % Ho);
+        const long long pc = i / ((long long)Wo * Ho);
+        const Src<S> ys = src_index<S>(y, Hi, Ho), xs = src_index<S>(x, Wi, Wo);
+        out[i] = resize_at<S>(in + pc * Hi * Wi, Hi, Wi, ys, xs);
+    }
+}
+
+// Backward of the resize as a gather: each source pixel scans the (few) output
+// pixels whose two taps can reach it.  For a down-scale by s >= 1 an output pixel
+// o reads sources floor(s*(o+.5)-.5) and +1, so source k is touched only by
+// outputs in [ (k-1+.5)/s - .5 , (k+1+.5)/s - .5 ]  -> at most a handful.
+template <typename S>
+__global__ void __launch_bounds__(256) resize_bwd_kernel(const S *__restrict__ g_out, S *__restrict__ g_in,
+                                                          int BC, int Hi, int Wi, int Ho, int Wo) {
+    using N = Num<S>;
+    const long long n = (long long)BC * Hi * Wi;
+    const double sy = (double)Hi / Ho, sx = (double)Wi / Wo;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int kx = (int)(i % Wi);
+        const int ky = (int)((i / Wi) % Hi);
+        const long long pc = i / ((long long)Wi * Hi);
+        int oy0 = (int)::floor((ky - 0.5) / sy - 0.5) - 1, oy1 = (int)::ceil((ky + 1.5) / sy - 0.5) + 1;
+        int ox0 = (int)::floor((kx - 0.5) / sx - 0.5) - 1, ox1 = (int)::ceil((kx + 1.5) / sx - 0.5) + 1;
+        if (oy0 < 0) oy0 = 0;
+        if (ox0 < 0) ox0 = 0;
+        if (oy1 > Ho - 1) oy1 = Ho - 1;
+        if (ox1 > Wo - 1) ox1 = Wo - 1;
+        const S *gp = g_out + pc * Ho * Wo;
+        S acc = (S)0;
+        for (int oy = oy0; oy <= oy1; ++oy) {
+            const Src<S> ys = src_index<S>(oy, Hi, Ho);
+            S wy = (S)0;
+            if (ys.i0 == ky) wy = N::add(wy, ys.l0);
+            if (ys.i1 == ky) wy = N::add(wy, ys.l1);
+            if (wy == (S)0) continue;
+            for (int ox = ox0; ox <= ox1; ++ox) {
+                const Src<S> xs = src_index<S>(ox, Wi, Wo);
+                S wx = (S)0;
+                if (xs.i0 == kx) wx = N::add(wx, xs.l0);
+                if (xs.i1 == kx) wx = N::add(wx, xs.l1);
+                if (wx == (S)0) continue;
+                acc = N::fma(N::mul(wy, wx), gp[(long long)oy * Wo + ox], acc);
+            }
+        }
+        g_in[i] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Fused LRwarp_error forward: out = resize(imgR) - warp(resize(imgL), disp), with
+// the resize folded into the tap fetch (each warped tap interpolates its 4 source
+// pixels on the fly; nothing is materialised).  One thread per output pixel.
+// ---------------------------------------------------------------------------------
+template <typename S>
+__global__ void __launch_bounds__(256) lrwarp_fwd_kernel(const S *__restrict__ imgL, const S *__restrict__ disp,
+                                                          const S *__restrict__ imgR, S *__restrict__ out,
+                                                          int *neg_flag, int B, int C, int H0, int W0, int H, int W) {
+    using N = Num<S>;
+    const long long n = (long long)B * H * W;
+    const long long HW = (long long)H * W, HW0 = (long long)H0 * W0;
+    bool bad = false;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        const int y = (int)((i / W) % H);
+        const int b = (int)(i / HW);
+        const S dv = disp[i];
+        if (!(dv >= (S)0)) bad = true;
+        const Axis<S> ya = make_axis<S>(clamp_border<S>(unnorm<S>((S)y, H), H), H);
+        const Axis<S> xa = make_axis<S>(clamp_border<S>(unnorm<S>(N::sub((S)x, dv), W), W), W);
+        // source taps of the (up to) 2x2 warped taps and of the imgR pixel
+        const Src<S> sy0 = src_index<S>(ya.in0 ? ya.i0 : 0, H0, H), sy1 = src_index<S>(ya.in1 ? ya.i0 + 1 : 0, H0, H);
+        const Src<S> sx0 = src_index<S>(xa.in0 ? xa.i0 : 0, W0, W), sx1 = src_index<S>(xa.in1 ? xa.i0 + 1 : 0, W0, W);
+        const Src<S> ry = src_index<S>(y, H0, H), rx = src_index<S>(x, W0, W);
+        for (int c = 0; c < C; ++c) {
+            const S *pl = imgL + ((long long)b * C + c) * HW0;
+            const S *pr = imgR + ((long long)b * C + c) * HW0;
+            S acc = (S)0;
+            if (xa.in0 && ya.in0) acc = N::fma(resize_at<S>(pl, H0, W0, sy0, sx0), N::mul(ya.w0, xa.w0), acc);
+            if (xa.in1 && ya.in0) acc = N::fma(resize_at<S>(pl, H0, W0, sy0, sx1), N::mul(ya.w0, xa.w1), acc);
+            if (xa.in0 && ya.in1) acc = N::fma(resize_at<S>(pl, H0, W0, sy1, sx0), N::mul(ya.w1, xa.w0), acc);
+            if (xa.in1 && ya.in1) acc = N::fma(resize_at<S>(pl, H0, W0, sy1, sx1), N::mul(ya.w1, xa.w1), acc);
+            out[((long long)b * C + c) * HW + (long long)y * W + x] = N::sub(resize_at<S>(pr, H0, W0, ry, rx), acc);
+        }
+    }
+    if (bad && neg_flag) atomicOr(neg_flag, 1);
+}
+
+inline unsigned grid_for(long long n, int threads, int per_sm) {
+    long long nb = (n + threads - 1) / threads;
+    const long long cap = (long long)sm_count() * per_sm;
+    if (nb > cap) nb = cap;
+    if (nb < 1) nb = 1;
+    return (unsigned)nb;
+}
+
+template <typename S>
+int warp_fwd_typed(const void *img, const void *disp, void *warped, void *mask, int *neg_flag,
+                   int B, int C, int H, int W, int pad, cudaStream_t s) {
+    const long long nquads = (long long)B * H * ((W + 3) / 4);
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(disp) |
+                           reinterpret_cast<uintptr_t>(warped) | reinterpret_cast<uintptr_t>(mask);
+    const int vec = (W % 4 == 0) && ((bits & 15) == 0);
+    warp_fwd_kernel<S, false><<<grid_for(nquads, 256, 8), 256, 0, s>>>(
+        (const S *)img, (const S *)disp, nullptr, (S *)warped, (S *)mask, neg_flag, B, C, H, W, pad == DSSMD_PAD_BORDER, vec);
+    return check_launch("warp_fwd");
+}
+
+template <typename S>
+int warp_bwd_typed(const void *g, const void *img, const void *disp, void *g_img, void *g_disp,
+                   int B, int C, int H, int W, int pad, cudaStream_t s) {
+    // channels per shared-memory pass: at most 48 KB of accumulators
+    int cc = (int)((48 * 1024) / ((size_t)W * sizeof(S)));
+    if (cc < 1)
+        return fail(DSSMD_ERR_UNSUPPORTED, "warp_bwd: a row of W=%d does not fit the shared-memory accumulator", W);
+    if (cc > C) cc = C;
+    const size_t smem = (size_t)cc * W * sizeof(S);
+    warp_bwd_kernel<S><<<(unsigned)(B * H), 256, smem, s>>>((const S *)g, (const S *)img, (const S *)disp,
+                                                          (S *)g_img, (S *)g_disp, B, C, H, W,
+                                                          pad == DSSMD_PAD_BORDER, cc);
+    return check_launch("warp_bwd");
+}
+
+}  // namespace
+
+}  // namespace dssmd
+
+using namespace dssmd;
+
+#define DSSMD_CHECK_WARP_ARGS(name)                                                                       \
+    DSSMD_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, name ": sizes must be positive (B=%d C=%d H=%d W=%d)", B, C, H, W); \
+    DSSMD_REQUIRE(padding_mode == DSSMD_PAD_ZEROS || padding_mode == DSSMD_PAD_BORDER, name ": unknown padding_mode %d", padding_mode); \
+    DSSMD_REQUIRE((long long)B * H < (1LL << 31), name ": B*H too large");
+
+extern "C" int dssmd_warp_fwd(const void *img, const void *disp, void *warped, void *mask, int *neg_flag,
+                              int B, int C, int H, int W, int padding_mode, int dtype, void *stream) {
+    DSSMD_REQUIRE(img && disp && warped, "warp_fwd: null pointer");
+    DSSMD_CHECK_WARP_ARGS("warp_fwd")
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    switch (dtype) {
+        case DSSMD_F32: return warp_fwd_typed<float>(img, disp, warped, mask, neg_flag, B, C, H, W, padding_mode, s);
+        case DSSMD_F64: return warp_fwd_typed<double>(img, disp, warped, mask, neg_flag, B, C, H, W, padding_mode, s);
+        case DSSMD_BF16:
+        case DSSMD_F16:
+            return fail(DSSMD_ERR_UNSUPPORTED, "warp_fwd: 16-bit dtypes are not supported (coordinates need fp32; see DESIGN.md)");
+        default: return fail(DSSMD_ERR_INVALID_ARGUMENT, "warp_fwd: unknown dtype %d", dtype);
+    }
+}
+
+extern "C" int dssmd_warp_bwd(const void *g, const void *img, const void *disp, void *g_img, void *g_disp,
+                              int B, int C, int H, int W, int padding_mode, int dtype, void *stream) {
+    DSSMD_REQUIRE(g && img && disp, "warp_bwd: null input pointer");
+    DSSMD_CHECK_WARP_ARGS("warp_bwd")
+    if (!g_img && !g_disp) return DSSMD_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    switch (dtype) {
+        case DSSMD_F32: return warp_bwd_typed<float>(g, img, disp, g_img, g_disp, B, C, H, W, padding_mode, s);
+        case DSSMD_F64: return warp_bwd_typed<double>(g, img, disp, g_img, g_disp, B, C, H, W, padding_mode, s);
+        case DSSMD_BF16:
+        case DSSMD_F16:
+            return fail(DSSMD_ERR_UNSUPPORTED, "warp_bwd: 16-bit dtypes are not supported (coordinates need fp32; see DESIGN.md)");
+        default: return fail(DSSMD_ERR_INVALID_ARGUMENT, "warp_bwd: unknown dtype %d", dtype);
+    }
+}
+
+extern "C" int dssmd_resize_bilinear_fwd(const void *in, void *out, int B, int C, int Hi, int Wi, int Ho, int Wo,
+                                         int dtype, void *stream) {
+    DSSMD_REQUIRE(in && out, "resize_bilinear_fwd: null pointer");
+    DSSMD_REQUIRE(B > 0 && C > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "resize_bilinear_fwd: sizes must be positive");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long n = (long long)B * C * Ho * Wo;
+    if (dtype == DSSMD_F32)
+        resize_fwd_kernel<float><<<grid_for(n, 256, 8), 256, 0, s>>>((const float *)in, (float *)out, B * C, Hi, Wi, Ho, Wo);
+    else if (dtype == DSSMD_F64)
+        resize_fwd_kernel<double><<<grid_for(n, 256, 8), 256, 0, s>>>((const double *)in, (double *)out, B * C, Hi, Wi, Ho, Wo);
+    else
+        return fail(DSSMD_ERR_UNSUPPORTED, "resize_bilinear_fwd: dtype %d not supported", dtype);
+    return check_launch("resize_bilinear_fwd");
+}
+
+extern "C" int dssmd_resize_bilinear_bwd(const void *g_out, void *g_in, int B, int C, int Hi, int Wi, int Ho, int Wo,
+                                         int dtype, void *stream) {
+    DSSMD_REQUIRE(g_out && g_in, "resize_bilinear_bwd: null pointer");
+    DSSMD_REQUIRE(B > 0 && C > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "resize_bilinear_bwd: sizes must be positive");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long n = (long long)B * C * Hi * Wi;
+    if (dtype == DSSMD_F32)
+        resize_bwd_kernel<float><<<grid_for(n, 256, 8), 256, 0, s>>>((const float *)g_out, (float *)g_in, B * C, Hi, Wi, Ho, Wo);
+    else if (dtype == DSSMD_F64)
+        resize_bwd_kernel<double><<<grid_for(n, 256, 8), 256, 0, s>>>((const double *)g_out, (double *)g_in, B * C, Hi, Wi, Ho, Wo);
+    else
+        return fail(DSSMD_ERR_UNSUPPORTED, "resize_bilinear_bwd: dtype %d not supported", dtype);
+    return check_launch("resize_bilinear_bwd");
+}
+
+extern "C" int dssmd_lrwarp_error_fwd(const void *imgL, const void *disp, const void *imgR, void *out, int *neg_flag,
+                                      int B, int C, int H0, int W0, int H, int W, int dtype, void *stream) {
+    DSSMD_REQUIRE(imgL && disp && imgR && out, "lrwarp_error_fwd: null pointer");
+    DSSMD_REQUIRE(B > 0 && C > 0 && H0 > 0 && W0 > 0 && H > 0 && W > 0, "lrwarp_error_fwd: sizes must be positive");
+    DSSMD_REQUIRE(W0 > W || (W0 == W && H0 == H),
+                  "lrwarp_error_fwd: images no wider than disp must already have disp's size (got %dx%d vs %dx%d)", H0, W0, H, W);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long n = (long long)B * H * W;
+    if (dtype == DSSMD_F32)
+        lrwarp_fwd_kernel<float><<<grid_for(n, 256, 8), 256, 0, s>>>((const float *)imgL, (const float *)disp, (const float *)imgR,
+                                                                   (float *)out, neg_flag, B, C, H0, W0, H, W);
+    else if (dtype == DSSMD_F64)
+        lrwarp_fwd_kernel<double><<<grid_for(n, 256, 8), 256, 0, s>>>((const double *)imgL, (const double *)disp, (const double *)imgR,
+                                                                    (double *)out, neg_flag, B, C, H0, W0, H, W);
+    else
+        return fail(DSSMD_ERR_UNSUPPORTED, "lrwarp_error_fwd: dtype %d not supported", dtype);
+    return check_launch("lrwarp_error_fwd");
+}

@@ -1,0 +1,214 @@
+"""autograd wrappers around the C ABI.  Plumbing only: allocate outputs with
+torch (so the caching allocator and autograd see them), pick the device/stream
+of the input tensors, call the kernel, map errors."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_CHECK_NEGATIVE = True
+
+
+def set_check_negative_disparity(flag: bool) -> None:
+    """Upstream's `assert disp.min() >= 0` costs a device->host sync per warp.
+    The check is on by default (same behaviour); callers who guarantee
+    non-negative disparities can turn the read-back off."""
+    global _CHECK_NEGATIVE
+    _CHECK_NEGATIVE = bool(flag)
+
+
+def _check4(name, t):
+    if t.dim() != 4:
+        raise RuntimeError(f"{name}: expected a 4-D [B,C,H,W] tensor, got shape {tuple(t.shape)}")
+
+
+class CorrelationFn(torch.autograd.Function):
+    """out[b,d,y,x] = mean_c L[b,c,y,x] * R[b,c,y,x-d] (upstream build_corr)."""
+
+    @staticmethod
+    def forward(ctx, left, right, max_disp):
+        _lib.require_cuda("build_corr", left, right)
+        _check4("build_corr", left); _check4("build_corr", right)
+        if left.shape != right.shape:
+            raise RuntimeError(f"build_corr: left {tuple(left.shape)} and right {tuple(right.shape)} differ")
+        if left.dtype != right.dtype:
+            raise RuntimeError(f"build_corr: left is {left.dtype}, right is {right.dtype}")
+        D = int(max_disp)
+        B, C, H, W = left.shape
+        L, R = left.contiguous(), right.contiguous()
+        out = torch.empty((B, max(D, 0), H, W), dtype=L.dtype, device=L.device)
+        if out.numel() > 0 and C > 0:
+            with torch.cuda.device(L.device):
+                _lib.check(_lib.lib().dssmd_corr_fwd(_lib.ptr(L), _lib.ptr(R), _lib.ptr(out), B, C, H, W, D,
+                                                     _lib.dtype_code(L), _lib.stream_ptr(L.device)))
+        elif out.numel() > 0:
+            out.fill_(float("nan"))  # mean over zero channels
+        ctx.save_for_backward(L, R)
+        ctx.D = D
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L, R = ctx.saved_tensors
+        B, C, H, W = L.shape
+        need_l, need_r = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gL = torch.empty_like(L) if need_l else None
+        gR = torch.empty_like(R) if need_r else None
+        if (need_l or need_r) and L.numel() > 0:
+            if ctx.D == 0:
+                for t in (gL, gR):
+                    if t is not None:
+                        t.zero_()
+            else:
+                g = g.contiguous()
+                with torch.cuda.device(L.device):
+                    _lib.check(_lib.lib().dssmd_corr_bwd(_lib.ptr(g), _lib.ptr(L), _lib.ptr(R), _lib.ptr(gL), _lib.ptr(gR),
+                                                         B, C, H, W, ctx.D, _lib.dtype_code(L), _lib.stream_ptr(L.device)))
+        return gL, gR, None
+
+
+def _pad_code(padding_mode):
+    if padding_mode not in ("zeros", "border", "reflection"):
+        raise ValueError(f"nn.functional.grid_sample(): expected padding_mode to be 'zeros', 'border', or "
+                         f"'reflection', but got: '{padding_mode}'")
+    if padding_mode == "reflection":
+        raise NotImplementedError("disp_warp: padding_mode='reflection' is not implemented by the CUDA kernel "
+                                  "(upstream documents 'zeros' and 'border' only)")
+    return _lib.PAD_CODE[padding_mode]
+
+
+def _check_warp_args(name, img, disp):
+    _lib.require_cuda(name, img, disp)
+    _check4(name, img); _check4(name, disp)
+    if img.dtype != disp.dtype:
+        raise RuntimeError(f"{name}: expected img and disp to have the same dtype, got {img.dtype} and {disp.dtype}")
+    B, C, H, W = img.shape
+    if tuple(disp.shape) != (B, 1, H, W):
+        raise RuntimeError(f"{name}: disp must be [B,1,H,W]={(B, 1, H, W)}, got {tuple(disp.shape)}")
+    if img.dtype not in (torch.float32, torch.float64):
+        raise NotImplementedError(f"{name}: dtype {img.dtype} not supported (the sampling coordinates need fp32; "
+                                  "upstream's own 16-bit path is numerically meaningless at image widths)")
+
+
+def _raise_if_flag(flag):
+    if _CHECK_NEGATIVE and flag is not None and int(flag.item()) != 0:
+        raise AssertionError("disp.min() >= 0")  # upstream utils/disparity_warper.py:93
+
+
+class DispWarpFn(torch.autograd.Function):
+    """(warped, valid_mask) = disp_warp(img, disp, padding_mode)."""
+
+    @staticmethod
+    def forward(ctx, img, disp, padding_mode):
+        pad = _pad_code(padding_mode)
+        _check_warp_args("disp_warp", img, disp)
+        B, C, H, W = img.shape
+        I, Dp = img.contiguous(), disp.contiguous()
+        warped = torch.empty_like(I)
+        mask = torch.empty_like(I)
+        if I.numel() > 0:
+            flag = torch.zeros(1, dtype=torch.int32, device=I.device) if _CHECK_NEGATIVE else None
+            with torch.cuda.device(I.device):
+                _lib.check(_lib.lib().dssmd_warp_fwd(_lib.ptr(I), _lib.ptr(Dp), _lib.ptr(warped), _lib.ptr(mask), _lib.ptr(flag),
+                                                     B, C, H, W, pad, _lib.dtype_code(I), _lib.stream_ptr(I.device)))
+            _raise_if_flag(flag)
+        ctx.save_for_backward(I, Dp)
+        ctx.pad = pad
+        ctx.mark_non_differentiable(mask)
+        return warped, mask
+
+    @staticmethod
+    def backward(ctx, g_warped, _g_mask):
+        I, Dp = ctx.saved_tensors
+        B, C, H, W = I.shape
+        need_i, need_d = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g_img = torch.empty_like(I) if need_i else None
+        g_disp = torch.empty_like(Dp) if need_d else None
+        if (need_i or need_d) and I.numel() > 0:
+            g = g_warped.contiguous()
+            with torch.cuda.device(I.device):
+                _lib.check(_lib.lib().dssmd_warp_bwd(_lib.ptr(g), _lib.ptr(I), _lib.ptr(Dp), _lib.ptr(g_img), _lib.ptr(g_disp),
+                                                     B, C, H, W, ctx.pad, _lib.dtype_code(I), _lib.stream_ptr(I.device)))
+        return g_img, g_disp, None
+
+
+def resize_bilinear(img, size):
+    """F.interpolate(img, size=size, mode='bilinear', align_corners=False), forward only."""
+    _lib.require_cuda("resize_bilinear", img)
+    B, C, Hi, Wi = img.shape
+    Ho, Wo = int(size[0]), int(size[1])
+    src = img.contiguous()
+    out = torch.empty((B, C, Ho, Wo), dtype=img.dtype, device=img.device)
+    with torch.cuda.device(img.device):
+        _lib.check(_lib.lib().dssmd_resize_bilinear_fwd(_lib.ptr(src), _lib.ptr(out), B, C, Hi, Wi, Ho, Wo,
+                                                        _lib.dtype_code(src), _lib.stream_ptr(img.device)))
+    return out
+
+
+def _resize_bilinear_bwd(g_out, in_size):
+    B, C, Ho, Wo = g_out.shape
+    Hi, Wi = in_size
+    g = g_out.contiguous()
+    g_in = torch.empty((B, C, Hi, Wi), dtype=g.dtype, device=g.device)
+    with torch.cuda.device(g.device):
+        _lib.check(_lib.lib().dssmd_resize_bilinear_bwd(_lib.ptr(g), _lib.ptr(g_in), B, C, Hi, Wi, Ho, Wo,
+                                                        _lib.dtype_code(g), _lib.stream_ptr(g.device)))
+    return g_in
+
+
+class LRWarpErrorFn(torch.autograd.Function):
+    """imgR' - warp(imgL', disp): upstream LRwarp_error, one fused launch forward."""
+
+    @staticmethod
+    def forward(ctx, imgL, disp, imgR):
+        _lib.require_cuda("LRwarp_error", imgL, disp, imgR)
+        for t in (imgL, disp, imgR):
+            _check4("LRwarp_error", t)
+        if imgL.dtype != disp.dtype or imgR.dtype != disp.dtype:
+            raise RuntimeError("LRwarp_error: imgL, disp and imgR must share a dtype")
+        if imgL.dtype not in (torch.float32, torch.float64):
+            raise NotImplementedError(f"LRwarp_error: dtype {imgL.dtype} not supported")
+        if imgL.shape != imgR.shape:
+            raise RuntimeError(f"LRwarp_error: imgL {tuple(imgL.shape)} and imgR {tuple(imgR.shape)} differ")
+        B, C, H0, W0 = imgL.shape
+        Bd, one, H, W = disp.shape
+        if Bd != B or one != 1:
+            raise RuntimeError(f"LRwarp_error: disp must be [B,1,H,W], got {tuple(disp.shape)}")
+        if W0 <= W and (H0, W0) != (H, W):
+            raise RuntimeError(f"LRwarp_error: images {H0}x{W0} are not wider than disp {H}x{W} and do not match it")
+        Lc, Rc, Dc = imgL.contiguous(), imgR.contiguous(), disp.contiguous()
+        out = torch.empty((B, C, H, W), dtype=Lc.dtype, device=Lc.device)
+        if out.numel() > 0:
+            flag = torch.zeros(1, dtype=torch.int32, device=Lc.device) if _CHECK_NEGATIVE else None
+            with torch.cuda.device(Lc.device):
+                _lib.check(_lib.lib().dssmd_lrwarp_error_fwd(_lib.ptr(Lc), _lib.ptr(Dc), _lib.ptr(Rc), _lib.ptr(out), _lib.ptr(flag),
+                                                             B, C, H0, W0, H, W, _lib.dtype_code(Lc), _lib.stream_ptr(Lc.device)))
+            _raise_if_flag(flag)
+        ctx.save_for_backward(Lc, Dc)
+        ctx.in_size = (H0, W0)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        Lc, Dc = ctx.saved_tensors
+        B, C, H0, W0 = Lc.shape
+        H, W = Dc.shape[-2:]
+        resized = W0 > W
+        need_l, need_d, need_r = ctx.needs_input_grad
+        g = g.contiguous()
+        g_imgL = g_disp = g_imgR = None
+        if need_r:
+            g_imgR = _resize_bilinear_bwd(g, (H0, W0)) if resized else g
+        if need_l or need_d:
+            Ls = resize_bilinear(Lc, (H, W)) if resized else Lc
+            gw = g.neg()  # d(err)/d(warped) = -1
+            g_Ls = torch.empty_like(Ls) if need_l else None
+            g_disp = torch.empty_like(Dc) if need_d else None
+            with torch.cuda.device(Ls.device):
+                _lib.check(_lib.lib().dssmd_warp_bwd(_lib.ptr(gw), _lib.ptr(Ls), _lib.ptr(Dc), _lib.ptr(g_Ls), _lib.ptr(g_disp),
+                                                     B, C, H, W, _lib.PAD_CODE["border"], _lib.dtype_code(Ls),
+                                                     _lib.stream_ptr(Ls.device)))
+            if need_l:
+                g_imgL = _resize_bilinear_bwd(g_Ls, (H0, W0)) if resized else g_Ls
+        return g_imgL, g_disp, g_imgR

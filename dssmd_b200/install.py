@@ -1,0 +1,76 @@
+"""Swap the CUDA ops into an (unmodified) upstream DSSMD checkout.
+
+    import sys; sys.path.insert(0, "/path/to/DSSMD")
+    import dssmd_b200; dssmd_b200.install()
+    from models.DSSMD import DSSMMD        # now calls the B200 kernels
+
+Upstream's models obtain `build_corr` through `from models.UtilsNet.submoudles
+import *` (models/DSSMD.py:9 and the three siblings), so the name must be rebound
+both in the defining module and in every module that star-imported it.  The same
+holds for disp_warp / LRwarp_error / CostVolume.
+"""
+from __future__ import annotations
+
+import importlib
+import sys
+
+from . import cost_volume, disparity_warper, submoudles
+
+# upstream module -> {attribute: replacement}
+_DEFINING = {
+    "models.UtilsNet.submoudles": {"build_corr": submoudles.build_corr},
+    "models.UtilsNet.cost_volume": {"CostVolume": cost_volume.CostVolume},
+    "models.UtilsNet.stereo_op": {"disp_warp": disparity_warper.disp_warp,
+                                  "LRwarp_error": disparity_warper.LRwarp_error},
+    "utils.disparity_warper": {"disp_warp": disparity_warper.disp_warp,
+                               "LRwarp_error": disparity_warper.LRwarp_error},
+}
+# modules that copy those names into their own namespace at import time
+_IMPORTERS = ["models.DSSMD", "models.DSSMD_new", "models.SSMDNet", "models.SDNet"]
+
+_saved = {}
+
+
+def install(import_missing: bool = True):
+    """Rebind the hot-path functions in the upstream modules.  Returns the list
+    of (module, attribute) pairs that were patched.  With import_missing=True the
+    defining modules are imported first (upstream must be on sys.path)."""
+    patched = []
+    replacements = {}
+    for modname, attrs in _DEFINING.items():
+        mod = sys.modules.get(modname)
+        if mod is None and import_missing:
+            try:
+                mod = importlib.import_module(modname)
+            except ImportError:
+                mod = None
+        if mod is None:
+            continue
+        for attr, new in attrs.items():
+            old = getattr(mod, attr, None)
+            if old is None or old is new:
+                continue
+            _saved.setdefault((modname, attr), old)
+            replacements[id(old)] = new
+            setattr(mod, attr, new)
+            patched.append((modname, attr))
+    for modname in _IMPORTERS:
+        mod = sys.modules.get(modname)
+        if mod is None:
+            continue
+        for attr, val in list(vars(mod).items()):
+            new = replacements.get(id(val))
+            if new is not None:
+                _saved.setdefault((modname, attr), val)
+                setattr(mod, attr, new)
+                patched.append((modname, attr))
+    return patched
+
+
+def uninstall():
+    """Undo install()."""
+    for (modname, attr), old in list(_saved.items()):
+        mod = sys.modules.get(modname)
+        if mod is not None:
+            setattr(mod, attr, old)
+    _saved.clear()

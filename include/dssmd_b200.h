@@ -1,0 +1,121 @@
+/*
+ * dssmd_b200.h -- C ABI of libdssmd_b200.so: the DSSMD correlation cost volume and
+ * disparity warp as hand-written sm_100a CUDA kernels.
+ *
+ * The upstream project (Magicboomliu/DSSMD) is pure Python/PyTorch and has no FFI
+ * of its own; each entry point below replaces one upstream Python function (or
+ * the autograd backward PyTorch derives for it) and cites it.  Paths are
+ * relative to the upstream tree.  dssmd_b200/_lib.py is the ctypes binding;
+ * INTEGRATION.md shows the stub an upstream maintainer would add.
+ *
+ * Conventions
+ *  - All tensors are dense, contiguous NCHW device buffers owned by the caller.
+ *    The library never allocates, frees or retains a pointer after return.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *    Every call only enqueues work on that stream; nothing synchronises.
+ *  - Re-entrant and thread-safe (nn.DataParallel calls from one host thread per
+ *    GPU, upstream trainfiles/dssmd_traner_new.py:131-135): no global mutable
+ *    state other than the thread-local last-error string.  The caller makes the
+ *    buffers' device current (cudaSetDevice) before the call.
+ *  - Return value: 0 on success, a DSSMD_ERR_* code otherwise;
+ *    dssmd_last_error() then describes the failure.  Never aborts or throws.
+ */
+#ifndef DSSMD_B200_H_
+#define DSSMD_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSSMD_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DSSMD_API __attribute__((visibility("default")))
+#else
+#define DSSMD_API
+#endif
+
+/* element types (`dtype` arguments) */
+#define DSSMD_F32 0
+#define DSSMD_BF16 1
+#define DSSMD_F16 2
+#define DSSMD_F64 3
+
+/* grid_sample padding modes (`padding_mode` arguments) */
+#define DSSMD_PAD_ZEROS 0
+#define DSSMD_PAD_BORDER 1
+
+/* error codes */
+#define DSSMD_OK 0
+#define DSSMD_ERR_INVALID_ARGUMENT 1 /* null pointer, non-positive size, unknown enum */
+#define DSSMD_ERR_UNSUPPORTED 2      /* dtype/shape combination not implemented */
+#define DSSMD_ERR_CUDA 3             /* a CUDA runtime call or launch failed */
+
+DSSMD_API int dssmd_version(void);
+/* Thread-local, valid until the next failing call on the same thread. */
+DSSMD_API const char *dssmd_last_error(void);
+
+/* ---- correlation cost volume ------------------------------------------------
+ * Replaces build_corr(img_left, img_right, max_disp),
+ * models/UtilsNet/submoudles.py:301-311 (and the 'correlation' branch of
+ * CostVolume.forward, models/UtilsNet/cost_volume.py:39-47):
+ *   out[b,d,y,x] = (1/C) * sum_c L[b,c,y,x] * R[b,c,y,x-d]   for x >= d, else 0
+ * L, R: [B,C,H,W]; out: [B,D,H,W] (every element is written, no pre-zeroing
+ * needed); D = max_disp channels d = 0..D-1.  dtype F32/BF16/F16 accumulate in
+ * fp32, F64 in fp64. */
+DSSMD_API int dssmd_corr_fwd(const void *L, const void *R, void *out,
+                   int B, int C, int H, int W, int D, int dtype, void *stream);
+
+/* Backward of the above (the graph autograd builds from submoudles.py:304-308):
+ *   gL[b,c,y,x ] = (1/C) * sum_{d<=min(D-1,x)}      g[b,d,y,x]    * R[b,c,y,x-d]
+ *   gR[b,c,y,x'] = (1/C) * sum_{d<=min(D-1,W-1-x')} g[b,d,y,x'+d] * L[b,c,y,x'+d]
+ * g: [B,D,H,W]; gL, gR: [B,C,H,W], fully overwritten.  Either of gL / gR may be
+ * NULL to skip that gradient. */
+DSSMD_API int dssmd_corr_bwd(const void *g, const void *L, const void *R, void *gL, void *gR,
+                   int B, int C, int H, int W, int D, int dtype, void *stream);
+
+/* ---- disparity warp -----------------------------------------------------------
+ * Replaces disp_warp(img, disp, padding_mode), utils/disparity_warper.py:83-106
+ * (byte-identical copy at models/UtilsNet/stereo_op.py:41-63), including its
+ * helpers meshgrid (:60-80) and normalize_coords (:48-58) and the two
+ * F.grid_sample calls (:100, :103; bilinear, align_corners=False):
+ *   warped[b,c,y,x] = bilinear(img[b,c], ix, iy),  mask = 1[sum of in-bounds
+ *   bilinear weights at the un-clamped (ix,iy) >= 0.9999]
+ * img, warped, mask: [B,C,H,W]; disp: [B,1,H,W].  `mask` may be NULL (skipped).
+ * `neg_flag` (device int, may be NULL) is OR-ed with 1 if any disparity is
+ * negative or NaN -- the condition of upstream's `assert disp.min() >= 0` (:93);
+ * the caller zeroes it beforehand and raises after reading it back.
+ * dtype: F32 or F64. */
+DSSMD_API int dssmd_warp_fwd(const void *img, const void *disp, void *warped, void *mask, int *neg_flag,
+                   int B, int C, int H, int W, int padding_mode, int dtype, void *stream);
+
+/* Backward of disp_warp (aten::grid_sampler_2d_backward composed with the
+ * coordinate arithmetic of :95-99); the mask carries no gradient.
+ * g: [B,C,H,W] gradient of `warped`; g_img: [B,C,H,W]; g_disp: [B,1,H,W]; both
+ * fully overwritten, either may be NULL to skip it. */
+DSSMD_API int dssmd_warp_bwd(const void *g, const void *img, const void *disp, void *g_img, void *g_disp,
+                   int B, int C, int H, int W, int padding_mode, int dtype, void *stream);
+
+/* ---- bilinear resize (LRwarp_error's pre-scaling) -------------------------------
+ * Replaces F.interpolate(img, size=(Ho,Wo), mode='bilinear', align_corners=False)
+ * as called by LRwarp_error, utils/disparity_warper.py:110-113.
+ * in: [B,C,Hi,Wi]; out: [B,C,Ho,Wo].  dtype: F32 or F64. */
+DSSMD_API int dssmd_resize_bilinear_fwd(const void *in, void *out, int B, int C, int Hi, int Wi, int Ho, int Wo,
+                              int dtype, void *stream);
+/* g_out: [B,C,Ho,Wo]; g_in: [B,C,Hi,Wi], fully overwritten. */
+DSSMD_API int dssmd_resize_bilinear_bwd(const void *g_out, void *g_in, int B, int C, int Hi, int Wi, int Ho, int Wo,
+                              int dtype, void *stream);
+
+/* ---- fused left/right warp residual ----------------------------------------------
+ * Replaces LRwarp_error(imgL, disp, imgR), utils/disparity_warper.py:109-115
+ * (== models/UtilsNet/stereo_op.py:67-73) in one launch: both images are
+ * bilinearly resized to disp's [H,W] when wider (W0 > W), imgL is warped by disp
+ * with 'border' padding, and  out = imgR' - warped  is written.
+ * imgL, imgR: [B,C,H0,W0]; disp: [B,1,H,W]; out: [B,C,H,W].  dtype: F32 or F64. */
+DSSMD_API int dssmd_lrwarp_error_fwd(const void *imgL, const void *disp, const void *imgR, void *out, int *neg_flag,
+                           int B, int C, int H0, int W0, int H, int W, int dtype, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSSMD_B200_H_ */

@@ -1,0 +1,299 @@
+"""GPU parity tests: the CUDA kernels, called through the Python shim and the C
+ABI, against (1) the golden fixtures produced by the upstream functions, (2) the
+C oracle on seeded inputs, (3) a torch restatement at BASELINE.json's full sizes.
+
+Tolerances (north_star): 1e-5 relative (max-abs / max-abs) in fp32, 1e-2 in bf16.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import TOL_BF16, TOL_F32, load_cases, rel_err
+import ref_torch
+
+pytestmark = pytest.mark.gpu
+
+CORR = load_cases("corr")
+WARP = load_cases("warp")
+LRW = load_cases("lrwarp")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import dssmd_b200
+    from dssmd_b200 import _lib
+    _lib.lib()  # fail loudly if the extension is missing
+    return dssmd_b200
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import oracle as O
+    return O
+
+
+def cuda(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dtype)
+
+
+def feat(shape, seed, relu=True, dtype=torch.float32):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    t = torch.randn(shape, generator=g, device="cuda")
+    return (t.relu() if relu else t).to(dtype)
+
+
+# ------------------------------------------------------------------ correlation
+@pytest.mark.parametrize("name", sorted(CORR))
+def test_corr_golden(ops, name):
+    c = CORR[name]
+    bf16 = bool(c["bf16"])
+    dt = torch.bfloat16 if bf16 else torch.float32
+    tol = TOL_BF16 if bf16 else TOL_F32
+    L = cuda(c["L"], dt).requires_grad_(True)
+    R = cuda(c["R"], dt).requires_grad_(True)
+    out = ops.build_corr(L, R, int(c["D"]))
+    assert out.shape == c["out"].shape and out.is_contiguous() and out.dtype == dt
+    out.backward(cuda(c["g"], dt))
+    assert rel_err(out.detach().float().cpu().numpy(), c["out"]) <= tol
+    assert rel_err(L.grad.float().cpu().numpy(), c["gL"]) <= tol
+    assert rel_err(R.grad.float().cpu().numpy(), c["gR"]) <= tol
+
+
+CORR_SHAPES = [
+    # B, C, H, W, D, relu          what it covers
+    (1, 128, 40, 80, 24, True),    # cfg1 / model shape
+    (2, 256, 6, 160, 41, True),    # cfg2 rows (C=256, W=160, D=41)
+    (1, 128, 5, 120, 24, False),   # cfg5 row shape, cancellation inputs
+    (2, 128, 3, 156, 24, True),    # 384x1248 / 8: W*4 bytes not 16-B aligned for bf16
+    (1, 20, 3, 37, 11, False),     # ragged: W % 4 != 0, C not a power of two
+    (1, 16, 3, 6, 9, False),       # D > W
+    (1, 3, 2, 1, 2, True),         # W = 1
+    (1, 1, 1, 8, 1, True),         # C = 1, D = 1
+    (1, 64, 2, 300, 192, True),    # large D, x-tiled
+    (3, 8, 33, 16, 5, True),       # many rows per block
+    (1, 32, 4, 520, 40, False),    # W > 256: several x tiles
+]
+
+
+@pytest.mark.parametrize("shape", CORR_SHAPES, ids=lambda s: "x".join(map(str, s[:5])))
+def test_corr_vs_oracle_f32(ops, oracle, shape):
+    B, C, H, W, D, relu = shape
+    L = feat((B, C, H, W), 1, relu).requires_grad_(True)
+    R = feat((B, C, H, W), 2, relu).requires_grad_(True)
+    g = feat((B, D, H, W), 3, False)
+    out = ops.build_corr(L, R, D)
+    out.backward(g)
+    Ln, Rn, gn = (t.detach().cpu().numpy() for t in (L, R, g))
+    ref = oracle.corr_fwd(Ln, Rn, D)
+    ref64 = oracle.corr_fwd(Ln.astype(np.float64), Rn.astype(np.float64), D)
+    assert rel_err(out.detach().cpu().numpy(), ref) <= TOL_F32
+    assert rel_err(out.detach().cpu().numpy(), ref64) <= TOL_F32
+    gL, gR = oracle.corr_bwd(gn, Ln, Rn)
+    assert rel_err(L.grad.cpu().numpy(), gL) <= TOL_F32
+    assert rel_err(R.grad.cpu().numpy(), gR) <= TOL_F32
+    # exact structural zeros (Appendix B.2)
+    o = out.detach()
+    for d in range(min(D, W)):
+        assert torch.count_nonzero(o[:, d, :, :d]) == 0
+    if D > W:
+        assert torch.count_nonzero(o[:, W:]) == 0
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", CORR_SHAPES[:6], ids=lambda s: "x".join(map(str, s[:5])))
+def test_corr_vs_oracle_16bit(ops, oracle, shape, dt):
+    B, C, H, W, D, relu = shape
+    L = feat((B, C, H, W), 1, relu, dt).requires_grad_(True)
+    R = feat((B, C, H, W), 2, relu, dt).requires_grad_(True)
+    g = feat((B, D, H, W), 3, False, dt)
+    out = ops.build_corr(L, R, D)
+    assert out.dtype == dt
+    out.backward(g)
+    Ln, Rn, gn = (t.detach().float().cpu().numpy() for t in (L, R, g))
+    assert rel_err(out.detach().float().cpu().numpy(), oracle.corr_fwd(Ln, Rn, D)) <= TOL_BF16
+    gL, gR = oracle.corr_bwd(gn, Ln, Rn)
+    assert rel_err(L.grad.float().cpu().numpy(), gL) <= TOL_BF16
+    assert rel_err(R.grad.float().cpu().numpy(), gR) <= TOL_BF16
+
+
+def test_corr_f64_and_gradcheck(ops):
+    L = feat((1, 5, 3, 9), 1, False, torch.float64).requires_grad_(True)
+    R = feat((1, 5, 3, 9), 2, False, torch.float64).requires_grad_(True)
+    out = ops.build_corr(L, R, 4)
+    assert rel_err(out.detach().cpu().numpy(), ref_torch.corr_ref(L.detach(), R.detach(), 4).cpu().numpy()) <= 1e-12
+    assert torch.autograd.gradcheck(lambda a, b: ops.build_corr(a, b, 4), (L, R), eps=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("cfg", [
+    ("cfg2", 8, 256, 80, 160, 41),
+    ("cfg3", 8, 128, 40, 80, 24),
+    ("cfg4", 16, 128, 48, 160, 24),
+    ("cfg5", 4, 128, 72, 120, 24),
+    ("cfg5_d192", 4, 128, 72, 120, 192),
+], ids=lambda c: c[0])
+def test_corr_full_size_vs_torch(ops, cfg):
+    """BASELINE.json sizes: compare with the torch restatement on the same GPU
+    (fp32 and an fp64 arbiter) plus size-independent properties."""
+    _, B, C, H, W, D = cfg
+    L = feat((B, C, H, W), 11).requires_grad_(True)
+    R = feat((B, C, H, W), 12).requires_grad_(True)
+    g = feat((B, D, H, W), 13, False)
+    out = ops.build_corr(L, R, D)
+    out.backward(g)
+    L2, R2 = L.detach().clone().requires_grad_(True), R.detach().clone().requires_grad_(True)
+    ref = ref_torch.corr_ref(L2, R2, D)
+    ref.backward(g)
+    ref64 = ref_torch.corr_ref(L.detach().double(), R.detach().double(), D)
+    assert rel_err(out.detach().cpu().numpy(), ref64.cpu().numpy()) <= TOL_F32
+    assert rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) <= TOL_F32
+    assert rel_err(L.grad.cpu().numpy(), L2.grad.cpu().numpy()) <= TOL_F32
+    assert rel_err(R.grad.cpu().numpy(), R2.grad.cpu().numpy()) <= TOL_F32
+    # properties: channel 0 is the plain mean of products; linearity in L
+    assert rel_err(out.detach()[:, 0].cpu().numpy(), (L.detach() * R.detach()).mean(1).cpu().numpy()) <= TOL_F32
+    out2 = ops.build_corr(2.0 * L.detach(), R.detach(), D)
+    assert rel_err(out2.cpu().numpy(), (2.0 * out.detach()).cpu().numpy()) <= 1e-6
+    # <g, corr(L,R)> == <gL, L> == <gR, R>  (bilinearity => Euler identity)
+    s0 = float((g.double() * out.detach().double()).sum())
+    s1 = float((L.grad.double() * L.detach().double()).sum())
+    s2 = float((R.grad.double() * R.detach().double()).sum())
+    assert abs(s0 - s1) <= 1e-4 * abs(s0) and abs(s0 - s2) <= 1e-4 * abs(s0)
+
+
+def test_corr_noncontiguous_and_cost_volume(ops):
+    L = feat((2, 8, 6, 16), 1).to(memory_format=torch.channels_last)
+    R = feat((2, 8, 12, 16), 2)[:, :, ::2]
+    out = ops.build_corr(L, R, 5)
+    ref = ref_torch.corr_ref(L, R, 5)
+    assert out.is_contiguous() and rel_err(out.cpu().numpy(), ref.cpu().numpy()) <= TOL_F32
+    cv = ops.CostVolume(5)(L, R)
+    assert torch.equal(cv, out)
+    with pytest.raises(NotImplementedError):
+        ops.CostVolume(5, "cosine")(L, R)
+
+
+# ------------------------------------------------------------------------ warp
+@pytest.mark.parametrize("name", sorted(WARP))
+def test_warp_golden(ops, name):
+    c = WARP[name]
+    pad = str(c["pad"])
+    img = cuda(c["img"]).requires_grad_(True)
+    disp = cuda(c["disp"]).requires_grad_(True)
+    warped, mask = ops.disp_warp(img, disp, padding_mode=pad)
+    warped.backward(cuda(c["g"]))
+    assert rel_err(warped.detach().cpu().numpy(), c["warped"]) <= TOL_F32
+    assert np.array_equal(mask.cpu().numpy(), c["mask"])
+    assert rel_err(img.grad.cpu().numpy(), c["g_img"]) <= TOL_F32
+    assert rel_err(disp.grad.cpu().numpy(), c["g_disp"]) <= TOL_F32
+
+
+def images(B, C, H, W, seed, smooth=True):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    img = torch.rand((B, C, H, W), generator=g, device="cuda")
+    if smooth:
+        img = torch.nn.functional.avg_pool2d(img, 9, 1, 4)
+    base = torch.rand((B, 1, H // 8 + 1, W // 8 + 1), generator=g, device="cuda")
+    disp = torch.nn.functional.interpolate(base, size=(H, W), mode="bilinear", align_corners=True)
+    disp = 0.5 + disp * (192.0 * W / 960.0 - 0.5)
+    return img, disp.contiguous()
+
+
+@pytest.mark.parametrize("pad", ["border", "zeros"])
+@pytest.mark.parametrize("shape", [(2, 3, 40, 80), (1, 3, 33, 157), (1, 1, 2, 9), (1, 7, 16, 64), (2, 3, 64, 1280)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_warp_vs_oracle(ops, oracle, shape, pad):
+    B, C, H, W = shape
+    img, disp = images(B, C, H, W, 5, smooth=False)
+    img.requires_grad_(True); disp.requires_grad_(True)
+    g = feat((B, C, H, W), 6, False)
+    warped, mask = ops.disp_warp(img, disp, padding_mode=pad)
+    warped.backward(g)
+    In, Dn, gn = (t.detach().cpu().numpy() for t in (img, disp, g))
+    w_ref, m_ref, bad = oracle.warp_fwd(In, Dn, pad)
+    assert not bad
+    assert rel_err(warped.detach().cpu().numpy(), w_ref) <= TOL_F32
+    assert np.array_equal(mask.cpu().numpy(), m_ref)
+    gi_ref, gd_ref = oracle.warp_bwd(gn, In, Dn, pad)
+    assert rel_err(img.grad.cpu().numpy(), gi_ref) <= TOL_F32
+    assert rel_err(disp.grad.cpu().numpy(), gd_ref) <= TOL_F32
+    m = mask.cpu().numpy()
+    assert np.all(m[:, :, 0] == 0) and np.all(m[:, :, -1] == 0)
+    assert set(np.unique(m)) <= {0.0, 1.0}
+
+
+@pytest.mark.parametrize("cfg", [("cfg3", 8, 320, 640), ("cfg4", 2, 384, 1280), ("cfg5", 4, 576, 960)], ids=lambda c: c[0])
+def test_warp_full_size_vs_torch(ops, cfg):
+    _, B, H, W = cfg
+    img, disp = images(B, 3, H, W, 9)
+    img.requires_grad_(True); disp.requires_grad_(True)
+    g = feat((B, 3, H, W), 10, False)
+    warped, mask = ops.disp_warp(img, disp)
+    warped.backward(g)
+    i2, d2 = img.detach().clone().requires_grad_(True), disp.detach().clone().requires_grad_(True)
+    w_ref, m_ref = ref_torch.warp_ref(i2, d2)
+    w_ref.backward(g)
+    assert rel_err(warped.detach().cpu().numpy(), w_ref.detach().cpu().numpy()) <= TOL_F32
+    # the 0/1 mask may differ only where the weight sum sits within rounding of the threshold
+    assert float((mask != m_ref).float().mean()) <= 1e-5
+    assert rel_err(img.grad.cpu().numpy(), i2.grad.cpu().numpy()) <= TOL_F32
+    assert rel_err(disp.grad.cpu().numpy(), d2.grad.cpu().numpy()) <= TOL_F32
+    frac = float(mask.mean())
+    assert 0.7 < frac < 1.0
+
+
+def test_warp_f64_gradcheck(ops):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    img = torch.rand((1, 2, 5, 8), generator=g, device="cuda", dtype=torch.float64).requires_grad_(True)
+    disp = (torch.rand((1, 1, 5, 8), generator=g, device="cuda", dtype=torch.float64) * 3 + 0.3).requires_grad_(True)
+    for pad in ("border", "zeros"):
+        assert torch.autograd.gradcheck(lambda a, b: ops.disp_warp(a, b, pad)[0], (img, disp), eps=1e-6, atol=1e-5)
+
+
+def test_warp_error_conventions(ops):
+    img = torch.rand(1, 3, 6, 8, device="cuda")
+    disp = torch.rand(1, 1, 6, 8, device="cuda")
+    bad = disp.clone(); bad[0, 0, 2, 2] = -1.0
+    with pytest.raises(AssertionError):
+        ops.disp_warp(img, bad)
+    nan = disp.clone(); nan[0, 0, 1, 1] = float("nan")
+    with pytest.raises(AssertionError):
+        ops.disp_warp(img, nan)
+    with pytest.raises(RuntimeError):
+        ops.disp_warp(img, disp.double())
+    with pytest.raises(RuntimeError):
+        ops.disp_warp(img.cpu(), disp.cpu())
+    with pytest.raises(ValueError):
+        ops.disp_warp(img, disp, padding_mode="nope")
+    with pytest.raises(AssertionError):
+        ops.normalize_coords(torch.zeros(1, 3, 4, 4, device="cuda"))
+    w, m = ops.disp_warp(img, disp)
+    assert not m.requires_grad and w.shape == img.shape and m.shape == img.shape
+
+
+# ---------------------------------------------------------------- LRwarp_error
+@pytest.mark.parametrize("name", sorted(LRW))
+def test_lrwarp_golden(ops, name):
+    c = LRW[name]
+    L = cuda(c["imgL"]).requires_grad_(True)
+    R = cuda(c["imgR"]).requires_grad_(True)
+    d = cuda(c["disp"]).requires_grad_(True)
+    err = ops.LRwarp_error(L, d, R)
+    err.backward(cuda(c["g"]))
+    assert rel_err(err.detach().cpu().numpy(), c["err"]) <= TOL_F32
+    assert rel_err(L.grad.cpu().numpy(), c["g_imgL"]) <= TOL_F32
+    assert rel_err(R.grad.cpu().numpy(), c["g_imgR"]) <= TOL_F32
+    assert rel_err(d.grad.cpu().numpy(), c["g_disp"]) <= TOL_F32
+
+
+@pytest.mark.parametrize("scale", [1, 2, 4, 8])
+def test_lrwarp_pyramid_vs_torch(ops, scale):
+    B, H0, W0 = 2, 320, 640
+    imgL, _ = images(B, 3, H0, W0, 21)
+    imgR, _ = images(B, 3, H0, W0, 22)
+    _, disp = images(B, 3, H0 // scale, W0 // scale, 23)
+    err = ops.LRwarp_error(imgL, disp, imgR)
+    ref = ref_torch.lrwarp_ref(imgL, disp, imgR)
+    assert err.shape == ref.shape
+    assert rel_err(err.cpu().numpy(), ref.cpu().numpy()) <= TOL_F32
+    rs = ops.resize_bilinear(imgL, disp.shape[-2:])
+    rr = torch.nn.functional.interpolate(imgL, size=disp.shape[-2:], mode="bilinear", align_corners=False)
+    assert rel_err(rs.cpu().numpy(), rr.cpu().numpy()) <= TOL_F32
