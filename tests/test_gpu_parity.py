@@ -222,20 +222,27 @@ def test_warp_vs_oracle(ops, oracle, shape, pad):
 
 @pytest.mark.parametrize("cfg", [("cfg3", 8, 320, 640), ("cfg4", 2, 384, 1280), ("cfg5", 4, 576, 960)], ids=lambda c: c[0])
 def test_warp_full_size_vs_torch(ops, cfg):
+    """Full BASELINE sizes.  The parity reference is the torch restatement run on
+    the CPU (that is what upstream's functions do there, and what the golden
+    fixtures and the oracle are pinned to): 1e-5.  torch's *CUDA* elementwise
+    kernels evaluate `t / (W-1)` as `t * (1/(W-1))`, so upstream itself differs
+    between CPU and CUDA by ~1e-5 at these widths; against that variant the bound
+    is 5e-5 and the mask may flip only within rounding of the 0.9999 threshold."""
     _, B, H, W = cfg
     img, disp = images(B, 3, H, W, 9)
     img.requires_grad_(True); disp.requires_grad_(True)
     g = feat((B, 3, H, W), 10, False)
     warped, mask = ops.disp_warp(img, disp)
     warped.backward(g)
-    i2, d2 = img.detach().clone().requires_grad_(True), disp.detach().clone().requires_grad_(True)
-    w_ref, m_ref = ref_torch.warp_ref(i2, d2)
-    w_ref.backward(g)
-    assert rel_err(warped.detach().cpu().numpy(), w_ref.detach().cpu().numpy()) <= TOL_F32
-    # the 0/1 mask may differ only where the weight sum sits within rounding of the threshold
-    assert float((mask != m_ref).float().mean()) <= 1e-5
-    assert rel_err(img.grad.cpu().numpy(), i2.grad.cpu().numpy()) <= TOL_F32
-    assert rel_err(disp.grad.cpu().numpy(), d2.grad.cpu().numpy()) <= TOL_F32
+    for dev, tol, mask_tol in (("cpu", TOL_F32, 0.0), ("cuda", 5e-5, 1e-5)):
+        i2 = img.detach().to(dev).clone().requires_grad_(True)
+        d2 = disp.detach().to(dev).clone().requires_grad_(True)
+        w_ref, m_ref = ref_torch.warp_ref(i2, d2)
+        w_ref.backward(g.to(dev))
+        assert rel_err(warped.detach().cpu().numpy(), w_ref.detach().cpu().numpy()) <= tol
+        assert float((mask.cpu() != m_ref.cpu()).float().mean()) <= mask_tol
+        assert rel_err(img.grad.cpu().numpy(), i2.grad.cpu().numpy()) <= tol
+        assert rel_err(disp.grad.cpu().numpy(), d2.grad.cpu().numpy()) <= tol
     frac = float(mask.mean())
     assert 0.7 < frac < 1.0
 
