@@ -18,6 +18,8 @@
 // Algorithmic HBM bytes per launch pair: (B*D*H*W + 4*B*C*H*W) * sizeof(T).
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace dssmd {
 
 namespace {
@@ -25,6 +27,7 @@ namespace {
 constexpr int kPix = 8;   // pixels per thread
 constexpr int kCh = 8;    // channels per thread
 constexpr int kMaxRows = 16;
+constexpr int kMaxFill = 4;  // 16-byte chunks one lane copies per operand line (<= 128 chunks per line)
 
 struct CorrBwdParams {
     const void *g;
@@ -44,7 +47,8 @@ struct CorrBwdParams {
     int RXc;    // chunks per line of the operand band
     int NLG;    // g lines   (ROWS*DP, padded odd)
     int NL;     // operand lines (ROWS*CK, padded odd)
-    int NKC;    // channel chunks
+    int CPB;    // channels per block (grid.y splits C)
+    int NKC;    // channel chunks per block
     int c_pow2;
 };
 
@@ -72,6 +76,8 @@ __global__ void __launch_bounds__(256) corr_bwd_kernel(const CorrBwdParams p) {
     const int xt = blockIdx.x % p.XT;
     const int R0 = (blockIdx.x / p.XT) * p.ROWS;
     const int X0 = xt * p.TX;
+    const int CB0 = blockIdx.y * p.CPB;  // first channel of this block
+    const int CEND = (CB0 + p.CPB < p.C) ? CB0 + p.CPB : p.C;
     const long long HW = (long long)p.H * p.W;
 
     if (tid < p.ROWS) {
@@ -107,6 +113,13 @@ __global__ void __launch_bounds__(256) corr_bwd_kernel(const CorrBwdParams p) {
                 if constexpr (ASYNC && MODE == 0) {
                     const bool ok = lv && gx < p.W;
                     cp_async16(smem_u32(dst), ok ? (const void *)(row + gx) : (const void *)Gg, ok ? 16 : 0);
+                } else if constexpr (ASYNC) {
+                    // skewed row: source start x0+4j+d is only 4-byte aligned -> four 4-byte async copies
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const bool ok = lv && gx + i < p.W;
+                        cp_async4(smem_u32(dst) + 4 * i, ok ? (const void *)(row + gx + i) : (const void *)Gg, ok ? 4 : 0);
+                    }
                 } else {
                     *dst = load4_generic<T>(row, gx, p.W, lv);
                 }
@@ -134,18 +147,29 @@ __global__ void __launch_bounds__(256) corr_bwd_kernel(const CorrBwdParams p) {
 
     const float Cf = (float)p.C, invC = 1.0f / Cf;
 
+    // per-lane fill descriptors (line-invariant): operand chunks this lane copies
+    int f_dst[kMaxFill], f_gx[kMaxFill];
+#pragma unroll
+    for (int k = 0; k < kMaxFill; ++k) {
+        const int j = lane + 32 * k;
+        f_dst[k] = (j < p.RXc) ? swz(j) * p.NL : -1;
+        f_gx[k] = IX0 + 4 * j;
+    }
+
     for (int kc = 0; kc < p.NKC; ++kc) {
         __syncthreads();  // previous chunk fully consumed
         // ---- stage CK channels of the operand band ------------------------------------
         for (int line = warp; line < nlines_in; line += nwarps) {
             const int rr = line / p.CK, cc = line - rr * p.CK;
-            const int c = kc * p.CK + cc;
+            const int c = CB0 + kc * p.CK + cc;
             const long long rb = s_rowbase_in[rr];
-            const bool lv = (rb >= 0) && (c < p.C);
+            const bool lv = (rb >= 0) && (c < CEND);
             const T *row = Ig + (lv ? rb + (long long)c * HW : 0);
-            for (int j = lane; j < p.RXc; j += 32) {
-                float4 *dst = is + swz(j) * p.NL + line;
-                const int gx = IX0 + 4 * j;
+#pragma unroll
+            for (int k = 0; k < kMaxFill; ++k) {
+                if (f_dst[k] < 0) break;
+                float4 *dst = is + f_dst[k] + line;
+                const int gx = f_gx[k];
                 if constexpr (ASYNC) {
                     const bool ok = lv && gx >= 0 && gx < p.W;
                     cp_async16(smem_u32(dst), ok ? (const void *)(row + gx) : (const void *)Ig, ok ? 16 : 0);
@@ -160,8 +184,8 @@ __global__ void __launch_bounds__(256) corr_bwd_kernel(const CorrBwdParams p) {
         }
         __syncthreads();
 
-        const int c0 = kc * p.CK + cg * kCh;
-        if (!row_ok || c0 >= p.C) continue;
+        const int c0 = CB0 + kc * p.CK + cg * kCh;
+        if (!row_ok || c0 >= CEND) continue;
 
         float acc[kCh][kPix];
         float kept[kCh][8];
@@ -221,7 +245,7 @@ __global__ void __launch_bounds__(256) corr_bwd_kernel(const CorrBwdParams p) {
 #pragma unroll
         for (int i = 0; i < kCh; ++i) {
             const int c = c0 + i;
-            if (c >= p.C) break;
+            if (c >= CEND) break;
             float v[kPix];
 #pragma unroll
             for (int px = 0; px < kPix; ++px)
@@ -259,6 +283,11 @@ __global__ void corr_bwd_f64_kernel(const double *g, const double *L, const doub
     }
 }
 
+int env_int(const char *name, int dflt) {
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
 template <typename T, int MODE>
 int launch_mode(const void *g, const void *In, void *out, int B, int C, int H, int W, int D, cudaStream_t stream) {
     CorrBwdParams p{};
@@ -271,24 +300,30 @@ int launch_mode(const void *g, const void *In, void *out, int B, int C, int H, i
 
     const int NPGF = ceil_div(W, kPix);
     const int cgroups = ceil_div(C, kCh);
-    const size_t budget = 72 * 1024;  // keeps >= 3 blocks per SM resident
+    const size_t budget = (size_t)env_int("DSSMD_CORR_BWD_SMEM_KB", 40) * 1024;
 
-    // tile width: whole row if it fits 32 pixel groups, else 256-pixel tiles
-    p.NPG = NPGF < 32 ? NPGF : 32;
-    // shrink the tile until the g tile alone takes at most half the budget
-    while (p.NPG > 4 && (size_t)(p.NPG * 2) * (p.DP | 1) * 16 > budget / 2) p.NPG = (p.NPG + 1) / 2;
+    // tile width: whole row when its band fits 128 chunks, and the g tile at most half the budget
+    int npg_cap = (128 * 4 - p.HALO) / kPix;
+    if (npg_cap > 32) npg_cap = 32;
+    while (npg_cap > 4 && (size_t)(npg_cap * 2) * (p.DP | 1) * 16 > budget / 2) npg_cap = (npg_cap + 1) / 2;
+    if (npg_cap < 1) npg_cap = 1;
+    p.XT = ceil_div(NPGF, npg_cap);
+    p.NPG = ceil_div(NPGF, p.XT);
     p.TX = p.NPG * kPix;
-    p.XT = ceil_div(NPGF, p.NPG);
     p.TXc = p.TX / 4;
     p.RXc = (p.TX + p.HALO) / 4;
 
-    // threads: ROWS x CG x NPG <= 256; prefer CG a power of two dividing the channel groups
+    // threads: ROWS x CG x NPG; channel groups per stage CG (power of two), ~64-128 threads per block
     int cg = 1;
-    while (cg * 2 <= cgroups && cg * 2 * p.NPG <= 128 && cg < 8) cg *= 2;
-    int rows = 128 / (cg * p.NPG);
+    while (cg * 2 <= cgroups && cg * 2 * p.NPG <= 64 && cg < 8) cg *= 2;
+    cg = env_int("DSSMD_CORR_BWD_CG", cg);
+    if (cg < 1 || cg > 16 || cg * p.NPG > 256) cg = 1;
+    int rows = 64 / (cg * p.NPG);
+    rows = env_int("DSSMD_CORR_BWD_ROWS", rows);
     if (rows < 1) rows = 1;
     if (rows > kMaxRows) rows = kMaxRows;
     if (rows > p.NR) rows = p.NR;
+    while (rows > 1 && rows * cg * p.NPG > 256) --rows;
     size_t smem_bytes = 0;
     for (;;) {
         p.ROWS = rows; p.CG = cg; p.CK = cg * kCh;
@@ -302,12 +337,27 @@ int launch_mode(const void *g, const void *In, void *out, int B, int C, int H, i
     }
     if (smem_bytes > 200 * 1024)
         return fail(DSSMD_ERR_UNSUPPORTED, "corr_bwd: tile needs %zu B of shared memory (W=%d D=%d)", smem_bytes, W, D);
-    p.NKC = ceil_div(C, p.CK);
+
+    // channel ranges per block (grid.y): enough blocks for >= ~10 warps per SM, each block >= 1 chunk
+    const int nchunks = ceil_div(C, p.CK);
+    const long blocks_xy = (long)p.XT * ceil_div(p.NR, p.ROWS);
+    const int warps_blk = ceil_div(p.ROWS * p.CG * p.NPG, 32);
+    int cz = 1;
+    while (cz < nchunks && blocks_xy * cz * warps_blk < (long)sm_count() * 12) cz *= 2;
+    cz = env_int("DSSMD_CORR_BWD_CZ", cz);
+    if (cz < 1) cz = 1;
+    if (cz > nchunks) cz = nchunks;
+    p.NKC = ceil_div(nchunks, cz);
+    p.CPB = p.NKC * p.CK;
+    cz = ceil_div(C, p.CPB);
 
     const int threads = round_up(p.ROWS * p.CG * p.NPG, 32);
     const bool async = (sizeof(T) == 4) && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(g) & 15) == 0) &&
                        ((reinterpret_cast<uintptr_t>(In) & 15) == 0);
-    dim3 grid((unsigned)(p.XT * ceil_div(p.NR, p.ROWS)));
+    dim3 grid((unsigned)(p.XT * ceil_div(p.NR, p.ROWS)), (unsigned)cz);
+    if (env_int("DSSMD_CORR_DEBUG", 0))
+        fprintf(stderr, "corr_bwd cfg: mode=%d NPG=%d XT=%d ROWS=%d CG=%d CK=%d CZ=%d NKC=%d threads=%d grid=(%u,%u) smem=%zu async=%d\n",
+                MODE, p.NPG, p.XT, p.ROWS, p.CG, p.CK, cz, p.NKC, threads, grid.x, grid.y, smem_bytes, (int)async);
     cudaError_t e;
     if (async) {
         if constexpr (sizeof(T) == 4) {

@@ -11,11 +11,16 @@
 //   * a thread owns 8 consecutive pixels x DT consecutive disparities: per
 //     channel it issues 2 + (DT+8)/4 LDS.128 and 8*DT FFMA, accumulators stay
 //     in registers over the whole channel loop;
+//   * small problems (fewer work items than the chip has warp slots) split the
+//     channels of each stage over CS thread groups and reduce the partial sums
+//     through shared memory at the end;
 //   * shared memory is laid out [16-byte chunk][line] with an XOR swizzle on
 //     the chunk index so that 8 lanes reading chunks 2*lane+k hit 8 distinct
 //     bank groups, and with an odd line count so the fill is conflict-free.
 // Algorithmic HBM bytes per launch: (2*B*C*H*W + B*D*H*W) * sizeof(T).
 #include "common.cuh"
+
+#include <cstdlib>
 
 namespace dssmd {
 
@@ -24,6 +29,7 @@ namespace {
 constexpr int kPix = 8;        // pixels per thread
 constexpr int kMaxRows = 16;   // rows per block upper bound
 constexpr int kStages = 3;     // cp.async pipeline depth
+constexpr int kMaxFill = 4;    // 16-byte chunks one lane copies per line (=> <= 128 chunks per line)
 
 struct CorrFwdParams {
     const void *L;
@@ -36,6 +42,8 @@ struct CorrFwdParams {
     int NDGB;   // disparity groups per block
     int ROWS;   // rows per block
     int XT;     // x tiles per row
+    int CS;     // channel-split groups (power of two, divides CK)
+    int LOGCS;
     int CK;     // channels per stage (power of two)
     int LOGCK;
     int NL;     // lines (= ROWS*CK) padded to an odd count
@@ -43,6 +51,7 @@ struct CorrFwdParams {
     int RXc;    // 16-byte chunks of the R band per line
     int HALO;   // left halo of the R band in pixels (multiple of 8)
     int NKC;    // channel chunks = ceil(C/CK)
+    int NITEMS; // ROWS*NDGB*NPG work items per block
     int c_pow2; // C is a power of two -> multiply by exact 1/C
 };
 
@@ -60,16 +69,16 @@ __device__ __forceinline__ float4 load4_generic(const T *row, int gx, int W, boo
     return make_float4(v[0], v[1], v[2], v[3]);
 }
 
-template <typename T, int DT, int NT, bool ASYNC>
-__global__ void __launch_bounds__(NT) corr_fwd_kernel(const CorrFwdParams p) {
+template <typename T, int DT, bool ASYNC>
+__global__ void __launch_bounds__(256) corr_fwd_kernel(const CorrFwdParams p) {
     extern __shared__ float4 smem[];
     __shared__ long long s_rowbase[kMaxRows];  // element offset of (b, c=0, y, x=0); -1 = no such row
 
     constexpr int NCH = (DT + 8) / 4;  // R chunks per thread per channel
-    constexpr int NWARPS = NT / 32;
     constexpr int STAGES = ASYNC ? kStages : 1;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = blockDim.x >> 5;
     const int xt = blockIdx.x % p.XT;
     const int R0 = (blockIdx.x / p.XT) * p.ROWS;
     const int X0 = xt * p.TX;
@@ -87,17 +96,19 @@ __global__ void __launch_bounds__(NT) corr_fwd_kernel(const CorrFwdParams p) {
     }
     __syncthreads();
 
-    // ---- this thread's work item ------------------------------------------------
-    const int pg = tid % p.NPG;
-    const int t2 = tid / p.NPG;
+    // ---- this thread's work item: (row r, disparity group dgl, pixel group pg) x channel split cs ----
+    const int item = tid % p.NITEMS;
+    const int cs = tid / p.NITEMS;
+    const int pg = item % p.NPG;
+    const int t2 = item / p.NPG;
     const int dgl = t2 % p.NDGB;
     const int r = t2 / p.NDGB;
     const int d0 = DB0 + dgl * DT;
     const int xs = pg * kPix;  // tile-local first pixel
-    const bool active = (r < p.ROWS) && (R0 + r < p.NR) && (d0 < p.D) && (X0 + xs < p.W);
+    const bool active = (cs < p.CS) && (R0 + r < p.NR) && (d0 < p.D) && (X0 + xs < p.W);
 
     const int stage_cells = (p.TXc + p.RXc) * p.NL;
-    const int line0 = (active ? r : 0) << p.LOGCK;
+    const int line0 = (r << p.LOGCK) + (cs < p.CS ? cs : 0);
     int oL[2], oR[NCH];
     {
         const int jl = 2 * pg;
@@ -120,21 +131,36 @@ __global__ void __launch_bounds__(NT) corr_fwd_kernel(const CorrFwdParams p) {
     const int ncells_line = p.TXc + p.RXc;
     const int RX0 = X0 - p.HALO - DB0;  // global x of R-band local index 0
 
+    // ---- per-lane fill descriptors: which chunks of a line this lane copies (line-invariant) ----
+    int f_dst[kMaxFill];   // cell offset (without line), -1 = none
+    int f_gx[kMaxFill];    // global x of the chunk's first element
+    bool f_isR[kMaxFill];  // chunk belongs to the R band (else the L tile)
+#pragma unroll
+    for (int k = 0; k < kMaxFill; ++k) {
+        const int j = lane + 32 * k;
+        const bool isR = j >= p.TXc;
+        const int jj = isR ? j - p.TXc : j;
+        const int gx = (isR ? RX0 : X0) + 4 * jj;
+        f_dst[k] = (j < ncells_line) ? ((isR ? p.TXc : 0) + swz(jj)) * p.NL : -1;
+        f_gx[k] = gx;
+        f_isR[k] = isR;
+    }
+
     auto fill = [&](int stage, int kc) {
         float4 *st = smem + stage * stage_cells;
-        for (int line = warp; line < nlines; line += NWARPS) {
+        for (int line = warp; line < nlines; line += nwarps) {
             const int rr = line >> p.LOGCK;
             const int c = (kc << p.LOGCK) + (line & (p.CK - 1));
             const long long rb = s_rowbase[rr];
             const bool lv = (rb >= 0) && (c < p.C);
             const long long off = lv ? rb + (long long)c * HW : 0;
             const T *lrow = Lg + off, *rrow = Rg + off;
-            for (int j = lane; j < ncells_line; j += 32) {
-                const bool isR = j >= p.TXc;
-                const int jj = isR ? j - p.TXc : j;
-                const int gx = (isR ? RX0 : X0) + 4 * jj;
-                float4 *dst = st + ((isR ? p.TXc : 0) + swz(jj)) * p.NL + line;
-                const T *row = isR ? rrow : lrow;
+#pragma unroll
+            for (int k = 0; k < kMaxFill; ++k) {
+                if (f_dst[k] < 0) break;
+                float4 *dst = st + f_dst[k] + line;
+                const T *row = f_isR[k] ? rrow : lrow;
+                const int gx = f_gx[k];
                 if constexpr (ASYNC) {
                     const bool ok = lv && gx >= 0 && gx < p.W;  // W % 4 == 0: chunk all-in or all-out
                     cp_async16(smem_u32(dst), ok ? (const void *)(row + gx) : (const void *)Lg, ok ? 16 : 0);
@@ -148,7 +174,7 @@ __global__ void __launch_bounds__(NT) corr_fwd_kernel(const CorrFwdParams p) {
     auto compute = [&](int stage) {
         const float4 *st = smem + stage * stage_cells;
 #pragma unroll 2
-        for (int cc = 0; cc < p.CK; ++cc) {
+        for (int cc = 0; cc < p.CK; cc += p.CS) {
             const float4 a0 = st[oL[0] + cc], a1 = st[oL[1] + cc];
             const float l[kPix] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             float w[NCH * 4];
@@ -190,11 +216,221 @@ __global__ void __launch_bounds__(NT) corr_fwd_kernel(const CorrFwdParams p) {
         }
     }
 
-    if (!active) return;
+    // ---- reduce the channel-split partial sums through shared memory -----------------
+    if (p.CS > 1) {
+        constexpr int NV = kPix * DT / 4;  // float4s per thread
+        __syncthreads();                   // pipeline buffers are free now
+        float4 *red = smem;                // [cs-1][NV][NITEMS]
+        if (active && cs > 0) {
+            float4 *dst = red + (size_t)(cs - 1) * NV * p.NITEMS + item;
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                const int e = 4 * q;
+                dst[q * p.NITEMS] = make_float4(acc[e / DT][e % DT], acc[(e + 1) / DT][(e + 1) % DT],
+                                               acc[(e + 2) / DT][(e + 2) % DT], acc[(e + 3) / DT][(e + 3) % DT]);
+            }
+        }
+        __syncthreads();
+        if (active && cs == 0) {
+            for (int s = 1; s < p.CS; ++s) {
+                const float4 *src = red + (size_t)(s - 1) * NV * p.NITEMS + item;
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    const float4 v = src[q * p.NITEMS];
+                    const int e = 4 * q;
+                    acc[e / DT][e % DT] += v.x;
+                    acc[(e + 1) / DT][(e + 1) % DT] += v.y;
+                    acc[(e + 2) / DT][(e + 2) % DT] += v.z;
+                    acc[(e + 3) / DT][(e + 3) % DT] += v.w;
+                }
+            }
+        }
+    }
+    if (!active || cs != 0) return;
 
     // ---- epilogue: mean over C, zero left border, store ----------------------------
     const int row = R0 + r;
     const int b = row / p.H, y = row - b * p.H;
+    const int xg = X0 + xs;
+    const float Cf = (float)p.C;
+    const float invC = 1.0f / Cf;
+    T *ob = static_cast<T *>(p.out) + ((long long)b * p.D * p.H + y) * p.W + xg;
+    const bool vec = (sizeof(T) == 4) && ((p.W & 3) == 0) && (xg + kPix <= p.W) &&
+                     ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+#pragma unroll
+    for (int dd = 0; dd < DT; ++dd) {
+        const int d = d0 + dd;
+        if (d >= p.D) break;
+        float v[kPix];
+#pragma unroll
+        for (int px = 0; px < kPix; ++px) {
+            const float m = p.c_pow2 ? acc[px][dd] * invC : __fdiv_rn(acc[px][dd], Cf);
+            v[px] = (xg + px >= d) ? m : 0.f;
+        }
+        T *o = ob + (long long)d * HW;
+        if (vec) {
+            st_global_cs(reinterpret_cast<float4 *>(o), make_float4(v[0], v[1], v[2], v[3]));
+            st_global_cs(reinterpret_cast<float4 *>(o) + 1, make_float4(v[4], v[5], v[6], v[7]));
+        } else {
+#pragma unroll
+            for (int px = 0; px < kPix; ++px)
+                if (xg + px < p.W) o[px] = from_f32<T>(v[px]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Narrow-tile variant (the default for D <= 64): a thread owns 8 pixels x 4
+// disparities (32 accumulators, ~64 registers => 4x the resident warps of the wide
+// tile), and the lanes of a warp run over the *disparity groups* of a pixel group
+// first: the L chunks are then a warp-wide broadcast and the R chunks of neighbouring
+// lanes are neighbouring 16-byte chunks, so no swizzle is needed and, with the line
+// count NL a compile-time constant, every LDS.128 address is base + immediate.
+// One image row per block; CS thread groups split the channels of a stage.
+// ---------------------------------------------------------------------------------
+template <typename T, int CK, int CS, bool ASYNC>
+__global__ void __maxnreg__(96) corr_fwd_d4_kernel(const CorrFwdParams p) {
+    extern __shared__ float4 smem[];
+    constexpr int DT = 4;
+    constexpr int NL = CK + 1;           // odd => conflict-free [chunk][line] layout
+    constexpr int STAGES = ASYNC ? kStages : 1;
+    constexpr int CPT = CK / CS;         // channels per thread per stage
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int xt = blockIdx.x % p.XT;
+    const int row = blockIdx.x / p.XT;
+    const int X0 = xt * p.TX;
+    const long long HW = (long long)p.H * p.W;
+    const int b = row / p.H, y = row - b * p.H;
+    const long long rowbase = (long long)b * p.C * HW + (long long)y * p.W;
+
+    // work item: pixel group pg, disparity group dg (fastest), channel split cs
+    const int item = tid % p.NITEMS;
+    const int cs = tid / p.NITEMS;
+    const int dg = item % p.NDGB;
+    const int pg = item / p.NDGB;
+    const int d0 = dg * DT;
+    const int xs = pg * kPix;
+    const bool active = (cs < CS) && (X0 + xs < p.W);
+
+    const int stage_cells = (p.TXc + p.RXc) * NL;
+    const int csafe = cs < CS ? cs : 0;
+    const int oL = (2 * pg) * NL + csafe;                                        // + k*NL + i*CS
+    const int oR = (p.TXc + 2 * pg + p.HALO / 4 - dg - 1) * NL + csafe;          // + k*NL + i*CS
+
+    float acc[kPix][DT];
+#pragma unroll
+    for (int i = 0; i < kPix; ++i)
+#pragma unroll
+        for (int j = 0; j < DT; ++j) acc[i][j] = 0.f;
+
+    const T *Lg = static_cast<const T *>(p.L) + rowbase;
+    const T *Rg = static_cast<const T *>(p.R) + rowbase;
+    const int ncells_line = p.TXc + p.RXc;
+    const int RX0 = X0 - p.HALO;  // global x of R-band local index 0
+
+    int f_dst[kMaxFill], f_gx[kMaxFill];
+    bool f_isR[kMaxFill];
+#pragma unroll
+    for (int k = 0; k < kMaxFill; ++k) {
+        const int j = lane + 32 * k;
+        const bool isR = j >= p.TXc;
+        const int jj = isR ? j - p.TXc : j;
+        f_dst[k] = (j < ncells_line) ? j * NL : -1;
+        f_gx[k] = (isR ? RX0 : X0) + 4 * jj;
+        f_isR[k] = isR;
+    }
+
+    auto fill = [&](int stage, int kc) {
+        float4 *st = smem + stage * stage_cells;
+        for (int line = warp; line < CK; line += nwarps) {
+            const int c = kc * CK + line;
+            const bool lv = c < p.C;
+            const long long off = lv ? (long long)c * HW : 0;
+            const T *lrow = Lg + off, *rrow = Rg + off;
+#pragma unroll
+            for (int k = 0; k < kMaxFill; ++k) {
+                if (f_dst[k] < 0) break;
+                float4 *dst = st + f_dst[k] + line;
+                const T *src = f_isR[k] ? rrow : lrow;
+                const int gx = f_gx[k];
+                if constexpr (ASYNC) {
+                    const bool ok = lv && gx >= 0 && gx < p.W;
+                    cp_async16(smem_u32(dst), ok ? (const void *)(src + gx) : (const void *)Lg, ok ? 16 : 0);
+                } else {
+                    *dst = load4_generic<T>(src, gx, p.W, lv);
+                }
+            }
+        }
+    };
+
+    auto compute = [&](int stage) {
+        const float4 *sl = smem + stage * stage_cells + oL;
+        const float4 *sr = smem + stage * stage_cells + oR;
+#pragma unroll 4
+        for (int i = 0; i < CPT; ++i) {
+            const float4 a0 = sl[i * CS], a1 = sl[NL + i * CS];
+            const float4 w0 = sr[i * CS], w1 = sr[NL + i * CS], w2 = sr[2 * NL + i * CS];
+            const float l[kPix] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float w[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+            // w[i] = R[xs_global - d0 - 4 + i]  =>  R[x - d] = w[px - dd + 4]
+#pragma unroll
+            for (int px = 0; px < kPix; ++px)
+#pragma unroll
+                for (int dd = 0; dd < DT; ++dd)
+                    acc[px][dd] = fmaf(l[px], w[px - dd + DT], acc[px][dd]);
+        }
+    };
+
+    if constexpr (ASYNC) {
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; ++s) {
+            if (s < p.NKC) fill(s, s);
+            cp_async_commit();
+        }
+        for (int kc = 0; kc < p.NKC; ++kc) {
+            cp_async_wait<STAGES - 2>();
+            __syncthreads();
+            const int nk = kc + STAGES - 1;
+            if (nk < p.NKC) fill(nk % STAGES, nk);
+            cp_async_commit();
+            if (active) compute(kc % STAGES);
+        }
+        cp_async_wait<0>();
+    } else {
+        for (int kc = 0; kc < p.NKC; ++kc) {
+            __syncthreads();
+            fill(0, kc);
+            __syncthreads();
+            if (active) compute(0);
+        }
+    }
+
+    if constexpr (CS > 1) {
+        constexpr int NV = kPix * DT / 4;
+        __syncthreads();
+        float4 *red = smem;  // [cs-1][NV][NITEMS]
+        if (active && cs > 0) {
+            float4 *dst = red + (size_t)(cs - 1) * NV * p.NITEMS + item;
+#pragma unroll
+            for (int q = 0; q < NV; ++q) dst[q * p.NITEMS] = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+        }
+        __syncthreads();
+        if (active && cs == 0) {
+#pragma unroll
+            for (int s = 1; s < CS; ++s) {
+                const float4 *src = red + (size_t)(s - 1) * NV * p.NITEMS + item;
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    const float4 v = src[q * p.NITEMS];
+                    acc[q][0] += v.x; acc[q][1] += v.y; acc[q][2] += v.z; acc[q][3] += v.w;
+                }
+            }
+        }
+    }
+    if (!active || cs != 0) return;
+
     const int xg = X0 + xs;
     const float Cf = (float)p.C;
     const float invC = 1.0f / Cf;
@@ -245,19 +481,112 @@ __global__ void corr_fwd_f64_kernel(const double *L, const double *R, double *ou
     }
 }
 
+int env_int(const char *name, int dflt) {
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
 template <typename T, int DT, bool ASYNC>
-int launch_cfg(CorrFwdParams &p, size_t smem_bytes, dim3 grid, cudaStream_t stream) {
-    constexpr int NT = 128;
-    auto kern = corr_fwd_kernel<T, DT, NT, ASYNC>;
+int launch_cfg(CorrFwdParams &p, size_t smem_bytes, dim3 grid, int threads, cudaStream_t stream) {
+    auto kern = corr_fwd_kernel<T, DT, ASYNC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_fwd: cudaFuncSetAttribute(%zu B): %s", smem_bytes, cudaGetErrorString(e));
-    kern<<<grid, NT, smem_bytes, stream>>>(p);
+    kern<<<grid, threads, smem_bytes, stream>>>(p);
     return check_launch("corr_fwd");
+}
+
+template <typename T, int CK, int CS, bool ASYNC>
+int launch_d4_cfg(CorrFwdParams &p, size_t smem_bytes, dim3 grid, int threads, cudaStream_t stream) {
+    auto kern = corr_fwd_d4_kernel<T, CK, CS, ASYNC>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_fwd: cudaFuncSetAttribute(%zu B): %s", smem_bytes, cudaGetErrorString(e));
+    kern<<<grid, threads, smem_bytes, stream>>>(p);
+    return check_launch("corr_fwd");
+}
+
+template <typename T, int CK, bool ASYNC>
+int launch_d4_cs(CorrFwdParams &p, size_t smem_bytes, dim3 grid, int threads, cudaStream_t stream) {
+    switch (p.CS) {
+        case 1: return launch_d4_cfg<T, CK, 1, ASYNC>(p, smem_bytes, grid, threads, stream);
+        case 2: return launch_d4_cfg<T, CK, 2, ASYNC>(p, smem_bytes, grid, threads, stream);
+        case 4: return launch_d4_cfg<T, CK, 4, ASYNC>(p, smem_bytes, grid, threads, stream);
+        default: return fail(DSSMD_ERR_UNSUPPORTED, "corr_fwd: channel split %d", p.CS);
+    }
+}
+
+// narrow-tile path; returns -1 when the shape is outside its limits (caller falls back)
+template <typename T>
+int launch_d4(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, cudaStream_t stream) {
+    CorrFwdParams p{};
+    p.L = L; p.R = R; p.out = out;
+    p.B = B; p.C = C; p.H = H; p.W = W; p.D = D;
+    p.NR = B * H;
+    p.c_pow2 = (C & (C - 1)) == 0;
+    const int max_threads = 224;  // __launch_bounds__(224, 3): 96 registers, 3 blocks per SM
+    const int NDG = ceil_div(D, 4);
+    if (NDG > 16) return -1;
+    p.NDGB = NDG;
+    p.HALO = 4 * NDG;
+    const int NPGF = ceil_div(W, kPix);
+    int npg_cap = max_threads / NDG;
+    const int cap2 = (128 * 4 - p.HALO) / (2 * kPix);  // <= 128 chunks per line
+    if (npg_cap > cap2) npg_cap = cap2;
+    if (npg_cap < 1) return -1;
+    // x tiles: enough (row, tile) units for >= 6 per SM so the block scheduler can balance the
+    // SMs, but tiles no narrower than 40 pixels (the R band re-reads HALO pixels per tile)
+    int xt = ceil_div(NPGF, npg_cap);
+    while ((long)p.NR * xt < (long)sm_count() * 6 && ceil_div(NPGF, xt + 1) >= 5) ++xt;
+    xt = env_int("DSSMD_CORR_FWD_XT", xt);
+    if (xt < ceil_div(NPGF, npg_cap)) xt = ceil_div(NPGF, npg_cap);
+    if (xt > NPGF) xt = NPGF;
+    p.XT = xt;
+    p.NPG = ceil_div(NPGF, p.XT);
+    p.TX = p.NPG * kPix;
+    p.TXc = p.TX / 4;
+    p.RXc = (p.TX + p.HALO) / 4;
+    p.ROWS = 1;
+    p.NITEMS = p.NPG * NDG;
+
+    const long base_warps = ((long)p.NR * p.XT * p.NITEMS + 31) / 32;
+    const long want_warps = (long)sm_count() * 16;
+    int cs = 1;
+    while (cs < 4 && base_warps * cs < want_warps && p.NITEMS * cs * 2 <= max_threads) cs *= 2;
+    cs = env_int("DSSMD_CORR_FWD_CS", cs);
+    if ((cs != 1 && cs != 2 && cs != 4) || p.NITEMS * cs > max_threads) cs = 1;
+    p.CS = cs;
+    const int threads = round_up(p.NITEMS * cs, 32);
+
+    const bool async = (sizeof(T) == 4) && (W % 4 == 0) &&
+                       ((reinterpret_cast<uintptr_t>(L) & 15) == 0) && ((reinterpret_cast<uintptr_t>(R) & 15) == 0);
+    const int stages = async ? kStages : 1;
+    int ck = env_int("DSSMD_CORR_FWD_CK", 0);
+    if (ck != 8 && ck != 16) ck = ((size_t)stages * (p.TXc + p.RXc) * 17 * 16 <= 36 * 1024) ? 16 : 8;
+    p.CK = ck;
+    p.NL = ck + 1;
+    size_t smem_bytes = (size_t)stages * (p.TXc + p.RXc) * p.NL * 16;
+    const size_t red_bytes = cs > 1 ? (size_t)(cs - 1) * 8 * p.NITEMS * 16 : 0;
+    if (red_bytes > smem_bytes) smem_bytes = red_bytes;
+    p.NKC = ceil_div(C, ck);
+    dim3 grid((unsigned)(p.XT * p.NR));
+    if (env_int("DSSMD_CORR_DEBUG", 0))
+        fprintf(stderr, "corr_fwd d4 cfg: NDG=%d NPG=%d XT=%d CS=%d CK=%d threads=%d grid=%u smem=%zu async=%d\n",
+                NDG, p.NPG, p.XT, p.CS, p.CK, threads, grid.x, smem_bytes, (int)async);
+    if (async) {
+        if constexpr (sizeof(T) == 4) {
+            return ck == 16 ? launch_d4_cs<T, 16, true>(p, smem_bytes, grid, threads, stream)
+                            : launch_d4_cs<T, 8, true>(p, smem_bytes, grid, threads, stream);
+        }
+    }
+    return ck == 16 ? launch_d4_cs<T, 16, false>(p, smem_bytes, grid, threads, stream)
+                    : launch_d4_cs<T, 8, false>(p, smem_bytes, grid, threads, stream);
 }
 
 template <typename T>
 int launch_typed(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, cudaStream_t stream) {
-    constexpr int NT = 128;
+    if (env_int("DSSMD_CORR_FWD_VARIANT", 1) == 1 && D <= 64) {
+        const int rc = launch_d4<T>(L, R, out, B, C, H, W, D, stream);
+        if (rc >= 0) return rc;
+    }
     CorrFwdParams p{};
     p.L = L; p.R = R; p.out = out;
     p.B = B; p.C = C; p.H = H; p.W = W; p.D = D;
@@ -272,34 +601,64 @@ int launch_typed(const void *L, const void *R, void *out, int B, int C, int H, i
             const long cost = (long)ceil_div(D, cand) * (cand + 16);
             if (best < 0 || cost < best) { best = cost; DT = cand; }
         }
+        const int o = env_int("DSSMD_CORR_FWD_DT", 0);  // tuning override
+        if (o == 8 || o == 12 || o == 16) DT = o;
     }
+    const int max_threads = 256;
     const int NDG = ceil_div(D, DT);
     const int NPGF = ceil_div(W, kPix);
-    p.NDGB = NDG < NT / 4 ? NDG : NT / 4;
-    p.NPG = NPGF < NT / p.NDGB ? NPGF : NT / p.NDGB;
+
+    // tile: all disparity groups of a pixel group live in one block (they share the R band)
+    p.NDGB = NDG < 16 ? NDG : 16;  // HALO <= 256 keeps a line within 128 chunks
+    p.HALO = round_up(p.NDGB * DT, 8);
+    int npg_cap = (128 * 4 - p.HALO) / (2 * kPix);  // <= 128 chunks per line (fill descriptors)
+    if (npg_cap > max_threads / p.NDGB) npg_cap = max_threads / p.NDGB;
+    if (npg_cap < 1) npg_cap = 1;
+    p.XT = ceil_div(NPGF, npg_cap);
+    p.NPG = ceil_div(NPGF, p.XT);  // balance the tiles
     p.TX = p.NPG * kPix;
-    p.XT = ceil_div(NPGF, p.NPG);
-    int rows = NT / (p.NPG * p.NDGB);
+    p.TXc = p.TX / 4;
+    p.RXc = (p.TX + p.HALO) / 4;
+    const int items_row = p.NPG * p.NDGB;
+
+    // parallelism: want >= 8 warps per SM; small problems split the channels over CS groups
+    const long base_warps = ((long)p.NR * p.XT * ceil_div(NDG, p.NDGB) * items_row + 31) / 32;
+    const long want_warps = (long)sm_count() * 8;
+    int cs = 1;
+    while (cs < 8 && base_warps * cs < want_warps && items_row * cs * 2 <= max_threads && cs * 2 <= C) cs *= 2;
+    cs = env_int("DSSMD_CORR_FWD_CS", cs);
+    if (cs < 1 || (cs & (cs - 1)) || items_row * cs > max_threads) cs = 1;
+    p.CS = cs;
+    p.LOGCS = 0;
+    while ((1 << p.LOGCS) < cs) ++p.LOGCS;
+
+    // rows per block: fill at least 64 threads, never more than one wave needs
+    int rows = 64 / (items_row * cs);
+    rows = env_int("DSSMD_CORR_FWD_ROWS", rows);
     if (rows < 1) rows = 1;
     if (rows > kMaxRows) rows = kMaxRows;
     if (rows > p.NR) rows = p.NR;
+    while (rows > 1 && rows * items_row * cs > max_threads) --rows;
     p.ROWS = rows;
-    p.HALO = round_up(p.NDGB * DT, 8);
-    p.TXc = p.TX / 4;
-    p.RXc = (p.TX + p.HALO) / 4;
+    p.NITEMS = rows * items_row;
+    const int threads = round_up(p.NITEMS * cs, 32);
 
     const bool async = (sizeof(T) == 4) && (W % 4 == 0) &&
                        ((reinterpret_cast<uintptr_t>(L) & 15) == 0) && ((reinterpret_cast<uintptr_t>(R) & 15) == 0);
     const int stages = async ? kStages : 1;
-    const size_t budget = 100 * 1024;
-    int ck = 16;
-    while (ck > 1 && ck / 2 >= C) ck /= 2;  // no point staging more channels than exist
+    const size_t budget = (size_t)env_int("DSSMD_CORR_FWD_SMEM_KB", 40) * 1024;
+    int ck = env_int("DSSMD_CORR_FWD_CK", 16);
+    if (ck < 1 || (ck & (ck - 1))) ck = 16;
+    while (ck > 1 && ck / 2 >= C && ck / 2 >= cs) ck /= 2;  // no point staging more channels than exist
+    if (ck < cs) ck = cs;
     size_t smem_bytes = 0;
     for (;; ck /= 2) {
         const int nl = (p.ROWS * ck) | 1;
         smem_bytes = (size_t)stages * (p.TXc + p.RXc) * nl * 16;
-        if (smem_bytes <= budget || ck == 1) { p.CK = ck; p.NL = nl; break; }
+        if (smem_bytes <= budget || ck <= cs) { p.CK = ck; p.NL = nl; break; }
     }
+    const size_t red_bytes = cs > 1 ? (size_t)(cs - 1) * (kPix * DT / 4) * p.NITEMS * 16 : 0;
+    if (red_bytes > smem_bytes) smem_bytes = red_bytes;
     if (smem_bytes > 200 * 1024)
         return fail(DSSMD_ERR_UNSUPPORTED, "corr_fwd: tile needs %zu B of shared memory (W=%d D=%d)", smem_bytes, W, D);
     p.LOGCK = 0;
@@ -307,10 +666,13 @@ int launch_typed(const void *L, const void *R, void *out, int B, int C, int H, i
     p.NKC = ceil_div(C, p.CK);
 
     dim3 grid((unsigned)(p.XT * ceil_div(p.NR, p.ROWS)), (unsigned)ceil_div(NDG, p.NDGB));
+    if (env_int("DSSMD_CORR_DEBUG", 0))
+        fprintf(stderr, "corr_fwd cfg: DT=%d NDGB=%d NPG=%d XT=%d ROWS=%d CS=%d CK=%d NL=%d threads=%d grid=(%u,%u) smem=%zu async=%d\n",
+                DT, p.NDGB, p.NPG, p.XT, p.ROWS, p.CS, p.CK, p.NL, threads, grid.x, grid.y, smem_bytes, (int)async);
 #define DSSMD_CORR_FWD_CASE(dt)                                                              \
     case dt:                                                                                 \
-        return async ? launch_cfg<T, dt, true>(p, smem_bytes, grid, stream)                  \
-                     : launch_cfg<T, dt, false>(p, smem_bytes, grid, stream);
+        return async ? launch_cfg<T, dt, true>(p, smem_bytes, grid, threads, stream)         \
+                     : launch_cfg<T, dt, false>(p, smem_bytes, grid, threads, stream);
     if constexpr (sizeof(T) == 4) {
         switch (DT) {
             DSSMD_CORR_FWD_CASE(16)
@@ -319,9 +681,9 @@ int launch_typed(const void *L, const void *R, void *out, int B, int C, int H, i
         }
     } else {
         switch (DT) {
-            case 16: return launch_cfg<T, 16, false>(p, smem_bytes, grid, stream);
-            case 12: return launch_cfg<T, 12, false>(p, smem_bytes, grid, stream);
-            case 8: return launch_cfg<T, 8, false>(p, smem_bytes, grid, stream);
+            case 16: return launch_cfg<T, 16, false>(p, smem_bytes, grid, threads, stream);
+            case 12: return launch_cfg<T, 12, false>(p, smem_bytes, grid, threads, stream);
+            case 8: return launch_cfg<T, 8, false>(p, smem_bytes, grid, threads, stream);
         }
     }
 #undef DSSMD_CORR_FWD_CASE

@@ -241,8 +241,17 @@ def test_warp_full_size_vs_torch(ops, cfg):
         w_ref.backward(g.to(dev))
         assert rel_err(warped.detach().cpu().numpy(), w_ref.detach().cpu().numpy()) <= tol
         assert float((mask.cpu() != m_ref.cpu()).float().mean()) <= mask_tol
-        assert rel_err(img.grad.cpu().numpy(), i2.grad.cpu().numpy()) <= tol
-        assert rel_err(disp.grad.cpu().numpy(), d2.grad.cpu().numpy()) <= tol
+        if dev == "cpu":
+            assert rel_err(img.grad.cpu().numpy(), i2.grad.cpu().numpy()) <= tol
+            assert rel_err(disp.grad.cpu().numpy(), d2.grad.cpu().numpy()) <= tol
+        else:
+            # a 1-ulp coordinate difference can move floor(ix) across an integer: the sample
+            # is continuous there but its derivative is not, so isolated pixels may differ
+            for ours, ref in ((img.grad, i2.grad), (disp.grad, d2.grad)):
+                diff = (ours.cpu() - ref.cpu()).abs()
+                scale = float(ref.abs().max())
+                assert float((diff > 1e-4 * scale).float().mean()) <= 1e-4
+                assert float(diff.mean()) <= 1e-6 * scale
     frac = float(mask.mean())
     assert 0.7 < frac < 1.0
 
