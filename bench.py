@@ -149,6 +149,7 @@ def make_set(torch, w, device, seed):
     s["gL"], s["gR"] = torch.empty_like(s["L"]), torch.empty_like(s["R"])
     s["warped"], s["mask"] = torch.empty_like(s["img"]), torch.empty_like(s["img"])
     s["d_img"], s["d_disp"] = torch.empty_like(s["img"]), torch.empty_like(s["disp"])
+    s["ws"] = torch.empty_like(s["img"])  # warp_bwd scratch (caller-owned; the library never allocates)
     return s
 
 
@@ -167,7 +168,7 @@ def kernel_calls(torch, lib, _lib, w, s):
         "corr_bwd_gL": lambda: chk(lib.dssmd_corr_bwd(p["g_vol"], p["L"], p["R"], p["gL"], null, B, C, Hf, Wf, D, F32, st())),
         "corr_bwd_gR": lambda: chk(lib.dssmd_corr_bwd(p["g_vol"], p["L"], p["R"], null, p["gR"], B, C, Hf, Wf, D, F32, st())),
         "warp_fwd": lambda: chk(lib.dssmd_warp_fwd(p["img"], p["disp"], p["warped"], p["mask"], null, B, 3, H, W, BORDER, F32, st())),
-        "warp_bwd": lambda: chk(lib.dssmd_warp_bwd(p["g_img"], p["img"], p["disp"], p["d_img"], p["d_disp"], B, 3, H, W, BORDER, F32, st())),
+        "warp_bwd": lambda: chk(lib.dssmd_warp_bwd(p["g_img"], p["img"], p["disp"], p["d_img"], p["d_disp"], p["ws"], ctypes.c_size_t(s["ws"].numel() * 4), B, 3, H, W, BORDER, F32, st())),
     }
 
 

@@ -26,7 +26,7 @@ SIGNATURES = {
     "dssmd_corr_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "dssmd_corr_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "dssmd_warp_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
-    "dssmd_warp_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "dssmd_warp_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _i, _i, _i, _i, _i, _i, _vp],
     "dssmd_resize_bilinear_fwd": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "dssmd_resize_bilinear_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "dssmd_lrwarp_error_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
@@ -53,6 +53,8 @@ def lib() -> ctypes.CDLL:
                 handle = ctypes.CDLL(LIB_PATH)
                 handle.dssmd_version.restype = ctypes.c_int
                 handle.dssmd_last_error.restype = ctypes.c_char_p
+                handle.dssmd_warp_bwd_workspace_bytes.argtypes = [_i, _i, _i, _i, _i]
+                handle.dssmd_warp_bwd_workspace_bytes.restype = ctypes.c_size_t
                 for name, argtypes in SIGNATURES.items():
                     fn = getattr(handle, name)
                     fn.argtypes = argtypes

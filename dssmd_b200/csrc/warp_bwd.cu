@@ -184,6 +184,429 @@ __global__ void __launch_bounds__(256, 4) warp_bwd_fixed_kernel(const float *__r
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Same algorithm, shaped for latency: the block covers the whole row with PXT pixels
+// per thread (no strided loops), the <= 6 (output row, weight) candidates sit in fixed
+// shared slots, and all address arithmetic is hoisted.  Used for W <= 4096.
+// ---------------------------------------------------------------------------------
+template <int PXT>
+__global__ void __launch_bounds__(1024, 1) warp_bwd_row_kernel(const float *__restrict__ g, const float *__restrict__ img,
+                                                                const float *__restrict__ disp, float *__restrict__ g_img,
+                                                                float *__restrict__ g_disp,
+                                                                int B, int C, int H, int W, int border, int flags) {
+    using S = float;
+    using N = Num<S>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned int *acc_lo = reinterpret_cast<unsigned int *>(smem_raw);   // [kCC][W]
+    int *acc_hi = reinterpret_cast<int *>(smem_raw) + (size_t)kCC * W;   // [kCC][W]
+    __shared__ int s_y[6];
+    __shared__ float s_w[6];
+    __shared__ unsigned int s_maxbits[2];
+
+    const int yy = blockIdx.x % H;
+    const int b = blockIdx.x / H;
+    const int HW = H * W;  // < 2^31 checked on the host
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const float *dispb = disp + (long long)b * HW;
+    const S halfW = N::div((S)W, (S)2);
+    const S wm1 = (S)(W - 1);
+
+    if (tid < 3) {
+        const int y = yy - 1 + tid;
+        int y0s = -1, y1s = -1;
+        float w0 = 0.f, w1 = 0.f;
+        if (y >= 0 && y < H) {
+            const S iy_raw = unnorm<S>((S)y, H);
+            const Axis<S> ya = make_axis<S>(border ? clamp_border<S>(iy_raw, H) : iy_raw, H);
+            if (ya.in0 && ya.i0 == yy) { y0s = y; w0 = ya.w0; }
+            if (ya.in1 && ya.i0 + 1 == yy) { y1s = y; w1 = ya.w1; }
+        }
+        s_y[2 * tid] = y0s; s_w[2 * tid] = w0;
+        s_y[2 * tid + 1] = y1s; s_w[2 * tid + 1] = w1;
+    }
+    if (tid < 2) s_maxbits[tid] = 0u;
+
+    // ---- g_disp of output row yy (a gather) ------------------------------------------------
+    if (g_disp) {
+        const S iy_raw = unnorm<S>((S)yy, H);
+        const Axis<S> ya = make_axis<S>(border ? clamp_border<S>(iy_raw, H) : iy_raw, H);
+        const S tscale = N::div((S)2, wm1);  // d gx / d t
+#pragma unroll
+        for (int j = 0; j < PXT; ++j) {
+            const int x = tid + j * nt;
+            if (x >= W) break;
+            const S dv = dispb[yy * W + x];
+            S ix = unnorm<S>(N::sub((S)x, dv), W);
+            S gmult = halfW;
+            if (border) {
+                // clip_coordinates_set_grad: borders count as out of bounds for the gradient
+                if (ix <= (S)0) { ix = (S)0; gmult = (S)0; }
+                else if (ix >= wm1) { ix = wm1; gmult = (S)0; }
+            }
+            const Axis<S> xa = make_axis<S>(ix, W);
+            S gix = (S)0;
+            const float *gp = g + (long long)b * C * HW + yy * W + x;
+            const float *p0 = img + (long long)b * C * HW + ya.i0 * W + xa.i0;
+            for (int c = 0; c < C; ++c, gp += HW, p0 += HW) {
+                const S go = *gp;
+                // d(sample)/d(ix) over in-bounds taps, ATen order nw, ne, sw, se
+                if (xa.in0 && ya.in0) gix = N::sub(gix, N::mul(N::mul(p0[0], ya.w0), go));
+                if (xa.in1 && ya.in0) gix = N::add(gix, N::mul(N::mul(p0[1], ya.w0), go));
+                if (xa.in0 && ya.in1) gix = N::sub(gix, N::mul(N::mul(p0[W], ya.w1), go));
+                if (xa.in1 && ya.in1) gix = N::add(gix, N::mul(N::mul(p0[W + 1], ya.w1), go));
+            }
+            // chain rule: ix <- gx (W/2, 0 where clipped) <- t (2/(W-1)) <- disp (-1)
+            g_disp[(long long)b * HW + yy * W + x] = -N::mul(tscale, N::mul(gmult, gix));
+        }
+    }
+    if (!g_img) return;
+    __syncthreads();
+
+    int parity = 0;
+    for (int c0 = 0; c0 < C; c0 += kCC) {
+        const int nc = (C - c0 < kCC) ? C - c0 : kCC;
+        const float *gb = g + ((long long)b * C + c0) * HW;
+        // ---- scale: largest |g * wy| this block will add; zero the accumulators ----------
+        unsigned int mbits = 0u;
+        for (int sl = 0; sl < 6; ++sl) {
+            const int y = s_y[sl];
+            if (y < 0) continue;
+            const S wy = s_w[sl];
+#pragma unroll
+            for (int j = 0; j < PXT; ++j) {
+                const int x = tid + j * nt;
+                if (x < W)
+                    for (int c = 0; c < nc; ++c) {
+                        const unsigned int bits = __float_as_uint(N::mul(gb[c * HW + y * W + x], wy)) & 0x7fffffffu;
+                        mbits = bits > mbits ? bits : mbits;  // NaN/inf bit patterns compare largest
+                    }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PXT; ++j) {
+            const int x = tid + j * nt;
+            if (x < W)
+                for (int c = 0; c < nc; ++c) { acc_lo[c * W + x] = 0u; acc_hi[c * W + x] = 0; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned int other = __shfl_xor_sync(0xffffffffu, mbits, o);
+            mbits = other > mbits ? other : mbits;
+        }
+        if ((tid & 31) == 0) atomicMax(&s_maxbits[parity], mbits);
+        __syncthreads();
+        const unsigned int maxbits = s_maxbits[parity];
+        if (tid == 0) s_maxbits[parity ^ 1] = 0u;  // idle slot, next used after the barriers below
+        parity ^= 1;
+        const int mexp = (int)(maxbits >> 23);
+        const bool finite = mexp != 0xff;
+        int e = 156 - (mexp > 0 ? mexp : 1);  // |v| < 2^(mexp-126)  =>  |v * 2^e| < 2^30
+        if (e > 127) e = 127;
+        const S up = __uint_as_float((unsigned)(e + 127) << 23);
+        const S down = (e < 127) ? __uint_as_float((unsigned)(127 - e) << 23) : __uint_as_float(0x00400000u);
+
+        if (finite && maxbits != 0u) {
+            for (int sl = 0; sl < 6; ++sl) {
+                const int y = s_y[sl];
+                if (y < 0) continue;
+                const S wy = s_w[sl];
+#pragma unroll
+                for (int j = 0; j < PXT; ++j) {
+                    const int x = tid + j * nt;
+                    const bool inrow = x < W;
+                    const int xc = inrow ? x : W - 1;
+                    S ix = unnorm<S>(N::sub((S)xc, dispb[y * W + xc]), W);
+                    if (border) ix = clamp_border<S>(ix, W);
+                    const Axis<S> xa = make_axis<S>(ix, W);
+                    // cells of the two taps (negative = none)
+                    const int kL = (inrow && xa.in0) ? xa.i0 : -1000;
+                    const int kR = (inrow && xa.in1) ? xa.i0 + 1 : -2000;
+                    // x' is close to monotone in x, so the right tap of lane l usually lands on the
+                    // left-tap cell of lane l+1: hand it over through a shuffle and halve the atomics
+                    // (exact: the merge happens on the quantised integers)
+                    const int lane = tid & 31;
+                    const int nextL = __shfl_down_sync(0xffffffffu, kL, 1);
+                    const int prevR = __shfl_up_sync(0xffffffffu, kR, 1);
+                    const bool hand_out = (flags & 1) && lane < 31 && kR >= 0 && nextL == kR;
+                    const bool take_in = (flags & 1) && lane > 0 && kL >= 0 && prevR == kL;
+                    const S wl = N::mul(wy, xa.w0), wr = N::mul(wy, xa.w1);
+                    const float *gp = gb + y * W + xc;
+                    unsigned int *lo = acc_lo + xa.i0;
+                    int *hi = acc_hi + xa.i0;
+                    for (int c = 0; c < nc; ++c, gp += HW, lo += W, hi += W) {
+                        const S go = *gp;
+                        int q0 = kL >= 0 ? __float2int_rn(N::mul(N::mul(go, wl), up)) : 0;
+                        const int q1 = kR >= 0 ? __float2int_rn(N::mul(N::mul(go, wr), up)) : 0;
+                        const int qin = __shfl_up_sync(0xffffffffu, q1, 1);
+                        if (take_in) q0 += qin;
+                        if (!(flags & 2)) {
+                            if (kL >= 0) {
+                                atomicAdd(lo, (unsigned int)q0 & 0xffffu);
+                                atomicAdd(hi, q0 >> 16);
+                            }
+                            if (kR >= 0 && !hand_out) {
+                                atomicAdd(lo + 1, (unsigned int)q1 & 0xffffu);
+                                atomicAdd(hi + 1, q1 >> 16);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- write the row once -----------------------------------------------------------------
+        float *ob = g_img + ((long long)b * C + c0) * HW + yy * W;
+#pragma unroll
+        for (int j = 0; j < PXT; ++j) {
+            const int x = tid + j * nt;
+            if (x >= W) break;
+            for (int c = 0; c < nc; ++c) {
+                S v;
+                if (!finite) v = __uint_as_float(0x7fc00000u);  // a non-finite gradient poisons the row chunk
+                else v = N::mul((S)(((long long)acc_hi[c * W + x] << 16) + (long long)acc_lo[c * W + x]), down);
+                ob[c * HW + x] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Two-kernel path (used when the caller provides a B*C*H*W workspace): the warp is
+// separable -- the vertical blend weights are per-row constants -- so
+//   K1 (warp_bwd_hscatter_kernel): per OUTPUT row y, gV[c][y][k] = sum_x g[c][y][x] * wx(x->k)
+//       (horizontal 2-tap scatter with the exact fixed-point shared atomics; every row is
+//       scattered once instead of once per image row it touches) and g_disp[y] (gather);
+//   K2 (warp_bwd_vmix_kernel): g_img[c][yy] = sum over the <= 3 rows y whose vertical taps
+//       reach yy of wy * gV[c][y]  -- dense, coalesced, read from L2.
+// ---------------------------------------------------------------------------------
+template <int PXT, int NCT>  // NCT > 0: exactly NCT channels (C == NCT); NCT == 0: any C in chunks of kCC
+__global__ void __launch_bounds__(1024, 1) warp_bwd_hscatter_kernel(const float *__restrict__ g, const float *__restrict__ img,
+                                                                     const float *__restrict__ disp, float *__restrict__ gV,
+                                                                     float *__restrict__ g_disp,
+                                                                     int B, int C, int H, int W, int border, int flags) {
+    using S = float;
+    using N = Num<S>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned int *acc_lo = reinterpret_cast<unsigned int *>(smem_raw);   // [kCC][W]
+    int *acc_hi = reinterpret_cast<int *>(smem_raw) + (size_t)kCC * W;   // [kCC][W]
+    __shared__ unsigned int s_maxbits[2];
+
+    const int y = blockIdx.x % H;
+    const int b = blockIdx.x / H;
+    const int HW = H * W;  // C*H*W < 2^31 checked on the host
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    // per-row constants: computed by one thread (they cost several IEEE divisions), shared by all
+    __shared__ float s_rowc[6];  // halfW, tscale, ya.w0, ya.w1 | s_rowi: ya.i0, in-flags
+    __shared__ int s_rowi[2];
+    if (tid == 0) {
+        const S iy_raw = unnorm<S>((S)y, H);
+        const Axis<S> a = make_axis<S>(border ? clamp_border<S>(iy_raw, H) : iy_raw, H);
+        s_rowc[0] = N::div((S)W, (S)2);
+        s_rowc[1] = N::div((S)2, (S)(W - 1));
+        s_rowc[2] = a.w0; s_rowc[3] = a.w1;
+        s_rowi[0] = a.i0; s_rowi[1] = (a.in0 ? 1 : 0) | (a.in1 ? 2 : 0);
+        s_maxbits[0] = 0u; s_maxbits[1] = 0u;
+    }
+    __syncthreads();
+    const S halfW = s_rowc[0];
+    const S tscale = s_rowc[1];  // d gx / d t
+    const S wm1 = (S)(W - 1);
+    Axis<S> ya;
+    ya.w0 = s_rowc[2]; ya.w1 = s_rowc[3]; ya.i0 = s_rowi[0];
+    ya.in0 = (s_rowi[1] & 1) != 0; ya.in1 = (s_rowi[1] & 2) != 0;
+    const S inv_wm1_unused = (S)0; (void)inv_wm1_unused;
+
+    // horizontal taps of this thread's pixels: computed once, reused by every channel chunk
+    int kL[PXT], kR[PXT];
+    S w0[PXT], w1[PXT], gmult[PXT];
+    bool hand_out[PXT], take_in[PXT];
+#pragma unroll
+    for (int j = 0; j < PXT; ++j) {
+        const int x = tid + j * nt;
+        const bool inrow = x < W;
+        const int xc = inrow ? x : W - 1;
+        // unnorm() with the shared W/2: gx = 2*(t/(W-1)) - 1; ix = fma(gx+1, W/2, -0.5)
+        const S t = N::sub((S)xc, disp[(long long)b * HW + y * W + xc]);
+        const S gxn = N::sub(N::mul((S)2, N::div(t, wm1)), (S)1);
+        S ix = N::fma(N::add(gxn, (S)1), halfW, (S)-0.5);
+        gmult[j] = halfW;
+        if (border) {
+            // clip_coordinates_set_grad: borders count as out of bounds for the gradient
+            if (ix <= (S)0) { ix = (S)0; gmult[j] = (S)0; }
+            else if (ix >= wm1) { ix = wm1; gmult[j] = (S)0; }
+            else if (!(ix == ix)) ix = clamp_border<S>(ix, W);
+        }
+        const Axis<S> xa = make_axis<S>(ix, W);
+        kL[j] = (inrow && xa.in0) ? xa.i0 : -1000;
+        kR[j] = (inrow && xa.in1) ? xa.i0 + 1 : -2000;
+        w0[j] = xa.w0; w1[j] = xa.w1;
+        // x' is close to monotone in x: the right tap of lane l usually lands on the left-tap
+        // cell of lane l+1 -> hand it over through a shuffle (exact: merged as integers)
+        const int nextL = __shfl_down_sync(0xffffffffu, kL[j], 1);
+        const int prevR = __shfl_up_sync(0xffffffffu, kR[j], 1);
+        hand_out[j] = (flags & 1) && lane < 31 && kR[j] >= 0 && nextL == kR[j];
+        take_in[j] = (flags & 1) && lane > 0 && kL[j] >= 0 && prevR == kL[j];
+    }
+
+    S gix[PXT];
+#pragma unroll
+    for (int j = 0; j < PXT; ++j) gix[j] = (S)0;
+
+    int parity = 0;
+    constexpr int NCMAX = NCT > 0 ? NCT : kCC;
+    for (int c0 = 0; c0 < C; c0 += NCMAX) {
+        const int nc = NCT > 0 ? NCT : ((C - c0 < kCC) ? C - c0 : kCC);
+        const float *gb = g + ((long long)b * C + c0) * HW + y * W;
+        const float *ib = img + ((long long)b * C + c0) * HW;
+        S go[PXT][NCMAX];
+        unsigned int mbits = 0u;
+#pragma unroll
+        for (int j = 0; j < PXT; ++j) {
+            const int x = tid + j * nt;
+            const bool inrow = x < W;
+#pragma unroll
+            for (int c = 0; c < NCMAX; ++c) {
+                go[j][c] = (inrow && c < nc) ? gb[c * HW + x] : (S)0;
+                const unsigned int bits = __float_as_uint(go[j][c]) & 0x7fffffffu;
+                mbits = bits > mbits ? bits : mbits;  // NaN/inf bit patterns compare largest
+                if (inrow && c < nc) { acc_lo[c * W + x] = 0u; acc_hi[c * W + x] = 0; }
+            }
+            if (g_disp && inrow) {
+                // taps of the un-merged axis: left cell i0 = kL or kR-1
+                const bool in0 = kL[j] >= 0, in1 = kR[j] >= 0;
+                const int i0 = in0 ? kL[j] : kR[j] - 1;
+                const float *p0 = ib + ya.i0 * W + i0;
+#pragma unroll
+                for (int c = 0; c < NCMAX; ++c) {
+                    if (c < nc) {
+                        const float *pc = p0 + c * HW;
+                        // d(sample)/d(ix) over in-bounds taps, ATen order nw, ne, sw, se
+                        if (in0 && ya.in0) gix[j] = N::sub(gix[j], N::mul(N::mul(pc[0], ya.w0), go[j][c]));
+                        if (in1 && ya.in0) gix[j] = N::add(gix[j], N::mul(N::mul(pc[1], ya.w0), go[j][c]));
+                        if (in0 && ya.in1) gix[j] = N::sub(gix[j], N::mul(N::mul(pc[W], ya.w1), go[j][c]));
+                        if (in1 && ya.in1) gix[j] = N::add(gix[j], N::mul(N::mul(pc[W + 1], ya.w1), go[j][c]));
+                    }
+                }
+            }
+        }
+        if (!gV) continue;  // only g_disp requested (block-uniform)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned int other = __shfl_xor_sync(0xffffffffu, mbits, o);
+            mbits = other > mbits ? other : mbits;
+        }
+        if (lane == 0) atomicMax(&s_maxbits[parity], mbits);
+        __syncthreads();
+        const unsigned int maxbits = s_maxbits[parity];
+        if (tid == 0) s_maxbits[parity ^ 1] = 0u;  // idle slot until after the barriers below
+        parity ^= 1;
+        const int mexp = (int)(maxbits >> 23);
+        const bool finite = mexp != 0xff;
+        int e = 156 - (mexp > 0 ? mexp : 1);  // |g * wx| <= |g| < 2^(mexp-126)  =>  |v * 2^e| < 2^30
+        if (e > 127) e = 127;
+        const S up = __uint_as_float((unsigned)(e + 127) << 23);
+        const S down = (e < 127) ? __uint_as_float((unsigned)(127 - e) << 23) : __uint_as_float(0x00400000u);
+
+        if (finite && maxbits != 0u) {
+#pragma unroll
+            for (int j = 0; j < PXT; ++j) {
+#pragma unroll
+                for (int c = 0; c < NCMAX; ++c) {
+                    if (c >= nc) break;
+                    int q0 = kL[j] >= 0 ? __float2int_rn(N::mul(N::mul(go[j][c], w0[j]), up)) : 0;
+                    const int q1 = kR[j] >= 0 ? __float2int_rn(N::mul(N::mul(go[j][c], w1[j]), up)) : 0;
+                    const int qin = __shfl_up_sync(0xffffffffu, q1, 1);
+                    if (take_in[j]) q0 += qin;
+                    if (kL[j] >= 0) {
+                        atomicAdd(&acc_lo[c * W + kL[j]], (unsigned int)q0 & 0xffffu);
+                        atomicAdd(&acc_hi[c * W + kL[j]], q0 >> 16);
+                    }
+                    if (kR[j] >= 0 && !hand_out[j]) {
+                        atomicAdd(&acc_lo[c * W + kR[j]], (unsigned int)q1 & 0xffffu);
+                        atomicAdd(&acc_hi[c * W + kR[j]], q1 >> 16);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        float *ob = gV + ((long long)b * C + c0) * HW + y * W;
+#pragma unroll
+        for (int j = 0; j < PXT; ++j) {
+            const int x = tid + j * nt;
+            if (x < W) {
+#pragma unroll
+                for (int c = 0; c < NCMAX; ++c) {
+                    if (c < nc) {
+                        S v;
+                        if (!finite) v = __uint_as_float(0x7fc00000u);  // a non-finite gradient poisons the row
+                        else v = N::mul((S)(((long long)acc_hi[c * W + x] << 16) + (long long)acc_lo[c * W + x]), down);
+                        ob[c * HW + x] = v;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (g_disp) {
+#pragma unroll
+        for (int j = 0; j < PXT; ++j) {
+            const int x = tid + j * nt;
+            // chain rule: ix <- gx (W/2, 0 where clipped) <- t (2/(W-1)) <- disp (-1)
+            if (x < W) g_disp[(long long)b * HW + y * W + x] = -N::mul(tscale, N::mul(gmult[j], gix[j]));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) warp_bwd_vmix_kernel(const float *__restrict__ gV, float *__restrict__ g_img,
+                                                             int B, int C, int H, int W, int border, int vec) {
+    using S = float;
+    using N = Num<S>;
+    __shared__ int s_y[6];
+    __shared__ float s_w[6];
+    const int yy = blockIdx.x % H;
+    const int b = blockIdx.x / H;
+    const long long HW = (long long)H * W;
+    const int tid = threadIdx.x;
+    __shared__ int s_n;
+    if (tid == 0) {
+        int n = 0;
+        for (int y = (yy > 0 ? yy - 1 : 0); y <= yy + 1 && y < H; ++y) {
+            const S iy_raw = unnorm<S>((S)y, H);
+            const Axis<S> ya = make_axis<S>(border ? clamp_border<S>(iy_raw, H) : iy_raw, H);
+            if (ya.in0 && ya.i0 == yy) { s_y[n] = y; s_w[n] = ya.w0; ++n; }
+            if (ya.in1 && ya.i0 + 1 == yy) { s_y[n] = y; s_w[n] = ya.w1; ++n; }
+        }
+        s_n = n;
+    }
+    __syncthreads();
+    const int n = s_n;
+    const unsigned int HWu = (unsigned)(H * W);
+    const float *src0 = gV + (long long)b * C * HW;
+    float *dst0 = g_img + (long long)b * C * HW + (long long)yy * W;
+    if (vec) {
+        const int W4 = W >> 2;
+        for (int i = tid; i < C * W4; i += blockDim.x) {
+            const int c = i / W4, x4 = i - c * W4;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int sl = 0; sl < n; ++sl) {
+                const float wy = s_w[sl];
+                const float4 v = *reinterpret_cast<const float4 *>(src0 + c * HWu + (unsigned)(s_y[sl] * W + 4 * x4));
+                a.x = N::fma(wy, v.x, a.x); a.y = N::fma(wy, v.y, a.y);
+                a.z = N::fma(wy, v.z, a.z); a.w = N::fma(wy, v.w, a.w);
+            }
+            st_global_cs(reinterpret_cast<float4 *>(dst0 + c * HWu) + x4, a);
+        }
+    } else {
+        for (int i = tid; i < C * W; i += blockDim.x) {
+            const int c = i / W, x = i - c * W;
+            float a = 0.f;
+            for (int sl = 0; sl < n; ++sl) a = N::fma(s_w[sl], src0[c * HWu + (unsigned)(s_y[sl] * W + x)], a);
+            dst0[c * HWu + x] = a;
+        }
+    }
+}
+
 int env_int(const char *name, int dflt) {
     const char *v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
@@ -191,18 +614,61 @@ int env_int(const char *name, int dflt) {
 
 template <typename S>
 int warp_bwd_typed(const void *g, const void *img, const void *disp, void *g_img, void *g_disp,
+                   void *workspace, size_t workspace_bytes,
                    int B, int C, int H, int W, int pad, cudaStream_t s) {
-    const int variant = env_int("DSSMD_WARP_BWD_VARIANT", 1);
+    const int variant = env_int("DSSMD_WARP_BWD_VARIANT", 3);
     if constexpr (sizeof(S) == 4) {
         const size_t smem = (size_t)2 * kCC * W * sizeof(int);
+        const int border = pad == DSSMD_PAD_BORDER;
+        const float *gp = (const float *)g, *ip = (const float *)img, *dp = (const float *)disp;
+        float *gi = (float *)g_img, *gd = (float *)g_disp;
+        const bool have_ws = workspace && workspace_bytes >= (size_t)B * C * H * W * sizeof(float);
+        if (variant >= 3 && W <= 4096 && (long long)C * H * W < (1LL << 31) && (have_ws || !g_img)) {
+            int pxt = W <= 256 ? 1 : (W <= 512 ? 2 : 4);  // ~256-thread blocks: 3-4 resident per SM
+            const int o = env_int("DSSMD_WARP_BWD_PXT", 0);
+            if ((o == 1 || o == 2 || o == 4) && ceil_div(W, o) <= 1024) pxt = o;
+            const int nt = round_up(ceil_div(W, pxt), 32);
+            void (*kern)(const float *, const float *, const float *, float *, float *, int, int, int, int, int, int) = nullptr;
+#define DSSMD_HS_PICK(P)                                                                            \
+    if (pxt == P) kern = C == 1 ? warp_bwd_hscatter_kernel<P, 1> : C == 2 ? warp_bwd_hscatter_kernel<P, 2> \
+                       : C == 3 ? warp_bwd_hscatter_kernel<P, 3> : C == 4 ? warp_bwd_hscatter_kernel<P, 4> \
+                                                                          : warp_bwd_hscatter_kernel<P, 0>;
+            DSSMD_HS_PICK(1) DSSMD_HS_PICK(2) DSSMD_HS_PICK(4)
+#undef DSSMD_HS_PICK
+            if (smem > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "warp_bwd: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+            }
+            const int flags = env_int("DSSMD_WARP_BWD_FLAGS", 1);
+            float *gv = g_img ? (float *)workspace : nullptr;
+            kern<<<(unsigned)(B * H), nt, smem, s>>>(gp, ip, dp, gv, gd, B, C, H, W, border, flags);
+            int rc = check_launch("warp_bwd(hscatter)");
+            if (rc || !g_img) return rc;
+            const int vec = (W % 4 == 0) && (((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(g_img)) & 15) == 0);
+            warp_bwd_vmix_kernel<<<(unsigned)(B * H), 256, 0, s>>>(gv, gi, B, C, H, W, border, vec);
+            return check_launch("warp_bwd(vmix)");
+        }
+        if (variant >= 2 && W <= 4096 && (long long)C * H * W < (1LL << 31)) {
+            int pxt = W <= 512 ? 1 : (W <= 2048 ? 2 : 4);
+            const int o = env_int("DSSMD_WARP_BWD_PXT", 0);
+            if ((o == 1 || o == 2 || o == 4) && ceil_div(W, o) <= 1024) pxt = o;
+            const int nt = round_up(ceil_div(W, pxt), 32);
+            auto kern = pxt == 1 ? warp_bwd_row_kernel<1> : (pxt == 2 ? warp_bwd_row_kernel<2> : warp_bwd_row_kernel<4>);
+            if (smem > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "warp_bwd: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+            }
+            // flags: bit 0 = merge neighbouring taps through shuffles (default on); bit 1 = debug, skip the atomics
+            const int flags = env_int("DSSMD_WARP_BWD_FLAGS", 1);
+            kern<<<(unsigned)(B * H), nt, smem, s>>>(gp, ip, dp, gi, gd, B, C, H, W, border, flags);
+            return check_launch("warp_bwd");
+        }
         if (variant != 0 && W <= 65535 && smem <= 160 * 1024) {
             if (smem > 48 * 1024) {
                 cudaError_t e = cudaFuncSetAttribute(warp_bwd_fixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "warp_bwd: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
             }
-            warp_bwd_fixed_kernel<<<(unsigned)(B * H), 256, smem, s>>>((const float *)g, (const float *)img, (const float *)disp,
-                                                                    (float *)g_img, (float *)g_disp, B, C, H, W,
-                                                                    pad == DSSMD_PAD_BORDER);
+            warp_bwd_fixed_kernel<<<(unsigned)(B * H), 256, smem, s>>>(gp, ip, dp, gi, gd, B, C, H, W, border);
             return check_launch("warp_bwd");
         }
     }
@@ -215,7 +681,13 @@ int warp_bwd_typed(const void *g, const void *img, const void *disp, void *g_img
 
 using namespace dssmd;
 
+extern "C" size_t dssmd_warp_bwd_workspace_bytes(int B, int C, int H, int W, int dtype) {
+    if (dtype != DSSMD_F32 || B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+    return (size_t)B * C * H * W * sizeof(float);
+}
+
 extern "C" int dssmd_warp_bwd(const void *g, const void *img, const void *disp, void *g_img, void *g_disp,
+                              void *workspace, size_t workspace_bytes,
                               int B, int C, int H, int W, int padding_mode, int dtype, void *stream) {
     DSSMD_REQUIRE(g && img && disp, "warp_bwd: null input pointer");
     DSSMD_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "warp_bwd: sizes must be positive (B=%d C=%d H=%d W=%d)", B, C, H, W);
@@ -224,8 +696,8 @@ extern "C" int dssmd_warp_bwd(const void *g, const void *img, const void *disp, 
     if (!g_img && !g_disp) return DSSMD_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     switch (dtype) {
-        case DSSMD_F32: return warp_bwd_typed<float>(g, img, disp, g_img, g_disp, B, C, H, W, padding_mode, s);
-        case DSSMD_F64: return warp_bwd_typed<double>(g, img, disp, g_img, g_disp, B, C, H, W, padding_mode, s);
+        case DSSMD_F32: return warp_bwd_typed<float>(g, img, disp, g_img, g_disp, workspace, workspace_bytes, B, C, H, W, padding_mode, s);
+        case DSSMD_F64: return warp_bwd_typed<double>(g, img, disp, g_img, g_disp, workspace, workspace_bytes, B, C, H, W, padding_mode, s);
         case DSSMD_BF16:
         case DSSMD_F16:
             return fail(DSSMD_ERR_UNSUPPORTED, "warp_bwd: 16-bit dtypes are not supported (coordinates need fp32; see DESIGN.md)");

@@ -91,6 +91,18 @@ def _check_warp_args(name, img, disp):
                                   "upstream's own 16-bit path is numerically meaningless at image widths)")
 
 
+def _warp_bwd(g, I, Dp, g_img, g_disp, pad):
+    """dssmd_warp_bwd with the scratch buffer the fast two-kernel path wants."""
+    B, C, H, W = I.shape
+    lib = _lib.lib()
+    code = _lib.dtype_code(I)
+    nbytes = int(lib.dssmd_warp_bwd_workspace_bytes(B, C, H, W, code)) if g_img is not None else 0
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=I.device) if nbytes else None
+    with torch.cuda.device(I.device):
+        _lib.check(lib.dssmd_warp_bwd(_lib.ptr(g), _lib.ptr(I), _lib.ptr(Dp), _lib.ptr(g_img), _lib.ptr(g_disp),
+                                      _lib.ptr(ws), nbytes, B, C, H, W, pad, code, _lib.stream_ptr(I.device)))
+
+
 def _raise_if_flag(flag):
     if _CHECK_NEGATIVE and flag is not None and int(flag.item()) != 0:
         raise AssertionError("disp.min() >= 0")  # upstream utils/disparity_warper.py:93
@@ -126,10 +138,7 @@ class DispWarpFn(torch.autograd.Function):
         g_img = torch.empty_like(I) if need_i else None
         g_disp = torch.empty_like(Dp) if need_d else None
         if (need_i or need_d) and I.numel() > 0:
-            g = g_warped.contiguous()
-            with torch.cuda.device(I.device):
-                _lib.check(_lib.lib().dssmd_warp_bwd(_lib.ptr(g), _lib.ptr(I), _lib.ptr(Dp), _lib.ptr(g_img), _lib.ptr(g_disp),
-                                                     B, C, H, W, ctx.pad, _lib.dtype_code(I), _lib.stream_ptr(I.device)))
+            _warp_bwd(g_warped.contiguous(), I, Dp, g_img, g_disp, ctx.pad)
         return g_img, g_disp, None
 
 
@@ -205,10 +214,7 @@ class LRWarpErrorFn(torch.autograd.Function):
             gw = g.neg()  # d(err)/d(warped) = -1
             g_Ls = torch.empty_like(Ls) if need_l else None
             g_disp = torch.empty_like(Dc) if need_d else None
-            with torch.cuda.device(Ls.device):
-                _lib.check(_lib.lib().dssmd_warp_bwd(_lib.ptr(gw), _lib.ptr(Ls), _lib.ptr(Dc), _lib.ptr(g_Ls), _lib.ptr(g_disp),
-                                                     B, C, H, W, _lib.PAD_CODE["border"], _lib.dtype_code(Ls),
-                                                     _lib.stream_ptr(Ls.device)))
+            _warp_bwd(gw, Ls, Dc, g_Ls, g_disp, _lib.PAD_CODE["border"])
             if need_l:
                 g_imgL = _resize_bilinear_bwd(g_Ls, (H0, W0)) if resized else g_Ls
         return g_imgL, g_disp, g_imgR

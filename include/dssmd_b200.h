@@ -92,8 +92,14 @@ DSSMD_API int dssmd_warp_fwd(const void *img, const void *disp, void *warped, vo
 /* Backward of disp_warp (aten::grid_sampler_2d_backward composed with the
  * coordinate arithmetic of :95-99); the mask carries no gradient.
  * g: [B,C,H,W] gradient of `warped`; g_img: [B,C,H,W]; g_disp: [B,1,H,W]; both
- * fully overwritten, either may be NULL to skip it. */
+ * fully overwritten, either may be NULL to skip it.
+ * `workspace` is an optional caller-owned device scratch buffer of at least
+ * dssmd_warp_bwd_workspace_bytes(...) bytes (contents undefined afterwards); with
+ * it the fast two-kernel path runs, with NULL a slower single-kernel path. */
+#include <stddef.h>
+DSSMD_API size_t dssmd_warp_bwd_workspace_bytes(int B, int C, int H, int W, int dtype);
 DSSMD_API int dssmd_warp_bwd(const void *g, const void *img, const void *disp, void *g_img, void *g_disp,
+                   void *workspace, size_t workspace_bytes,
                    int B, int C, int H, int W, int padding_mode, int dtype, void *stream);
 
 /* ---- bilinear resize (LRwarp_error's pre-scaling) -------------------------------
