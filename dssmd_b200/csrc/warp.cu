@@ -18,103 +18,121 @@ namespace dssmd {
 namespace {
 
 // ---------------------------------------------------------------------------------
-// Forward.  One thread per output pixel column-quad (4 consecutive x) and all C
-// channels: the coordinate work is done once per pixel, not once per channel and
-// per grid_sample call as in the reference.
-//   SUB = false: warped = sample, mask written when non-null      (disp_warp)
-//   SUB = true : out = other - sample, no mask                    (LRwarp_error tail)
+// Forward.  One block per image row; a thread owns 4 consecutive pixels and all C
+// channels: the coordinate work is done once per pixel (the reference redoes it per
+// channel and per grid_sample call), the per-row constants (several IEEE divisions)
+// once per block.  The mask and the negative-disparity flag are fused in.
+//   NCT > 0: exactly NCT channels (unrolled); NCT == 0: any C.
 // ---------------------------------------------------------------------------------
-template <typename S, bool SUB>
-__global__ void __launch_bounds__(256) warp_fwd_kernel(const S *__restrict__ img, const S *__restrict__ disp,
-                                                        const S *__restrict__ other, S *__restrict__ out,
-                                                        S *__restrict__ mask, int *neg_flag,
+template <typename S, int NCT>
+__global__ void __launch_bounds__(512) warp_fwd_kernel(const S *__restrict__ img, const S *__restrict__ disp,
+                                                        S *__restrict__ out, S *__restrict__ mask, int *neg_flag,
                                                         int B, int C, int H, int W, int border, int vec) {
     using N = Num<S>;
-    const int WQ = (W + 3) >> 2;
-    const long long nquads = (long long)B * H * WQ;
+    __shared__ S s_c[6];    // W/2, ym.w0, ym.w1, yi.w0, yi.w1
+    __shared__ int s_i[4];  // ym.i0, ym flags, yi.i0, yi flags
+    const int y = blockIdx.x % H;
+    const int b = blockIdx.x / H;
     const long long HW = (long long)H * W;
-    const bool vec_ok = vec != 0;  // W % 4 == 0 and every pointer 16-byte aligned
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        const S iy_raw = unnorm<S>((S)y, H);
+        const Axis<S> m = make_axis<S>(iy_raw, H);                                         // mask: un-clamped
+        const Axis<S> a = make_axis<S>(border ? clamp_border<S>(iy_raw, H) : iy_raw, H);   // image sample
+        s_c[0] = N::div((S)W, (S)2);
+        s_c[1] = m.w0; s_c[2] = m.w1; s_c[3] = a.w0; s_c[4] = a.w1;
+        s_i[0] = m.i0; s_i[1] = (m.in0 ? 1 : 0) | (m.in1 ? 2 : 0);
+        s_i[2] = a.i0; s_i[3] = (a.in0 ? 1 : 0) | (a.in1 ? 2 : 0);
+    }
+    __syncthreads();
+    const S halfW = s_c[0], wm1 = (S)(W - 1);
+    const S mw0 = s_c[1], mw1 = s_c[2], yw0 = s_c[3], yw1 = s_c[4];
+    const bool min0 = s_i[1] & 1, min1 = s_i[1] & 2, yin0 = s_i[3] & 1, yin1 = s_i[3] & 2;
+    const int yi0 = s_i[2];
+    const int nc = NCT > 0 ? NCT : C;
     bool bad = false;
 
-    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nquads;
-         q += (long long)gridDim.x * blockDim.x) {
-        const int xq = (int)(q % WQ);
-        const int y = (int)((q / WQ) % H);
-        const int b = (int)(q / ((long long)WQ * H));
-        const int x0 = xq << 2;
-        const long long rowoff = (long long)y * W;
+    const S *drow = disp + (long long)b * HW + (long long)y * W;
+    const S *ibase = img + (long long)b * C * HW + (long long)yi0 * W;
+    S *obase = out + (long long)b * C * HW + (long long)y * W;
+    S *mbase = mask ? mask + (long long)b * C * HW + (long long)y * W : nullptr;
 
-        // per-row vertical taps
-        const S iy_raw = unnorm<S>((S)y, H);
-        const Axis<S> ym = make_axis<S>(iy_raw, H);                                   // mask: un-clamped
-        const Axis<S> yi = make_axis<S>(border ? clamp_border<S>(iy_raw, H) : iy_raw, H);
-
+    for (int x0 = tid * 4; x0 < W; x0 += blockDim.x * 4) {
         S dv[4];
-        if (vec_ok) {
+        if (vec) {
             if constexpr (sizeof(S) == 4) {
-                const float4 t = *reinterpret_cast<const float4 *>(disp + (long long)b * HW + rowoff + x0);
+                const float4 t = *reinterpret_cast<const float4 *>(drow + x0);
                 dv[0] = t.x; dv[1] = t.y; dv[2] = t.z; dv[3] = t.w;
             } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dv[i] = disp[(long long)b * HW + rowoff + x0 + i];
+                for (int i = 0; i < 4; ++i) dv[i] = drow[x0 + i];
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) dv[i] = (x0 + i < W) ? disp[(long long)b * HW + rowoff + x0 + i] : (S)0;
+            for (int i = 0; i < 4; ++i) dv[i] = (x0 + i < W) ? drow[x0 + i] : (S)0;
         }
-
-        Axis<S> xi[4];
+        int xi0[4], tin[4];             // low x tap; in-bounds bits of taps nw, ne, sw, se
+        S wa[4], wb[4], wc[4], wd[4];  // tap weights nw, ne, sw, se
         S mv[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             if (!(dv[i] >= (S)0)) bad = true;
-            const S ix_raw = unnorm<S>(N::sub((S)(x0 + i), dv[i]), W);
+            // reference op order: t = x - d; gx = 2*(t/(W-1)) - 1; ix = fma(gx+1, W/2, -0.5)
+            const S t = N::sub((S)(x0 + i), dv[i]);
+            const S gxn = N::sub(N::mul((S)2, N::div(t, wm1)), (S)1);
+            const S ix_raw = N::fma(N::add(gxn, (S)1), halfW, (S)-0.5);
             const Axis<S> xm = make_axis<S>(ix_raw, W);
-            // sum of in-bounds weights, reference accumulation order nw, ne, sw, se
+            // sum of in-bounds weights of the un-clamped sample, reference order nw, ne, sw, se
             S m = (S)0;
-            if (xm.in0 && ym.in0) m = N::add(m, N::mul(ym.w0, xm.w0));
-            if (xm.in1 && ym.in0) m = N::add(m, N::mul(ym.w0, xm.w1));
-            if (xm.in0 && ym.in1) m = N::add(m, N::mul(ym.w1, xm.w0));
-            if (xm.in1 && ym.in1) m = N::add(m, N::mul(ym.w1, xm.w1));
+            if (xm.in0 && min0) m = N::add(m, N::mul(mw0, xm.w0));
+            if (xm.in1 && min0) m = N::add(m, N::mul(mw0, xm.w1));
+            if (xm.in0 && min1) m = N::add(m, N::mul(mw1, xm.w0));
+            if (xm.in1 && min1) m = N::add(m, N::mul(mw1, xm.w1));
             mv[i] = (m >= (S)0.9999) ? (S)1 : (S)0;
-            xi[i] = make_axis<S>(border ? clamp_border<S>(ix_raw, W) : ix_raw, W);
+            Axis<S> xa = xm;
+            if (border && !(ix_raw >= (S)0 && ix_raw <= wm1)) xa = make_axis<S>(clamp_border<S>(ix_raw, W), W);
+            xi0[i] = xa.i0;
+            tin[i] = ((xa.in0 && yin0) ? 1 : 0) | ((xa.in1 && yin0) ? 2 : 0) | ((xa.in0 && yin1) ? 4 : 0) | ((xa.in1 && yin1) ? 8 : 0);
+            wa[i] = N::mul(yw0, xa.w0);
+            wb[i] = N::mul(yw0, xa.w1);
+            wc[i] = N::mul(yw1, xa.w0);
+            wd[i] = N::mul(yw1, xa.w1);
         }
-
-        for (int c = 0; c < C; ++c) {
-            const long long plane = ((long long)b * C + c) * HW;
-            const S *p0 = img + plane + (long long)yi.i0 * W;
-            const S *p1 = p0 + W;
-            S v[4];
+        auto channel = [&](int cc) {
+            {
+                const S *p0 = ibase + (long long)cc * HW;
+                S v[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                S acc = (S)0;
-                const Axis<S> &xa = xi[i];
-                if (xa.in0 && yi.in0) acc = N::fma(p0[xa.i0], N::mul(yi.w0, xa.w0), acc);
-                if (xa.in1 && yi.in0) acc = N::fma(p0[xa.i0 + 1], N::mul(yi.w0, xa.w1), acc);
-                if (xa.in0 && yi.in1) acc = N::fma(p1[xa.i0], N::mul(yi.w1, xa.w0), acc);
-                if (xa.in1 && yi.in1) acc = N::fma(p1[xa.i0 + 1], N::mul(yi.w1, xa.w1), acc);
-                v[i] = acc;
-            }
-            S *o = out + plane + rowoff + x0;
-            if constexpr (SUB) {
-                const S *r = other + plane + rowoff + x0;
+                for (int i = 0; i < 4; ++i) {
+                    S acc = (S)0;
+                    // only in-bounds taps are read (grid_sample zero-pads the rest)
+                    if (tin[i] & 1) acc = N::fma(p0[xi0[i]], wa[i], acc);
+                    if (tin[i] & 2) acc = N::fma(p0[xi0[i] + 1], wb[i], acc);
+                    if (tin[i] & 4) acc = N::fma(p0[W + xi0[i]], wc[i], acc);
+                    if (tin[i] & 8) acc = N::fma(p0[W + xi0[i] + 1], wd[i], acc);
+                    v[i] = acc;
+                }
+                S *o = obase + (long long)cc * HW + x0;
+                if (vec && sizeof(S) == 4) {
+                    st_global_cs(reinterpret_cast<float4 *>(o), make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]));
+                    if (mbase)
+                        st_global_cs(reinterpret_cast<float4 *>(mbase + (long long)cc * HW + x0),
+                                     make_float4((float)mv[0], (float)mv[1], (float)mv[2], (float)mv[3]));
+                } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (x0 + i < W) v[i] = N::sub(r[i], v[i]);
+                    for (int i = 0; i < 4; ++i)
+                        if (x0 + i < W) {
+                            o[i] = v[i];
+                            if (mbase) mbase[(long long)cc * HW + x0 + i] = mv[i];
+                        }
+                }
             }
-            if (vec_ok && sizeof(S) == 4) {
-                st_global_cs(reinterpret_cast<float4 *>(o), make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]));
-                if (!SUB && mask)
-                    st_global_cs(reinterpret_cast<float4 *>(mask + plane + rowoff + x0),
-                                 make_float4((float)mv[0], (float)mv[1], (float)mv[2], (float)mv[3]));
-            } else {
+        };
+        if constexpr (NCT > 0) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (x0 + i < W) {
-                        o[i] = v[i];
-                        if (!SUB && mask) mask[plane + rowoff + x0 + i] = mv[i];
-                    }
-            }
+            for (int cc = 0; cc < NCT; ++cc) channel(cc);
+        } else {
+            for (int cc = 0; cc < nc; ++cc) channel(cc);
         }
     }
     if (bad && neg_flag) atomicOr(neg_flag, 1);
@@ -313,12 +331,22 @@ __global__ void __launch_bounds__(256) lrwarp_fwd_kernel(const S *__restrict__ i
 template <typename S>
 int warp_fwd_typed(const void *img, const void *disp, void *warped, void *mask, int *neg_flag,
                    int B, int C, int H, int W, int pad, cudaStream_t s) {
-    const long long nquads = (long long)B * H * ((W + 3) / 4);
     const uintptr_t bits = reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(disp) |
                            reinterpret_cast<uintptr_t>(warped) | reinterpret_cast<uintptr_t>(mask);
     const int vec = (W % 4 == 0) && ((bits & 15) == 0);
-    warp_fwd_kernel<S, false><<<grid_for(nquads, 256, 8), 256, 0, s>>>(
-        (const S *)img, (const S *)disp, nullptr, (S *)warped, (S *)mask, neg_flag, B, C, H, W, pad == DSSMD_PAD_BORDER, vec);
+    int nt = round_up(ceil_div(W, 4), 32);
+    if (nt > 512) nt = 512;
+    const int border = pad == DSSMD_PAD_BORDER;
+    const unsigned grid = (unsigned)(B * H);
+    const S *ip = (const S *)img, *dp = (const S *)disp;
+    S *op = (S *)warped, *mp = (S *)mask;
+    switch (C) {
+        case 1: warp_fwd_kernel<S, 1><<<grid, nt, 0, s>>>(ip, dp, op, mp, neg_flag, B, C, H, W, border, vec); break;
+        case 2: warp_fwd_kernel<S, 2><<<grid, nt, 0, s>>>(ip, dp, op, mp, neg_flag, B, C, H, W, border, vec); break;
+        case 3: warp_fwd_kernel<S, 3><<<grid, nt, 0, s>>>(ip, dp, op, mp, neg_flag, B, C, H, W, border, vec); break;
+        case 4: warp_fwd_kernel<S, 4><<<grid, nt, 0, s>>>(ip, dp, op, mp, neg_flag, B, C, H, W, border, vec); break;
+        default: warp_fwd_kernel<S, 0><<<grid, nt, 0, s>>>(ip, dp, op, mp, neg_flag, B, C, H, W, border, vec); break;
+    }
     return check_launch("warp_fwd");
 }
 

@@ -50,7 +50,7 @@ def main():
                         ("DSSMD_CORR_BWD_SMEM_KB", ["", "40", "100"])],
         "corr_bwd_gR": [("DSSMD_CORR_BWD_CG", ["", "1", "2", "4", "8"]), ("DSSMD_CORR_BWD_ROWS", ["", "1", "2", "4"]),
                         ("DSSMD_CORR_BWD_SMEM_KB", ["", "40", "100"])],
-        "warp_fwd": [("DSSMD_WARP_FWD_VARIANT", ["", "0", "1"])],
+        "warp_fwd": [("DSSMD_WARP_FWD_X", [""])],
         "warp_bwd": [("DSSMD_WARP_BWD_FLAGS", ["", "0", "1", "2", "3"]), ("DSSMD_WARP_BWD_PXT", ["2", "4"])],
     }[which]
     for wname in workloads:
