@@ -532,10 +532,10 @@ int launch_d4(const void *L, const void *R, void *out, int B, int C, int H, int 
     const int cap2 = (128 * 4 - p.HALO) / (2 * kPix);  // <= 128 chunks per line
     if (npg_cap > cap2) npg_cap = cap2;
     if (npg_cap < 1) return -1;
-    // x tiles: enough (row, tile) units for >= 6 per SM so the block scheduler can balance the
-    // SMs, but tiles no narrower than 40 pixels (the R band re-reads HALO pixels per tile)
+    // x tiles: split a row only when its work items exceed one 128-thread block (measured on
+    // B200: 80x160/D=41 runs 1.6x faster as two 110-item tiles, model shapes are best unsplit)
     int xt = ceil_div(NPGF, npg_cap);
-    while ((long)p.NR * xt < (long)sm_count() * 6 && ceil_div(NPGF, xt + 1) >= 5) ++xt;
+    while (ceil_div(NPGF, xt) * NDG > 128 && ceil_div(NPGF, xt + 1) >= 5) ++xt;
     xt = env_int("DSSMD_CORR_FWD_XT", xt);
     if (xt < ceil_div(NPGF, npg_cap)) xt = ceil_div(NPGF, npg_cap);
     if (xt > NPGF) xt = NPGF;
