@@ -24,6 +24,9 @@
 
 namespace dssmd {
 
+// tensor-core path (corr_fwd_umma.cu); returns -1 when the shape is outside its limits
+int corr_fwd_umma_f32(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, cudaStream_t stream);
+
 namespace {
 
 constexpr int kPix = 8;        // pixels per thread
@@ -583,7 +586,14 @@ int launch_d4(const void *L, const void *R, void *out, int B, int C, int H, int 
 
 template <typename T>
 int launch_typed(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, cudaStream_t stream) {
-    if (env_int("DSSMD_CORR_FWD_VARIANT", 1) == 1 && D <= 64) {
+    const int variant = env_int("DSSMD_CORR_FWD_VARIANT", 1);  // 0 wide FFMA tile, 1 narrow FFMA tile, 2 tcgen05
+    if constexpr (sizeof(T) == 4) {
+        if (variant == 2) {
+            const int rc = corr_fwd_umma_f32(L, R, out, B, C, H, W, D, stream);
+            if (rc >= 0) return rc;
+        }
+    }
+    if (variant >= 1 && D <= 64) {
         const int rc = launch_d4<T>(L, R, out, B, C, H, W, D, stream);
         if (rc >= 0) return rc;
     }
