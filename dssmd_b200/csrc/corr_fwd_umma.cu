@@ -36,6 +36,8 @@
 //                           main loop of tile t+1.
 #include "common.cuh"
 
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include <cstdlib>
 
 namespace dssmd {
@@ -47,13 +49,12 @@ constexpr int kKC = 16;            // channels per pipeline stage (= 2 MMA K ste
 constexpr int kChunksK = kKC / 4;  // 16-byte chunks along K per operand row
 constexpr int kMaxSeg = 4;         // image rows one 128-pixel tile may touch
 constexpr int kOpStages = 2;      // operand (hi/lo, K-major) buffers
-constexpr int kRawStages = 4;     // raw fp32 ring filled by bulk async copies (TMA engine)
+constexpr int kRawStages = 3;     // raw fp32 ring filled by TMA tensor copies
 constexpr int kEpiWarps = 4, kXfWarps = 8;
 constexpr int kXfThreads = kXfWarps * 32;
 constexpr int kLoadWarp = kEpiWarps + kXfWarps;               // 12
 constexpr int kMmaWarp = kLoadWarp + 1;                       // 13
 constexpr int kThreads = (kEpiWarps + kXfWarps + 2) * 32;     // 448
-constexpr int kMaxCopies = 2 * kMaxSeg;                       // bulk copies per channel row: A and B part of each segment
 constexpr int kMaxXfItems = 6;     // (128 + 256) rows * 4 chunks / 256 threads
 
 struct UmmaParams {
@@ -62,7 +63,10 @@ struct UmmaParams {
     float *out;
     int B, C, H, W, D;
     int P;        // B*H*W pixels (< 2^31)
-    int ntiles;   // ceil(P / 128)
+    int tpi;      // tiles per batch image = ceil(H*W / 128)
+    int ntiles;   // B * tpi
+    int SMAX;     // max image rows a tile touches
+    int raw_stage_floats;  // 16 * (128 + SMAX * W)
     int HALO;     // D - 1
     int NMMA;     // MMA N (multiple of 16, <= 256)
     int NS;       // pipeline stages per tile = ceil(C / kKC)
@@ -142,8 +146,12 @@ __device__ __forceinline__ int op_off(int r, int j) { return ((r >> 3) * kChunks
 
 // rows of the image a tile touches and where their R columns live in the B operand
 __device__ __forceinline__ int tile_segments(const UmmaParams &p, int tile, Segment *seg) {
-    const int P0 = tile * kTileM;
-    const int qend = (P0 + kTileM < p.P) ? P0 + kTileM : p.P;
+    // tiles never cross a batch image: tile = (b, t) with t < tiles_per_img; rows are flattened b*H + y
+    const int b = tile / p.tpi, t = tile - b * p.tpi;
+    const int img0 = b * p.H * p.W;
+    const int P0 = img0 + t * kTileM;
+    const int pend = img0 + p.H * p.W;
+    const int qend = (P0 + kTileM < pend) ? P0 + kTileM : pend;
     int n = 0, col = 0, q = P0;
 #pragma unroll
     for (int it = 0; it < kMaxSeg; ++it) {
@@ -152,9 +160,9 @@ __device__ __forceinline__ int tile_segments(const UmmaParams &p, int tile, Segm
             const int xa = q - row * p.W;
             const int len = (p.W - xa < qend - q) ? p.W - xa : qend - q;
             seg[it].row = row; seg[it].xa = xa; seg[it].len = len; seg[it].m0 = q - P0;
-            seg[it].xp0 = (xa - p.HALO) & ~3;  // floor to a multiple of 4 (two's complement floors negatives)
+            seg[it].xp0 = xa - p.HALO;
             seg[it].col0 = col;
-            seg[it].ncol = ((xa + len - seg[it].xp0) + 3) & ~3;
+            seg[it].ncol = len + p.HALO;
             col += seg[it].ncol;
             q += len;
             n = it + 1;
@@ -166,7 +174,8 @@ __device__ __forceinline__ int tile_segments(const UmmaParams &p, int tile, Segm
 }
 
 template <int NW16>  // epilogue window = 16*NW16 accumulator columns per thread
-__global__ void __launch_bounds__(kThreads, 1) corr_fwd_umma_kernel(const UmmaParams p) {
+__global__ void __launch_bounds__(kThreads, 1) corr_fwd_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap mapA,
+                                                                     const __grid_constant__ CUtensorMap mapB) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t s_bars[kNumBars];
     __shared__ uint32_t s_tmem;
@@ -195,54 +204,42 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fwd_umma_kernel(const UmmaPa
     const uint32_t tmem_base = s_tmem;
 
     const int NR = kTileM + p.NMMA;      // operand rows: [A pixels | B columns]
-    const int RP = NR;                   // raw row pitch in floats
-    float *raw = reinterpret_cast<float *>(smem + (size_t)kOpStages * op_bytes);  // [kRawStages][kKC][RP]
+    // raw stage: A box [kKC][128] then, per image row the tile touches, a full R row box [kKC][W]
+    float *raw = reinterpret_cast<float *>(smem + (size_t)kOpStages * op_bytes);  // [kRawStages][raw_stage_floats]
 
     if (warp == kLoadWarp) {
         // =============================== LOAD ==================================================
-        // Bulk async copies (cp.async.bulk, executed by the TMA engine): per channel row one
-        // contiguous copy for the pixels of each image-row segment (A part) and one for its
-        // R columns at x' >= 0 (B part).  Lane l < 16 issues the copies of channel l of the
-        // stage; completion is counted in bytes on the stage's mbarrier.
-        uint32_t gs = 0;
-        for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-            Segment seg[kMaxSeg];
-            tile_segments(p, tile, seg);
-            long long c_src[kMaxCopies];  // element offset within channel 0
-            int c_dst[kMaxCopies];        // float offset within a raw row
-            int c_bytes[kMaxCopies];      // 0 = unused
-            uint32_t row_bytes = 0;
-#pragma unroll
-            for (int s = 0; s < kMaxSeg; ++s) {
-                const int b = seg[s].row / p.H;
-                const long long base = (long long)b * p.C * HW + (long long)(seg[s].row - b * p.H) * p.W;
-                // A: pixels xa .. xa+len-1 -> raw columns m0 ..
-                c_src[2 * s] = base + seg[s].xa; c_dst[2 * s] = seg[s].m0; c_bytes[2 * s] = seg[s].len * 4;
-                // B: x' = max(xp0,0) .. xp0+ncol-1 -> raw columns 128 + col0 + (x' - xp0)
-                const int x0 = seg[s].xp0 < 0 ? 0 : seg[s].xp0;
-                const int nb = seg[s].len > 0 ? seg[s].xp0 + seg[s].ncol - x0 : 0;
-                c_src[2 * s + 1] = base + x0; c_dst[2 * s + 1] = kTileM + seg[s].col0 + (x0 - seg[s].xp0); c_bytes[2 * s + 1] = nb * 4;
-                row_bytes += (uint32_t)(c_bytes[2 * s] + c_bytes[2 * s + 1]);
-            }
-            for (int s = 0; s < p.NS; ++s, ++gs) {
-                const uint32_t slot = gs % kRawStages, ph = (gs / kRawStages) & 1u;
-                mbar_wait(BAR(kRawEmpty, slot), ph ^ 1u);
-                const uint32_t full = BAR(kRawFull, slot);
-                if (lane == 0)
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(row_bytes * kKC) : "memory");
-                __syncwarp();
-                if (lane < kKC && !(p.dbg & 4)) {
-                    const long long coff = (long long)(s * kKC + lane) * HW;
-                    const uint32_t drow = smem_u32(raw + (size_t)slot * kKC * RP + lane * RP);
-#pragma unroll
-                    for (int k = 0; k < kMaxCopies; ++k) {
-                        if (c_bytes[k] == 0) continue;
-                        const float *g = ((k & 1) ? p.R : p.L) + c_src[k] + coff;
-                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                     ::"r"(drow + 4u * (uint32_t)c_dst[k]), "l"(g), "r"(c_bytes[k]), "r"(full) : "memory");
+        // TMA tensor copies, one thread: per stage one box {128 pixels, 16 channels} of L from
+        // the [B][C][H*W] view (a tile is contiguous in H*W; pixels past the image are zero
+        // filled by the TMA unit) and, per image row the tile touches, one box {W, 1 row, 16
+        // channels} of R from the [B][C][H][W] view.  Completion is byte-counted on the mbarrier.
+        if (lane == 0) {
+            uint32_t gs = 0;
+            for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                Segment seg[kMaxSeg];
+                const int nseg = tile_segments(p, tile, seg);
+                const int b = tile / p.tpi, t = tile - b * p.tpi;
+                const uint32_t bytes = (uint32_t)(kKC * (kTileM + nseg * p.W) * 4);
+                for (int s = 0; s < p.NS; ++s, ++gs) {
+                    const uint32_t slot = gs % kRawStages, ph = (gs / kRawStages) & 1u;
+                    mbar_wait(BAR(kRawEmpty, slot), ph ^ 1u);
+                    const uint32_t full = BAR(kRawFull, slot);
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(bytes) : "memory");
+                    if (p.dbg & 4) {
+                        asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(full), "r"(bytes) : "memory");
+                        continue;
                     }
-                } else if (lane < kKC) {  // debug: no copies, complete the byte count by hand
-                    asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(full), "r"(row_bytes) : "memory");
+                    const uint32_t dst = smem_u32(raw + (size_t)slot * p.raw_stage_floats);
+                    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&mapA)), "r"(t * kTileM), "r"(s * kKC), "r"(b), "r"(full) : "memory");
+#pragma unroll
+                    for (int k = 0; k < kMaxSeg; ++k) {
+                        if (k >= nseg) break;
+                        const int y = seg[k].row - b * p.H;
+                        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                                     ::"r"(dst + 4u * (uint32_t)(kKC * (kTileM + k * p.W))), "l"(reinterpret_cast<uint64_t>(&mapB)),
+                                       "r"(0), "r"(y), "r"(s * kKC), "r"(b), "r"(full) : "memory");
+                    }
                 }
             }
         }
@@ -251,14 +248,14 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fwd_umma_kernel(const UmmaPa
         // transpose + hi/lo split of a landed raw stage into an operand buffer
         const int t = tid - kEpiWarps * 32;  // 0..255
         // item k of this thread = (K chunk j, operand row r); lanes run over rows (conflict-free both ways)
-        int t_src[kMaxXfItems], t_dst[kMaxXfItems], t_lo[kMaxXfItems], t_row[kMaxXfItems];
+        int t_j[kMaxXfItems], t_dst[kMaxXfItems], t_lo[kMaxXfItems], t_row[kMaxXfItems];
 #pragma unroll
         for (int k = 0; k < kMaxXfItems; ++k) {
             const int i = t + k * kXfThreads;
-            t_src[k] = -1; t_dst[k] = 0; t_lo[k] = 0; t_row[k] = -1;
+            t_j[k] = 0; t_dst[k] = 0; t_lo[k] = 0; t_row[k] = -1;
             if (i < NR * kChunksK) {
                 const int j = i / NR, r = i - j * NR;
-                t_src[k] = (4 * j) * RP + r;
+                t_j[k] = j;
                 t_row[k] = r;
                 const bool isB = r >= kTileM;
                 t_dst[k] = (isB ? 2 * a_bytes : 0) + op_off(isB ? r - kTileM : r, j);
@@ -267,22 +264,27 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fwd_umma_kernel(const UmmaPa
         }
         uint32_t gs = 0;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-            // rows the copies never write (x' < 0, columns between / after the segments, pixels past the
-            // end) must read as zero whatever an earlier tile left in the ring
+            // where each operand row of this tile lives in a raw stage (float offset of its channel 4j)
+            // and its channel stride; -1: the row is all zero (x' < 0, unused column, pixel past the image)
             Segment seg[kMaxSeg];
             tile_segments(p, tile, seg);
-            bool valid[kMaxXfItems];
+            int src_off[kMaxXfItems], src_cs[kMaxXfItems];
 #pragma unroll
             for (int k = 0; k < kMaxXfItems; ++k) {
-                valid[k] = false;
+                src_off[k] = -1; src_cs[k] = 0;
                 const int r = t_row[k];
+                if (r < 0) continue;
 #pragma unroll
                 for (int s = 0; s < kMaxSeg; ++s) {
+                    if (seg[s].len == 0) continue;
                     if (r < kTileM) {
-                        if (r >= seg[s].m0 && r < seg[s].m0 + seg[s].len) valid[k] = true;
+                        if (r >= seg[s].m0 && r < seg[s].m0 + seg[s].len) { src_off[k] = 4 * t_j[k] * kTileM + r; src_cs[k] = kTileM; }
                     } else {
                         const int n = r - kTileM;
-                        if (seg[s].len > 0 && n >= seg[s].col0 && n < seg[s].col0 + seg[s].ncol && seg[s].xp0 + (n - seg[s].col0) >= 0) valid[k] = true;
+                        const int xp = seg[s].xp0 + (n - seg[s].col0);
+                        if (n >= seg[s].col0 && n < seg[s].col0 + seg[s].ncol && xp >= 0) {
+                            src_off[k] = kKC * (kTileM + s * p.W) + 4 * t_j[k] * p.W + xp; src_cs[k] = p.W;
+                        }
                     }
                 }
             }
@@ -291,16 +293,15 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fwd_umma_kernel(const UmmaPa
                 const uint32_t ob = gs % kOpStages, oph = (gs / kOpStages) & 1u;
                 mbar_wait(BAR(kRawFull, slot), rph);
                 mbar_wait(BAR(kOpEmpty, ob), oph ^ 1u);
-                const float *rs = raw + (size_t)slot * kKC * RP;
+                const float *rs = raw + (size_t)slot * p.raw_stage_floats;
                 unsigned char *opb = ops + (size_t)ob * op_bytes;
 #pragma unroll
                 for (int k = 0; k < kMaxXfItems; ++k) {
-                    if (t_src[k] < 0 || (p.dbg & 2)) continue;
-                    const float *src = rs + t_src[k];
+                    if (t_row[k] < 0 || (p.dbg & 2)) continue;
                     float hi[4], lo[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float v = valid[k] ? src[q * RP] : 0.f;
+                        const float v = src_off[k] >= 0 ? rs[src_off[k] + q * src_cs[k]] : 0.f;
                         // round to nearest TF32 (10 mantissa bits): |lo| <= 2^-11 |v|, dropped lo*lo is 2^-22
                         hi[q] = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
                         lo[q] = v - hi[q];
@@ -426,29 +427,76 @@ int env_int(const char *name, int dflt) {
 
 }  // namespace
 
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            sym = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(sym);
+    }();
+    return fn;
+}
+
+// fp32 tensor map; dims/box fastest first; strides in bytes for dims 1..rank-1
+bool make_tmap_f32(CUtensorMap *m, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides, const cuuint32_t *box) {
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) return false;
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
 // Returns -1 when the shape is outside this kernel's limits (caller falls back to FFMA).
 int corr_fwd_umma_f32(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, cudaStream_t stream) {
-    if (W % 4 != 0 || W < 43 || D < 2 || D > 58) return -1;
+    if (W % 4 != 0 || W < 43 || W > 256 || D < 2 || D > 58) return -1;
     if (((reinterpret_cast<uintptr_t>(L) | reinterpret_cast<uintptr_t>(R)) & 15) != 0) return -1;
     if (C % kKC != 0) return -1;
     if ((long long)B * H * W >= (1LL << 31) - 256) return -1;
     const int smax = 2 + 126 / W;
     if (smax > kMaxSeg) return -1;
-    const int nmma = round_up(kTileM + smax * (D - 1 + 6), 16);
+    const int nmma = round_up(kTileM + smax * (D - 1), 16);
     if (nmma > 256) return -1;
     UmmaParams p{};
     p.L = (const float *)L; p.R = (const float *)R; p.out = (float *)out;
     p.B = B; p.C = C; p.H = H; p.W = W; p.D = D;
     p.P = B * H * W;
-    p.ntiles = (p.P + kTileM - 1) / kTileM;
+    p.tpi = (H * W + kTileM - 1) / kTileM;
+    p.ntiles = B * p.tpi;
+    p.SMAX = smax;
+    p.raw_stage_floats = kKC * (kTileM + smax * W);
     p.HALO = D - 1;
     p.NMMA = nmma;
-    p.NS = ceil_div(C, kKC);
+    p.NS = C / kKC;
     p.c_pow2 = (C & (C - 1)) == 0;
     p.dbg = env_int("DSSMD_UMMA_SKIP", 0);
     const size_t op_bytes = (size_t)2 * (kTileM + nmma) * kKC * 4;
-    const size_t raw_stage = (size_t)kKC * (kTileM + nmma) * 4;
-    const size_t smem = kOpStages * op_bytes + kRawStages * raw_stage;
+    const size_t smem = kOpStages * op_bytes + (size_t)kRawStages * p.raw_stage_floats * 4;
+    if (smem > 225 * 1024) return -1;
+
+    alignas(64) CUtensorMap mapA, mapB;
+    const cuuint64_t HWl = (cuuint64_t)H * W;
+    {
+        const cuuint64_t dims[3] = {HWl, (cuuint64_t)C, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {HWl * 4, HWl * 4 * (cuuint64_t)C};
+        const cuuint32_t box[3] = {(cuuint32_t)kTileM, (cuuint32_t)kKC, 1};
+        if (!make_tmap_f32(&mapA, L, 3, dims, strides, box)) return -1;
+    }
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+        const cuuint64_t strides[3] = {(cuuint64_t)W * 4, HWl * 4, HWl * 4 * (cuuint64_t)C};
+        const cuuint32_t box[4] = {(cuuint32_t)W, 1, (cuuint32_t)kKC, 1};
+        if (!make_tmap_f32(&mapB, R, 4, dims, strides, box)) return -1;
+    }
     const int cap = sm_count();  // one persistent CTA per SM
     const unsigned grid = (unsigned)(p.ntiles < cap ? p.ntiles : cap);
     const int nw16 = (D + 38 <= 80) ? 5 : 6;
@@ -456,14 +504,14 @@ int corr_fwd_umma_f32(const void *L, const void *R, void *out, int B, int C, int
     if (nw16 == 5) {
         e = cudaFuncSetAttribute(corr_fwd_umma_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_fwd(umma): cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
-        corr_fwd_umma_kernel<5><<<grid, kThreads, smem, stream>>>(p);
+        corr_fwd_umma_kernel<5><<<grid, kThreads, smem, stream>>>(p, mapA, mapB);
     } else {
         e = cudaFuncSetAttribute(corr_fwd_umma_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_fwd(umma): cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
-        corr_fwd_umma_kernel<6><<<grid, kThreads, smem, stream>>>(p);
+        corr_fwd_umma_kernel<6><<<grid, kThreads, smem, stream>>>(p, mapA, mapB);
     }
     if (env_int("DSSMD_CORR_DEBUG", 0))
-        fprintf(stderr, "corr_fwd umma cfg: NMMA=%d NS=%d smem=%zu grid=%u nw16=%d\n", nmma, p.NS, smem, grid, nw16);
+        fprintf(stderr, "corr_fwd umma cfg: NMMA=%d NS=%d smem=%zu grid=%u nw16=%d tiles=%d\n", nmma, p.NS, smem, grid, nw16, p.ntiles);
     return check_launch("corr_fwd(umma)");
 }
 
