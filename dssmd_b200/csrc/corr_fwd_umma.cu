@@ -19,21 +19,23 @@
 // K step into the same fp32 accumulator.  Dropped Llo*Rlo is 2^-22 relative.
 //
 // One persistent, warp-specialised CTA per SM (448 threads), mbarrier hand-offs only:
-//   warp  12     LOAD       bulk async copies (cp.async.bulk = TMA engine, byte-counted on an
-//                           mbarrier) of raw fp32 [channel][operand row] stages, ring of 4.
-//                           (Per-thread cp.async/LDGSTS was measured at ~25 B/clk/SM issue
-//                           throughput on B200 -- not enough to stream at HBM rate.)
-//   warps  4-11  TRANSFORM  transpose + hi/lo split of a landed stage into the K-major,
-//                           un-swizzled UMMA core-matrix layout (8 rows x 16 B; SBO = 512 B,
-//                           LBO = 128 B); two operand buffers
-//   warp  13     MMA        one thread issues 6 tcgen05.mma per stage (3 products x 2 K
-//                           steps of 8) and tcgen05.commit -> frees the operand buffer
-//   warps  0-3   EPILOGUE   (= the four TMEM lane quarters) tcgen05.ld the 32+D+7 wide
-//                           window, a 6-stage barrel shift by (lane - first lane) puts each
-//                           thread's diagonal band in registers 0..D-1, then D coalesced
-//                           128-byte stores.  The accumulator is double-buffered in TMEM
-//                           (2 x 256 columns) so the epilogue of tile t overlaps the
-//                           main loop of tile t+1.
+//   warp  12     LOAD       TMA tensor copies (cp.async.bulk.tensor, 128B swizzle with 32B atoms): per stage of
+//                           16 channels, boxes {32 pixels, 16 channels} land in shared memory
+//                           exactly in the MN-major SWIZZLE_128B_BASE32B layout tcgen05.mma reads
+//                           (row = one channel, 128 B = 32 consecutive pixels): 4 boxes of L for
+//                           the tile, and for every image row it touches the boxes of R covering
+//                           x - (D-1) .. x_last (negative x' and pixels past the image are zero
+//                           filled by the TMA unit = the reference's zero border).  No transpose.
+//                           (Per-thread cp.async/LDGSTS measured ~25 B/clk/SM on B200: too slow.)
+//   warps  4-11  SPLIT      element-wise, in place: hi = tf32(v) overwrites v, lo = v - hi goes to
+//                           a second buffer with the same layout (one LDS.128 + 2 STS.128 per 4)
+//   warp  13     MMA        one thread issues 6 tcgen05.mma per stage (3 products x 2 K steps of
+//                           8 channels) and tcgen05.commit -> frees the stage
+//   warps  0-3   EPILOGUE   (= the four TMEM lane quarters) tcgen05.ld the 32+D+7 wide window, a
+//                           6-stage barrel shift by (lane - first lane) puts each thread's
+//                           diagonal band in registers 0..D-1, then D coalesced 128-byte stores.
+//                           The accumulator is double-buffered in TMEM (2 x 256 columns) so the
+//                           epilogue of tile t overlaps the main loop of tile t+1.
 #include "common.cuh"
 
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
@@ -46,16 +48,15 @@ namespace {
 
 constexpr int kTileM = 128;
 constexpr int kKC = 16;            // channels per pipeline stage (= 2 MMA K steps of 8)
-constexpr int kChunksK = kKC / 4;  // 16-byte chunks along K per operand row
 constexpr int kMaxSeg = 4;         // image rows one 128-pixel tile may touch
-constexpr int kOpStages = 2;      // operand (hi/lo, K-major) buffers
-constexpr int kRawStages = 3;     // raw fp32 ring filled by TMA tensor copies
+constexpr int kStages = 4;        // ring of operand stages: [hi (TMA lands raw here) | lo]
+constexpr int kBoxX = 32;         // pixels per TMA box = one 128-byte swizzle row
+constexpr int kBoxBytes = kBoxX * kKC * 4;  // 2048
 constexpr int kEpiWarps = 4, kXfWarps = 8;
 constexpr int kXfThreads = kXfWarps * 32;
 constexpr int kLoadWarp = kEpiWarps + kXfWarps;               // 12
 constexpr int kMmaWarp = kLoadWarp + 1;                       // 13
 constexpr int kThreads = (kEpiWarps + kXfWarps + 2) * 32;     // 448
-constexpr int kMaxXfItems = 6;     // (128 + 256) rows * 4 chunks / 256 threads
 
 struct UmmaParams {
     const float *L;
@@ -66,7 +67,6 @@ struct UmmaParams {
     int tpi;      // tiles per batch image = ceil(H*W / 128)
     int ntiles;   // B * tpi
     int SMAX;     // max image rows a tile touches
-    int raw_stage_floats;  // 16 * (128 + SMAX * W)
     int HALO;     // D - 1
     int NMMA;     // MMA N (multiple of 16, <= 256)
     int NS;       // pipeline stages per tile = ceil(C / kKC)
@@ -86,11 +86,10 @@ struct Segment {
 
 // barriers (shared): indices into one array
 enum {
-    kRawFull = 0,                        // [kRawStages]  LOAD (bulk-copy complete_tx) -> TRANSFORM
-    kRawEmpty = kRawFull + kRawStages,   // [kRawStages]  TRANSFORM -> LOAD
-    kOpFull = kRawEmpty + kRawStages,    // [kOpStages]   TRANSFORM -> MMA
-    kOpEmpty = kOpFull + kOpStages,      // [kOpStages]   MMA (tcgen05.commit) -> TRANSFORM
-    kAccFull = kOpEmpty + kOpStages,     // [2]           MMA (tcgen05.commit) -> EPILOGUE
+    kRawFull = 0,                        // [kStages]  LOAD (TMA complete_tx) -> SPLIT
+    kOpFull = kRawFull + kStages,        // [kStages]  SPLIT -> MMA
+    kOpEmpty = kOpFull + kStages,        // [kStages]  MMA (tcgen05.commit) -> LOAD
+    kAccFull = kOpEmpty + kStages,       // [2]        MMA (tcgen05.commit) -> EPILOGUE
     kAccEmpty = kAccFull + 2,            // [2]           EPILOGUE -> MMA
     kNumBars = kAccEmpty + 2
 };
@@ -116,9 +115,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
-    // K-major, no swizzle: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48)
-    const uint64_t lbo = 128 >> 4, sbo = (kChunksK * 128) >> 4;
-    return (uint64_t)((smem_addr >> 4) & 0x3fff) | (lbo << 16) | (sbo << 32) | (1ull << 46);
+    // MN-major tf32 operands only exist in the SWIZZLE_128B_BASE32B layout (32-byte swizzle atoms, 4-row
+    // K groups): start>>4 [0,14) | LBO>>4 [16,30) = stride between 32-pixel boxes | SBO>>4 [32,46) =
+    // stride between groups of 4 channel rows | version=1 [46,48) | layout=1 [61,64)
+    const uint64_t lbo = kBoxBytes >> 4, sbo = 512 >> 4;
+    return (uint64_t)((smem_addr >> 4) & 0x3fff) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (1ull << 61);
 }
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
@@ -141,9 +142,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// operand byte offset of (row r, 16-byte K chunk j) in the K-major core-matrix layout
-__device__ __forceinline__ int op_off(int r, int j) { return ((r >> 3) * kChunksK + j) * 128 + (r & 7) * 16; }
-
 // rows of the image a tile touches and where their R columns live in the B operand
 __device__ __forceinline__ int tile_segments(const UmmaParams &p, int tile, Segment *seg) {
     // tiles never cross a batch image: tile = (b, t) with t < tiles_per_img; rows are flattened b*H + y
@@ -160,9 +158,9 @@ __device__ __forceinline__ int tile_segments(const UmmaParams &p, int tile, Segm
             const int xa = q - row * p.W;
             const int len = (p.W - xa < qend - q) ? p.W - xa : qend - q;
             seg[it].row = row; seg[it].xa = xa; seg[it].len = len; seg[it].m0 = q - P0;
-            seg[it].xp0 = xa - p.HALO;
+            seg[it].xp0 = (xa - p.HALO) & ~3;  // TMA box starts must be 16-byte aligned: floor to a multiple of 4
             seg[it].col0 = col;
-            seg[it].ncol = len + p.HALO;
+            seg[it].ncol = ((xa + len - seg[it].xp0 + kBoxX - 1) / kBoxX) * kBoxX;  // whole 32-column boxes
             col += seg[it].ncol;
             q += len;
             n = it + 1;
@@ -182,15 +180,14 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fwd_umma_kernel(const UmmaPa
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long HW = (long long)p.H * p.W;
-    const int a_bytes = kTileM * kKC * 4, b_bytes = p.NMMA * kKC * 4;
-    const int op_bytes = 2 * (a_bytes + b_bytes);  // one operand buffer: A_hi | A_lo | B_hi | B_lo
-    unsigned char *ops = smem;                     // [kOpStages][op_bytes]
+    // one stage = [hi: A boxes (4) | B boxes (NMMA/32)] [lo: same]; every box is 2048 B = 16 channel rows x 128 B
+    const int a_bytes = (kTileM / kBoxX) * kBoxBytes, b_bytes = (p.NMMA / kBoxX) * kBoxBytes;
+    const int half_bytes = a_bytes + b_bytes, stage_bytes = 2 * half_bytes;
     const uint32_t bars = smem_u32(&s_bars[0]);
 #define BAR(which, idx) (bars + 8u * (uint32_t)((which) + (idx)))
 
     if (tid == 0) {
-        for (int i = 0; i < kRawStages; ++i) { mbar_init(BAR(kRawFull, i), 1); mbar_init(BAR(kRawEmpty, i), kXfWarps); }
-        for (int i = 0; i < kOpStages; ++i) { mbar_init(BAR(kOpFull, i), kXfWarps); mbar_init(BAR(kOpEmpty, i), 1); }
+        for (int i = 0; i < kStages; ++i) { mbar_init(BAR(kRawFull, i), 1); mbar_init(BAR(kOpFull, i), kXfWarps); mbar_init(BAR(kOpEmpty, i), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(BAR(kAccFull, i), 1); mbar_init(BAR(kAccEmpty, i), kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -203,125 +200,82 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fwd_umma_kernel(const UmmaPa
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = s_tmem;
 
-    const int NR = kTileM + p.NMMA;      // operand rows: [A pixels | B columns]
-    // raw stage: A box [kKC][128] then, per image row the tile touches, a full R row box [kKC][W]
-    float *raw = reinterpret_cast<float *>(smem + (size_t)kOpStages * op_bytes);  // [kRawStages][raw_stage_floats]
 
     if (warp == kLoadWarp) {
         // =============================== LOAD ==================================================
-        // TMA tensor copies, one thread: per stage one box {128 pixels, 16 channels} of L from
-        // the [B][C][H*W] view (a tile is contiguous in H*W; pixels past the image are zero
-        // filled by the TMA unit) and, per image row the tile touches, one box {W, 1 row, 16
-        // channels} of R from the [B][C][H][W] view.  Completion is byte-counted on the mbarrier.
         if (lane == 0) {
             uint32_t gs = 0;
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
                 Segment seg[kMaxSeg];
                 const int nseg = tile_segments(p, tile, seg);
                 const int b = tile / p.tpi, t = tile - b * p.tpi;
-                const uint32_t bytes = (uint32_t)(kKC * (kTileM + nseg * p.W) * 4);
+                int nboxB = 0;
+#pragma unroll
+                for (int k = 0; k < kMaxSeg; ++k) nboxB += seg[k].ncol / kBoxX;
+                const uint32_t bytes = (uint32_t)((kTileM / kBoxX + nboxB) * kBoxBytes);
                 for (int s = 0; s < p.NS; ++s, ++gs) {
-                    const uint32_t slot = gs % kRawStages, ph = (gs / kRawStages) & 1u;
-                    mbar_wait(BAR(kRawEmpty, slot), ph ^ 1u);
+                    const uint32_t slot = gs % kStages, ph = (gs / kStages) & 1u;
+                    mbar_wait(BAR(kOpEmpty, slot), ph ^ 1u);
                     const uint32_t full = BAR(kRawFull, slot);
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(bytes) : "memory");
                     if (p.dbg & 4) {
                         asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(full), "r"(bytes) : "memory");
                         continue;
                     }
-                    const uint32_t dst = smem_u32(raw + (size_t)slot * p.raw_stage_floats);
-                    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&mapA)), "r"(t * kTileM), "r"(s * kKC), "r"(b), "r"(full) : "memory");
+                    const uint32_t dst = smem_u32(smem + (size_t)slot * stage_bytes);
+#pragma unroll
+                    for (int i = 0; i < kTileM / kBoxX; ++i)
+                        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                                     ::"r"(dst + (uint32_t)(i * kBoxBytes)), "l"(reinterpret_cast<uint64_t>(&mapA)),
+                                       "r"(t * kTileM + i * kBoxX), "r"(s * kKC), "r"(b), "r"(full) : "memory");
 #pragma unroll
                     for (int k = 0; k < kMaxSeg; ++k) {
                         if (k >= nseg) break;
                         const int y = seg[k].row - b * p.H;
-                        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-                                     ::"r"(dst + 4u * (uint32_t)(kKC * (kTileM + k * p.W))), "l"(reinterpret_cast<uint64_t>(&mapB)),
-                                       "r"(0), "r"(y), "r"(s * kKC), "r"(b), "r"(full) : "memory");
+                        for (int i = 0; i < seg[k].ncol / kBoxX; ++i)
+                            asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                                         ::"r"(dst + (uint32_t)(a_bytes + (seg[k].col0 / kBoxX + i) * kBoxBytes)), "l"(reinterpret_cast<uint64_t>(&mapB)),
+                                           "r"(seg[k].xp0 + i * kBoxX), "r"(y), "r"(s * kKC), "r"(b), "r"(full) : "memory");
                     }
                 }
             }
         }
     } else if (warp >= kEpiWarps && warp < kLoadWarp) {
-        // =============================== TRANSFORM =============================================
-        // transpose + hi/lo split of a landed raw stage into an operand buffer
+        // =============================== SPLIT =================================================
         const int t = tid - kEpiWarps * 32;  // 0..255
-        // item k of this thread = (K chunk j, operand row r); lanes run over rows (conflict-free both ways)
-        int t_j[kMaxXfItems], t_dst[kMaxXfItems], t_lo[kMaxXfItems], t_row[kMaxXfItems];
-#pragma unroll
-        for (int k = 0; k < kMaxXfItems; ++k) {
-            const int i = t + k * kXfThreads;
-            t_j[k] = 0; t_dst[k] = 0; t_lo[k] = 0; t_row[k] = -1;
-            if (i < NR * kChunksK) {
-                const int j = i / NR, r = i - j * NR;
-                t_j[k] = j;
-                t_row[k] = r;
-                const bool isB = r >= kTileM;
-                t_dst[k] = (isB ? 2 * a_bytes : 0) + op_off(isB ? r - kTileM : r, j);
-                t_lo[k] = isB ? b_bytes : a_bytes;
-            }
-        }
+        const int nvec = half_bytes >> 4;    // float4s per half stage
         uint32_t gs = 0;
         for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-            // where each operand row of this tile lives in a raw stage (float offset of its channel 4j)
-            // and its channel stride; -1: the row is all zero (x' < 0, unused column, pixel past the image)
-            Segment seg[kMaxSeg];
-            tile_segments(p, tile, seg);
-            int src_off[kMaxXfItems], src_cs[kMaxXfItems];
-#pragma unroll
-            for (int k = 0; k < kMaxXfItems; ++k) {
-                src_off[k] = -1; src_cs[k] = 0;
-                const int r = t_row[k];
-                if (r < 0) continue;
-#pragma unroll
-                for (int s = 0; s < kMaxSeg; ++s) {
-                    if (seg[s].len == 0) continue;
-                    if (r < kTileM) {
-                        if (r >= seg[s].m0 && r < seg[s].m0 + seg[s].len) { src_off[k] = 4 * t_j[k] * kTileM + r; src_cs[k] = kTileM; }
-                    } else {
-                        const int n = r - kTileM;
-                        const int xp = seg[s].xp0 + (n - seg[s].col0);
-                        if (n >= seg[s].col0 && n < seg[s].col0 + seg[s].ncol && xp >= 0) {
-                            src_off[k] = kKC * (kTileM + s * p.W) + 4 * t_j[k] * p.W + xp; src_cs[k] = p.W;
-                        }
-                    }
-                }
-            }
             for (int s = 0; s < p.NS; ++s, ++gs) {
-                const uint32_t slot = gs % kRawStages, rph = (gs / kRawStages) & 1u;
-                const uint32_t ob = gs % kOpStages, oph = (gs / kOpStages) & 1u;
-                mbar_wait(BAR(kRawFull, slot), rph);
-                mbar_wait(BAR(kOpEmpty, ob), oph ^ 1u);
-                const float *rs = raw + (size_t)slot * p.raw_stage_floats;
-                unsigned char *opb = ops + (size_t)ob * op_bytes;
-#pragma unroll
-                for (int k = 0; k < kMaxXfItems; ++k) {
-                    if (t_row[k] < 0 || (p.dbg & 2)) continue;
-                    float hi[4], lo[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float v = src_off[k] >= 0 ? rs[src_off[k] + q * src_cs[k]] : 0.f;
+                const uint32_t slot = gs % kStages, ph = (gs / kStages) & 1u;
+                mbar_wait(BAR(kRawFull, slot), ph);
+                float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)slot * stage_bytes);
+                float4 *lo = reinterpret_cast<float4 *>(smem + (size_t)slot * stage_bytes + half_bytes);
+                if (!(p.dbg & 2)) {
+#pragma unroll 2
+                    for (int i = t; i < nvec; i += kXfThreads) {
+                        const float4 v = hi[i];
+                        float4 h, l;
                         // round to nearest TF32 (10 mantissa bits): |lo| <= 2^-11 |v|, dropped lo*lo is 2^-22
-                        hi[q] = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
-                        lo[q] = v - hi[q];
+                        h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xffffe000u); l.x = v.x - h.x;
+                        h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xffffe000u); l.y = v.y - h.y;
+                        h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xffffe000u); l.z = v.z - h.z;
+                        h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xffffe000u); l.w = v.w - h.w;
+                        hi[i] = h;
+                        lo[i] = l;
                     }
-                    *reinterpret_cast<float4 *>(opb + t_dst[k]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<float4 *>(opb + t_dst[k] + t_lo[k]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the tensor core
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(BAR(kOpFull, ob));
-                    mbar_arrive(BAR(kRawEmpty, slot));
-                }
+                if (lane == 0) mbar_arrive(BAR(kOpFull, slot));
             }
         }
     } else if (warp == kMmaWarp) {
         // =============================== MMA ===================================================
         if (lane == 0) {
             // instruction descriptor: D=F32, A=B=TF32, K-major both, N, M=128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.NMMA >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+            // (A and B are MN-major: bits 15 and 16)
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.NMMA >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
             uint32_t gs = 0, tl = 0;
             for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++tl) {
                 const uint32_t ab = tl & 1u, aph = (tl >> 1) & 1u;
@@ -329,14 +283,14 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fwd_umma_kernel(const UmmaPa
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc = tmem_base + ab * 256u;
                 for (int s = 0; s < p.NS; ++s, ++gs) {
-                    const uint32_t ob = gs % kOpStages, oph = (gs / kOpStages) & 1u;
+                    const uint32_t ob = gs % kStages, oph = (gs / kStages) & 1u;
                     mbar_wait(BAR(kOpFull, ob), oph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t ah = smem_u32(ops + (size_t)ob * op_bytes), al = ah + a_bytes, bh = ah + 2 * a_bytes, bl = bh + b_bytes;
+                    const uint32_t ah = smem_u32(smem + (size_t)ob * stage_bytes), bh = ah + a_bytes, al = ah + half_bytes, bl = al + a_bytes;
                     if (p.dbg & 1) { mbar_arrive(BAR(kOpEmpty, ob)); continue; }
 #pragma unroll
                     for (int ks = 0; ks < kKC / 8; ++ks) {
-                        const uint32_t o = ks * 2 * 128;  // two 16-byte K chunks per step
+                        const uint32_t o = ks * 1024;  // 8 channel rows of 128 B per K step
                         umma_tf32(acc, make_desc(al + o), make_desc(bh + o), idesc, (s > 0 || ks > 0) ? 1u : 0u);
                         umma_tf32(acc, make_desc(ah + o), make_desc(bl + o), idesc, 1u);
                         umma_tf32(acc, make_desc(ah + o), make_desc(bh + o), idesc, 1u);
@@ -450,7 +404,7 @@ bool make_tmap_f32(CUtensorMap *m, const void *base, int rank, const cuuint64_t 
     if (!fn) return false;
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -458,14 +412,30 @@ bool make_tmap_f32(CUtensorMap *m, const void *base, int rank, const cuuint64_t 
 
 // Returns -1 when the shape is outside this kernel's limits (caller falls back to FFMA).
 int corr_fwd_umma_f32(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, cudaStream_t stream) {
-    if (W % 4 != 0 || W < 43 || W > 256 || D < 2 || D > 58) return -1;
+    if (W % 4 != 0 || W < 43 || D < 2 || D > 58) return -1;
     if (((reinterpret_cast<uintptr_t>(L) | reinterpret_cast<uintptr_t>(R)) & 15) != 0) return -1;
     if (C % kKC != 0) return -1;
     if ((long long)B * H * W >= (1LL << 31) - 256) return -1;
     const int smax = 2 + 126 / W;
     if (smax > kMaxSeg) return -1;
-    const int nmma = round_up(kTileM + smax * (D - 1), 16);
-    if (nmma > 256) return -1;
+    // B columns come in whole 32-pixel boxes per image row the tile touches: exact maximum over the tiles of an image
+    int maxbox = 0;
+    {
+        const int HWi = H * W, tpi = (HWi + kTileM - 1) / kTileM;
+        for (int t = 0; t < tpi; ++t) {
+            int q = t * kTileM, nb = 0;
+            const int qend = q + kTileM < HWi ? q + kTileM : HWi;
+            while (q < qend) {
+                const int xa = q % W;
+                const int len = (W - xa < qend - q) ? W - xa : qend - q;
+                nb += (xa + len - ((xa - (D - 1)) & ~3) + kBoxX - 1) / kBoxX;
+                q += len;
+            }
+            if (nb > maxbox) maxbox = nb;
+        }
+    }
+    const int nmma = kBoxX * maxbox;
+    if (nmma > 256 || nmma < 16) return -1;
     UmmaParams p{};
     p.L = (const float *)L; p.R = (const float *)R; p.out = (float *)out;
     p.B = B; p.C = C; p.H = H; p.W = W; p.D = D;
@@ -473,14 +443,12 @@ int corr_fwd_umma_f32(const void *L, const void *R, void *out, int B, int C, int
     p.tpi = (H * W + kTileM - 1) / kTileM;
     p.ntiles = B * p.tpi;
     p.SMAX = smax;
-    p.raw_stage_floats = kKC * (kTileM + smax * W);
     p.HALO = D - 1;
     p.NMMA = nmma;
     p.NS = C / kKC;
     p.c_pow2 = (C & (C - 1)) == 0;
     p.dbg = env_int("DSSMD_UMMA_SKIP", 0);
-    const size_t op_bytes = (size_t)2 * (kTileM + nmma) * kKC * 4;
-    const size_t smem = kOpStages * op_bytes + (size_t)kRawStages * p.raw_stage_floats * 4;
+    const size_t smem = (size_t)kStages * 2 * (kTileM + nmma) * kKC * 4;
     if (smem > 225 * 1024) return -1;
 
     alignas(64) CUtensorMap mapA, mapB;
@@ -488,13 +456,13 @@ int corr_fwd_umma_f32(const void *L, const void *R, void *out, int B, int C, int
     {
         const cuuint64_t dims[3] = {HWl, (cuuint64_t)C, (cuuint64_t)B};
         const cuuint64_t strides[2] = {HWl * 4, HWl * 4 * (cuuint64_t)C};
-        const cuuint32_t box[3] = {(cuuint32_t)kTileM, (cuuint32_t)kKC, 1};
+        const cuuint32_t box[3] = {(cuuint32_t)kBoxX, (cuuint32_t)kKC, 1};
         if (!make_tmap_f32(&mapA, L, 3, dims, strides, box)) return -1;
     }
     {
         const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
         const cuuint64_t strides[3] = {(cuuint64_t)W * 4, HWl * 4, HWl * 4 * (cuuint64_t)C};
-        const cuuint32_t box[4] = {(cuuint32_t)W, 1, (cuuint32_t)kKC, 1};
+        const cuuint32_t box[4] = {(cuuint32_t)kBoxX, 1, (cuuint32_t)kKC, 1};
         if (!make_tmap_f32(&mapB, R, 4, dims, strides, box)) return -1;
     }
     const int cap = sm_count();  // one persistent CTA per SM
