@@ -586,7 +586,11 @@ int launch_d4(const void *L, const void *R, void *out, int B, int C, int H, int 
 
 template <typename T>
 int launch_typed(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, cudaStream_t stream) {
-    const int variant = env_int("DSSMD_CORR_FWD_VARIANT", 1);  // 0 wide FFMA tile, 1 narrow FFMA tile, 2 tcgen05
+    // 0 wide FFMA tile, 1 narrow FFMA tile, 2 tcgen05 (3xTF32); unset = by size: the persistent
+    // tensor-core kernel needs several 128-pixel tiles per SM to amortise its pipeline fill
+    // (measured: wins at 800/960 tiles, loses at 270/200 -- profiles/r01q)
+    int variant = env_int("DSSMD_CORR_FWD_VARIANT", -1);
+    if (variant < 0) variant = (sizeof(T) == 4 && C >= 64 && (long)B * H * W / 128 >= 3L * sm_count()) ? 2 : 1;
     if constexpr (sizeof(T) == 4) {
         if (variant == 2) {
             const int rc = corr_fwd_umma_f32(L, R, out, B, C, H, W, D, stream);

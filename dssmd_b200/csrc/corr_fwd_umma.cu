@@ -251,7 +251,20 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fwd_umma_kernel(const UmmaPa
                 mbar_wait(BAR(kRawFull, slot), ph);
                 float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)slot * stage_bytes);
                 float4 *lo = reinterpret_cast<float4 *>(smem + (size_t)slot * stage_bytes + half_bytes);
-                if (!(p.dbg & 2)) {
+                if (p.dbg & 16) {
+                    // truncation split: the tensor core reads only the top 19 bits of an fp32 word, so
+                    // the raw value already is hi = trunc(v); only lo = v - trunc(v) has to be written
+#pragma unroll 2
+                    for (int i = t; i < nvec; i += kXfThreads) {
+                        const float4 v = hi[i];
+                        float4 l;
+                        l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                        l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                        l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                        l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                        lo[i] = l;
+                    }
+                } else if (!(p.dbg & 2)) {
 #pragma unroll 2
                     for (int i = t; i < nvec; i += kXfThreads) {
                         const float4 v = hi[i];

@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(512) warp_fwd_kernel(const S *__restrict__ img
             for (int cc = 0; cc < nc; ++cc) channel(cc);
         }
     }
-    if (bad && neg_flag) atomicOr(neg_flag, 1);
+    if (bad && neg_flag) *reinterpret_cast<volatile int *>(neg_flag) = 1;  // plain store: the flag may live in mapped host memory
 }
 
 // ---------------------------------------------------------------------------------
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(256) lrwarp_fwd_kernel(const S *__restrict__ i
             out[((long long)b * C + c) * HW + (long long)y * W + x] = N::sub(resize_at<S>(pr, H0, W0, ry, rx), acc);
         }
     }
-    if (bad && neg_flag) atomicOr(neg_flag, 1);
+    if (bad && neg_flag) *reinterpret_cast<volatile int *>(neg_flag) = 1;  // plain store: the flag may live in mapped host memory
 }
 
 template <typename S>

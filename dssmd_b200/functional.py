@@ -103,8 +103,20 @@ def _warp_bwd(g, I, Dp, g_img, g_disp, pad):
                                       _lib.ptr(ws), nbytes, B, C, H, W, pad, code, _lib.stream_ptr(I.device)))
 
 
-def _raise_if_flag(flag):
-    if _CHECK_NEGATIVE and flag is not None and int(flag.item()) != 0:
+def _new_flag():
+    """One int32 in pinned host memory, which the GPU can write directly (unified addressing):
+    reading it back needs an event wait on the launch stream, not a device->host copy that
+    would queue behind whatever the copy engine is already moving."""
+    return torch.zeros(1, dtype=torch.int32).pin_memory() if _CHECK_NEGATIVE else None
+
+
+def _raise_if_flag(flag, device):
+    if flag is None:
+        return
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(device))
+    ev.synchronize()
+    if int(flag[0]) != 0:
         raise AssertionError("disp.min() >= 0")  # upstream utils/disparity_warper.py:93
 
 
@@ -120,11 +132,11 @@ class DispWarpFn(torch.autograd.Function):
         warped = torch.empty_like(I)
         mask = torch.empty_like(I)
         if I.numel() > 0:
-            flag = torch.zeros(1, dtype=torch.int32, device=I.device) if _CHECK_NEGATIVE else None
+            flag = _new_flag()
             with torch.cuda.device(I.device):
                 _lib.check(_lib.lib().dssmd_warp_fwd(_lib.ptr(I), _lib.ptr(Dp), _lib.ptr(warped), _lib.ptr(mask), _lib.ptr(flag),
                                                      B, C, H, W, pad, _lib.dtype_code(I), _lib.stream_ptr(I.device)))
-            _raise_if_flag(flag)
+            _raise_if_flag(flag, I.device)
         ctx.save_for_backward(I, Dp)
         ctx.pad = pad
         ctx.mark_non_differentiable(mask)
@@ -189,11 +201,11 @@ class LRWarpErrorFn(torch.autograd.Function):
         Lc, Rc, Dc = imgL.contiguous(), imgR.contiguous(), disp.contiguous()
         out = torch.empty((B, C, H, W), dtype=Lc.dtype, device=Lc.device)
         if out.numel() > 0:
-            flag = torch.zeros(1, dtype=torch.int32, device=Lc.device) if _CHECK_NEGATIVE else None
+            flag = _new_flag()
             with torch.cuda.device(Lc.device):
                 _lib.check(_lib.lib().dssmd_lrwarp_error_fwd(_lib.ptr(Lc), _lib.ptr(Dc), _lib.ptr(Rc), _lib.ptr(out), _lib.ptr(flag),
                                                              B, C, H0, W0, H, W, _lib.dtype_code(Lc), _lib.stream_ptr(Lc.device)))
-            _raise_if_flag(flag)
+            _raise_if_flag(flag, Lc.device)
         ctx.save_for_backward(Lc, Dc)
         ctx.in_size = (H0, W0)
         return out

@@ -82,9 +82,11 @@ DSSMD_API int dssmd_corr_bwd(const void *g, const void *L, const void *R, void *
  *   warped[b,c,y,x] = bilinear(img[b,c], ix, iy),  mask = 1[sum of in-bounds
  *   bilinear weights at the un-clamped (ix,iy) >= 0.9999]
  * img, warped, mask: [B,C,H,W]; disp: [B,1,H,W].  `mask` may be NULL (skipped).
- * `neg_flag` (device int, may be NULL) is OR-ed with 1 if any disparity is
- * negative or NaN -- the condition of upstream's `assert disp.min() >= 0` (:93);
- * the caller zeroes it beforehand and raises after reading it back.
+ * `neg_flag` (one int, may be NULL) is set to 1 with a plain store if any disparity
+ * is negative or NaN -- the condition of upstream's `assert disp.min() >= 0` (:93).
+ * It may live in device memory or in pinned (device-accessible) host memory; the
+ * caller zeroes it beforehand and raises after the launch has completed.  A pinned
+ * flag needs only an event wait on `stream`, no device->host copy.
  * dtype: F32 or F64. */
 DSSMD_API int dssmd_warp_fwd(const void *img, const void *disp, void *warped, void *mask, int *neg_flag,
                    int B, int C, int H, int W, int padding_mode, int dtype, void *stream);

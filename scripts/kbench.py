@@ -39,7 +39,7 @@ def time_kernel(calls, name, nsets, rounds=20):
 
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "corr_fwd"
-    workloads = sys.argv[2].split(",") if len(sys.argv) > 2 else ["sceneflow_576x960", "corr_micro", "kitti_384x1280", "train_320x640"]
+    workloads = sys.argv[2].split(",") if len(sys.argv) > 2 and sys.argv[2] != "all" else ["sceneflow_576x960", "corr_micro", "kitti_384x1280", "train_320x640"]
     lib = _lib.lib()
     dev = torch.device("cuda", 0)
     peak, _ = bench.measured_peak()
@@ -53,6 +53,9 @@ def main():
         "warp_fwd": [("DSSMD_WARP_FWD_X", [""])],
         "warp_bwd": [("DSSMD_WARP_BWD_FLAGS", ["", "0", "1", "2", "3"]), ("DSSMD_WARP_BWD_PXT", ["2", "4"])],
     }[which]
+    if len(sys.argv) > 3:   # custom sweep: VAR=v1,v2,...  ('-' = unset)
+        var, vals = sys.argv[3].split("=")
+        sweeps = [(var, ["" if v == "-" else v for v in vals.split(",")])]
     for wname in workloads:
         w = bench.WORKLOADS[wname]
         nsets = 4

@@ -2,6 +2,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch, dssmd_b200
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 def timeit(fn, reps=20):
     for _ in range(3): fn()
     torch.cuda.synchronize()
@@ -11,9 +12,12 @@ def timeit(fn, reps=20):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) * 1e3 / reps
 os.environ["DSSMD_CORR_FWD_VARIANT"] = "2"
-for (B, C, H, W, D) in [(8, 256, 80, 160, 41)]:
+for (B, C, H, W, D) in [(8, 256, 80, 160, 41), (16, 128, 48, 160, 24)]:
     L = torch.randn(B, C, H, W, device="cuda").relu(); R = torch.randn(B, C, H, W, device="cuda").relu()
-    for env in [{}, {"DSSMD_UMMA_SKIP": "1"}, {"DSSMD_UMMA_SKIP": "2"}, {"DSSMD_UMMA_SKIP": "4"}, {"DSSMD_UMMA_SKIP": "8"}, {"DSSMD_UMMA_SKIP": "15"}, {"DSSMD_UMMA_SKIP": "11"}]:
-        for k in ("DSSMD_UMMA_PASSES", "DSSMD_UMMA_N256", "DSSMD_UMMA_SKIP"): os.environ.pop(k, None)
+    ref = torch.stack([torch.cat([torch.zeros(B, H, d, device="cuda", dtype=torch.float64), (L[..., d:].double() * R[..., :W - d].double()).mean(1)], -1) if d else (L.double() * R.double()).mean(1) for d in range(D)], 1)
+    for env in [{}, {"DSSMD_UMMA_SKIP": "16"}]:
+        os.environ.pop("DSSMD_UMMA_SKIP", None)
         os.environ.update(env)
-        print((B, C, H, W, D), env, round(timeit(lambda: dssmd_b200.build_corr(L, R, D)), 1), "us", flush=True)
+        out = dssmd_b200.build_corr(L, R, D)
+        err = float((out.double() - ref).abs().max() / ref.abs().max())
+        print((B, C, H, W, D), env, round(timeit(lambda: dssmd_b200.build_corr(L, R, D)), 1), "us  rel err %.3e" % err, flush=True)

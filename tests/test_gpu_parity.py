@@ -116,6 +116,40 @@ def test_corr_vs_oracle_16bit(ops, oracle, shape, dt):
     assert rel_err(R.grad.float().cpu().numpy(), gR) <= TOL_BF16
 
 
+UMMA_SHAPES = [
+    # B, C, H, W, D, relu            tcgen05 kernel: 128-pixel tiles over the flattened H*W of one image
+    (1, 16, 2, 64, 5, True),         # one tile = two whole rows, one pipeline stage
+    (1, 32, 3, 80, 24, True),        # tiles cross rows mid-row; halo 23 (TMA box start needs flooring to 16 B)
+    (2, 128, 4, 120, 24, False),     # cfg5 row shape, cancellation inputs, two images
+    (1, 256, 4, 160, 41, True),      # cfg2 row shape: widest band (N = 256)
+    (1, 32, 3, 44, 7, False),        # narrowest supported width: four segments per tile
+    (3, 64, 7, 160, 58, True),       # largest supported D, ragged last tile per image
+    (1, 48, 5, 300, 33, False),      # wide rows: tiles inside one row
+]
+
+
+@pytest.mark.parametrize("shape", UMMA_SHAPES, ids=lambda s: "x".join(map(str, s[:5])))
+def test_corr_fwd_tensor_core_variant(ops, oracle, shape, monkeypatch, capfd):
+    """DSSMD_CORR_FWD_VARIANT=2 forces the TMA + tcgen05 (3xTF32) forward that the
+    library otherwise selects by size; it must meet the same fp32 bar as the FFMA kernel."""
+    B, C, H, W, D, relu = shape
+    L = feat((B, C, H, W), 21, relu)
+    R = feat((B, C, H, W), 22, relu)
+    monkeypatch.setenv("DSSMD_CORR_FWD_VARIANT", "2")
+    monkeypatch.setenv("DSSMD_CORR_DEBUG", "1")
+    tc = ops.build_corr(L, R, D)
+    torch.cuda.synchronize()
+    assert "corr_fwd umma cfg" in capfd.readouterr().err, "shape fell back to the FFMA kernel"
+    monkeypatch.setenv("DSSMD_CORR_FWD_VARIANT", "1")
+    ff = ops.build_corr(L, R, D)
+    assert "corr_fwd umma cfg" not in capfd.readouterr().err
+    ref64 = oracle.corr_fwd(L.cpu().numpy().astype(np.float64), R.cpu().numpy().astype(np.float64), D)
+    assert rel_err(tc.cpu().numpy(), ref64) <= TOL_F32
+    assert rel_err(tc.cpu().numpy(), ff.cpu().numpy()) <= TOL_F32
+    for d in range(min(D, W)):                       # exact structural zeros
+        assert torch.count_nonzero(tc[:, d, :, :d]) == 0
+
+
 def test_corr_f64_and_gradcheck(ops):
     L = feat((1, 5, 3, 9), 1, False, torch.float64).requires_grad_(True)
     R = feat((1, 5, 3, 9), 2, False, torch.float64).requires_grad_(True)
