@@ -558,6 +558,206 @@ __global__ void __launch_bounds__(1024, 1) warp_bwd_hscatter_kernel(const float 
     }
 }
 
+// ---------------------------------------------------------------------------------
+// K1, vectorised (fp32, C <= 4, W % 4 == 0, 16-byte aligned rows): same contract as
+// warp_bwd_hscatter_kernel, about a third of its instructions per pixel.
+//   * a thread owns 4 CONSECUTIVE pixels: disp / g / gV / g_disp move as float4, and the
+//     right tap of pixel j is merged into the left tap of pixel j+1 in registers when they
+//     land on the same cell (x' = x - disp is close to monotone), across lanes by shuffle;
+//   * the accumulator of a cell is ONE native 32-bit shared atomic per merged tap: the
+//     low word starts at 2^31 and the high word only sees an atomic when the low word
+//     wraps (returned old value -> carry), i.e. when |partial sum| reaches 2^31 quanta --
+//     rare, but it keeps the sum exact (cells at a clamped border collect hundreds of taps);
+//   * cells live in 4 planes (cell k -> plane k & 3, slot k >> 2) so that lanes, whose
+//     cells are 4 apart, hit consecutive banks;
+//   * the y-axis taps are recomputed per thread (one division) instead of shared through a barrier.
+// ---------------------------------------------------------------------------------
+template <int NCT>
+__global__ void __launch_bounds__(1024) warp_bwd_hs4_kernel(const float *__restrict__ g, const float *__restrict__ img,
+                                                            const float *__restrict__ disp, float *__restrict__ gV,
+                                                            float *__restrict__ g_disp, int H, int W, int border,
+                                                            float halfW, float tscale, float halfH) {
+    using S = float;
+    using N = Num<S>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int W4 = W >> 2;
+    const int P = (W4 + 3) & ~3;                                          // slots per plane
+    unsigned int *acc_lo = reinterpret_cast<unsigned int *>(smem_raw);  // [NCT][4][P]
+    int *acc_hi = reinterpret_cast<int *>(smem_raw) + NCT * 4 * P;      // [NCT][4][P]
+    __shared__ unsigned int s_maxbits;
+    __shared__ int s_anyhi;
+
+    const int y = blockIdx.x % H;
+    const int b = blockIdx.x / H;
+    const int HW = H * W;  // C*H*W < 2^31 checked on the host
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const bool active = tid < W4;
+    if (tid == 0) { s_maxbits = 0u; s_anyhi = 0; }
+    __syncthreads();  // the row maximum is accumulated before the next barrier
+    if (gV) {
+        uint4 *lo4 = reinterpret_cast<uint4 *>(acc_lo);
+        int4 *hi4 = reinterpret_cast<int4 *>(acc_hi);
+        for (int i = tid; i < NCT * P; i += nt) {
+            lo4[i] = make_uint4(0x80000000u, 0x80000000u, 0x80000000u, 0x80000000u);
+            hi4[i] = make_int4(0, 0, 0, 0);
+        }
+    }
+
+    // vertical taps of this output row (per thread: one division, no barrier)
+    const S wm1 = (S)(W - 1);
+    Axis<S> ya;
+    {
+        const S gy = N::sub(N::mul((S)2, N::div((S)y, (S)(H - 1))), (S)1);
+        const S iy_raw = N::fma(N::add(gy, (S)1), halfH, (S)-0.5);
+        ya = make_axis<S>(border ? clamp_border<S>(iy_raw, H) : iy_raw, H);
+    }
+
+    const float *grow = g + (size_t)b * NCT * HW + y * W;
+    const int x0 = tid * 4;
+    float go[NCT][4];
+    float dd[4];
+    {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 d4 = active ? *reinterpret_cast<const float4 *>(disp + (size_t)b * HW + y * W + x0) : z;
+        dd[0] = d4.x; dd[1] = d4.y; dd[2] = d4.z; dd[3] = d4.w;
+#pragma unroll
+        for (int c = 0; c < NCT; ++c) {
+            const float4 v = active ? *reinterpret_cast<const float4 *>(grow + c * HW + x0) : z;
+            go[c][0] = v.x; go[c][1] = v.y; go[c][2] = v.z; go[c][3] = v.w;
+        }
+    }
+    unsigned int mbits = 0u;
+#pragma unroll
+    for (int c = 0; c < NCT; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned int bits = __float_as_uint(go[c][j]) & 0x7fffffffu;
+            mbits = bits > mbits ? bits : mbits;  // NaN/inf bit patterns compare largest
+        }
+    if (gV) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned int other = __shfl_xor_sync(0xffffffffu, mbits, o);
+            mbits = other > mbits ? other : mbits;
+        }
+        if (lane == 0 && mbits) atomicMax(&s_maxbits, mbits);
+    }
+
+    // horizontal taps
+    int kL[4], kR[4];   // cell of the left / right tap, negative when out of bounds
+    S w0[4], w1[4], gmult[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const S t = N::sub((S)(x0 + j), dd[j]);
+        const S gxn = N::sub(N::mul((S)2, N::div(t, wm1)), (S)1);
+        S ix = N::fma(N::add(gxn, (S)1), halfW, (S)-0.5);
+        gmult[j] = halfW;
+        if (border) {
+            // clip_coordinates_set_grad: borders count as out of bounds for the gradient
+            if (ix <= (S)0) { ix = (S)0; gmult[j] = (S)0; }
+            else if (ix >= wm1) { ix = wm1; gmult[j] = (S)0; }
+            else if (!(ix == ix)) ix = clamp_border<S>(ix, W);
+        }
+        const Axis<S> xa = make_axis<S>(ix, W);
+        kL[j] = (active && xa.in0) ? xa.i0 : -1000;
+        kR[j] = (active && xa.in1) ? xa.i0 + 1 : -2000;
+        w0[j] = xa.w0; w1[j] = xa.w1;
+    }
+
+    if (g_disp && active) {
+        float gd[4];
+        const float *ib = img + (size_t)b * NCT * HW + ya.i0 * W;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool in0 = kL[j] >= 0, in1 = kR[j] >= 0;
+            const int i0 = in0 ? kL[j] : kR[j] - 1;
+            S gix = (S)0;
+#pragma unroll
+            for (int c = 0; c < NCT; ++c) {
+                const float *pc = ib + c * HW + i0;
+                // d(sample)/d(ix) over in-bounds taps, ATen order nw, ne, sw, se
+                if (in0 && ya.in0) gix = N::sub(gix, N::mul(N::mul(pc[0], ya.w0), go[c][j]));
+                if (in1 && ya.in0) gix = N::add(gix, N::mul(N::mul(pc[1], ya.w0), go[c][j]));
+                if (in0 && ya.in1) gix = N::sub(gix, N::mul(N::mul(pc[W], ya.w1), go[c][j]));
+                if (in1 && ya.in1) gix = N::add(gix, N::mul(N::mul(pc[W + 1], ya.w1), go[c][j]));
+            }
+            // chain rule: ix <- gx (W/2, 0 where clipped) <- t (2/(W-1)) <- disp (-1)
+            gd[j] = -N::mul(tscale, N::mul(gmult[j], gix));
+        }
+        *reinterpret_cast<float4 *>(g_disp + (size_t)b * HW + y * W + x0) = make_float4(gd[0], gd[1], gd[2], gd[3]);
+    }
+    if (!gV) return;  // only g_disp requested (block-uniform)
+
+    // links: right tap of pixel j lands on the left cell of pixel j+1 (j = 3: next lane's pixel 0)
+    bool lk[4];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) lk[j] = kR[j] >= 0 && kR[j] == kL[j + 1];
+    {
+        const int nextL = __shfl_down_sync(0xffffffffu, kL[0], 1);
+        lk[3] = lane < 31 && kR[3] >= 0 && nextL == kR[3];
+    }
+    const bool tin = __shfl_up_sync(0xffffffffu, (int)lk[3], 1) != 0 && lane > 0;
+
+    __syncthreads();  // accumulators filled, row maximum known
+    const unsigned int maxbits = s_maxbits;
+    const int mexp = (int)(maxbits >> 23);
+    const bool finite = mexp != 0xff;
+    int e = 156 - (mexp > 0 ? mexp : 1);  // |g * wx| <= |g| < 2^(mexp-126)  =>  |v * 2^e| < 2^30
+    if (e > 127) e = 127;
+    const S up = __uint_as_float((unsigned)(e + 127) << 23);
+    const S down = (e < 127) ? __uint_as_float((unsigned)(127 - e) << 23) : __uint_as_float(0x00400000u);
+
+    if (finite && maxbits != 0u) {
+        int sL[4], sR[4];  // slot of each tap inside one channel's planes
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            sL[j] = (kL[j] & 3) * P + (kL[j] >> 2);
+            sR[j] = (kR[j] & 3) * P + (kR[j] >> 2);
+        }
+        auto add = [&](int slot, int q) {
+            const unsigned int old = atomicAdd(&acc_lo[slot], (unsigned int)q);
+            const unsigned int nw = old + (unsigned int)q;
+            const int hadd = (q >> 31) + (nw < old ? 1 : 0);
+            if (hadd != 0) { atomicAdd(&acc_hi[slot], hadd); s_anyhi = 1; }
+        };
+#pragma unroll
+        for (int c = 0; c < NCT; ++c) {
+            int qL[4], qR[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                qL[j] = kL[j] >= 0 ? __float2int_rn(N::mul(N::mul(go[c][j], w0[j]), up)) : 0;
+                qR[j] = kR[j] >= 0 ? __float2int_rn(N::mul(N::mul(go[c][j], w1[j]), up)) : 0;
+            }
+            const int qin = __shfl_up_sync(0xffffffffu, qR[3], 1);
+            if (tin) qL[0] += qin;
+#pragma unroll
+            for (int j = 1; j < 4; ++j)
+                if (lk[j - 1]) qL[j] += qR[j - 1];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (kL[j] >= 0) add(c * 4 * P + sL[j], qL[j]);
+                if (kR[j] >= 0 && !lk[j]) add(c * 4 * P + sR[j], qR[j]);
+            }
+        }
+    }
+    __syncthreads();
+    if (!active) return;
+    const bool anyhi = s_anyhi != 0;
+    float *ob = gV + (size_t)b * NCT * HW + y * W + x0;
+#pragma unroll
+    for (int c = 0; c < NCT; ++c) {
+        float v[4];
+#pragma unroll
+        for (int pl = 0; pl < 4; ++pl) {
+            const int slot = c * 4 * P + pl * P + tid;
+            if (!finite) v[pl] = __uint_as_float(0x7fc00000u);  // a non-finite gradient poisons the row
+            else if (!anyhi) v[pl] = N::mul((S)(int)(acc_lo[slot] ^ 0x80000000u), down);
+            else v[pl] = N::mul((S)((((long long)acc_hi[slot]) << 32) + (long long)acc_lo[slot] - 0x80000000LL), down);
+        }
+        *reinterpret_cast<float4 *>(ob + c * HW) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
 __global__ void __launch_bounds__(256) warp_bwd_vmix_kernel(const float *__restrict__ gV, float *__restrict__ g_img,
                                                              int B, int C, int H, int W, int border, int vec) {
     using S = float;
@@ -616,13 +816,34 @@ template <typename S>
 int warp_bwd_typed(const void *g, const void *img, const void *disp, void *g_img, void *g_disp,
                    void *workspace, size_t workspace_bytes,
                    int B, int C, int H, int W, int pad, cudaStream_t s) {
-    const int variant = env_int("DSSMD_WARP_BWD_VARIANT", 3);
+    const int variant = env_int("DSSMD_WARP_BWD_VARIANT", 4);
     if constexpr (sizeof(S) == 4) {
         const size_t smem = (size_t)2 * kCC * W * sizeof(int);
         const int border = pad == DSSMD_PAD_BORDER;
         const float *gp = (const float *)g, *ip = (const float *)img, *dp = (const float *)disp;
         float *gi = (float *)g_img, *gd = (float *)g_disp;
         const bool have_ws = workspace && workspace_bytes >= (size_t)B * C * H * W * sizeof(float);
+        if (variant >= 4 && C <= 4 && W % 4 == 0 && W <= 4096 && H >= 2 && (long long)C * H * W < (1LL << 31) && (have_ws || !g_img) &&
+            ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(disp) | reinterpret_cast<uintptr_t>(workspace) |
+              reinterpret_cast<uintptr_t>(g_disp)) & 15) == 0) {
+            void (*kern)(const float *, const float *, const float *, float *, float *, int, int, int, float, float, float) =
+                C == 1 ? warp_bwd_hs4_kernel<1> : C == 2 ? warp_bwd_hs4_kernel<2> : C == 3 ? warp_bwd_hs4_kernel<3> : warp_bwd_hs4_kernel<4>;
+            const int W4 = W / 4, P = (W4 + 3) & ~3;
+            const size_t smem4 = (size_t)2 * C * 4 * P * sizeof(int);
+            if (smem4 > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+                if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "warp_bwd: cudaFuncSetAttribute(%zu B): %s", smem4, cudaGetErrorString(e));
+            }
+            float *gv = g_img ? (float *)workspace : nullptr;
+            // W/2, 2/(W-1), H/2: IEEE single divisions, the same values the device would compute
+            const float halfW = (float)W / 2.0f, tscale = 2.0f / (float)(W - 1), halfH = (float)H / 2.0f;
+            kern<<<(unsigned)(B * H), round_up(W4, 32), smem4, s>>>(gp, ip, dp, gv, gd, H, W, border, halfW, tscale, halfH);
+            int rc = check_launch("warp_bwd(hscatter4)");
+            if (rc || !g_img) return rc;
+            const int vec = (((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(g_img)) & 15) == 0);
+            warp_bwd_vmix_kernel<<<(unsigned)(B * H), 256, 0, s>>>(gv, gi, B, C, H, W, border, vec);
+            return check_launch("warp_bwd(vmix)");
+        }
         if (variant >= 3 && W <= 4096 && (long long)C * H * W < (1LL << 31) && (have_ws || !g_img)) {
             int pxt = W <= 256 ? 1 : (W <= 512 ? 2 : 4);  // ~256-thread blocks: 3-4 resident per SM
             const int o = env_int("DSSMD_WARP_BWD_PXT", 0);
