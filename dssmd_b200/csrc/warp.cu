@@ -13,9 +13,16 @@
 // C g_img + 1 g_disp)*s per pixel.
 #include "warp_common.cuh"
 
+#include <cstdlib>
+
 namespace dssmd {
 
 namespace {
+
+int env_int(const char *name, int dflt) {
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
 
 // ---------------------------------------------------------------------------------
 // Forward.  One block per image row; a thread owns 4 consecutive pixels and all C
@@ -328,6 +335,123 @@ __global__ void __launch_bounds__(256) lrwarp_fwd_kernel(const S *__restrict__ i
     if (bad && neg_flag) *reinterpret_cast<volatile int *>(neg_flag) = 1;  // plain store: the flag may live in mapped host memory
 }
 
+// ---------------------------------------------------------------------------------
+// Forward, staged (fp32, C <= 4, W % 4 == 0, 16-byte aligned rows).  The row kernel
+// above spends most of its instructions on 64-bit tap addresses and bounds predicates;
+// here the block first copies the two source rows its output row samples (all channels,
+// coalesced float4 loads issued before the coordinate arithmetic) into shared memory,
+// zero-padded on both sides and zero-filled when a row is out of bounds, so a tap is an
+// unpredicated LDS: an out-of-bounds tap reads 0 and fma(0, w, acc) == acc.
+// Row layout: position = x + 4 (4 zero cells left, 4 right), position p lives in plane
+// p & 3, slot p >> 2 -- a thread's taps are ~4 positions from its neighbour lane's, so
+// the lanes of a warp read one plane at consecutive slots (no bank conflicts).
+// ---------------------------------------------------------------------------------
+template <int NCT>
+__global__ void __launch_bounds__(1024) warp_fwd_staged_kernel(const float *__restrict__ img, const float *__restrict__ disp,
+                                                               float *__restrict__ out, float *__restrict__ mask, int *neg_flag,
+                                                               int H, int W, int border, float halfW, float halfH) {
+    using S = float;
+    using N = Num<S>;
+    extern __shared__ __align__(16) float s_rows[];  // [NCT][2][4][PS]
+    const int W4 = W >> 2, PS = W4 + 2;
+    const int y = blockIdx.x % H;
+    const int b = blockIdx.x / H;
+    const int HW = H * W;  // C*H*W < 2^31 checked on the host
+    const int tid = threadIdx.x;
+    const bool active = tid < W4;
+    const int x0 = tid * 4;
+    const S wm1 = (S)(W - 1);
+
+    // vertical taps: un-clamped for the mask, clamped (border) for the image sample
+    const S gy = N::sub(N::mul((S)2, N::div((S)y, (S)(H - 1))), (S)1);
+    const S iy_raw = N::fma(N::add(gy, (S)1), halfH, (S)-0.5);
+    const Axis<S> ym = make_axis<S>(iy_raw, H);
+    const Axis<S> ya = make_axis<S>(border ? clamp_border<S>(iy_raw, H) : iy_raw, H);
+
+    // source rows -> registers (in flight while the coordinates are computed)
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 st[NCT][2];
+    {
+        const float *ib = img + (size_t)b * NCT * HW + x0;
+#pragma unroll
+        for (int c = 0; c < NCT; ++c) {
+            st[c][0] = (active && ya.in0) ? *reinterpret_cast<const float4 *>(ib + c * HW + ya.i0 * W) : z4;
+            st[c][1] = (active && ya.in1) ? *reinterpret_cast<const float4 *>(ib + c * HW + (ya.i0 + 1) * W) : z4;
+        }
+    }
+    const float4 d4 = active ? *reinterpret_cast<const float4 *>(disp + (size_t)b * HW + y * W + x0) : z4;
+    const S dv[4] = {d4.x, d4.y, d4.z, d4.w};
+
+    int s0[4], s1[4];               // shared-memory slot (inside one row) of the low / high x tap
+    S wa[4], wb[4], wc[4], wd[4];  // tap weights nw, ne, sw, se (0 where the tap is out of bounds)
+    S mv[4];
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (!(dv[i] >= (S)0)) bad = true;
+        // reference op order: t = x - d; gx = 2*(t/(W-1)) - 1; ix = fma(gx+1, W/2, -0.5)
+        const S t = N::sub((S)(x0 + i), dv[i]);
+        const S gxn = N::sub(N::mul((S)2, N::div(t, wm1)), (S)1);
+        const S ix_raw = N::fma(N::add(gxn, (S)1), halfW, (S)-0.5);
+        const Axis<S> xm = make_axis<S>(ix_raw, W);
+        // sum of in-bounds weights of the un-clamped sample, reference order nw, ne, sw, se
+        S m = (S)0;
+        if (xm.in0 && ym.in0) m = N::add(m, N::mul(ym.w0, xm.w0));
+        if (xm.in1 && ym.in0) m = N::add(m, N::mul(ym.w0, xm.w1));
+        if (xm.in0 && ym.in1) m = N::add(m, N::mul(ym.w1, xm.w0));
+        if (xm.in1 && ym.in1) m = N::add(m, N::mul(ym.w1, xm.w1));
+        mv[i] = (m >= (S)0.9999) ? (S)1 : (S)0;
+        Axis<S> xa = xm;
+        if (border && !(ix_raw >= (S)0 && ix_raw <= wm1)) xa = make_axis<S>(clamp_border<S>(ix_raw, W), W);
+        const S xw0 = xa.in0 ? xa.w0 : (S)0, xw1 = xa.in1 ? xa.w1 : (S)0;
+        wa[i] = N::mul(ya.w0, xw0);
+        wb[i] = N::mul(ya.w0, xw1);
+        wc[i] = N::mul(ya.w1, xw0);
+        wd[i] = N::mul(ya.w1, xw1);
+        const int p0 = xa.i0 + 4, p1 = xa.i0 + 5;  // make_axis keeps i0 in [-2, W]
+        s0[i] = (p0 & 3) * PS + (p0 >> 2);
+        s1[i] = (p1 & 3) * PS + (p1 >> 2);
+    }
+    if (active && bad && neg_flag) *reinterpret_cast<volatile int *>(neg_flag) = 1;  // plain store: may be mapped host memory
+
+#pragma unroll
+    for (int c = 0; c < NCT; ++c)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            float *row = s_rows + (c * 2 + r) * 4 * PS;
+            if (active) {
+                row[0 * PS + tid + 1] = st[c][r].x;
+                row[1 * PS + tid + 1] = st[c][r].y;
+                row[2 * PS + tid + 1] = st[c][r].z;
+                row[3 * PS + tid + 1] = st[c][r].w;
+            }
+        }
+    for (int i = tid; i < NCT * 2 * 8; i += blockDim.x) {  // the 4 + 4 pad cells of every staged row
+        const int rowi = i >> 3, k = i & 7;
+        s_rows[rowi * 4 * PS + (k & 3) * PS + ((k >> 2) ? W4 + 1 : 0)] = 0.f;
+    }
+    __syncthreads();
+    if (!active) return;
+
+#pragma unroll
+    for (int c = 0; c < NCT; ++c) {
+        const float *r0 = s_rows + (c * 2) * 4 * PS, *r1 = r0 + 4 * PS;
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            S acc = (S)0;
+            acc = N::fma(r0[s0[i]], wa[i], acc);
+            acc = N::fma(r0[s1[i]], wb[i], acc);
+            acc = N::fma(r1[s0[i]], wc[i], acc);
+            acc = N::fma(r1[s1[i]], wd[i], acc);
+            v[i] = acc;
+        }
+        const size_t o = ((size_t)b * NCT + c) * HW + y * W + x0;
+        st_global_cs(reinterpret_cast<float4 *>(out + o), make_float4(v[0], v[1], v[2], v[3]));
+        if (mask) st_global_cs(reinterpret_cast<float4 *>(mask + o), make_float4(mv[0], mv[1], mv[2], mv[3]));
+    }
+}
+
 template <typename S>
 int warp_fwd_typed(const void *img, const void *disp, void *warped, void *mask, int *neg_flag,
                    int B, int C, int H, int W, int pad, cudaStream_t s) {
@@ -340,6 +464,21 @@ int warp_fwd_typed(const void *img, const void *disp, void *warped, void *mask, 
     const unsigned grid = (unsigned)(B * H);
     const S *ip = (const S *)img, *dp = (const S *)disp;
     S *op = (S *)warped, *mp = (S *)mask;
+    if constexpr (sizeof(S) == 4) {
+        if (vec && C <= 4 && W <= 4096 && H >= 2 && (long long)C * H * W < (1LL << 31) && env_int("DSSMD_WARP_FWD_VARIANT", 1) >= 1) {
+            void (*kern)(const float *, const float *, float *, float *, int *, int, int, int, float, float) =
+                C == 1 ? warp_fwd_staged_kernel<1> : C == 2 ? warp_fwd_staged_kernel<2>
+                : C == 3 ? warp_fwd_staged_kernel<3> : warp_fwd_staged_kernel<4>;
+            const size_t smem = (size_t)C * 2 * 4 * (W / 4 + 2) * sizeof(float);
+            if (smem > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "warp_fwd: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+            }
+            // W/2 and H/2: IEEE single divisions, the same values the device would compute
+            kern<<<grid, round_up(W / 4, 32), smem, s>>>(ip, dp, op, mp, neg_flag, H, W, border, (float)W / 2.0f, (float)H / 2.0f);
+            return check_launch("warp_fwd(staged)");
+        }
+    }
     switch (C) {
         case 1: warp_fwd_kernel<S, 1><<<grid, nt, 0, s>>>(ip, dp, op, mp, neg_flag, B, C, H, W, border, vec); break;
         case 2: warp_fwd_kernel<S, 2><<<grid, nt, 0, s>>>(ip, dp, op, mp, neg_flag, B, C, H, W, border, vec); break;

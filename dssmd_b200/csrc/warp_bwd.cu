@@ -581,9 +581,11 @@ __global__ void __launch_bounds__(1024) warp_bwd_hs4_kernel(const float *__restr
     using N = Num<S>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int W4 = W >> 2;
-    const int P = (W4 + 3) & ~3;                                          // slots per plane
+    const int P = (W4 + 3) & ~3;                                          // accumulator slots per plane
+    const int PS = W4 + 2;                                                // staged image row: slots per plane
     unsigned int *acc_lo = reinterpret_cast<unsigned int *>(smem_raw);  // [NCT][4][P]
     int *acc_hi = reinterpret_cast<int *>(smem_raw) + NCT * 4 * P;      // [NCT][4][P]
+    float *s_rows = reinterpret_cast<float *>(smem_raw) + 2 * NCT * 4 * P;  // [NCT][2][4][PS], only with g_disp
     __shared__ unsigned int s_maxbits;
     __shared__ int s_anyhi;
 
@@ -592,16 +594,9 @@ __global__ void __launch_bounds__(1024) warp_bwd_hs4_kernel(const float *__restr
     const int HW = H * W;  // C*H*W < 2^31 checked on the host
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     const bool active = tid < W4;
+    const int x0 = tid * 4;
     if (tid == 0) { s_maxbits = 0u; s_anyhi = 0; }
     __syncthreads();  // the row maximum is accumulated before the next barrier
-    if (gV) {
-        uint4 *lo4 = reinterpret_cast<uint4 *>(acc_lo);
-        int4 *hi4 = reinterpret_cast<int4 *>(acc_hi);
-        for (int i = tid; i < NCT * P; i += nt) {
-            lo4[i] = make_uint4(0x80000000u, 0x80000000u, 0x80000000u, 0x80000000u);
-            hi4[i] = make_int4(0, 0, 0, 0);
-        }
-    }
 
     // vertical taps of this output row (per thread: one division, no barrier)
     const S wm1 = (S)(W - 1);
@@ -612,17 +607,52 @@ __global__ void __launch_bounds__(1024) warp_bwd_hs4_kernel(const float *__restr
         ya = make_axis<S>(border ? clamp_border<S>(iy_raw, H) : iy_raw, H);
     }
 
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g_disp) {
+        // the two image rows the gather of d(sample)/d(ix) reads: zero-padded planar copy in shared
+        // memory (same layout as warp_fwd_staged_kernel), so every tap is an unpredicated LDS
+        float4 st[NCT][2];
+        const float *ib = img + (size_t)b * NCT * HW + x0;
+#pragma unroll
+        for (int c = 0; c < NCT; ++c) {
+            st[c][0] = (active && ya.in0) ? *reinterpret_cast<const float4 *>(ib + c * HW + ya.i0 * W) : z4;
+            st[c][1] = (active && ya.in1) ? *reinterpret_cast<const float4 *>(ib + c * HW + (ya.i0 + 1) * W) : z4;
+        }
+#pragma unroll
+        for (int c = 0; c < NCT; ++c)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                float *row = s_rows + (c * 2 + r) * 4 * PS;
+                if (active) {
+                    row[0 * PS + tid + 1] = st[c][r].x;
+                    row[1 * PS + tid + 1] = st[c][r].y;
+                    row[2 * PS + tid + 1] = st[c][r].z;
+                    row[3 * PS + tid + 1] = st[c][r].w;
+                }
+            }
+        for (int i = tid; i < NCT * 2 * 8; i += nt) {  // the 4 + 4 pad cells of every staged row
+            const int rowi = i >> 3, k = i & 7;
+            s_rows[rowi * 4 * PS + (k & 3) * PS + ((k >> 2) ? W4 + 1 : 0)] = 0.f;
+        }
+    }
+    if (gV) {
+        uint4 *lo4 = reinterpret_cast<uint4 *>(acc_lo);
+        int4 *hi4 = reinterpret_cast<int4 *>(acc_hi);
+        for (int i = tid; i < NCT * P; i += nt) {
+            lo4[i] = make_uint4(0x80000000u, 0x80000000u, 0x80000000u, 0x80000000u);
+            hi4[i] = make_int4(0, 0, 0, 0);
+        }
+    }
+
     const float *grow = g + (size_t)b * NCT * HW + y * W;
-    const int x0 = tid * 4;
     float go[NCT][4];
     float dd[4];
     {
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 d4 = active ? *reinterpret_cast<const float4 *>(disp + (size_t)b * HW + y * W + x0) : z;
+        const float4 d4 = active ? *reinterpret_cast<const float4 *>(disp + (size_t)b * HW + y * W + x0) : z4;
         dd[0] = d4.x; dd[1] = d4.y; dd[2] = d4.z; dd[3] = d4.w;
 #pragma unroll
         for (int c = 0; c < NCT; ++c) {
-            const float4 v = active ? *reinterpret_cast<const float4 *>(grow + c * HW + x0) : z;
+            const float4 v = active ? *reinterpret_cast<const float4 *>(grow + c * HW + x0) : z4;
             go[c][0] = v.x; go[c][1] = v.y; go[c][2] = v.z; go[c][3] = v.w;
         }
     }
@@ -645,6 +675,7 @@ __global__ void __launch_bounds__(1024) warp_bwd_hs4_kernel(const float *__restr
 
     // horizontal taps
     int kL[4], kR[4];   // cell of the left / right tap, negative when out of bounds
+    int xi0[4];         // low tap index as make_axis returns it, always in [-2, W]
     S w0[4], w1[4], gmult[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -659,34 +690,11 @@ __global__ void __launch_bounds__(1024) warp_bwd_hs4_kernel(const float *__restr
             else if (!(ix == ix)) ix = clamp_border<S>(ix, W);
         }
         const Axis<S> xa = make_axis<S>(ix, W);
+        xi0[j] = xa.i0;
         kL[j] = (active && xa.in0) ? xa.i0 : -1000;
         kR[j] = (active && xa.in1) ? xa.i0 + 1 : -2000;
         w0[j] = xa.w0; w1[j] = xa.w1;
     }
-
-    if (g_disp && active) {
-        float gd[4];
-        const float *ib = img + (size_t)b * NCT * HW + ya.i0 * W;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const bool in0 = kL[j] >= 0, in1 = kR[j] >= 0;
-            const int i0 = in0 ? kL[j] : kR[j] - 1;
-            S gix = (S)0;
-#pragma unroll
-            for (int c = 0; c < NCT; ++c) {
-                const float *pc = ib + c * HW + i0;
-                // d(sample)/d(ix) over in-bounds taps, ATen order nw, ne, sw, se
-                if (in0 && ya.in0) gix = N::sub(gix, N::mul(N::mul(pc[0], ya.w0), go[c][j]));
-                if (in1 && ya.in0) gix = N::add(gix, N::mul(N::mul(pc[1], ya.w0), go[c][j]));
-                if (in0 && ya.in1) gix = N::sub(gix, N::mul(N::mul(pc[W], ya.w1), go[c][j]));
-                if (in1 && ya.in1) gix = N::add(gix, N::mul(N::mul(pc[W + 1], ya.w1), go[c][j]));
-            }
-            // chain rule: ix <- gx (W/2, 0 where clipped) <- t (2/(W-1)) <- disp (-1)
-            gd[j] = -N::mul(tscale, N::mul(gmult[j], gix));
-        }
-        *reinterpret_cast<float4 *>(g_disp + (size_t)b * HW + y * W + x0) = make_float4(gd[0], gd[1], gd[2], gd[3]);
-    }
-    if (!gV) return;  // only g_disp requested (block-uniform)
 
     // links: right tap of pixel j lands on the left cell of pixel j+1 (j = 3: next lane's pixel 0)
     bool lk[4];
@@ -698,7 +706,31 @@ __global__ void __launch_bounds__(1024) warp_bwd_hs4_kernel(const float *__restr
     }
     const bool tin = __shfl_up_sync(0xffffffffu, (int)lk[3], 1) != 0 && lane > 0;
 
-    __syncthreads();  // accumulators filled, row maximum known
+    __syncthreads();  // accumulators filled, image rows staged, row maximum known
+
+    if (g_disp && active) {
+        float gd[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int p0 = xi0[j] + 4, p1 = xi0[j] + 5;
+            const int s0 = (p0 & 3) * PS + (p0 >> 2), s1 = (p1 & 3) * PS + (p1 >> 2);
+            S gix = (S)0;
+#pragma unroll
+            for (int c = 0; c < NCT; ++c) {
+                const float *r0 = s_rows + (c * 2) * 4 * PS, *r1 = r0 + 4 * PS;
+                // d(sample)/d(ix), ATen order nw, ne, sw, se; out-of-bounds taps read the zero padding
+                gix = N::sub(gix, N::mul(N::mul(r0[s0], ya.w0), go[c][j]));
+                gix = N::add(gix, N::mul(N::mul(r0[s1], ya.w0), go[c][j]));
+                gix = N::sub(gix, N::mul(N::mul(r1[s0], ya.w1), go[c][j]));
+                gix = N::add(gix, N::mul(N::mul(r1[s1], ya.w1), go[c][j]));
+            }
+            // chain rule: ix <- gx (W/2, 0 where clipped) <- t (2/(W-1)) <- disp (-1)
+            gd[j] = -N::mul(tscale, N::mul(gmult[j], gix));
+        }
+        *reinterpret_cast<float4 *>(g_disp + (size_t)b * HW + y * W + x0) = make_float4(gd[0], gd[1], gd[2], gd[3]);
+    }
+    if (!gV) return;  // only g_disp requested (block-uniform)
+
     const unsigned int maxbits = s_maxbits;
     const int mexp = (int)(maxbits >> 23);
     const bool finite = mexp != 0xff;
@@ -829,7 +861,7 @@ int warp_bwd_typed(const void *g, const void *img, const void *disp, void *g_img
             void (*kern)(const float *, const float *, const float *, float *, float *, int, int, int, float, float, float) =
                 C == 1 ? warp_bwd_hs4_kernel<1> : C == 2 ? warp_bwd_hs4_kernel<2> : C == 3 ? warp_bwd_hs4_kernel<3> : warp_bwd_hs4_kernel<4>;
             const int W4 = W / 4, P = (W4 + 3) & ~3;
-            const size_t smem4 = (size_t)2 * C * 4 * P * sizeof(int);
+            const size_t smem4 = ((size_t)2 * C * 4 * P + (g_disp ? (size_t)C * 2 * 4 * (W4 + 2) : 0)) * sizeof(int);
             if (smem4 > 48 * 1024) {
                 cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
                 if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "warp_bwd: cudaFuncSetAttribute(%zu B): %s", smem4, cudaGetErrorString(e));
