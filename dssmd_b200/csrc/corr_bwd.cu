@@ -22,6 +22,9 @@
 
 namespace dssmd {
 
+// corr_bwd_reg.cu: fp32 fast path (g slab in registers); -1 = shape not eligible
+int corr_bwd_reg_f32(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, cudaStream_t stream);
+
 namespace {
 
 constexpr int kPix = 8;   // pixels per thread
@@ -290,6 +293,12 @@ int env_int(const char *name, int dflt) {
 
 template <typename T, int MODE>
 int launch_mode(const void *g, const void *In, void *out, int B, int C, int H, int W, int D, cudaStream_t stream) {
+    if constexpr (sizeof(T) == 4) {
+        if (env_int("DSSMD_CORR_BWD_VARIANT", 1) >= 1) {
+            const int rc = corr_bwd_reg_f32(g, In, out, MODE, B, C, H, W, D, stream);
+            if (rc >= 0) return rc;
+        }
+    }
     CorrBwdParams p{};
     p.g = g; p.In = In; p.out = out;
     p.B = B; p.C = C; p.H = H; p.W = W; p.D = D;

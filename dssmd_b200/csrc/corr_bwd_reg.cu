@@ -1,0 +1,261 @@
+// corr_bwd_reg.cu -- fp32 backward of the correlation volume with the gradient slab held
+// in registers and the tiles staged by TMA (fast path of corr_bwd.cu; same maths, see the
+// formulas there).
+//
+//   gL[c,x ] = (1/C) * sum_d g[d,x]    * R[c,x-d]        (MODE 0)
+//   gR[c,x'] = (1/C) * sum_d g[d,x'+d] * L[c,x'+d]       (MODE 1)
+//
+// For one image row the g values a pixel needs do not depend on the channel, the operand
+// values do.  So a lane keeps a PX-pixel x 12-disparity slab of g in registers (MODE 1:
+// skewed, gs[d][x'] = g[d][x'+d]) and walks over the channels; per channel it reads ONE
+// aligned (PX+12)-word window of the operand row from shared memory and issues PX*12 FFMAs
+// -- 12 (PX=4) or 19 (PX=8) FFMAs per LDS.128, against the 4 an LDS.128 (4 shared-memory
+// wavefronts) has to feed to keep the FMA pipe busy.  The D disparities are split in NH parts
+// of 12 over neighbouring lanes (lane = group*NH + part); the parts are summed with log2(NH)
+// shuffles in a fixed order (deterministic, no atomics).
+//
+// Work item = (row (b,y), x tile, block of CB channels).  A persistent block walks a contiguous
+// range of items, channel blocks fastest, so the g slab stays in registers while the row and x
+// tile do not change.  Both tiles of an item arrive by ONE TMA box each ([W,H,C,B] views of the
+// operand and of g): the box starts 12*NH pixels left of the tile (MODE 0) or extends 12*NH
+// pixels to its right (MODE 1) and TMA zero-fills what falls outside the row, which is exactly
+// the x-d < 0 / x'+d >= W boundary of the sums -- the inner loop has no bounds tests.  Two
+// stages: the boxes of item i+1 are in flight while item i is computed.
+#include "common.cuh"
+#include "tma.cuh"
+
+#include <cstdlib>
+
+namespace dssmd {
+
+namespace {
+
+constexpr int kDP = 12;  // disparities per lane
+
+struct RegParams {
+    float *out;
+    int C, H, W, D;
+    int NH, LOGNH;  // lanes per pixel group (power of two), D <= 12*NH
+    int WPR;        // warps side by side along x
+    int CGW;        // channel groups of warps
+    int CB;         // channels per item
+    int NCB;        // channel blocks
+    int TX;         // x tile in pixels
+    int XT;         // x tiles per row
+    int WP;         // operand box width in words (TX + 12*NH)
+    int GW;         // g box width in words (MODE 0: TX, MODE 1: WP)
+    int nitems, ipb;  // work items, items per block
+    uint32_t op_bytes, g_bytes;
+    float invC;
+};
+
+template <int MODE, int PX>
+__global__ void __launch_bounds__(512) corr_bwd_reg_kernel(const RegParams p, const __grid_constant__ CUtensorMap mapIn,
+                                                           const __grid_constant__ CUtensorMap mapG) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    // stage s: operand tile [CB][WP] then g tile [D][GW], each 128-byte aligned
+    const uint32_t op_stride = (p.op_bytes + 127u) & ~127u, g_stride = (p.g_bytes + 127u) & ~127u;
+    const uint32_t stage_bytes = op_stride + g_stride;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i0 = blockIdx.x * p.ipb;
+    const int i1 = (i0 + p.ipb < p.nitems) ? i0 + p.ipb : p.nitems;
+    if (i0 >= i1) return;
+
+    if (tid == 0) {
+        mbar_init(smem_u32(&s_bar[0]), 1);
+        mbar_init(smem_u32(&s_bar[1]), 1);
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    auto issue = [&](int it, int s) {  // one thread
+        const int cb = it % p.NCB, rx = it / p.NCB;
+        const int xt = rx % p.XT, row = rx / p.XT;
+        const int b = row / p.H, y = row - b * p.H;
+        const bool newg = (it == i0) || (cb == 0);
+        const uint32_t bar = smem_u32(&s_bar[s]);
+        const uint32_t dst = smem_u32(smem_raw) + (uint32_t)s * stage_bytes;
+        fence_proxy_async();  // the stage was read through the generic proxy before the block barrier
+        mbar_arrive_expect_tx(bar, p.op_bytes + (newg ? p.g_bytes : 0u));
+        const int X0 = xt * p.TX;
+        tma_load_4d(dst, &mapIn, MODE == 0 ? X0 - kDP * p.NH : X0, y, cb * p.CB, b, bar);
+        if (newg) tma_load_4d(dst + op_stride, &mapG, X0, y, 0, b, bar);
+    };
+    if (tid == 0) issue(i0, 0);
+
+    // this lane's pixels (inside the x tile) and disparity part
+    const int wseg = warp % p.WPR, cgw = warp / p.WPR;
+    const int h = lane & (p.NH - 1), pgl = lane >> p.LOGNH;
+    const int xl = (wseg * (32 >> p.LOGNH) + pgl) * PX;  // < TX by construction
+    const int woff = MODE == 0 ? xl + kDP * p.NH - kDP * (h + 1) : xl + kDP * h;  // window start inside a staged row
+    const size_t HW = (size_t)p.H * p.W;
+
+    float gv[kDP][PX];
+    for (int it = i0; it < i1; ++it) {
+        const int s = (it - i0) & 1;
+        const uint32_t ph = ((it - i0) >> 1) & 1u;
+        if (tid == 0 && it + 1 < i1) issue(it + 1, s ^ 1);  // stage s^1 was released by the barrier ending item it-1
+        const int cb = it % p.NCB, rx = it / p.NCB;
+        const int xt = rx % p.XT, row = rx / p.XT;
+        const int b = row / p.H, y = row - b * p.H;
+        const int X0 = xt * p.TX;
+        const float *ops = reinterpret_cast<const float *>(smem_raw + (size_t)s * stage_bytes);
+        mbar_wait(smem_u32(&s_bar[s]), ph);
+
+        if (it == i0 || cb == 0) {  // new row / x tile: reload the g slab
+            const float *gs = reinterpret_cast<const float *>(smem_raw + (size_t)s * stage_bytes + op_stride);
+#pragma unroll
+            for (int dd = 0; dd < kDP; ++dd) {
+                const int d = h * kDP + dd;
+                const bool dok = d < p.D;
+                const float *gd = gs + (dok ? d : 0) * p.GW + xl;
+                if (MODE == 0) {
+#pragma unroll
+                    for (int q = 0; q < PX / 4; ++q) {
+                        const float4 v = *reinterpret_cast<const float4 *>(gd + 4 * q);
+                        gv[dd][4 * q + 0] = dok ? v.x : 0.f; gv[dd][4 * q + 1] = dok ? v.y : 0.f;
+                        gv[dd][4 * q + 2] = dok ? v.z : 0.f; gv[dd][4 * q + 3] = dok ? v.w : 0.f;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < PX; ++i) gv[dd][i] = dok ? gd[i + d] : 0.f;
+                }
+            }
+        }
+
+        const int c0 = cb * p.CB;
+        const int cn = (p.C - c0 < p.CB) ? p.C - c0 : p.CB;
+        const int x = X0 + xl;
+        float *orow = p.out + ((size_t)b * p.C + c0) * HW + (size_t)y * p.W + x;
+#pragma unroll 2
+        for (int c = cgw; c < cn; c += p.CGW) {
+            const float4 *wp = reinterpret_cast<const float4 *>(ops + c * p.WP + woff);
+            float w[PX + kDP];
+#pragma unroll
+            for (int q = 0; q < (PX + kDP) / 4; ++q) {
+                const float4 v = wp[q];
+                w[4 * q + 0] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+            }
+            float acc[PX];
+#pragma unroll
+            for (int i = 0; i < PX; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int dd = 0; dd < kDP; ++dd)
+#pragma unroll
+                for (int i = 0; i < PX; ++i)
+                    acc[i] = fmaf(gv[dd][i], w[MODE == 0 ? i - dd + kDP : i + dd], acc[i]);
+            for (int sft = 1; sft < p.NH; sft <<= 1)
+#pragma unroll
+                for (int i = 0; i < PX; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], sft);
+            if (h == 0) {
+                float *o = orow + (size_t)c * HW;
+#pragma unroll
+                for (int q = 0; q < PX / 4; ++q)
+                    if (x + 4 * q < p.W)
+                        st_global_cs(reinterpret_cast<float4 *>(o) + q,
+                                     make_float4(acc[4 * q] * p.invC, acc[4 * q + 1] * p.invC, acc[4 * q + 2] * p.invC, acc[4 * q + 3] * p.invC));
+            }
+        }
+        __syncthreads();  // everyone is done with stage s (and, on a new row, has its g slab)
+    }
+}
+
+int env_int_reg(const char *name, int dflt) {
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
+template <int MODE, int PX>
+int launch_reg(RegParams p, const CUtensorMap &mapIn, const CUtensorMap &mapG, int threads, size_t smem, cudaStream_t stream) {
+    auto kern = corr_bwd_reg_kernel<MODE, PX>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_bwd: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+    }
+    // persistent grid: exactly the blocks that are resident at once, each with an equal share of items
+    int bps = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, threads, smem) != cudaSuccess || bps < 1) bps = 1;
+    const int o = env_int_reg("DSSMD_CORR_BWD_BPS", 0);
+    if (o >= 1 && o < bps) bps = o;
+    int grid = sm_count() * bps;
+    if (grid > p.nitems) grid = p.nitems;
+    p.ipb = ceil_div(p.nitems, grid);
+    grid = ceil_div(p.nitems, p.ipb);
+    if (env_int_reg("DSSMD_CORR_DEBUG", 0))
+        fprintf(stderr, "corr_bwd reg cfg: mode=%d PX=%d NH=%d WPR=%d TX=%d XT=%d CGW=%d CB=%d items=%d ipb=%d grid=%d (x%d/SM) threads=%d smem=%zu\n",
+                MODE, PX, p.NH, p.WPR, p.TX, p.XT, p.CGW, p.CB, p.nitems, p.ipb, grid, bps, threads, smem);
+    kern<<<(unsigned)grid, threads, smem, stream>>>(p, mapIn, mapG);
+    return check_launch(MODE == 0 ? "corr_bwd(gL, reg)" : "corr_bwd(gR, reg)");
+}
+
+}  // namespace
+
+// mode 0: out = gL, in = R;  mode 1: out = gR, in = L.  Returns -1 when the shape is not
+// eligible (the caller falls back to the generic kernel), else a DSSMD_* code.
+int corr_bwd_reg_f32(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, cudaStream_t stream) {
+    if (W % 4 != 0 || D > kDP * 16) return -1;
+    if (((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) != 0) return -1;
+    if ((long long)B * H * 64 >= (1LL << 31)) return -1;
+    RegParams p{};
+    p.out = (float *)out;
+    p.C = C; p.H = H; p.W = W; p.D = D;
+    p.invC = 1.0f / (float)C;
+    int nh = 1, lognh = 0;
+    while (nh * kDP < D) { nh *= 2; ++lognh; }
+    p.NH = nh; p.LOGNH = lognh;
+    const int px = (env_int_reg("DSSMD_CORR_BWD_PX", 4) == 8 && W % 8 == 0) ? 8 : 4;
+    const int pxw = (32 / nh) * px;                 // pixels one warp covers
+    // x tile: the operand box (tile + 12*NH halo words) must fit a 256-element TMA box
+    int wpr = ceil_div(W, pxw);
+    while (wpr > 1 && wpr * pxw + kDP * nh > 256) wpr = (wpr + 1) / 2;
+    if (wpr * pxw + kDP * nh > 256) return -1;
+    p.WPR = wpr;
+    p.TX = wpr * pxw;
+    p.XT = ceil_div(W, p.TX);
+    p.WP = p.TX + kDP * nh;
+    p.GW = mode == 0 ? p.TX : p.WP;
+    int cgw = env_int_reg("DSSMD_CORR_BWD_CGW", 0);
+    if (cgw < 1) cgw = 8 / wpr;
+    if (cgw < 1) cgw = 1;
+    while (cgw > 1 && wpr * cgw > 16) --cgw;
+    if (cgw > C) cgw = C;
+    p.CGW = cgw;
+    // channels per item: small enough that every SM sees several items (the pipeline needs a
+    // few to hide its first load), large enough to amortise the per-item barrier
+    int cb = env_int_reg("DSSMD_CORR_BWD_CB", 0);
+    if (cb < 1) {
+        cb = C;
+        while (cb > 8 * cgw && (long)B * H * p.XT * ceil_div(C, cb) < 6L * sm_count()) cb = (cb + 1) / 2;
+        cb = round_up(cb, cgw);
+    }
+    if (cb > 256) cb = 256;
+    if (cb > C) cb = C;
+    p.CB = cb;
+    p.NCB = ceil_div(C, cb);
+    p.op_bytes = (uint32_t)((size_t)cb * p.WP * sizeof(float));
+    p.g_bytes = (uint32_t)((size_t)D * p.GW * sizeof(float));
+    const size_t stage = (size_t)((p.op_bytes + 127u) & ~127u) + ((p.g_bytes + 127u) & ~127u);
+    const size_t smem = 2 * stage + 128;
+    if (smem > 200 * 1024) return -1;
+    p.nitems = B * H * p.XT * p.NCB;
+    const int threads = wpr * cgw * 32;
+    CUtensorMap mapIn, mapG;
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+        const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
+        const cuuint32_t box[4] = {(cuuint32_t)p.WP, 1, (cuuint32_t)cb, 1};
+        if (!make_tmap_f32(&mapIn, in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
+    }
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+        const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)D * H * W * 4};
+        const cuuint32_t box[4] = {(cuuint32_t)p.GW, 1, (cuuint32_t)D, 1};
+        if (!make_tmap_f32(&mapG, g, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
+    }
+    if (mode == 0) return px == 8 ? launch_reg<0, 8>(p, mapIn, mapG, threads, smem, stream) : launch_reg<0, 4>(p, mapIn, mapG, threads, smem, stream);
+    return px == 8 ? launch_reg<1, 8>(p, mapIn, mapG, threads, smem, stream) : launch_reg<1, 4>(p, mapIn, mapG, threads, smem, stream);
+}
+
+}  // namespace dssmd

@@ -37,6 +37,7 @@
 //                           The accumulator is double-buffered in TMEM (2 x 256 columns) so the
 //                           epilogue of tile t overlaps the main loop of tile t+1.
 #include "common.cuh"
+#include "tma.cuh"
 
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
@@ -93,26 +94,6 @@ enum {
     kAccEmpty = kAccFull + 2,            // [2]           EPILOGUE -> MMA
     kNumBars = kAccEmpty + 2
 };
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// bounded wait: a protocol bug must trap, not hang the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (int spin = 0; spin < (1 << 26); ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return;
-    }
-    __trap();
-}
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     // MN-major tf32 operands only exist in the SWIZZLE_128B_BASE32B layout (32-byte swizzle atoms, 4-row
@@ -396,31 +377,6 @@ int env_int(const char *name, int dflt) {
 
 namespace {
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_tiled() {
-    static EncodeTiledFn fn = [] {
-        void *sym = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-            sym = nullptr;
-        return reinterpret_cast<EncodeTiledFn>(sym);
-    }();
-    return fn;
-}
-
-// fp32 tensor map; dims/box fastest first; strides in bytes for dims 1..rank-1
-bool make_tmap_f32(CUtensorMap *m, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides, const cuuint32_t *box) {
-    EncodeTiledFn fn = encode_tiled();
-    if (!fn) return false;
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 }  // namespace
 
 // Returns -1 when the shape is outside this kernel's limits (caller falls back to FFMA).
@@ -470,13 +426,13 @@ int corr_fwd_umma_f32(const void *L, const void *R, void *out, int B, int C, int
         const cuuint64_t dims[3] = {HWl, (cuuint64_t)C, (cuuint64_t)B};
         const cuuint64_t strides[2] = {HWl * 4, HWl * 4 * (cuuint64_t)C};
         const cuuint32_t box[3] = {(cuuint32_t)kBoxX, (cuuint32_t)kKC, 1};
-        if (!make_tmap_f32(&mapA, L, 3, dims, strides, box)) return -1;
+        if (!make_tmap_f32(&mapA, L, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return -1;
     }
     {
         const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
         const cuuint64_t strides[3] = {(cuuint64_t)W * 4, HWl * 4, HWl * 4 * (cuuint64_t)C};
         const cuuint32_t box[4] = {(cuuint32_t)kBoxX, 1, (cuuint32_t)kKC, 1};
-        if (!make_tmap_f32(&mapB, R, 4, dims, strides, box)) return -1;
+        if (!make_tmap_f32(&mapB, R, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return -1;
     }
     const int cap = sm_count();  // one persistent CTA per SM
     const unsigned grid = (unsigned)(p.ntiles < cap ? p.ntiles : cap);
