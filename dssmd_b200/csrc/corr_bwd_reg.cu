@@ -49,7 +49,7 @@ struct RegParams {
     float invC;
 };
 
-template <int MODE, int PX>
+template <int MODE, int LOGNH>
 __global__ void __launch_bounds__(512) corr_bwd_reg_kernel(const RegParams p, const __grid_constant__ CUtensorMap mapIn,
                                                            const __grid_constant__ CUtensorMap mapG) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(512) corr_bwd_reg_kernel(const RegParams p, co
     const uint32_t op_stride = (p.op_bytes + 127u) & ~127u, g_stride = (p.g_bytes + 127u) & ~127u;
     const uint32_t stage_bytes = op_stride + g_stride;
 
+    constexpr int PX = 4, NH = 1 << LOGNH;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i0 = blockIdx.x * p.ipb;
     const int i1 = (i0 + p.ipb < p.nitems) ? i0 + p.ipb : p.nitems;
@@ -80,16 +81,16 @@ __global__ void __launch_bounds__(512) corr_bwd_reg_kernel(const RegParams p, co
         fence_proxy_async();  // the stage was read through the generic proxy before the block barrier
         mbar_arrive_expect_tx(bar, p.op_bytes + (newg ? p.g_bytes : 0u));
         const int X0 = xt * p.TX;
-        tma_load_4d(dst, &mapIn, MODE == 0 ? X0 - kDP * p.NH : X0, y, cb * p.CB, b, bar);
+        tma_load_4d(dst, &mapIn, MODE == 0 ? X0 - kDP * NH : X0, y, cb * p.CB, b, bar);
         if (newg) tma_load_4d(dst + op_stride, &mapG, X0, y, 0, b, bar);
     };
     if (tid == 0) issue(i0, 0);
 
     // this lane's pixels (inside the x tile) and disparity part
     const int wseg = warp % p.WPR, cgw = warp / p.WPR;
-    const int h = lane & (p.NH - 1), pgl = lane >> p.LOGNH;
-    const int xl = (wseg * (32 >> p.LOGNH) + pgl) * PX;  // < TX by construction
-    const int woff = MODE == 0 ? xl + kDP * p.NH - kDP * (h + 1) : xl + kDP * h;  // window start inside a staged row
+    const int h = lane & (NH - 1), pgl = lane >> LOGNH;
+    const int xl = (wseg * (32 >> LOGNH) + pgl) * PX;  // < TX by construction
+    const int woff = MODE == 0 ? xl + kDP * NH - kDP * (h + 1) : xl + kDP * h;  // window start inside a staged row
     const size_t HW = (size_t)p.H * p.W;
 
     float gv[kDP][PX];
@@ -115,12 +116,12 @@ __global__ void __launch_bounds__(512) corr_bwd_reg_kernel(const RegParams p, co
 #pragma unroll
                     for (int q = 0; q < PX / 4; ++q) {
                         const float4 v = *reinterpret_cast<const float4 *>(gd + 4 * q);
-                        gv[dd][4 * q + 0] = dok ? v.x : 0.f; gv[dd][4 * q + 1] = dok ? v.y : 0.f;
-                        gv[dd][4 * q + 2] = dok ? v.z : 0.f; gv[dd][4 * q + 3] = dok ? v.w : 0.f;
+                        gv[dd][4 * q + 0] = dok ? v.x * p.invC : 0.f; gv[dd][4 * q + 1] = dok ? v.y * p.invC : 0.f;
+                        gv[dd][4 * q + 2] = dok ? v.z * p.invC : 0.f; gv[dd][4 * q + 3] = dok ? v.w * p.invC : 0.f;
                     }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < PX; ++i) gv[dd][i] = dok ? gd[i + d] : 0.f;
+                    for (int i = 0; i < PX; ++i) gv[dd][i] = dok ? gd[i + d] * p.invC : 0.f;
                 }
             }
         }
@@ -128,10 +129,17 @@ __global__ void __launch_bounds__(512) corr_bwd_reg_kernel(const RegParams p, co
         const int c0 = cb * p.CB;
         const int cn = (p.C - c0 < p.CB) ? p.C - c0 : p.CB;
         const int x = X0 + xl;
-        float *orow = p.out + ((size_t)b * p.C + c0) * HW + (size_t)y * p.W + x;
+        // lanes of a pixel group share the store: after the butterfly every lane holds the 4 sums,
+        // lane h writes 4/NH of them (NH = 2: a float2 each, NH >= 4: lanes 0..3 one float each)
+        constexpr int SPL = NH >= 4 ? 1 : 4 / NH;   // floats per storing lane
+        const bool storer = (NH <= 4 || h < 4) && (x + h * SPL < p.W);
+        float *o = p.out + ((size_t)b * p.C + c0 + cgw) * HW + (size_t)y * p.W + x + h * SPL;
+        const size_t ostep = (size_t)p.CGW * HW;
+        const float *wrow = ops + cgw * p.WP + woff;
+        const int wstep = p.CGW * p.WP;
 #pragma unroll 2
-        for (int c = cgw; c < cn; c += p.CGW) {
-            const float4 *wp = reinterpret_cast<const float4 *>(ops + c * p.WP + woff);
+        for (int c = cgw; c < cn; c += p.CGW, o += ostep, wrow += wstep) {
+            const float4 *wp = reinterpret_cast<const float4 *>(wrow);
             float w[PX + kDP];
 #pragma unroll
             for (int q = 0; q < (PX + kDP) / 4; ++q) {
@@ -146,16 +154,20 @@ __global__ void __launch_bounds__(512) corr_bwd_reg_kernel(const RegParams p, co
 #pragma unroll
                 for (int i = 0; i < PX; ++i)
                     acc[i] = fmaf(gv[dd][i], w[MODE == 0 ? i - dd + kDP : i + dd], acc[i]);
-            for (int sft = 1; sft < p.NH; sft <<= 1)
+#pragma unroll
+            for (int sft = 1; sft < NH; sft <<= 1)
 #pragma unroll
                 for (int i = 0; i < PX; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], sft);
-            if (h == 0) {
-                float *o = orow + (size_t)c * HW;
-#pragma unroll
-                for (int q = 0; q < PX / 4; ++q)
-                    if (x + 4 * q < p.W)
-                        st_global_cs(reinterpret_cast<float4 *>(o) + q,
-                                     make_float4(acc[4 * q] * p.invC, acc[4 * q + 1] * p.invC, acc[4 * q + 2] * p.invC, acc[4 * q + 3] * p.invC));
+            if (storer) {
+                if constexpr (NH == 1) {
+                    st_global_cs(reinterpret_cast<float4 *>(o), make_float4(acc[0], acc[1], acc[2], acc[3]));
+                } else if constexpr (NH == 2) {
+                    const float2 v = h ? make_float2(acc[2], acc[3]) : make_float2(acc[0], acc[1]);
+                    asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(o), "f"(v.x), "f"(v.y) : "memory");
+                } else {
+                    const float v = (h & 2) ? ((h & 1) ? acc[3] : acc[2]) : ((h & 1) ? acc[1] : acc[0]);
+                    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(o), "f"(v) : "memory");
+                }
             }
         }
         __syncthreads();  // everyone is done with stage s (and, on a new row, has its g slab)
@@ -167,9 +179,9 @@ int env_int_reg(const char *name, int dflt) {
     return (v && *v) ? std::atoi(v) : dflt;
 }
 
-template <int MODE, int PX>
+template <int MODE, int LOGNH>
 int launch_reg(RegParams p, const CUtensorMap &mapIn, const CUtensorMap &mapG, int threads, size_t smem, cudaStream_t stream) {
-    auto kern = corr_bwd_reg_kernel<MODE, PX>;
+    auto kern = corr_bwd_reg_kernel<MODE, LOGNH>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_bwd: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
@@ -184,8 +196,8 @@ int launch_reg(RegParams p, const CUtensorMap &mapIn, const CUtensorMap &mapG, i
     p.ipb = ceil_div(p.nitems, grid);
     grid = ceil_div(p.nitems, p.ipb);
     if (env_int_reg("DSSMD_CORR_DEBUG", 0))
-        fprintf(stderr, "corr_bwd reg cfg: mode=%d PX=%d NH=%d WPR=%d TX=%d XT=%d CGW=%d CB=%d items=%d ipb=%d grid=%d (x%d/SM) threads=%d smem=%zu\n",
-                MODE, PX, p.NH, p.WPR, p.TX, p.XT, p.CGW, p.CB, p.nitems, p.ipb, grid, bps, threads, smem);
+        fprintf(stderr, "corr_bwd reg cfg: mode=%d NH=%d WPR=%d TX=%d XT=%d CGW=%d CB=%d items=%d ipb=%d grid=%d (x%d/SM) threads=%d smem=%zu\n",
+                MODE, p.NH, p.WPR, p.TX, p.XT, p.CGW, p.CB, p.nitems, p.ipb, grid, bps, threads, smem);
     kern<<<(unsigned)grid, threads, smem, stream>>>(p, mapIn, mapG);
     return check_launch(MODE == 0 ? "corr_bwd(gL, reg)" : "corr_bwd(gR, reg)");
 }
@@ -205,7 +217,7 @@ int corr_bwd_reg_f32(const void *g, const void *in, void *out, int mode, int B, 
     int nh = 1, lognh = 0;
     while (nh * kDP < D) { nh *= 2; ++lognh; }
     p.NH = nh; p.LOGNH = lognh;
-    const int px = (env_int_reg("DSSMD_CORR_BWD_PX", 4) == 8 && W % 8 == 0) ? 8 : 4;
+    const int px = 4;
     const int pxw = (32 / nh) * px;                 // pixels one warp covers
     // x tile: the operand box (tile + 12*NH halo words) must fit a 256-element TMA box
     int wpr = ceil_div(W, pxw);
@@ -232,6 +244,13 @@ int corr_bwd_reg_f32(const void *g, const void *in, void *out, int mode, int B, 
     }
     if (cb > 256) cb = 256;
     if (cb > C) cb = C;
+    // two stages of (operand tile + g tile) must leave room for two resident blocks
+    {
+        const size_t gbytes = (size_t)D * p.GW * sizeof(float) + 128, rowb = (size_t)p.WP * sizeof(float);
+        const size_t budget = (size_t)env_int_reg("DSSMD_CORR_BWD_SMEM_KB2", 100) * 1024 / 2;
+        if (gbytes + rowb * cgw > budget) return -1;
+        while (cb > cgw && gbytes + rowb * cb + 128 > budget) cb -= cgw;
+    }
     p.CB = cb;
     p.NCB = ceil_div(C, cb);
     p.op_bytes = (uint32_t)((size_t)cb * p.WP * sizeof(float));
@@ -254,8 +273,17 @@ int corr_bwd_reg_f32(const void *g, const void *in, void *out, int mode, int B, 
         const cuuint32_t box[4] = {(cuuint32_t)p.GW, 1, (cuuint32_t)D, 1};
         if (!make_tmap_f32(&mapG, g, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
     }
-    if (mode == 0) return px == 8 ? launch_reg<0, 8>(p, mapIn, mapG, threads, smem, stream) : launch_reg<0, 4>(p, mapIn, mapG, threads, smem, stream);
-    return px == 8 ? launch_reg<1, 8>(p, mapIn, mapG, threads, smem, stream) : launch_reg<1, 4>(p, mapIn, mapG, threads, smem, stream);
+#define DSSMD_REG_LAUNCH(M)                                                                     \
+    switch (lognh) {                                                                            \
+        case 0: return launch_reg<M, 0>(p, mapIn, mapG, threads, smem, stream);                 \
+        case 1: return launch_reg<M, 1>(p, mapIn, mapG, threads, smem, stream);                 \
+        case 2: return launch_reg<M, 2>(p, mapIn, mapG, threads, smem, stream);                 \
+        case 3: return launch_reg<M, 3>(p, mapIn, mapG, threads, smem, stream);                 \
+        default: return launch_reg<M, 4>(p, mapIn, mapG, threads, smem, stream);                \
+    }
+    if (mode == 0) { DSSMD_REG_LAUNCH(0) }
+    DSSMD_REG_LAUNCH(1)
+#undef DSSMD_REG_LAUNCH
 }
 
 }  // namespace dssmd
