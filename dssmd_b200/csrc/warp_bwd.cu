@@ -564,30 +564,35 @@ __global__ void __launch_bounds__(1024, 1) warp_bwd_hscatter_kernel(const float 
 //   * a thread owns 4 CONSECUTIVE pixels: disp / g / gV / g_disp move as float4, and the
 //     right tap of pixel j is merged into the left tap of pixel j+1 in registers when they
 //     land on the same cell (x' = x - disp is close to monotone), across lanes by shuffle;
-//   * the accumulator of a cell is ONE native 32-bit shared atomic per merged tap: the
-//     low word starts at 2^31 and the high word only sees an atomic when the low word
-//     wraps (returned old value -> carry), i.e. when |partial sum| reaches 2^31 quanta --
-//     rare, but it keeps the sum exact (cells at a clamped border collect hundreds of taps);
+//   * the accumulator of a cell is ONE 32-bit integer and every merged tap ONE fire-and-forget
+//     shared atomic: contributions are quantised to q = rn(v * 2^e) with e chosen per row from
+//     S = max_c sum_x |g[c]| such that S * 2^e <= 2^30.  Every cell sum is bounded by S (the tap
+//     weights of a pixel add up to <= 1), so no cell can overflow however many taps collect
+//     in it (cells at a clamped border collect hundreds), integer adds are associative, and
+//     the result is deterministic.  Quantum relative to the row's mean |g|: <= W * 2^-29;
 //   * cells live in 4 planes (cell k -> plane k & 3, slot k >> 2) so that lanes, whose
 //     cells are 4 apart, hit consecutive banks;
 //   * the y-axis taps are recomputed per thread (one division) instead of shared through a barrier.
 // ---------------------------------------------------------------------------------
+// predicated fire-and-forget 32-bit shared-memory add (native ATOMS/RED on sm_100a, no return value)
+__device__ __forceinline__ void red_shared_add(uint32_t addr, int q, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p red.shared.add.s32 [%0], %1;\n\t}" ::"r"(addr), "r"(q), "r"((int)pred) : "memory");
+}
+
 template <int NCT>
 __global__ void __launch_bounds__(1024) warp_bwd_hs4_kernel(const float *__restrict__ g, const float *__restrict__ img,
                                                             const float *__restrict__ disp, float *__restrict__ gV,
                                                             float *__restrict__ g_disp, int H, int W, int border,
                                                             float halfW, float tscale, float halfH) {
-    using S = float;
-    using N = Num<S>;
+    using S_t = float;
+    using N = Num<S_t>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int W4 = W >> 2;
     const int P = (W4 + 3) & ~3;                                          // accumulator slots per plane
     const int PS = W4 + 2;                                                // staged image row: slots per plane
-    unsigned int *acc_lo = reinterpret_cast<unsigned int *>(smem_raw);  // [NCT][4][P]
-    int *acc_hi = reinterpret_cast<int *>(smem_raw) + NCT * 4 * P;      // [NCT][4][P]
-    float *s_rows = reinterpret_cast<float *>(smem_raw) + 2 * NCT * 4 * P;  // [NCT][2][4][PS], only with g_disp
-    __shared__ unsigned int s_maxbits;
-    __shared__ int s_anyhi;
+    int *acc = reinterpret_cast<int *>(smem_raw);                        // [NCT][4][P]
+    float *s_rows = reinterpret_cast<float *>(smem_raw) + NCT * 4 * P;   // [NCT][2][4][PS], only with g_disp
+    __shared__ float s_part[NCT][32];                                     // per-warp, per-channel sums of |g|
 
     const int y = blockIdx.x % H;
     const int b = blockIdx.x / H;
@@ -595,16 +600,13 @@ __global__ void __launch_bounds__(1024) warp_bwd_hs4_kernel(const float *__restr
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     const bool active = tid < W4;
     const int x0 = tid * 4;
-    if (tid == 0) { s_maxbits = 0u; s_anyhi = 0; }
-    __syncthreads();  // the row maximum is accumulated before the next barrier
-
     // vertical taps of this output row (per thread: one division, no barrier)
-    const S wm1 = (S)(W - 1);
-    Axis<S> ya;
+    const S_t wm1 = (S_t)(W - 1);
+    Axis<S_t> ya;
     {
-        const S gy = N::sub(N::mul((S)2, N::div((S)y, (S)(H - 1))), (S)1);
-        const S iy_raw = N::fma(N::add(gy, (S)1), halfH, (S)-0.5);
-        ya = make_axis<S>(border ? clamp_border<S>(iy_raw, H) : iy_raw, H);
+        const S_t gy = N::sub(N::mul((S_t)2, N::div((S_t)y, (S_t)(H - 1))), (S_t)1);
+        const S_t iy_raw = N::fma(N::add(gy, (S_t)1), halfH, (S_t)-0.5);
+        ya = make_axis<S_t>(border ? clamp_border<S_t>(iy_raw, H) : iy_raw, H);
     }
 
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -636,12 +638,8 @@ __global__ void __launch_bounds__(1024) warp_bwd_hs4_kernel(const float *__restr
         }
     }
     if (gV) {
-        uint4 *lo4 = reinterpret_cast<uint4 *>(acc_lo);
-        int4 *hi4 = reinterpret_cast<int4 *>(acc_hi);
-        for (int i = tid; i < NCT * P; i += nt) {
-            lo4[i] = make_uint4(0x80000000u, 0x80000000u, 0x80000000u, 0x80000000u);
-            hi4[i] = make_int4(0, 0, 0, 0);
-        }
+        int4 *a4 = reinterpret_cast<int4 *>(acc);
+        for (int i = tid; i < NCT * P; i += nt) a4[i] = make_int4(0, 0, 0, 0);
     }
 
     const float *grow = g + (size_t)b * NCT * HW + y * W;
@@ -656,40 +654,35 @@ __global__ void __launch_bounds__(1024) warp_bwd_hs4_kernel(const float *__restr
             go[c][0] = v.x; go[c][1] = v.y; go[c][2] = v.z; go[c][3] = v.w;
         }
     }
-    unsigned int mbits = 0u;
-#pragma unroll
-    for (int c = 0; c < NCT; ++c)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const unsigned int bits = __float_as_uint(go[c][j]) & 0x7fffffffu;
-            mbits = bits > mbits ? bits : mbits;  // NaN/inf bit patterns compare largest
-        }
     if (gV) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned int other = __shfl_xor_sync(0xffffffffu, mbits, o);
-            mbits = other > mbits ? other : mbits;
+        for (int c = 0; c < NCT; ++c) {
+            float asum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) asum += fabsf(go[c][j]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) asum += __shfl_xor_sync(0xffffffffu, asum, o);
+            if (lane == 0) s_part[c][tid >> 5] = asum;
         }
-        if (lane == 0 && mbits) atomicMax(&s_maxbits, mbits);
     }
 
     // horizontal taps
     int kL[4], kR[4];   // cell of the left / right tap, negative when out of bounds
     int xi0[4];         // low tap index as make_axis returns it, always in [-2, W]
-    S w0[4], w1[4], gmult[4];
+    S_t w0[4], w1[4], gmult[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const S t = N::sub((S)(x0 + j), dd[j]);
-        const S gxn = N::sub(N::mul((S)2, N::div(t, wm1)), (S)1);
-        S ix = N::fma(N::add(gxn, (S)1), halfW, (S)-0.5);
+        const S_t t = N::sub((S_t)(x0 + j), dd[j]);
+        const S_t gxn = N::sub(N::mul((S_t)2, N::div(t, wm1)), (S_t)1);
+        S_t ix = N::fma(N::add(gxn, (S_t)1), halfW, (S_t)-0.5);
         gmult[j] = halfW;
         if (border) {
             // clip_coordinates_set_grad: borders count as out of bounds for the gradient
-            if (ix <= (S)0) { ix = (S)0; gmult[j] = (S)0; }
-            else if (ix >= wm1) { ix = wm1; gmult[j] = (S)0; }
-            else if (!(ix == ix)) ix = clamp_border<S>(ix, W);
+            if (ix <= (S_t)0) { ix = (S_t)0; gmult[j] = (S_t)0; }
+            else if (ix >= wm1) { ix = wm1; gmult[j] = (S_t)0; }
+            else if (!(ix == ix)) ix = clamp_border<S_t>(ix, W);
         }
-        const Axis<S> xa = make_axis<S>(ix, W);
+        const Axis<S_t> xa = make_axis<S_t>(ix, W);
         xi0[j] = xa.i0;
         kL[j] = (active && xa.in0) ? xa.i0 : -1000;
         kR[j] = (active && xa.in1) ? xa.i0 + 1 : -2000;
@@ -706,7 +699,7 @@ __global__ void __launch_bounds__(1024) warp_bwd_hs4_kernel(const float *__restr
     }
     const bool tin = __shfl_up_sync(0xffffffffu, (int)lk[3], 1) != 0 && lane > 0;
 
-    __syncthreads();  // accumulators filled, image rows staged, row maximum known
+    __syncthreads();  // accumulators zeroed, image rows staged, per-warp |g| sums written
 
     if (g_disp && active) {
         float gd[4];
@@ -714,7 +707,7 @@ __global__ void __launch_bounds__(1024) warp_bwd_hs4_kernel(const float *__restr
         for (int j = 0; j < 4; ++j) {
             const int p0 = xi0[j] + 4, p1 = xi0[j] + 5;
             const int s0 = (p0 & 3) * PS + (p0 >> 2), s1 = (p1 & 3) * PS + (p1 >> 2);
-            S gix = (S)0;
+            S_t gix = (S_t)0;
 #pragma unroll
             for (int c = 0; c < NCT; ++c) {
                 const float *r0 = s_rows + (c * 2) * 4 * PS, *r1 = r0 + 4 * PS;
@@ -731,34 +724,43 @@ __global__ void __launch_bounds__(1024) warp_bwd_hs4_kernel(const float *__restr
     }
     if (!gV) return;  // only g_disp requested (block-uniform)
 
-    const unsigned int maxbits = s_maxbits;
-    const int mexp = (int)(maxbits >> 23);
-    const bool finite = mexp != 0xff;
-    int e = 156 - (mexp > 0 ? mexp : 1);  // |g * wx| <= |g| < 2^(mexp-126)  =>  |v * 2^e| < 2^30
+    // S = largest per-channel sum of |g| over the row (same value in every thread: fixed order);
+    // fmaxf would drop a NaN, so non-finite sums are carried by the comparison written this way
+    float S = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCT; ++c) {
+        float sc = 0.f;
+        for (int i = 0; i < (nt >> 5); ++i) sc += s_part[c][i];
+        S = (sc <= S) ? S : sc;
+    }
+    const unsigned int sbits = __float_as_uint(S);
+    const int sexp = (int)(sbits >> 23);     // S >= 0 or NaN: no sign bit to mask
+    const bool finite = sexp < 0xff;          // inf / NaN gradients poison the row
+    int e = 156 - (sexp > 0 ? sexp : 1);      // S < 2^(sexp-126)  =>  S * 2^e < 2^30
     if (e > 127) e = 127;
-    const S up = __uint_as_float((unsigned)(e + 127) << 23);
-    const S down = (e < 127) ? __uint_as_float((unsigned)(127 - e) << 23) : __uint_as_float(0x00400000u);
+    const S_t up = __uint_as_float((unsigned)(e + 127) << 23);
+    const S_t down = (e < 127) ? __uint_as_float((unsigned)(127 - e) << 23) : __uint_as_float(0x00400000u);
 
-    if (finite && maxbits != 0u) {
-        int sL[4], sR[4];  // slot of each tap inside one channel's planes
+    if (finite && S > 0.f) {
+        // byte address of each tap's cell inside channel 0; out-of-bounds taps are never issued
+        uint32_t aL[4], aR[4];
+        S_t u0[4], u1[4];
+        const uint32_t base = smem_u32(acc);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            sL[j] = (kL[j] & 3) * P + (kL[j] >> 2);
-            sR[j] = (kR[j] & 3) * P + (kR[j] >> 2);
+            aL[j] = base + 4u * (uint32_t)((kL[j] & 3) * P + (kL[j] >> 2));
+            aR[j] = base + 4u * (uint32_t)((kR[j] & 3) * P + (kR[j] >> 2));
+            u0[j] = N::mul(w0[j], up);  // exact: up is a power of two
+            u1[j] = N::mul(w1[j], up);
         }
-        auto add = [&](int slot, int q) {
-            const unsigned int old = atomicAdd(&acc_lo[slot], (unsigned int)q);
-            const unsigned int nw = old + (unsigned int)q;
-            const int hadd = (q >> 31) + (nw < old ? 1 : 0);
-            if (hadd != 0) { atomicAdd(&acc_hi[slot], hadd); s_anyhi = 1; }
-        };
+        const uint32_t cstep = 16u * (uint32_t)P;  // bytes between channels
 #pragma unroll
         for (int c = 0; c < NCT; ++c) {
             int qL[4], qR[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                qL[j] = kL[j] >= 0 ? __float2int_rn(N::mul(N::mul(go[c][j], w0[j]), up)) : 0;
-                qR[j] = kR[j] >= 0 ? __float2int_rn(N::mul(N::mul(go[c][j], w1[j]), up)) : 0;
+                qL[j] = kL[j] >= 0 ? __float2int_rn(N::mul(go[c][j], u0[j])) : 0;
+                qR[j] = kR[j] >= 0 ? __float2int_rn(N::mul(go[c][j], u1[j])) : 0;
             }
             const int qin = __shfl_up_sync(0xffffffffu, qR[3], 1);
             if (tin) qL[0] += qin;
@@ -767,25 +769,20 @@ __global__ void __launch_bounds__(1024) warp_bwd_hs4_kernel(const float *__restr
                 if (lk[j - 1]) qL[j] += qR[j - 1];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (kL[j] >= 0) add(c * 4 * P + sL[j], qL[j]);
-                if (kR[j] >= 0 && !lk[j]) add(c * 4 * P + sR[j], qR[j]);
+                red_shared_add(aL[j] + c * cstep, qL[j], kL[j] >= 0);
+                red_shared_add(aR[j] + c * cstep, qR[j], kR[j] >= 0 && !lk[j]);
             }
         }
     }
     __syncthreads();
     if (!active) return;
-    const bool anyhi = s_anyhi != 0;
     float *ob = gV + (size_t)b * NCT * HW + y * W + x0;
 #pragma unroll
     for (int c = 0; c < NCT; ++c) {
         float v[4];
 #pragma unroll
-        for (int pl = 0; pl < 4; ++pl) {
-            const int slot = c * 4 * P + pl * P + tid;
-            if (!finite) v[pl] = __uint_as_float(0x7fc00000u);  // a non-finite gradient poisons the row
-            else if (!anyhi) v[pl] = N::mul((S)(int)(acc_lo[slot] ^ 0x80000000u), down);
-            else v[pl] = N::mul((S)((((long long)acc_hi[slot]) << 32) + (long long)acc_lo[slot] - 0x80000000LL), down);
-        }
+        for (int pl = 0; pl < 4; ++pl)
+            v[pl] = finite ? N::mul((S_t)acc[c * 4 * P + pl * P + tid], down) : __uint_as_float(0x7fc00000u);
         *reinterpret_cast<float4 *>(ob + c * HW) = make_float4(v[0], v[1], v[2], v[3]);
     }
 }
@@ -861,7 +858,7 @@ int warp_bwd_typed(const void *g, const void *img, const void *disp, void *g_img
             void (*kern)(const float *, const float *, const float *, float *, float *, int, int, int, float, float, float) =
                 C == 1 ? warp_bwd_hs4_kernel<1> : C == 2 ? warp_bwd_hs4_kernel<2> : C == 3 ? warp_bwd_hs4_kernel<3> : warp_bwd_hs4_kernel<4>;
             const int W4 = W / 4, P = (W4 + 3) & ~3;
-            const size_t smem4 = ((size_t)2 * C * 4 * P + (g_disp ? (size_t)C * 2 * 4 * (W4 + 2) : 0)) * sizeof(int);
+            const size_t smem4 = ((size_t)C * 4 * P + (g_disp ? (size_t)C * 2 * 4 * (W4 + 2) : 0)) * sizeof(int);
             if (smem4 > 48 * 1024) {
                 cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
                 if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "warp_bwd: cudaFuncSetAttribute(%zu B): %s", smem4, cudaGetErrorString(e));
