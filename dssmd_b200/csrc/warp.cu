@@ -346,14 +346,14 @@ __global__ void __launch_bounds__(256) lrwarp_fwd_kernel(const S *__restrict__ i
 // p & 3, slot p >> 2 -- a thread's taps are ~4 positions from its neighbour lane's, so
 // the lanes of a warp read one plane at consecutive slots (no bank conflicts).
 // ---------------------------------------------------------------------------------
-template <int NCT>
-__global__ void __launch_bounds__(1024) warp_fwd_staged_kernel(const float *__restrict__ img, const float *__restrict__ disp,
+template <int NCT, int PS>  // PS: slots per plane, compile-time (>= W/4 + 2): row / channel offsets become immediates
+__global__ void __launch_bounds__(PS - 2 < 1024 ? PS - 2 : 1024) warp_fwd_staged_kernel(const float *__restrict__ img, const float *__restrict__ disp,
                                                                float *__restrict__ out, float *__restrict__ mask, int *neg_flag,
                                                                int H, int W, int border, float halfW, float halfH) {
     using S = float;
     using N = Num<S>;
     extern __shared__ __align__(16) float s_rows[];  // [NCT][2][4][PS]
-    const int W4 = W >> 2, PS = W4 + 2;
+    const int W4 = W >> 2;
     const int y = blockIdx.x % H;
     const int b = blockIdx.x / H;
     const int HW = H * W;  // C*H*W < 2^31 checked on the host
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(1024) warp_fwd_staged_kernel(const float *__re
     const float4 d4 = active ? *reinterpret_cast<const float4 *>(disp + (size_t)b * HW + y * W + x0) : z4;
     const S dv[4] = {d4.x, d4.y, d4.z, d4.w};
 
-    int s0[4], s1[4];               // shared-memory slot (inside one row) of the low / high x tap
+    const float *t0[4], *t1[4];     // low / high x tap inside the first staged row
     S wa[4], wb[4], wc[4], wd[4];  // tap weights nw, ne, sw, se (0 where the tap is out of bounds)
     S mv[4];
     bool bad = false;
@@ -409,8 +409,8 @@ __global__ void __launch_bounds__(1024) warp_fwd_staged_kernel(const float *__re
         wc[i] = N::mul(ya.w1, xw0);
         wd[i] = N::mul(ya.w1, xw1);
         const int p0 = xa.i0 + 4, p1 = xa.i0 + 5;  // make_axis keeps i0 in [-2, W]
-        s0[i] = (p0 & 3) * PS + (p0 >> 2);
-        s1[i] = (p1 & 3) * PS + (p1 >> 2);
+        t0[i] = s_rows + (p0 & 3) * PS + (p0 >> 2);
+        t1[i] = s_rows + (p1 & 3) * PS + (p1 >> 2);
     }
     if (active && bad && neg_flag) *reinterpret_cast<volatile int *>(neg_flag) = 1;  // plain store: may be mapped host memory
 
@@ -435,15 +435,15 @@ __global__ void __launch_bounds__(1024) warp_fwd_staged_kernel(const float *__re
 
 #pragma unroll
     for (int c = 0; c < NCT; ++c) {
-        const float *r0 = s_rows + (c * 2) * 4 * PS, *r1 = r0 + 4 * PS;
+        constexpr int R = 4 * PS;  // one staged row
         float v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             S acc = (S)0;
-            acc = N::fma(r0[s0[i]], wa[i], acc);
-            acc = N::fma(r0[s1[i]], wb[i], acc);
-            acc = N::fma(r1[s0[i]], wc[i], acc);
-            acc = N::fma(r1[s1[i]], wd[i], acc);
+            acc = N::fma(t0[i][(2 * c) * R], wa[i], acc);
+            acc = N::fma(t1[i][(2 * c) * R], wb[i], acc);
+            acc = N::fma(t0[i][(2 * c + 1) * R], wc[i], acc);
+            acc = N::fma(t1[i][(2 * c + 1) * R], wd[i], acc);
             v[i] = acc;
         }
         const size_t o = ((size_t)b * NCT + c) * HW + y * W + x0;
@@ -466,10 +466,17 @@ int warp_fwd_typed(const void *img, const void *disp, void *warped, void *mask, 
     S *op = (S *)warped, *mp = (S *)mask;
     if constexpr (sizeof(S) == 4) {
         if (vec && C <= 4 && W <= 4096 && H >= 2 && (long long)C * H * W < (1LL << 31) && env_int("DSSMD_WARP_FWD_VARIANT", 1) >= 1) {
-            void (*kern)(const float *, const float *, float *, float *, int *, int, int, int, float, float) =
-                C == 1 ? warp_fwd_staged_kernel<1> : C == 2 ? warp_fwd_staged_kernel<2>
-                : C == 3 ? warp_fwd_staged_kernel<3> : warp_fwd_staged_kernel<4>;
-            const size_t smem = (size_t)C * 2 * 4 * (W / 4 + 2) * sizeof(float);
+            void (*kern)(const float *, const float *, float *, float *, int *, int, int, int, float, float) = nullptr;
+            int ps = 0;
+#define DSSMD_FWD_PICK(PSV)                                                                                        \
+    if (!kern && W / 4 + 2 <= PSV) {                                                                               \
+        ps = PSV;                                                                                                  \
+        kern = C == 1 ? warp_fwd_staged_kernel<1, PSV> : C == 2 ? warp_fwd_staged_kernel<2, PSV>                   \
+             : C == 3 ? warp_fwd_staged_kernel<3, PSV> : warp_fwd_staged_kernel<4, PSV>;                           \
+    }
+            DSSMD_FWD_PICK(66) DSSMD_FWD_PICK(130) DSSMD_FWD_PICK(258) DSSMD_FWD_PICK(514) DSSMD_FWD_PICK(1026)
+#undef DSSMD_FWD_PICK
+            const size_t smem = (size_t)C * 2 * 4 * ps * sizeof(float);
             if (smem > 48 * 1024) {
                 cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "warp_fwd: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));

@@ -579,8 +579,9 @@ __device__ __forceinline__ void red_shared_add(uint32_t addr, int q, bool pred) 
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p red.shared.add.s32 [%0], %1;\n\t}" ::"r"(addr), "r"(q), "r"((int)pred) : "memory");
 }
 
-template <int NCT>
-__global__ void __launch_bounds__(1024) warp_bwd_hs4_kernel(const float *__restrict__ g, const float *__restrict__ img,
+template <int NCT, int PS>  // PS: slots per shared-memory plane, a compile-time constant >= W/4 + 2 so that every
+                            // channel / row / plane offset folds into the LDS / RED immediates
+__global__ void __launch_bounds__(PS - 2 < 1024 ? PS - 2 : 1024) warp_bwd_hs4_kernel(const float *__restrict__ g, const float *__restrict__ img,
                                                             const float *__restrict__ disp, float *__restrict__ gV,
                                                             float *__restrict__ g_disp, int H, int W, int border,
                                                             float halfW, float tscale, float halfH) {
@@ -588,8 +589,7 @@ __global__ void __launch_bounds__(1024) warp_bwd_hs4_kernel(const float *__restr
     using N = Num<S_t>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int W4 = W >> 2;
-    const int P = (W4 + 3) & ~3;                                          // accumulator slots per plane
-    const int PS = W4 + 2;                                                // staged image row: slots per plane
+    constexpr int P = PS - 2;                                             // accumulator slots per plane (>= W/4)
     int *acc = reinterpret_cast<int *>(smem_raw);                        // [NCT][4][P]
     float *s_rows = reinterpret_cast<float *>(smem_raw) + NCT * 4 * P;   // [NCT][2][4][PS], only with g_disp
     __shared__ float s_part[NCT][32];                                     // per-warp, per-channel sums of |g|
@@ -706,16 +706,16 @@ __global__ void __launch_bounds__(1024) warp_bwd_hs4_kernel(const float *__restr
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int p0 = xi0[j] + 4, p1 = xi0[j] + 5;
-            const int s0 = (p0 & 3) * PS + (p0 >> 2), s1 = (p1 & 3) * PS + (p1 >> 2);
+            const float *t0 = s_rows + (p0 & 3) * PS + (p0 >> 2), *t1 = s_rows + (p1 & 3) * PS + (p1 >> 2);
             S_t gix = (S_t)0;
 #pragma unroll
             for (int c = 0; c < NCT; ++c) {
-                const float *r0 = s_rows + (c * 2) * 4 * PS, *r1 = r0 + 4 * PS;
+                constexpr int R = 4 * PS;  // one staged row
                 // d(sample)/d(ix), ATen order nw, ne, sw, se; out-of-bounds taps read the zero padding
-                gix = N::sub(gix, N::mul(N::mul(r0[s0], ya.w0), go[c][j]));
-                gix = N::add(gix, N::mul(N::mul(r0[s1], ya.w0), go[c][j]));
-                gix = N::sub(gix, N::mul(N::mul(r1[s0], ya.w1), go[c][j]));
-                gix = N::add(gix, N::mul(N::mul(r1[s1], ya.w1), go[c][j]));
+                gix = N::sub(gix, N::mul(N::mul(t0[(2 * c) * R], ya.w0), go[c][j]));
+                gix = N::add(gix, N::mul(N::mul(t1[(2 * c) * R], ya.w0), go[c][j]));
+                gix = N::sub(gix, N::mul(N::mul(t0[(2 * c + 1) * R], ya.w1), go[c][j]));
+                gix = N::add(gix, N::mul(N::mul(t1[(2 * c + 1) * R], ya.w1), go[c][j]));
             }
             // chain rule: ix <- gx (W/2, 0 where clipped) <- t (2/(W-1)) <- disp (-1)
             gd[j] = -N::mul(tscale, N::mul(gmult[j], gix));
@@ -724,13 +724,15 @@ __global__ void __launch_bounds__(1024) warp_bwd_hs4_kernel(const float *__restr
     }
     if (!gV) return;  // only g_disp requested (block-uniform)
 
-    // S = largest per-channel sum of |g| over the row (same value in every thread: fixed order);
-    // fmaxf would drop a NaN, so non-finite sums are carried by the comparison written this way
+    // S = largest per-channel sum of |g| over the row: every warp reduces the per-warp partials with
+    // the same butterfly, so all threads hold the same value.  Written as a comparison because
+    // fmaxf would drop a NaN.
     float S = 0.f;
 #pragma unroll
     for (int c = 0; c < NCT; ++c) {
-        float sc = 0.f;
-        for (int i = 0; i < (nt >> 5); ++i) sc += s_part[c][i];
+        float sc = lane < (nt >> 5) ? s_part[c][lane] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
         S = (sc <= S) ? S : sc;
     }
     const unsigned int sbits = __float_as_uint(S);
@@ -753,7 +755,7 @@ __global__ void __launch_bounds__(1024) warp_bwd_hs4_kernel(const float *__restr
             u0[j] = N::mul(w0[j], up);  // exact: up is a power of two
             u1[j] = N::mul(w1[j], up);
         }
-        const uint32_t cstep = 16u * (uint32_t)P;  // bytes between channels
+        constexpr uint32_t cstep = 16u * (uint32_t)P;  // bytes between channels
 #pragma unroll
         for (int c = 0; c < NCT; ++c) {
             int qL[4], qR[4];
@@ -855,10 +857,18 @@ int warp_bwd_typed(const void *g, const void *img, const void *disp, void *g_img
         if (variant >= 4 && C <= 4 && W % 4 == 0 && W <= 4096 && H >= 2 && (long long)C * H * W < (1LL << 31) && (have_ws || !g_img) &&
             ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(disp) | reinterpret_cast<uintptr_t>(workspace) |
               reinterpret_cast<uintptr_t>(g_disp)) & 15) == 0) {
-            void (*kern)(const float *, const float *, const float *, float *, float *, int, int, int, float, float, float) =
-                C == 1 ? warp_bwd_hs4_kernel<1> : C == 2 ? warp_bwd_hs4_kernel<2> : C == 3 ? warp_bwd_hs4_kernel<3> : warp_bwd_hs4_kernel<4>;
-            const int W4 = W / 4, P = (W4 + 3) & ~3;
-            const size_t smem4 = ((size_t)C * 4 * P + (g_disp ? (size_t)C * 2 * 4 * (W4 + 2) : 0)) * sizeof(int);
+            void (*kern)(const float *, const float *, const float *, float *, float *, int, int, int, float, float, float) = nullptr;
+            const int W4 = W / 4;
+            int ps = 0;
+#define DSSMD_HS4_PICK(PSV)                                                                                        \
+    if (!kern && W4 + 2 <= PSV) {                                                                                  \
+        ps = PSV;                                                                                                  \
+        kern = C == 1 ? warp_bwd_hs4_kernel<1, PSV> : C == 2 ? warp_bwd_hs4_kernel<2, PSV>                         \
+             : C == 3 ? warp_bwd_hs4_kernel<3, PSV> : warp_bwd_hs4_kernel<4, PSV>;                                 \
+    }
+            DSSMD_HS4_PICK(66) DSSMD_HS4_PICK(130) DSSMD_HS4_PICK(258) DSSMD_HS4_PICK(514) DSSMD_HS4_PICK(1026)
+#undef DSSMD_HS4_PICK
+            const size_t smem4 = ((size_t)C * 4 * (ps - 2) + (g_disp ? (size_t)C * 2 * 4 * ps : 0)) * sizeof(int);
             if (smem4 > 48 * 1024) {
                 cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
                 if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "warp_bwd: cudaFuncSetAttribute(%zu B): %s", smem4, cudaGetErrorString(e));

@@ -60,3 +60,12 @@ for k, (ex, smp) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
             srcs.setdefault(path, open(path).read().splitlines())
             text = srcs[path][k[1] - 1].strip()[:90]
     print(f"{str(k):28s} exec {100*ex/tot_ex:5.1f}%  samples {100*smp/tot_s:5.1f}%  {text}")
+if os.environ.get("NCU_LINES_UNMAPPED"):
+    print("---- unmapped instructions (offset, executed/warp-launch, sass) ----")
+    n = 0
+    for off in sorted(metrics):
+        if line_of.get(off) is None and metrics[off][0] > 0:
+            print(f"{off:6x} {metrics[off][0]:9d} {metrics[off][2][:100]}")
+            n += 1
+            if n > int(os.environ["NCU_LINES_UNMAPPED"]):
+                break
