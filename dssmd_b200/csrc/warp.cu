@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(256) lrwarp_fwd_kernel(const S *__restrict__ i
 // the lanes of a warp read one plane at consecutive slots (no bank conflicts).
 // ---------------------------------------------------------------------------------
 template <int NCT, int PS>  // PS: slots per plane, compile-time (>= W/4 + 2): row / channel offsets become immediates
-__global__ void __launch_bounds__(PS - 2 < 1024 ? PS - 2 : 1024) warp_fwd_staged_kernel(const float *__restrict__ img, const float *__restrict__ disp,
+__global__ void __launch_bounds__(PS - 2, 1024 / (PS - 2)) warp_fwd_staged_kernel(const float *__restrict__ img, const float *__restrict__ disp,
                                                                float *__restrict__ out, float *__restrict__ mask, int *neg_flag,
                                                                int H, int W, int border, float halfW, float halfH) {
     using S = float;

@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(1024, 1) warp_bwd_hscatter_kernel(const float 
 //     land on the same cell (x' = x - disp is close to monotone), across lanes by shuffle;
 //   * the accumulator of a cell is ONE 32-bit integer and every merged tap ONE fire-and-forget
 //     shared atomic: contributions are quantised to q = rn(v * 2^e) with e chosen per row from
-//     S = max_c sum_x |g[c]| such that S * 2^e <= 2^30.  Every cell sum is bounded by S (the tap
+//     S = sum_x |g[c]| (per channel) such that S * 2^e <= 2^30.  Every cell sum is bounded by S (the tap
 //     weights of a pixel add up to <= 1), so no cell can overflow however many taps collect
 //     in it (cells at a clamped border collect hundreds), integer adds are associative, and
 //     the result is deterministic.  Quantum relative to the row's mean |g|: <= W * 2^-29;
@@ -581,7 +581,7 @@ __device__ __forceinline__ void red_shared_add(uint32_t addr, int q, bool pred) 
 
 template <int NCT, int PS>  // PS: slots per shared-memory plane, a compile-time constant >= W/4 + 2 so that every
                             // channel / row / plane offset folds into the LDS / RED immediates
-__global__ void __launch_bounds__(PS - 2 < 1024 ? PS - 2 : 1024) warp_bwd_hs4_kernel(const float *__restrict__ g, const float *__restrict__ img,
+__global__ void __launch_bounds__(PS - 2, 1024 / (PS - 2)) warp_bwd_hs4_kernel(const float *__restrict__ g, const float *__restrict__ img,
                                                             const float *__restrict__ disp, float *__restrict__ gV,
                                                             float *__restrict__ g_disp, int H, int W, int border,
                                                             float halfW, float tscale, float halfH) {
@@ -724,36 +724,32 @@ __global__ void __launch_bounds__(PS - 2 < 1024 ? PS - 2 : 1024) warp_bwd_hs4_ke
     }
     if (!gV) return;  // only g_disp requested (block-uniform)
 
-    // S = largest per-channel sum of |g| over the row: every warp reduces the per-warp partials with
-    // the same butterfly, so all threads hold the same value.  Written as a comparison because
-    // fmaxf would drop a NaN.
-    float S = 0.f;
+    // S[c] = sum of |g[c]| over the row: every warp reduces the per-warp partials with the same
+    // butterfly, so all threads hold the same values.  One scale per channel and row.
+    S_t up[NCT], down[NCT];
+    bool finite[NCT], any = false;
 #pragma unroll
     for (int c = 0; c < NCT; ++c) {
         float sc = lane < (nt >> 5) ? s_part[c][lane] : 0.f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, o);
-        S = (sc <= S) ? S : sc;
+        const int sexp = (int)(__float_as_uint(sc) >> 23);  // sc >= 0 or NaN: no sign bit to mask
+        finite[c] = sexp < 0xff;                             // inf / NaN gradients poison the row
+        int e = 156 - (sexp > 0 ? sexp : 1);                 // sc < 2^(sexp-126)  =>  sc * 2^e < 2^30
+        if (e > 127) e = 127;
+        up[c] = (finite[c] && sc > 0.f) ? __uint_as_float((unsigned)(e + 127) << 23) : 0.f;  // 0: nothing to add
+        down[c] = (e < 127) ? __uint_as_float((unsigned)(127 - e) << 23) : __uint_as_float(0x00400000u);
+        any = any || up[c] != 0.f;
     }
-    const unsigned int sbits = __float_as_uint(S);
-    const int sexp = (int)(sbits >> 23);     // S >= 0 or NaN: no sign bit to mask
-    const bool finite = sexp < 0xff;          // inf / NaN gradients poison the row
-    int e = 156 - (sexp > 0 ? sexp : 1);      // S < 2^(sexp-126)  =>  S * 2^e < 2^30
-    if (e > 127) e = 127;
-    const S_t up = __uint_as_float((unsigned)(e + 127) << 23);
-    const S_t down = (e < 127) ? __uint_as_float((unsigned)(127 - e) << 23) : __uint_as_float(0x00400000u);
 
-    if (finite && S > 0.f) {
+    if (any) {
         // byte address of each tap's cell inside channel 0; out-of-bounds taps are never issued
         uint32_t aL[4], aR[4];
-        S_t u0[4], u1[4];
         const uint32_t base = smem_u32(acc);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             aL[j] = base + 4u * (uint32_t)((kL[j] & 3) * P + (kL[j] >> 2));
             aR[j] = base + 4u * (uint32_t)((kR[j] & 3) * P + (kR[j] >> 2));
-            u0[j] = N::mul(w0[j], up);  // exact: up is a power of two
-            u1[j] = N::mul(w1[j], up);
         }
         constexpr uint32_t cstep = 16u * (uint32_t)P;  // bytes between channels
 #pragma unroll
@@ -761,8 +757,10 @@ __global__ void __launch_bounds__(PS - 2 < 1024 ? PS - 2 : 1024) warp_bwd_hs4_ke
             int qL[4], qR[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                qL[j] = kL[j] >= 0 ? __float2int_rn(N::mul(go[c][j], u0[j])) : 0;
-                qR[j] = kR[j] >= 0 ? __float2int_rn(N::mul(go[c][j], u1[j])) : 0;
+                // scaling by a power of two is exact, so this is rn(g * w) * 2^e rounded to an integer
+                const S_t gs = N::mul(go[c][j], up[c]);
+                qL[j] = kL[j] >= 0 ? __float2int_rn(N::mul(gs, w0[j])) : 0;
+                qR[j] = kR[j] >= 0 ? __float2int_rn(N::mul(gs, w1[j])) : 0;
             }
             const int qin = __shfl_up_sync(0xffffffffu, qR[3], 1);
             if (tin) qL[0] += qin;
@@ -784,7 +782,7 @@ __global__ void __launch_bounds__(PS - 2 < 1024 ? PS - 2 : 1024) warp_bwd_hs4_ke
         float v[4];
 #pragma unroll
         for (int pl = 0; pl < 4; ++pl)
-            v[pl] = finite ? N::mul((S_t)acc[c * 4 * P + pl * P + tid], down) : __uint_as_float(0x7fc00000u);
+            v[pl] = finite[c] ? N::mul((S_t)acc[c * 4 * P + pl * P + tid], down[c]) : __uint_as_float(0x7fc00000u);
         *reinterpret_cast<float4 *>(ob + c * HW) = make_float4(v[0], v[1], v[2], v[3]);
     }
 }

@@ -72,6 +72,9 @@ CORR_SHAPES = [
     (1, 64, 2, 300, 192, True),    # large D, x-tiled
     (3, 8, 33, 16, 5, True),       # many rows per block
     (1, 32, 4, 520, 40, False),    # W > 256: several x tiles
+    (2, 70, 3, 244, 100, True),    # backward fast path: 16 lanes per pixel group, x-tiled, ragged channel blocks
+    (1, 24, 2, 1000, 12, False),   # backward fast path: one lane per group, D = 12 exactly, 5 x tiles
+    (1, 8, 2, 64, 192, True),      # backward fast path: largest supported D
 ]
 
 
@@ -232,7 +235,10 @@ def images(B, C, H, W, seed, smooth=True):
 
 
 @pytest.mark.parametrize("pad", ["border", "zeros"])
-@pytest.mark.parametrize("shape", [(2, 3, 40, 80), (1, 3, 33, 157), (1, 1, 2, 9), (1, 7, 16, 64), (2, 3, 64, 1280)],
+@pytest.mark.parametrize("shape", [(2, 3, 40, 80), (1, 3, 33, 157), (1, 1, 2, 9), (1, 7, 16, 64), (2, 3, 64, 1280),
+                                   (1, 4, 5, 256),    # staged kernels: 4 channels, widest row of the first plane class
+                                   (1, 2, 3, 2064),   # ... and of the last one (W/4 + 2 > 514)
+                                   (1, 3, 2, 12)],    # one warp per row, 3 of 32 lanes active
                          ids=lambda s: "x".join(map(str, s)))
 def test_warp_vs_oracle(ops, oracle, shape, pad):
     B, C, H, W = shape
@@ -296,6 +302,48 @@ def test_warp_f64_gradcheck(ops):
     disp = (torch.rand((1, 1, 5, 8), generator=g, device="cuda", dtype=torch.float64) * 3 + 0.3).requires_grad_(True)
     for pad in ("border", "zeros"):
         assert torch.autograd.gradcheck(lambda a, b: ops.disp_warp(a, b, pad)[0], (img, disp), eps=1e-6, atol=1e-5)
+
+
+def test_warp_bwd_many_taps_in_one_cell(ops, oracle):
+    """Border mode clamps every pixel whose disparity exceeds x to column 0: one cell of
+    g_img collects a whole row of gradients.  The integer accumulators must neither
+    overflow nor lose the small terms next to the large ones."""
+    B, C, H, W = 1, 3, 5, 512
+    g0 = torch.Generator(device="cuda").manual_seed(3)
+    img = torch.rand((B, C, H, W), generator=g0, device="cuda").requires_grad_(True)
+    disp = torch.full((B, 1, H, W), 600.0, device="cuda")
+    disp[:, :, :, W // 2:] = 3.25                     # right half: ordinary sub-pixel shift
+    disp.requires_grad_(True)
+    g = torch.randn((B, C, H, W), generator=g0, device="cuda")
+    g[:, 0] = g[:, 0].abs() * 1e3 + 1.0               # same-sign, large: the sum is ~256x a single term
+    g[:, 1, :, 7] = 1e6                               # one outlier next to unit-sized terms
+    warped, _ = ops.disp_warp(img, disp)
+    warped.backward(g)
+    gi_ref, gd_ref = oracle.warp_bwd(g.cpu().numpy(), img.detach().cpu().numpy(), disp.detach().cpu().numpy(), "border")
+    assert rel_err(img.grad.cpu().numpy(), gi_ref) <= TOL_F32
+    assert rel_err(disp.grad.cpu().numpy(), gd_ref) <= TOL_F32
+    # per channel too: the outlier of channel 1 must not wash out channels 0 and 2
+    for c in range(C):
+        assert rel_err(img.grad[:, c].cpu().numpy(), gi_ref[:, c]) <= TOL_F32
+    # bit-for-bit repeatable
+    img2 = img.detach().clone().requires_grad_(True)
+    w2, _ = ops.disp_warp(img2, disp.detach())
+    w2.backward(g)
+    assert torch.equal(img2.grad, img.grad)
+
+
+def test_warp_bwd_nonfinite_gradient_poisons_only_its_rows(ops):
+    B, C, H, W = 1, 3, 8, 64
+    img, disp = images(B, C, H, W, 9)
+    img.requires_grad_(True)
+    g = torch.ones((B, C, H, W), device="cuda")
+    g[0, 1, 4, 10] = float("inf")
+    warped, _ = ops.disp_warp(img, disp)
+    warped.backward(g)
+    gi = img.grad
+    bad_rows = (~torch.isfinite(gi)).any(dim=3).any(dim=1)[0].nonzero().flatten().tolist()
+    assert bad_rows and set(bad_rows) <= {3, 4, 5}   # output row 4 blends into image rows 3..5 at most
+    assert torch.isfinite(gi[:, :, :3]).all() and torch.isfinite(gi[:, :, 6:]).all()
 
 
 def test_warp_error_conventions(ops):
