@@ -131,6 +131,16 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------
 # synthetic data, seeded like upstream scripts/train.sh:33
 # ----------------------------------------------------------------------------------
+def measured_traffic(workload, kernel):
+    """DRAM bytes (read + write) per call of `kernel`, from the committed ncu --set full capture
+    of this workload (profiles/traffic.json, written by scripts/profile_summary.py); None if absent."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as f:
+            return json.load(f)[workload][kernel]["dram_bytes"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def make_set(torch, w, device, seed):
     g = torch.Generator(device=device).manual_seed(seed)
     B, C, Hf, Wf, D, H, W = (w[k] for k in ("B", "C", "Hf", "Wf", "D", "H", "W"))
@@ -270,7 +280,8 @@ def run_gpu(args, w):
     stream = torch.cuda.current_stream(device)
     calls = [kernel_calls(torch, lib, _lib, w, s) for s in sets]
     names = list(calls[0].keys())
-    launches_per_step = len(names)
+    # dssmd_warp_bwd is two kernels (horizontal scatter, vertical mix); the other calls are one each
+    launches_per_step = sum(2 if n == "warp_bwd" else 1 for n in names)
     set_bytes = sum(t.numel() * t.element_size() for t in sets[0].values())
 
     def eager_step(i):
@@ -428,7 +439,7 @@ def run_gpu(args, w):
     if rank == 0:
         dom = max(kern, key=lambda n: kern[n]["us"])
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                    "frac": kern[dom]["frac_of_peak"], "traffic": None, "peak_source": peak_src,
+                    "frac": kern[dom]["frac_of_peak"], "traffic": measured_traffic(args.workload, dom), "peak_source": peak_src,
                     "share_of_step": round(kern[dom]["us"] / sum(k["us"] for k in kern.values()), 3)}
         # CPU baseline: oracle port, bounded sample (one per-GPU batch, best of 2)
         cpu = None

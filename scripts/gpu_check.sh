@@ -8,6 +8,7 @@ OUT=gpurun_out/$TAG
 mkdir -p "$OUT"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > "$OUT/gpu.csv" 2>&1
 
+if [ "${MODE:-launches}" = "launches" ]; then
 timeout 1200 python -m pytest tests -m gpu -q --timeout 300 -p no:cacheprovider > "$OUT/pytest.log" 2>&1
 echo "pytest exit $?" >> "$OUT/pytest.log"
 tail -n 30 "$OUT/pytest.log"
@@ -22,16 +23,19 @@ for w in sceneflow_576x960 corr_micro kitti_384x1280 train_320x640; do
 done
 cat "$OUT/bench_sceneflow_576x960.json"
 
-if [ "${SKIP_NCU:-0}" != "1" ]; then
-  CMD="python bench.py --steps 4 --warmup 3 --no-graph --no-cpu-baseline"
+fi
+
+# One ncu pattern per gpurun call: MODE=launches (default) or MODE=full
+CMD="python bench.py --steps 4 --warmup 3 --no-graph --no-cpu-baseline"
+if [ "${MODE:-launches}" = "launches" ]; then
   timeout 300 $CMD > "$OUT/ncu_plain.log" 2>&1 &&
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
       --log-file "$OUT/launches.csv" $CMD > "$OUT/ncu_launches.log" 2>&1
   echo "ncu launches exit $?"
-  CMD2="python bench.py --workload corr_micro --steps 4 --warmup 3 --no-graph --no-cpu-baseline"
-  timeout 300 $CMD2 > "$OUT/ncu_plain2.log" 2>&1 &&
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'corr_|warp_' -s 20 -c 5 \
-      -o "$OUT/prof_corr_micro" $CMD2 > "$OUT/ncu_full.log" 2>&1
+else
+  timeout 300 $CMD > "$OUT/ncu_plain.log" 2>&1 &&
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'corr_|warp_' -s 12 -c 6 \
+      -o "$OUT/prof" $CMD > "$OUT/ncu_full.log" 2>&1
   echo "ncu full exit $?"
 fi
 ls -la "$OUT"
