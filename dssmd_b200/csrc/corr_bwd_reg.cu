@@ -49,16 +49,63 @@ struct RegParams {
     float invC;
 };
 
-template <int MODE, int LOGNH>
-__global__ void __launch_bounds__(512) corr_bwd_reg_kernel(const RegParams p, const __grid_constant__ CUtensorMap mapIn,
-                                                           const __grid_constant__ CUtensorMap mapG) {
+// Lane -> (pixel group pgl, disparity part h).  A lane's window starts at 16-byte chunk
+// (PX/4)*pgl -+ 3*h of the staged row, and an LDS.128 is served a quarter-warp (8 consecutive lanes) at a
+// time: the map puts the lane bits so that the 8 chunks of every quarter-warp are distinct modulo 8, i.e. the
+// window loads are free of bank conflicts.  kHPos[k] is the lane bit that carries bit k of h.
+template <int LOGNH, int PX> struct LaneMap;
+template <int PX> struct LaneMap<0, PX> {
+    static __device__ __forceinline__ int h(int) { return 0; }
+    static __device__ __forceinline__ int pgl(int lane) { return lane; }
+    static __device__ __forceinline__ constexpr int hpos(int) { return 0; }
+};
+template <> struct LaneMap<1, 4> {  // chunks pgl - 3h: 8 consecutive pgl per quarter-warp
+    static __device__ __forceinline__ int h(int lane) { return lane >> 4; }
+    static __device__ __forceinline__ int pgl(int lane) { return lane & 15; }
+    static __device__ __forceinline__ constexpr int hpos(int) { return 4; }
+};
+template <> struct LaneMap<2, 4> {
+    static __device__ __forceinline__ int h(int lane) { return lane >> 3; }
+    static __device__ __forceinline__ int pgl(int lane) { return lane & 7; }
+    static __device__ __forceinline__ constexpr int hpos(int k) { return 3 + k; }
+};
+template <> struct LaneMap<3, 4> {  // quarter-warp: pgl 0..3 and h2 (-12 chunks = 4 mod 8)
+    static __device__ __forceinline__ int h(int lane) { return ((lane >> 3) & 3) | (lane & 4); }
+    static __device__ __forceinline__ int pgl(int lane) { return lane & 3; }
+    static __device__ __forceinline__ constexpr int hpos(int k) { return k == 2 ? 2 : 3 + k; }
+};
+template <> struct LaneMap<4, 4> {  // quarter-warp: pgl 0..1, h1 (-6 = 2), h2 (-12 = 4)
+    static __device__ __forceinline__ int h(int lane) { return ((lane >> 3) & 1) | (lane & 6) | ((lane >> 1) & 8); }
+    static __device__ __forceinline__ int pgl(int lane) { return lane & 1; }
+    static __device__ __forceinline__ constexpr int hpos(int k) { return k == 0 ? 3 : k == 3 ? 4 : k; }
+};
+template <> struct LaneMap<1, 8> {  // chunks 2*pgl - 3h: quarter-warp = pgl 0..3 (even chunks) x h0 (odd shift)
+    static __device__ __forceinline__ int h(int lane) { return (lane >> 2) & 1; }
+    static __device__ __forceinline__ int pgl(int lane) { return (lane & 3) | ((lane >> 1) & 12); }
+    static __device__ __forceinline__ constexpr int hpos(int) { return 2; }
+};
+template <> struct LaneMap<2, 8> {
+    static __device__ __forceinline__ int h(int lane) { return ((lane >> 2) & 1) | ((lane >> 3) & 2); }
+    static __device__ __forceinline__ int pgl(int lane) { return (lane & 3) | ((lane >> 1) & 4); }
+    static __device__ __forceinline__ constexpr int hpos(int k) { return k == 0 ? 2 : 4; }
+};
+template <> struct LaneMap<3, 8> {
+    static __device__ __forceinline__ int h(int lane) { return lane >> 2; }
+    static __device__ __forceinline__ int pgl(int lane) { return lane & 3; }
+    static __device__ __forceinline__ constexpr int hpos(int k) { return 2 + k; }
+};
+
+template <int MODE, int LOGNH, int PX>
+__global__ void __launch_bounds__(PX == 4 ? 512 : 256) corr_bwd_reg_kernel(const RegParams p, const __grid_constant__ CUtensorMap mapIn,
+                                                                            const __grid_constant__ CUtensorMap mapG) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long s_bar[2];
     // stage s: operand tile [CB][WP] then g tile [D][GW], each 128-byte aligned
     const uint32_t op_stride = (p.op_bytes + 127u) & ~127u, g_stride = (p.g_bytes + 127u) & ~127u;
     const uint32_t stage_bytes = op_stride + g_stride;
 
-    constexpr int PX = 4, NH = 1 << LOGNH;
+    constexpr int NH = 1 << LOGNH;
+    using LM = LaneMap<LOGNH, PX>;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i0 = blockIdx.x * p.ipb;
     const int i1 = (i0 + p.ipb < p.nitems) ? i0 + p.ipb : p.nitems;
@@ -88,7 +135,7 @@ __global__ void __launch_bounds__(512) corr_bwd_reg_kernel(const RegParams p, co
 
     // this lane's pixels (inside the x tile) and disparity part
     const int wseg = warp % p.WPR, cgw = warp / p.WPR;
-    const int h = lane & (NH - 1), pgl = lane >> LOGNH;
+    const int h = LM::h(lane), pgl = LM::pgl(lane);
     const int xl = (wseg * (32 >> LOGNH) + pgl) * PX;  // < TX by construction
     const int woff = MODE == 0 ? xl + kDP * NH - kDP * (h + 1) : xl + kDP * h;  // window start inside a staged row
     const size_t HW = (size_t)p.H * p.W;
@@ -129,11 +176,23 @@ __global__ void __launch_bounds__(512) corr_bwd_reg_kernel(const RegParams p, co
         const int c0 = cb * p.CB;
         const int cn = (p.C - c0 < p.CB) ? p.C - c0 : p.CB;
         const int x = X0 + xl;
-        // lanes of a pixel group share the store: after the butterfly every lane holds the 4 sums,
-        // lane h writes 4/NH of them (NH = 2: a float2 each, NH >= 4: lanes 0..3 one float each)
-        constexpr int SPL = NH >= 4 ? 1 : 4 / NH;   // floats per storing lane
-        const bool storer = (NH <= 4 || h < 4) && (x + h * SPL < p.W);
-        float *o = p.out + ((size_t)b * p.C + c0 + cgw) * HW + (size_t)y * p.W + x + h * SPL;
+        // The NH partial sums of a pixel group are combined by a reduce-scatter: in round r the lanes that
+        // differ in bit r of h exchange halves, so after min(LOGNH, log2 PX) rounds a lane owns PX >> rounds
+        // finished pixels (at offset `xo` inside the group); further rounds (NH > PX) are a butterfly on the
+        // single remaining value and only the lanes whose extra h bits are 0 store.  Fixed order: deterministic.
+        constexpr int LOGPX = PX == 8 ? 3 : 2;
+        constexpr int RS = LOGNH < LOGPX ? LOGNH : LOGPX;   // reduce-scatter rounds
+        constexpr int SPL = PX >> RS;                        // finished pixels per lane
+        int xo = 0;
+        bool storer = true;
+#pragma unroll
+        for (int r = 0; r < LOGNH; ++r) {
+            const int bit = (h >> r) & 1;
+            if (r < RS) xo += bit * (PX >> (r + 1));
+            else storer = storer && !bit;
+        }
+        storer = storer && (x + xo < p.W);   // W % 4 == 0 and x + xo is a multiple of SPL <= 4: all or nothing
+        float *o = p.out + ((size_t)b * p.C + c0 + cgw) * HW + (size_t)y * p.W + x + xo;
         const size_t ostep = (size_t)p.CGW * HW;
         const float *wrow = ops + cgw * p.WP + woff;
         const int wstep = p.CGW * p.WP;
@@ -147,26 +206,57 @@ __global__ void __launch_bounds__(512) corr_bwd_reg_kernel(const RegParams p, co
                 w[4 * q + 0] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
             }
             float acc[PX];
+            if constexpr (PX == 4) {  // two chains per pixel: a warp then has 8 (16 with the unroll) independent FFMAs in flight
+                float acb[PX];
 #pragma unroll
-            for (int i = 0; i < PX; ++i) acc[i] = 0.f;
+                for (int i = 0; i < PX; ++i) {
+                    acc[i] = gv[0][i] * w[MODE == 0 ? i + kDP : i];
+                    acb[i] = gv[1][i] * w[MODE == 0 ? i - 1 + kDP : i + 1];
+                }
 #pragma unroll
-            for (int dd = 0; dd < kDP; ++dd)
+                for (int dd = 2; dd < kDP; dd += 2)
 #pragma unroll
-                for (int i = 0; i < PX; ++i)
-                    acc[i] = fmaf(gv[dd][i], w[MODE == 0 ? i - dd + kDP : i + dd], acc[i]);
+                    for (int i = 0; i < PX; ++i) {
+                        acc[i] = fmaf(gv[dd][i], w[MODE == 0 ? i - dd + kDP : i + dd], acc[i]);
+                        acb[i] = fmaf(gv[dd + 1][i], w[MODE == 0 ? i - dd - 1 + kDP : i + dd + 1], acb[i]);
+                    }
 #pragma unroll
-            for (int sft = 1; sft < NH; sft <<= 1)
+                for (int i = 0; i < PX; ++i) acc[i] += acb[i];
+            } else {
 #pragma unroll
-                for (int i = 0; i < PX; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], sft);
-            if (storer) {
-                if constexpr (NH == 1) {
-                    st_global_cs(reinterpret_cast<float4 *>(o), make_float4(acc[0], acc[1], acc[2], acc[3]));
-                } else if constexpr (NH == 2) {
-                    const float2 v = h ? make_float2(acc[2], acc[3]) : make_float2(acc[0], acc[1]);
-                    asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(o), "f"(v.x), "f"(v.y) : "memory");
+                for (int i = 0; i < PX; ++i) acc[i] = 0.f;
+#pragma unroll
+                for (int dd = 0; dd < kDP; ++dd)
+#pragma unroll
+                    for (int i = 0; i < PX; ++i)
+                        acc[i] = fmaf(gv[dd][i], w[MODE == 0 ? i - dd + kDP : i + dd], acc[i]);
+            }
+#pragma unroll
+            for (int r = 0; r < LOGNH; ++r) {
+                const unsigned m = 1u << LM::hpos(r);
+                if (r < RS) {
+                    const int n2 = PX >> (r + 1);
+                    const bool bit = (h >> r) & 1;
+#pragma unroll
+                    for (int i = 0; i < n2; ++i) {
+                        const float send = bit ? acc[i] : acc[i + n2];
+                        const float keep = bit ? acc[i + n2] : acc[i];
+                        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+                    }
                 } else {
-                    const float v = (h & 2) ? ((h & 1) ? acc[3] : acc[2]) : ((h & 1) ? acc[1] : acc[0]);
-                    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(o), "f"(v) : "memory");
+                    acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], m);
+                }
+            }
+            if (storer) {
+                if constexpr (SPL == 8) {
+                    st_global_cs(reinterpret_cast<float4 *>(o), make_float4(acc[0], acc[1], acc[2], acc[3]));
+                    st_global_cs(reinterpret_cast<float4 *>(o) + 1, make_float4(acc[4], acc[5], acc[6], acc[7]));
+                } else if constexpr (SPL == 4) {
+                    st_global_cs(reinterpret_cast<float4 *>(o), make_float4(acc[0], acc[1], acc[2], acc[3]));
+                } else if constexpr (SPL == 2) {
+                    asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(o), "f"(acc[0]), "f"(acc[1]) : "memory");
+                } else {
+                    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(o), "f"(acc[0]) : "memory");
                 }
             }
         }
@@ -179,9 +269,9 @@ int env_int_reg(const char *name, int dflt) {
     return (v && *v) ? std::atoi(v) : dflt;
 }
 
-template <int MODE, int LOGNH>
+template <int MODE, int LOGNH, int PX>
 int launch_reg(RegParams p, const CUtensorMap &mapIn, const CUtensorMap &mapG, int threads, size_t smem, cudaStream_t stream) {
-    auto kern = corr_bwd_reg_kernel<MODE, LOGNH>;
+    auto kern = corr_bwd_reg_kernel<MODE, LOGNH, PX>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_bwd: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
@@ -196,8 +286,8 @@ int launch_reg(RegParams p, const CUtensorMap &mapIn, const CUtensorMap &mapG, i
     p.ipb = ceil_div(p.nitems, grid);
     grid = ceil_div(p.nitems, p.ipb);
     if (env_int_reg("DSSMD_CORR_DEBUG", 0))
-        fprintf(stderr, "corr_bwd reg cfg: mode=%d NH=%d WPR=%d TX=%d XT=%d CGW=%d CB=%d items=%d ipb=%d grid=%d (x%d/SM) threads=%d smem=%zu\n",
-                MODE, p.NH, p.WPR, p.TX, p.XT, p.CGW, p.CB, p.nitems, p.ipb, grid, bps, threads, smem);
+        fprintf(stderr, "corr_bwd reg cfg: mode=%d PX=%d NH=%d WPR=%d TX=%d XT=%d CGW=%d CB=%d items=%d ipb=%d grid=%d (x%d/SM) threads=%d smem=%zu\n",
+                MODE, PX, p.NH, p.WPR, p.TX, p.XT, p.CGW, p.CB, p.nitems, p.ipb, grid, bps, threads, smem);
     kern<<<(unsigned)grid, threads, smem, stream>>>(p, mapIn, mapG);
     return check_launch(MODE == 0 ? "corr_bwd(gL, reg)" : "corr_bwd(gR, reg)");
 }
@@ -217,7 +307,14 @@ int corr_bwd_reg_f32(const void *g, const void *in, void *out, int mode, int B, 
     int nh = 1, lognh = 0;
     while (nh * kDP < D) { nh *= 2; ++lognh; }
     p.NH = nh; p.LOGNH = lognh;
-    const int px = 4;
+    // pixels per lane: 8 (19 FFMAs per LDS.128 instead of 12, needs the D split so that the window loads stay
+    // conflict-free) when that does not leave more lanes idle at the end of the row than 4 does
+    auto lanes_used = [&](int px_) { const int pw = (32 / nh) * px_; return (double)W / (double)(ceil_div(W, pw) * pw); };
+    int px = (nh >= 4 && nh <= 8 && lanes_used(8) >= lanes_used(4)) ? 8 : 4;
+    {
+        const int o = env_int_reg("DSSMD_CORR_BWD_PX", 0);
+        if (o == 4 || (o == 8 && nh >= 2 && nh <= 8)) px = o;
+    }
     const int pxw = (32 / nh) * px;                 // pixels one warp covers
     // x tile: the operand box (tile + 12*NH halo words) must fit a 256-element TMA box
     int wpr = ceil_div(W, pxw);
@@ -231,7 +328,9 @@ int corr_bwd_reg_f32(const void *g, const void *in, void *out, int mode, int B, 
     int cgw = env_int_reg("DSSMD_CORR_BWD_CGW", 0);
     if (cgw < 1) cgw = 8 / wpr;
     if (cgw < 1) cgw = 1;
-    while (cgw > 1 && wpr * cgw > 16) --cgw;
+    const int max_warps = px == 4 ? 16 : 8;   // __launch_bounds__ of the kernel
+    if (wpr > max_warps) return -1;
+    while (cgw > 1 && wpr * cgw > max_warps) --cgw;
     if (cgw > C) cgw = C;
     p.CGW = cgw;
     // channels per item: small enough that every SM sees several items (the pipeline needs a
@@ -274,12 +373,19 @@ int corr_bwd_reg_f32(const void *g, const void *in, void *out, int mode, int B, 
         if (!make_tmap_f32(&mapG, g, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
     }
 #define DSSMD_REG_LAUNCH(M)                                                                     \
+    if (px == 8) {                                                                              \
+        switch (lognh) {                                                                        \
+            case 1: return launch_reg<M, 1, 8>(p, mapIn, mapG, threads, smem, stream);          \
+            case 2: return launch_reg<M, 2, 8>(p, mapIn, mapG, threads, smem, stream);          \
+            default: return launch_reg<M, 3, 8>(p, mapIn, mapG, threads, smem, stream);         \
+        }                                                                                       \
+    }                                                                                           \
     switch (lognh) {                                                                            \
-        case 0: return launch_reg<M, 0>(p, mapIn, mapG, threads, smem, stream);                 \
-        case 1: return launch_reg<M, 1>(p, mapIn, mapG, threads, smem, stream);                 \
-        case 2: return launch_reg<M, 2>(p, mapIn, mapG, threads, smem, stream);                 \
-        case 3: return launch_reg<M, 3>(p, mapIn, mapG, threads, smem, stream);                 \
-        default: return launch_reg<M, 4>(p, mapIn, mapG, threads, smem, stream);                \
+        case 0: return launch_reg<M, 0, 4>(p, mapIn, mapG, threads, smem, stream);              \
+        case 1: return launch_reg<M, 1, 4>(p, mapIn, mapG, threads, smem, stream);              \
+        case 2: return launch_reg<M, 2, 4>(p, mapIn, mapG, threads, smem, stream);              \
+        case 3: return launch_reg<M, 3, 4>(p, mapIn, mapG, threads, smem, stream);              \
+        default: return launch_reg<M, 4, 4>(p, mapIn, mapG, threads, smem, stream);             \
     }
     if (mode == 0) { DSSMD_REG_LAUNCH(0) }
     DSSMD_REG_LAUNCH(1)

@@ -836,9 +836,110 @@ __global__ void __launch_bounds__(256) warp_bwd_vmix_kernel(const float *__restr
     }
 }
 
+// K2, banded (16-byte aligned rows): block = (image, band of VR consecutive g_img rows).  The VR + 2 candidate
+// gV rows of a column are loaded once for the whole band (each gV row is read (VR + 2) / VR times instead of 3),
+// and the loads are in flight while VR + 2 lanes work out the vertical taps of the candidate rows in parallel.
+// Accumulation order per output (ascending source row, fma chain from 0) is the one of warp_bwd_vmix_kernel.
+template <int VR>
+__global__ void __launch_bounds__(256) warp_bwd_vmix_band_kernel(const float *__restrict__ gV, float *__restrict__ g_img,
+                                                                  int C, int H, int W, int border, float halfH) {
+    using S = float;
+    using N = Num<S>;
+    __shared__ int s_i0[VR + 2], s_in[VR + 2];
+    __shared__ float s_w0[VR + 2], s_w1[VR + 2];
+    __shared__ float s_wt[VR][3];  // weight of gV row yy - 1 + k in g_img row yy = y_lo + r
+    __shared__ int s_on[VR];       // bit k: that row is a tap of yy (a zero weight still propagates NaN, as in ATen)
+    const int nbands = (H + VR - 1) / VR;
+    const int band = blockIdx.x % nbands, b = blockIdx.x / nbands;
+    const int y_lo = band * VR;
+    const int tid = threadIdx.x;
+    const int W4 = W >> 2, n = C * W4;
+    const unsigned HWu = (unsigned)(H * W);
+    const float *src0 = gV + (size_t)b * C * HWu;
+    float *dst0 = g_img + (size_t)b * C * HWu;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    auto load = [&](int i, float4 (&v)[VR + 2]) {
+        const int c = i / W4, x4 = i - c * W4;
+        const float *p = src0 + c * HWu + 4 * x4;
+#pragma unroll
+        for (int t = 0; t < VR + 2; ++t) {
+            const int y = y_lo - 1 + t;
+            v[t] = (y >= 0 && y < H) ? *reinterpret_cast<const float4 *>(p + (unsigned)(y * W)) : z4;
+        }
+    };
+    auto mix = [&](int i, const float4 (&v)[VR + 2]) {
+        const int c = i / W4, x4 = i - c * W4;
+#pragma unroll
+        for (int r = 0; r < VR; ++r) {
+            const int yy = y_lo + r;
+            if (yy >= H) break;
+            const int on = s_on[r];
+            float4 a = z4;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (on & (1 << k)) {
+                    const float wy = s_wt[r][k];
+                    a.x = N::fma(wy, v[r + k].x, a.x); a.y = N::fma(wy, v[r + k].y, a.y);
+                    a.z = N::fma(wy, v[r + k].z, a.z); a.w = N::fma(wy, v[r + k].w, a.w);
+                }
+            st_global_cs(reinterpret_cast<float4 *>(dst0 + c * HWu + (unsigned)(yy * W)) + x4, a);
+        }
+    };
+
+    float4 v[VR + 2];
+    if (tid < n) load(tid, v);
+    if (tid < VR + 2) {
+        const int y = y_lo - 1 + tid;
+        int in = 0;
+        if (y >= 0 && y < H) {
+            const S gy = N::sub(N::mul((S)2, N::div((S)y, (S)(H - 1))), (S)1);
+            const S iy_raw = N::fma(N::add(gy, (S)1), halfH, (S)-0.5);
+            const Axis<S> ya = make_axis<S>(border ? clamp_border<S>(iy_raw, H) : iy_raw, H);
+            s_i0[tid] = ya.i0; s_w0[tid] = ya.w0; s_w1[tid] = ya.w1;
+            in = (ya.in0 ? 1 : 0) | (ya.in1 ? 2 : 0);
+        }
+        s_in[tid] = in;
+    }
+    if (tid < 32) {
+        __syncwarp();
+        if (tid < VR) {
+            const int yy = y_lo + tid;
+            int on = 0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int t = tid + k;
+                const int in = s_in[t];
+                float wy = 0.f;
+                if ((in & 1) && s_i0[t] == yy) { wy = s_w0[t]; on |= 1 << k; }
+                if ((in & 2) && s_i0[t] + 1 == yy) { wy = s_w1[t]; on |= 1 << k; }
+                s_wt[tid][k] = wy;
+            }
+            s_on[tid] = on;
+        }
+    }
+    __syncthreads();
+    if (tid < n) mix(tid, v);
+    for (int i = tid + 256; i < n; i += 256) {
+        load(i, v);
+        mix(i, v);
+    }
+}
+
 int env_int(const char *name, int dflt) {
     const char *v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
+}
+
+// K2 launch: banded kernel for 16-byte aligned rows (DSSMD_WARP_BWD_VMIX=0 forces the row kernel)
+int launch_vmix(const float *gv, float *gi, int B, int C, int H, int W, int border, int vec, cudaStream_t s) {
+    constexpr int VR = 4;
+    if (vec && env_int("DSSMD_WARP_BWD_VMIX", 1) != 0 && (long long)B * ceil_div(H, VR) < (1LL << 31)) {
+        warp_bwd_vmix_band_kernel<VR><<<(unsigned)(B * ceil_div(H, VR)), 256, 0, s>>>(gv, gi, C, H, W, border, (float)H / 2.0f);
+        return check_launch("warp_bwd(vmix band)");
+    }
+    warp_bwd_vmix_kernel<<<(unsigned)(B * H), 256, 0, s>>>(gv, gi, B, C, H, W, border, vec);
+    return check_launch("warp_bwd(vmix)");
 }
 
 template <typename S>
@@ -878,8 +979,7 @@ int warp_bwd_typed(const void *g, const void *img, const void *disp, void *g_img
             int rc = check_launch("warp_bwd(hscatter4)");
             if (rc || !g_img) return rc;
             const int vec = (((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(g_img)) & 15) == 0);
-            warp_bwd_vmix_kernel<<<(unsigned)(B * H), 256, 0, s>>>(gv, gi, B, C, H, W, border, vec);
-            return check_launch("warp_bwd(vmix)");
+            return launch_vmix(gv, gi, B, C, H, W, border, vec, s);
         }
         if (variant >= 3 && W <= 4096 && (long long)C * H * W < (1LL << 31) && (have_ws || !g_img)) {
             int pxt = W <= 256 ? 1 : (W <= 512 ? 2 : 4);  // ~256-thread blocks: 3-4 resident per SM
@@ -903,8 +1003,7 @@ int warp_bwd_typed(const void *g, const void *img, const void *disp, void *g_img
             int rc = check_launch("warp_bwd(hscatter)");
             if (rc || !g_img) return rc;
             const int vec = (W % 4 == 0) && (((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(g_img)) & 15) == 0);
-            warp_bwd_vmix_kernel<<<(unsigned)(B * H), 256, 0, s>>>(gv, gi, B, C, H, W, border, vec);
-            return check_launch("warp_bwd(vmix)");
+            return launch_vmix(gv, gi, B, C, H, W, border, vec, s);
         }
         if (variant >= 2 && W <= 4096 && (long long)C * H * W < (1LL << 31)) {
             int pxt = W <= 512 ? 1 : (W <= 2048 ? 2 : 4);
