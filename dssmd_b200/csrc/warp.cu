@@ -17,6 +17,10 @@
 
 namespace dssmd {
 
+// warp_lean.cu: instruction-lean kernels for image-like shapes; -1 = not eligible
+int warp_fwd_lean_f32(const float *img, const float *disp, float *out, float *mask, int *neg_flag,
+                      int B, int C, int H, int W, int border, cudaStream_t s);
+
 namespace {
 
 int env_int(const char *name, int dflt) {
@@ -465,6 +469,10 @@ int warp_fwd_typed(const void *img, const void *disp, void *warped, void *mask, 
     const S *ip = (const S *)img, *dp = (const S *)disp;
     S *op = (S *)warped, *mp = (S *)mask;
     if constexpr (sizeof(S) == 4) {
+        if (env_int("DSSMD_WARP_FWD_VARIANT", 1) >= 1) {
+            const int rc = warp_fwd_lean_f32(ip, dp, op, mp, neg_flag, B, C, H, W, border, s);
+            if (rc >= 0) return rc;
+        }
         if (vec && C <= 4 && W <= 4096 && H >= 2 && (long long)C * H * W < (1LL << 31) && env_int("DSSMD_WARP_FWD_VARIANT", 1) >= 1) {
             void (*kern)(const float *, const float *, float *, float *, int *, int, int, int, float, float) = nullptr;
             int ps = 0;

@@ -14,6 +14,10 @@
 
 namespace dssmd {
 
+// warp_lean.cu: instruction-lean horizontal-scatter kernel (K1) for image-like shapes; -1 = not eligible
+int warp_bwd_lean_f32(const float *g, const float *img, const float *disp, float *gV, float *g_disp,
+                      int B, int C, int H, int W, int border, cudaStream_t s);
+
 template <typename S>
 int warp_bwd_v1(const void *g, const void *img, const void *disp, void *g_img, void *g_disp,
                 int B, int C, int H, int W, int pad, cudaStream_t s);
@@ -946,7 +950,7 @@ template <typename S>
 int warp_bwd_typed(const void *g, const void *img, const void *disp, void *g_img, void *g_disp,
                    void *workspace, size_t workspace_bytes,
                    int B, int C, int H, int W, int pad, cudaStream_t s) {
-    const int variant = env_int("DSSMD_WARP_BWD_VARIANT", 4);
+    const int variant = env_int("DSSMD_WARP_BWD_VARIANT", 5);
     if constexpr (sizeof(S) == 4) {
         const size_t smem = (size_t)2 * kCC * W * sizeof(int);
         const int border = pad == DSSMD_PAD_BORDER;
@@ -975,8 +979,11 @@ int warp_bwd_typed(const void *g, const void *img, const void *disp, void *g_img
             float *gv = g_img ? (float *)workspace : nullptr;
             // W/2, 2/(W-1), H/2: IEEE single divisions, the same values the device would compute
             const float halfW = (float)W / 2.0f, tscale = 2.0f / (float)(W - 1), halfH = (float)H / 2.0f;
-            kern<<<(unsigned)(B * H), round_up(W4, 32), smem4, s>>>(gp, ip, dp, gv, gd, H, W, border, halfW, tscale, halfH);
-            int rc = check_launch("warp_bwd(hscatter4)");
+            int rc = variant >= 5 ? warp_bwd_lean_f32(gp, ip, dp, gv, gd, B, C, H, W, border, s) : -1;
+            if (rc < 0) {
+                kern<<<(unsigned)(B * H), round_up(W4, 32), smem4, s>>>(gp, ip, dp, gv, gd, H, W, border, halfW, tscale, halfH);
+                rc = check_launch("warp_bwd(hscatter4)");
+            }
             if (rc || !g_img) return rc;
             const int vec = (((reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(g_img)) & 15) == 0);
             return launch_vmix(gv, gi, B, C, H, W, border, vec, s);
