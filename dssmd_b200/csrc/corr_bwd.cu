@@ -19,11 +19,12 @@
 #include "common.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace dssmd {
 
 // corr_bwd_reg.cu: fp32 fast path (g slab in registers); -1 = shape not eligible
-int corr_bwd_reg_f32(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, cudaStream_t stream);
+int corr_bwd_reg(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, int dtype, cudaStream_t stream);
 
 namespace {
 
@@ -293,11 +294,10 @@ int env_int(const char *name, int dflt) {
 
 template <typename T, int MODE>
 int launch_mode(const void *g, const void *In, void *out, int B, int C, int H, int W, int D, cudaStream_t stream) {
-    if constexpr (sizeof(T) == 4) {
-        if (env_int("DSSMD_CORR_BWD_VARIANT", 1) >= 1) {
-            const int rc = corr_bwd_reg_f32(g, In, out, MODE, B, C, H, W, D, stream);
-            if (rc >= 0) return rc;
-        }
+    if (env_int("DSSMD_CORR_BWD_VARIANT", 1) >= 1) {
+        constexpr int dtype = sizeof(T) == 4 ? DSSMD_F32 : std::is_same<T, __nv_bfloat16>::value ? DSSMD_BF16 : DSSMD_F16;
+        const int rc = corr_bwd_reg(g, In, out, MODE, B, C, H, W, D, dtype, stream);
+        if (rc >= 0) return rc;
     }
     CorrBwdParams p{};
     p.g = g; p.In = In; p.out = out;

@@ -33,7 +33,7 @@ namespace {
 constexpr int kDP = 12;  // disparities per lane
 
 struct RegParams {
-    float *out;
+    void *out;
     int C, H, W, D;
     int NH, LOGNH;  // lanes per pixel group (power of two), D <= 12*NH
     int WPR;        // warps side by side along x
@@ -42,12 +42,62 @@ struct RegParams {
     int NCB;        // channel blocks
     int TX;         // x tile in pixels
     int XT;         // x tiles per row
-    int WP;         // operand box width in words (TX + 12*NH)
-    int GW;         // g box width in words (MODE 0: TX, MODE 1: WP)
+    int HALO;       // halo of the operand box in elements: 12*NH, rounded up so that the box is a multiple of 16 bytes
+    int WP;         // operand box width in elements (TX + HALO)
+    int GW;         // g box width in elements (MODE 0: TX, MODE 1: WP)
     int nitems, ipb;  // work items, items per block
     uint32_t op_bytes, g_bytes;
     float invC;
 };
+
+// ---- element types: fp32, or 16-bit storage with fp32 arithmetic ------------------------------
+__device__ __forceinline__ void unpack2(const __nv_bfloat16 *, uint32_t u, float &lo, float &hi) {
+    lo = __uint_as_float(u << 16);
+    hi = __uint_as_float(u & 0xffff0000u);
+}
+__device__ __forceinline__ void unpack2(const __half *, uint32_t u, float &lo, float &hi) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&u));
+    lo = f.x; hi = f.y;
+}
+__device__ __forceinline__ uint32_t pack2(const __nv_bfloat16 *, float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&v);
+}
+__device__ __forceinline__ uint32_t pack2(const __half *, float lo, float hi) {
+    const __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&v);
+}
+// 4 consecutive elements at a 4-element aligned shared-memory address
+template <typename T>
+__device__ __forceinline__ void load4(const T *p, float &a, float &b, float &c, float &d) {
+    if constexpr (sizeof(T) == 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(p);
+        a = v.x; b = v.y; c = v.z; d = v.w;
+    } else {
+        const uint2 v = *reinterpret_cast<const uint2 *>(p);
+        unpack2(p, v.x, a, b);
+        unpack2(p, v.y, c, d);
+    }
+}
+// N (1, 2 or 4) finished pixels -> global memory at an N-element aligned address, streaming
+template <typename T, int N>
+__device__ __forceinline__ void store_n(T *o, const float *v) {
+    if constexpr (sizeof(T) == 4) {
+        if constexpr (N == 4) st_global_cs(reinterpret_cast<float4 *>(o), make_float4(v[0], v[1], v[2], v[3]));
+        else if constexpr (N == 2) asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(o), "f"(v[0]), "f"(v[1]) : "memory");
+        else asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(o), "f"(v[0]) : "memory");
+    } else {
+        if constexpr (N == 4) {
+            const uint32_t a = pack2(o, v[0], v[1]), b = pack2(o, v[2], v[3]);
+            asm volatile("st.global.cs.v2.b32 [%0], {%1, %2};" ::"l"(o), "r"(a), "r"(b) : "memory");
+        } else if constexpr (N == 2) {
+            const uint32_t a = pack2(o, v[0], v[1]);
+            asm volatile("st.global.cs.b32 [%0], %1;" ::"l"(o), "r"(a) : "memory");
+        } else {
+            *o = from_f32<T>(v[0]);
+        }
+    }
+}
 
 // Lane -> (pixel group pgl, disparity part h).  A lane's window starts at 16-byte chunk
 // (PX/4)*pgl -+ 3*h of the staged row, and an LDS.128 is served a quarter-warp (8 consecutive lanes) at a
@@ -95,7 +145,7 @@ template <> struct LaneMap<3, 8> {
     static __device__ __forceinline__ constexpr int hpos(int k) { return 2 + k; }
 };
 
-template <int MODE, int LOGNH, int PX>
+template <typename T, int MODE, int LOGNH, int PX>
 __global__ void __launch_bounds__(PX == 4 ? 512 : 256) corr_bwd_reg_kernel(const RegParams p, const __grid_constant__ CUtensorMap mapIn,
                                                                             const __grid_constant__ CUtensorMap mapG) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -128,7 +178,7 @@ __global__ void __launch_bounds__(PX == 4 ? 512 : 256) corr_bwd_reg_kernel(const
         fence_proxy_async();  // the stage was read through the generic proxy before the block barrier
         mbar_arrive_expect_tx(bar, p.op_bytes + (newg ? p.g_bytes : 0u));
         const int X0 = xt * p.TX;
-        tma_load_4d(dst, &mapIn, MODE == 0 ? X0 - kDP * NH : X0, y, cb * p.CB, b, bar);
+        tma_load_4d(dst, &mapIn, MODE == 0 ? X0 - p.HALO : X0, y, cb * p.CB, b, bar);
         if (newg) tma_load_4d(dst + op_stride, &mapG, X0, y, 0, b, bar);
     };
     if (tid == 0) issue(i0, 0);
@@ -137,7 +187,7 @@ __global__ void __launch_bounds__(PX == 4 ? 512 : 256) corr_bwd_reg_kernel(const
     const int wseg = warp % p.WPR, cgw = warp / p.WPR;
     const int h = LM::h(lane), pgl = LM::pgl(lane);
     const int xl = (wseg * (32 >> LOGNH) + pgl) * PX;  // < TX by construction
-    const int woff = MODE == 0 ? xl + kDP * NH - kDP * (h + 1) : xl + kDP * h;  // window start inside a staged row
+    const int woff = MODE == 0 ? xl + p.HALO - kDP * (h + 1) : xl + kDP * h;  // window start inside a staged row
     const size_t HW = (size_t)p.H * p.W;
 
     float gv[kDP][PX];
@@ -149,26 +199,27 @@ __global__ void __launch_bounds__(PX == 4 ? 512 : 256) corr_bwd_reg_kernel(const
         const int xt = rx % p.XT, row = rx / p.XT;
         const int b = row / p.H, y = row - b * p.H;
         const int X0 = xt * p.TX;
-        const float *ops = reinterpret_cast<const float *>(smem_raw + (size_t)s * stage_bytes);
+        const T *ops = reinterpret_cast<const T *>(smem_raw + (size_t)s * stage_bytes);
         mbar_wait(smem_u32(&s_bar[s]), ph);
 
         if (it == i0 || cb == 0) {  // new row / x tile: reload the g slab
-            const float *gs = reinterpret_cast<const float *>(smem_raw + (size_t)s * stage_bytes + op_stride);
+            const T *gs = reinterpret_cast<const T *>(smem_raw + (size_t)s * stage_bytes + op_stride);
 #pragma unroll
             for (int dd = 0; dd < kDP; ++dd) {
                 const int d = h * kDP + dd;
                 const bool dok = d < p.D;
-                const float *gd = gs + (dok ? d : 0) * p.GW + xl;
+                const T *gd = gs + (dok ? d : 0) * p.GW + xl;
                 if (MODE == 0) {
 #pragma unroll
                     for (int q = 0; q < PX / 4; ++q) {
-                        const float4 v = *reinterpret_cast<const float4 *>(gd + 4 * q);
-                        gv[dd][4 * q + 0] = dok ? v.x * p.invC : 0.f; gv[dd][4 * q + 1] = dok ? v.y * p.invC : 0.f;
-                        gv[dd][4 * q + 2] = dok ? v.z * p.invC : 0.f; gv[dd][4 * q + 3] = dok ? v.w * p.invC : 0.f;
+                        float a, b2, c2, d2;
+                        load4<T>(gd + 4 * q, a, b2, c2, d2);
+                        gv[dd][4 * q + 0] = dok ? a * p.invC : 0.f; gv[dd][4 * q + 1] = dok ? b2 * p.invC : 0.f;
+                        gv[dd][4 * q + 2] = dok ? c2 * p.invC : 0.f; gv[dd][4 * q + 3] = dok ? d2 * p.invC : 0.f;
                     }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < PX; ++i) gv[dd][i] = dok ? gd[i + d] * p.invC : 0.f;
+                    for (int i = 0; i < PX; ++i) gv[dd][i] = dok ? to_f32<T>(gd[i + d]) * p.invC : 0.f;
                 }
             }
         }
@@ -192,19 +243,15 @@ __global__ void __launch_bounds__(PX == 4 ? 512 : 256) corr_bwd_reg_kernel(const
             else storer = storer && !bit;
         }
         storer = storer && (x + xo < p.W);   // W % 4 == 0 and x + xo is a multiple of SPL <= 4: all or nothing
-        float *o = p.out + ((size_t)b * p.C + c0 + cgw) * HW + (size_t)y * p.W + x + xo;
+        T *o = reinterpret_cast<T *>(p.out) + ((size_t)b * p.C + c0 + cgw) * HW + (size_t)y * p.W + x + xo;
         const size_t ostep = (size_t)p.CGW * HW;
-        const float *wrow = ops + cgw * p.WP + woff;
+        const T *wrow = ops + cgw * p.WP + woff;
         const int wstep = p.CGW * p.WP;
 #pragma unroll 2
         for (int c = cgw; c < cn; c += p.CGW, o += ostep, wrow += wstep) {
-            const float4 *wp = reinterpret_cast<const float4 *>(wrow);
             float w[PX + kDP];
 #pragma unroll
-            for (int q = 0; q < (PX + kDP) / 4; ++q) {
-                const float4 v = wp[q];
-                w[4 * q + 0] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
-            }
+            for (int q = 0; q < (PX + kDP) / 4; ++q) load4<T>(wrow + 4 * q, w[4 * q + 0], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
             float acc[PX];
             if constexpr (PX == 4) {  // two chains per pixel: a warp then has 8 (16 with the unroll) independent FFMAs in flight
                 float acb[PX];
@@ -249,14 +296,10 @@ __global__ void __launch_bounds__(PX == 4 ? 512 : 256) corr_bwd_reg_kernel(const
             }
             if (storer) {
                 if constexpr (SPL == 8) {
-                    st_global_cs(reinterpret_cast<float4 *>(o), make_float4(acc[0], acc[1], acc[2], acc[3]));
-                    st_global_cs(reinterpret_cast<float4 *>(o) + 1, make_float4(acc[4], acc[5], acc[6], acc[7]));
-                } else if constexpr (SPL == 4) {
-                    st_global_cs(reinterpret_cast<float4 *>(o), make_float4(acc[0], acc[1], acc[2], acc[3]));
-                } else if constexpr (SPL == 2) {
-                    asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(o), "f"(acc[0]), "f"(acc[1]) : "memory");
+                    store_n<T, 4>(o, acc);
+                    store_n<T, 4>(o + 4, acc + 4);
                 } else {
-                    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(o), "f"(acc[0]) : "memory");
+                    store_n<T, SPL>(o, acc);
                 }
             }
         }
@@ -269,9 +312,9 @@ int env_int_reg(const char *name, int dflt) {
     return (v && *v) ? std::atoi(v) : dflt;
 }
 
-template <int MODE, int LOGNH, int PX>
+template <typename T, int MODE, int LOGNH, int PX>
 int launch_reg(RegParams p, const CUtensorMap &mapIn, const CUtensorMap &mapG, int threads, size_t smem, cudaStream_t stream) {
-    auto kern = corr_bwd_reg_kernel<MODE, LOGNH, PX>;
+    auto kern = corr_bwd_reg_kernel<T, MODE, LOGNH, PX>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_bwd: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
@@ -286,44 +329,49 @@ int launch_reg(RegParams p, const CUtensorMap &mapIn, const CUtensorMap &mapG, i
     p.ipb = ceil_div(p.nitems, grid);
     grid = ceil_div(p.nitems, p.ipb);
     if (env_int_reg("DSSMD_CORR_DEBUG", 0))
-        fprintf(stderr, "corr_bwd reg cfg: mode=%d PX=%d NH=%d WPR=%d TX=%d XT=%d CGW=%d CB=%d items=%d ipb=%d grid=%d (x%d/SM) threads=%d smem=%zu\n",
-                MODE, PX, p.NH, p.WPR, p.TX, p.XT, p.CGW, p.CB, p.nitems, p.ipb, grid, bps, threads, smem);
+        fprintf(stderr, "corr_bwd reg cfg: es=%d mode=%d PX=%d NH=%d WPR=%d TX=%d XT=%d CGW=%d CB=%d items=%d ipb=%d grid=%d (x%d/SM) threads=%d smem=%zu\n",
+                (int)sizeof(T), MODE, PX, p.NH, p.WPR, p.TX, p.XT, p.CGW, p.CB, p.nitems, p.ipb, grid, bps, threads, smem);
     kern<<<(unsigned)grid, threads, smem, stream>>>(p, mapIn, mapG);
     return check_launch(MODE == 0 ? "corr_bwd(gL, reg)" : "corr_bwd(gR, reg)");
 }
 
 }  // namespace
 
-// mode 0: out = gL, in = R;  mode 1: out = gR, in = L.  Returns -1 when the shape is not
-// eligible (the caller falls back to the generic kernel), else a DSSMD_* code.
-int corr_bwd_reg_f32(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, cudaStream_t stream) {
-    if (W % 4 != 0 || D > kDP * 16) return -1;
+namespace {
+
+template <typename T>
+int corr_bwd_reg_typed(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, CUtensorMapDataType tmtype,
+                       cudaStream_t stream) {
+    constexpr int ES = (int)sizeof(T);
+    constexpr int EPV = 16 / ES;                    // elements per 16 bytes: rows and boxes are multiples of it
+    if (W % EPV != 0 || D > kDP * 16) return -1;
     if (((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) != 0) return -1;
     if ((long long)B * H * 64 >= (1LL << 31)) return -1;
     RegParams p{};
-    p.out = (float *)out;
+    p.out = out;
     p.C = C; p.H = H; p.W = W; p.D = D;
     p.invC = 1.0f / (float)C;
     int nh = 1, lognh = 0;
     while (nh * kDP < D) { nh *= 2; ++lognh; }
     p.NH = nh; p.LOGNH = lognh;
+    p.HALO = round_up(kDP * nh, EPV);
     // pixels per lane: 8 (19 FFMAs per LDS.128 instead of 12, needs the D split so that the window loads stay
-    // conflict-free) when that does not leave more lanes idle at the end of the row than 4 does
+    // conflict-free) when that does not leave more lanes idle at the end of the row than 4 does (fp32 only)
     auto lanes_used = [&](int px_) { const int pw = (32 / nh) * px_; return (double)W / (double)(ceil_div(W, pw) * pw); };
-    int px = (nh >= 4 && nh <= 8 && lanes_used(8) >= lanes_used(4)) ? 8 : 4;
-    {
+    int px = (ES == 4 && nh >= 4 && nh <= 8 && lanes_used(8) >= lanes_used(4)) ? 8 : 4;
+    if (ES == 4) {
         const int o = env_int_reg("DSSMD_CORR_BWD_PX", 0);
         if (o == 4 || (o == 8 && nh >= 2 && nh <= 8)) px = o;
     }
     const int pxw = (32 / nh) * px;                 // pixels one warp covers
-    // x tile: the operand box (tile + 12*NH halo words) must fit a 256-element TMA box
+    // x tile: the operand box (tile + halo) must fit a 256-element TMA box
     int wpr = ceil_div(W, pxw);
-    while (wpr > 1 && wpr * pxw + kDP * nh > 256) wpr = (wpr + 1) / 2;
-    if (wpr * pxw + kDP * nh > 256) return -1;
+    while (wpr > 1 && wpr * pxw + p.HALO > 256) wpr = (wpr + 1) / 2;
+    if (wpr * pxw + p.HALO > 256) return -1;
     p.WPR = wpr;
     p.TX = wpr * pxw;
     p.XT = ceil_div(W, p.TX);
-    p.WP = p.TX + kDP * nh;
+    p.WP = p.TX + p.HALO;
     p.GW = mode == 0 ? p.TX : p.WP;
     int cgw = env_int_reg("DSSMD_CORR_BWD_CGW", 0);
     if (cgw < 1) cgw = 8 / wpr;
@@ -345,15 +393,15 @@ int corr_bwd_reg_f32(const void *g, const void *in, void *out, int mode, int B, 
     if (cb > C) cb = C;
     // two stages of (operand tile + g tile) must leave room for two resident blocks
     {
-        const size_t gbytes = (size_t)D * p.GW * sizeof(float) + 128, rowb = (size_t)p.WP * sizeof(float);
+        const size_t gbytes = (size_t)D * p.GW * ES + 128, rowb = (size_t)p.WP * ES;
         const size_t budget = (size_t)env_int_reg("DSSMD_CORR_BWD_SMEM_KB2", 100) * 1024 / 2;
         if (gbytes + rowb * cgw > budget) return -1;
         while (cb > cgw && gbytes + rowb * cb + 128 > budget) cb -= cgw;
     }
     p.CB = cb;
     p.NCB = ceil_div(C, cb);
-    p.op_bytes = (uint32_t)((size_t)cb * p.WP * sizeof(float));
-    p.g_bytes = (uint32_t)((size_t)D * p.GW * sizeof(float));
+    p.op_bytes = (uint32_t)((size_t)cb * p.WP * ES);
+    p.g_bytes = (uint32_t)((size_t)D * p.GW * ES);
     const size_t stage = (size_t)((p.op_bytes + 127u) & ~127u) + ((p.g_bytes + 127u) & ~127u);
     const size_t smem = 2 * stage + 128;
     if (smem > 200 * 1024) return -1;
@@ -362,34 +410,49 @@ int corr_bwd_reg_f32(const void *g, const void *in, void *out, int mode, int B, 
     CUtensorMap mapIn, mapG;
     {
         const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
-        const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
+        const cuuint64_t strides[3] = {(cuuint64_t)W * ES, (cuuint64_t)H * W * ES, (cuuint64_t)C * H * W * ES};
         const cuuint32_t box[4] = {(cuuint32_t)p.WP, 1, (cuuint32_t)cb, 1};
-        if (!make_tmap_f32(&mapIn, in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
+        if (!make_tmap(&mapIn, tmtype, in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
     }
     {
         const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
-        const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)D * H * W * 4};
+        const cuuint64_t strides[3] = {(cuuint64_t)W * ES, (cuuint64_t)H * W * ES, (cuuint64_t)D * H * W * ES};
         const cuuint32_t box[4] = {(cuuint32_t)p.GW, 1, (cuuint32_t)D, 1};
-        if (!make_tmap_f32(&mapG, g, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
+        if (!make_tmap(&mapG, tmtype, g, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
     }
 #define DSSMD_REG_LAUNCH(M)                                                                     \
-    if (px == 8) {                                                                              \
-        switch (lognh) {                                                                        \
-            case 1: return launch_reg<M, 1, 8>(p, mapIn, mapG, threads, smem, stream);          \
-            case 2: return launch_reg<M, 2, 8>(p, mapIn, mapG, threads, smem, stream);          \
-            default: return launch_reg<M, 3, 8>(p, mapIn, mapG, threads, smem, stream);         \
+    if constexpr (ES == 4) {                                                                    \
+        if (px == 8) {                                                                          \
+            switch (lognh) {                                                                    \
+                case 1: return launch_reg<T, M, 1, 8>(p, mapIn, mapG, threads, smem, stream);   \
+                case 2: return launch_reg<T, M, 2, 8>(p, mapIn, mapG, threads, smem, stream);   \
+                default: return launch_reg<T, M, 3, 8>(p, mapIn, mapG, threads, smem, stream);  \
+            }                                                                                   \
         }                                                                                       \
     }                                                                                           \
     switch (lognh) {                                                                            \
-        case 0: return launch_reg<M, 0, 4>(p, mapIn, mapG, threads, smem, stream);              \
-        case 1: return launch_reg<M, 1, 4>(p, mapIn, mapG, threads, smem, stream);              \
-        case 2: return launch_reg<M, 2, 4>(p, mapIn, mapG, threads, smem, stream);              \
-        case 3: return launch_reg<M, 3, 4>(p, mapIn, mapG, threads, smem, stream);              \
-        default: return launch_reg<M, 4, 4>(p, mapIn, mapG, threads, smem, stream);             \
+        case 0: return launch_reg<T, M, 0, 4>(p, mapIn, mapG, threads, smem, stream);           \
+        case 1: return launch_reg<T, M, 1, 4>(p, mapIn, mapG, threads, smem, stream);           \
+        case 2: return launch_reg<T, M, 2, 4>(p, mapIn, mapG, threads, smem, stream);           \
+        case 3: return launch_reg<T, M, 3, 4>(p, mapIn, mapG, threads, smem, stream);           \
+        default: return launch_reg<T, M, 4, 4>(p, mapIn, mapG, threads, smem, stream);          \
     }
     if (mode == 0) { DSSMD_REG_LAUNCH(0) }
     DSSMD_REG_LAUNCH(1)
 #undef DSSMD_REG_LAUNCH
+}
+
+}  // namespace
+
+// mode 0: out = gL, in = R;  mode 1: out = gR, in = L.  dtype: DSSMD_F32 / BF16 / F16 (all tensors).  Returns -1 when
+// the shape is not eligible (the caller falls back to the generic kernel), else a DSSMD_* code.
+int corr_bwd_reg(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, int dtype, cudaStream_t stream) {
+    switch (dtype) {
+        case DSSMD_F32: return corr_bwd_reg_typed<float>(g, in, out, mode, B, C, H, W, D, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, stream);
+        case DSSMD_BF16: return corr_bwd_reg_typed<__nv_bfloat16>(g, in, out, mode, B, C, H, W, D, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, stream);
+        case DSSMD_F16: return corr_bwd_reg_typed<__half>(g, in, out, mode, B, C, H, W, D, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, stream);
+        default: return -1;
+    }
 }
 
 }  // namespace dssmd

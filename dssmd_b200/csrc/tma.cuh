@@ -55,15 +55,19 @@ inline EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-// fp32 tensor map; dims/box fastest first; strides in bytes for dims 1..rank-1; out-of-bounds reads give 0
-inline bool make_tmap_f32(CUtensorMap *m, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
-                          const cuuint32_t *box, CUtensorMapSwizzle swizzle) {
+// tensor map of `dtype` elements; dims/box fastest first; strides in bytes for dims 1..rank-1; out-of-bounds reads give 0
+inline bool make_tmap(CUtensorMap *m, CUtensorMapDataType dtype, const void *base, int rank, const cuuint64_t *dims,
+                      const cuuint64_t *strides, const cuuint32_t *box, CUtensorMapSwizzle swizzle) {
     EncodeTiledFn fn = encode_tiled();
     if (!fn) return false;
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), dims, strides, box, estr,
+    return fn(m, dtype, (cuuint32_t)rank, const_cast<void *>(base), dims, strides, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+inline bool make_tmap_f32(CUtensorMap *m, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
+                          const cuuint32_t *box, CUtensorMapSwizzle swizzle) {
+    return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides, box, swizzle);
 }
 
 }  // namespace dssmd
