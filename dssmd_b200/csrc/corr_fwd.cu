@@ -21,11 +21,14 @@
 #include "common.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace dssmd {
 
 // tensor-core path (corr_fwd_umma.cu); returns -1 when the shape is outside its limits
 int corr_fwd_umma_f32(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, cudaStream_t stream);
+// register-blocked, TMA-staged FFMA path (corr_fwd_reg.cu), fp32 / bf16 / fp16; -1 when the shape is not eligible
+int corr_fwd_reg(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, int dtype, cudaStream_t stream);
 
 namespace {
 
@@ -586,16 +589,22 @@ int launch_d4(const void *L, const void *R, void *out, int B, int C, int H, int 
 
 template <typename T>
 int launch_typed(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, cudaStream_t stream) {
-    // 0 wide FFMA tile, 1 narrow FFMA tile, 2 tcgen05 (3xTF32); unset = by size: the persistent
-    // tensor-core kernel needs several 128-pixel tiles per SM to amortise its pipeline fill
-    // (measured: wins at 800/960 tiles, loses at 270/200 -- profiles/r01q)
+    // 0 wide FFMA tile, 1 register-blocked / narrow FFMA tile, 2 tcgen05 (3xTF32); unset = by size: the persistent
+    // tensor-core kernel needs several 128-pixel tiles per SM to amortise its pipeline fill, and its work grows with
+    // 128 + D per tile where the FFMA kernels' grows with D (measured, C256 D41 800 tiles: 87 vs 108 us;
+    // C128 D24 960 tiles: 50 vs 42 us; 270 tiles: 21 vs 13 us)
     int variant = env_int("DSSMD_CORR_FWD_VARIANT", -1);
-    if (variant < 0) variant = (sizeof(T) == 4 && C >= 64 && (long)B * H * W / 128 >= 3L * sm_count()) ? 2 : 1;
+    if (variant < 0) variant = (sizeof(T) == 4 && C >= 64 && D >= 32 && (long)B * H * W / 128 >= 3L * sm_count()) ? 2 : 1;
     if constexpr (sizeof(T) == 4) {
         if (variant == 2) {
             const int rc = corr_fwd_umma_f32(L, R, out, B, C, H, W, D, stream);
             if (rc >= 0) return rc;
         }
+    }
+    if (variant >= 1 && env_int("DSSMD_CORR_FWD_REG", 1) != 0) {
+        constexpr int dtype = sizeof(T) == 4 ? DSSMD_F32 : std::is_same<T, __nv_bfloat16>::value ? DSSMD_BF16 : DSSMD_F16;
+        const int rc = corr_fwd_reg(L, R, out, B, C, H, W, D, dtype, stream);
+        if (rc >= 0) return rc;
     }
     if (variant >= 1 && D <= 64) {
         const int rc = launch_d4<T>(L, R, out, B, C, H, W, D, stream);

@@ -102,8 +102,18 @@ def test_corr_vs_oracle_f32(ops, oracle, shape):
         assert torch.count_nonzero(o[:, W:]) == 0
 
 
+CORR_SHAPES_16 = CORR_SHAPES[:6] + [
+    # 16-bit rows that are a multiple of 16 bytes take the TMA-staged register-blocked kernels
+    (1, 64, 2, 304, 192, True),    # 16 lanes per pixel group, x-tiled
+    (1, 32, 4, 520, 40, False),    # several x tiles, 4 lanes per group
+    (2, 72, 3, 248, 100, True),    # 8 lanes per group, ragged channel blocks
+    (1, 24, 2, 1000, 12, False),   # one lane per group: halo rounded up to 16 elements
+    (1, 8, 2, 64, 192, True),      # largest supported D, D > W
+]
+
+
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("shape", CORR_SHAPES[:6], ids=lambda s: "x".join(map(str, s[:5])))
+@pytest.mark.parametrize("shape", CORR_SHAPES_16, ids=lambda s: "x".join(map(str, s[:5])))
 def test_corr_vs_oracle_16bit(ops, oracle, shape, dt):
     B, C, H, W, D, relu = shape
     L = feat((B, C, H, W), 1, relu, dt).requires_grad_(True)
@@ -117,6 +127,24 @@ def test_corr_vs_oracle_16bit(ops, oracle, shape, dt):
     gL, gR = oracle.corr_bwd(gn, Ln, Rn)
     assert rel_err(L.grad.float().cpu().numpy(), gL) <= TOL_BF16
     assert rel_err(R.grad.float().cpu().numpy(), gR) <= TOL_BF16
+
+
+@pytest.mark.parametrize("shape", CORR_SHAPES, ids=lambda s: "x".join(map(str, s[:5])))
+def test_corr_fwd_register_blocked_variant(ops, oracle, shape, monkeypatch):
+    """The TMA-staged register-blocked forward forced on every shape it accepts (by default short fp32 rows and
+    large problems go to other kernels), incl. the cross-warp partial-sum path and ragged channel blocks."""
+    B, C, H, W, D, relu = shape
+    monkeypatch.setenv("DSSMD_CORR_FWD_VARIANT", "1")
+    monkeypatch.setenv("DSSMD_CORR_FWD_REG", "2")
+    L, R = feat((B, C, H, W), 1, relu), feat((B, C, H, W), 2, relu)
+    ref = oracle.corr_fwd(L.cpu().numpy(), R.cpu().numpy(), D)
+    for cgw, cb in (("0", "0"), ("1", "0"), ("3", "9")):
+        monkeypatch.setenv("DSSMD_CORR_FWD_CGW", cgw)
+        monkeypatch.setenv("DSSMD_CORR_FWD_CB", cb)
+        out = ops.build_corr(L, R, D)
+        assert rel_err(out.cpu().numpy(), ref) <= TOL_F32, (cgw, cb)
+        for d in range(min(D, W)):
+            assert torch.count_nonzero(out[:, d, :, :d]) == 0
 
 
 UMMA_SHAPES = [
