@@ -8,12 +8,13 @@ from .cost_volume import CostVolume
 from .disparity_warper import LRwarp_error, disp_warp, meshgrid, normalize_coords, read_pfm
 from .functional import resize_bilinear, set_check_negative_disparity
 from .install import install, uninstall
+from .losses import photometric_l1, photometric_loss
 from .stereo_op import print_tensor_shape
 from .submoudles import build_corr
 
 __all__ = [
     "build_corr", "CostVolume", "disp_warp", "LRwarp_error", "normalize_coords", "meshgrid",
     "read_pfm", "print_tensor_shape", "resize_bilinear", "set_check_negative_disparity",
-    "install", "uninstall",
+    "install", "uninstall", "photometric_l1", "photometric_loss",
 ]
 __version__ = "0.1.0"

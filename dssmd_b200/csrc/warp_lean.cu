@@ -436,6 +436,139 @@ __global__ void __launch_bounds__(PS - 2, 1024 / (PS - 2)) warp_bwd_lean_kernel(
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Fused L1 photometric term on the warp residual (built from upstream's
+// LRwarp_error, utils/disparity_warper.py:109-115, with its 'border' warp):
+//   err = imgR - warp(imgL, disp);   partial[b*H + y] = sum_{c,x} |err|;
+//   g_unit[b,0,y,x] = d(sum |err|)/d(disp) = (2/(W-1)) * gmult * sum_c sign(err_c) * d(sample_c)/d(ix)
+// in ONE pass: the forward kernel's two taps t0, t1 of the pre-blended row already give
+// d(sample)/d(ix) = t1 - t0, so the gradient w.r.t. the disparity is a by-product of the forward --
+// the residual is never written, no backward kernel and no scatter are needed (images carry no
+// gradient here).  Row sums are reduced in a fixed order: deterministic.
+// ---------------------------------------------------------------------------------
+template <int NCT, int PS>
+__global__ void __launch_bounds__(PS - 2, 1024 / (PS - 2)) photo_l1_lean_kernel(const float *__restrict__ imgL, const float *__restrict__ imgR,
+                                                                                const float *__restrict__ disp, float *__restrict__ g_unit,
+                                                                                float *__restrict__ partial, int *neg_flag, int H, int W,
+                                                                                float halfW, float tscale, float halfH) {
+    constexpr int VW = NCT == 3 ? 4 : NCT;
+    extern __shared__ __align__(16) float s_row[];  // [4][PS] cells of VW floats
+    __shared__ float s_sum[32];
+    const int W4 = W >> 2;
+    const int y = blockIdx.x, b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned HW = (unsigned)(H * W);
+    const bool active = tid < W4;
+    const int x0 = tid * 4;
+    const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+
+    const float iy_raw = unnorm_f((float)y, hm1, halfH);
+    int yi0;
+    float yw0, yw1;
+    axis_border(iy_raw, hm1, yi0, yw0, yw1);
+
+    const int xl = active ? x0 : W - 4;
+    const int ya = min(max(yi0, 0), H - 1), yb = min(max(yi0 + 1, 0), H - 1);
+    float4 st[NCT][2], rr[NCT];
+    {
+        const float *ib = imgL + (size_t)b * NCT * HW + xl;
+        const float *rb = imgR + (size_t)b * NCT * HW + (unsigned)(y * W + xl);
+#pragma unroll
+        for (int c = 0; c < NCT; ++c) {
+            st[c][0] = __ldg(reinterpret_cast<const float4 *>(ib + c * HW + (unsigned)(ya * W)));
+            st[c][1] = __ldg(reinterpret_cast<const float4 *>(ib + c * HW + (unsigned)(yb * W)));
+            rr[c] = __ldg(reinterpret_cast<const float4 *>(rb + c * HW));
+        }
+    }
+    const float4 d4 = __ldg(reinterpret_cast<const float4 *>(disp + (size_t)b * HW + (unsigned)(y * W + xl)));
+    const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+
+    uint32_t a0[4], a1[4];
+    float w0[4], w1[4], gmult[4];
+    bool bad = false;
+    const float xf0 = (float)xl;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        bad = bad || !(dv[i] >= 0.0f);
+        const float t = __fsub_rn(xf0 + (float)i, dv[i]);
+        const float ix = unnorm_f(t, wm1, halfW);
+        gmult[i] = (ix > 0.0f && ix < wm1) ? halfW : 0.0f;   // clip_coordinates_set_grad
+        int i0;
+        axis_border(ix, wm1, i0, w0[i], w1[i]);
+        const uint32_t p = (uint32_t)(i0 + 4);
+        a0[i] = vcell_off<PS, VW>(p);
+        a1[i] = vcell_off<PS, VW>(p + 1u);
+    }
+    if (active && bad && neg_flag) *reinterpret_cast<volatile int *>(neg_flag) = 1;
+
+    if (active) {
+        const uint32_t sa = (uint32_t)(VW * 4) * ((uint32_t)tid + 1u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float cell[VW];
+#pragma unroll
+            for (int c = 0; c < VW; ++c)
+                cell[c] = c < NCT ? fmaf(yw1, f4c(st[c < NCT ? c : 0][1], j), yw0 * f4c(st[c < NCT ? c : 0][0], j)) : 0.f;
+            sts_cell<VW>(s_row, sa + (uint32_t)(j * PS * VW * 4), cell);
+        }
+    }
+    if (tid < 8) {
+        float z[VW];
+#pragma unroll
+        for (int c = 0; c < VW; ++c) z[c] = 0.f;
+        sts_cell<VW>(s_row, (uint32_t)(((tid & 3) * PS + ((tid >> 2) ? W4 + 1 : 0)) * VW * 4), z);
+    }
+    __syncthreads();
+
+    float asum = 0.f;
+    float gd[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float t0[VW], t1[VW];
+        lds_cell<VW>(s_row, a0[i], t0);
+        lds_cell<VW>(s_row, a1[i], t1);
+        float gix = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCT; ++c) {
+            const float smp = fmaf(t1[c], w1[i], t0[c] * w0[i]);
+            const float err = f4c(rr[c], i) - smp;
+            asum += fabsf(err);
+            const float sg = err > 0.f ? 1.f : (err < 0.f ? -1.f : 0.f);
+            gix = fmaf(sg, t1[c] - t0[c], gix);
+        }
+        gd[i] = tscale * (gmult[i] * gix);
+    }
+    if (active && g_unit)
+        *reinterpret_cast<float4 *>(g_unit + (size_t)b * HW + (unsigned)(y * W + x0)) = make_float4(gd[0], gd[1], gd[2], gd[3]);
+    asum = active ? asum : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) asum += __shfl_xor_sync(0xffffffffu, asum, o);
+    if (lane == 0) s_sum[tid >> 5] = asum;
+    __syncthreads();
+    if (tid == 0) {
+        float tot = 0.f;
+        const int nw = (int)(blockDim.x >> 5);
+        for (int k = 0; k < nw; ++k) tot += s_sum[k];
+        partial[(size_t)b * H + y] = tot;
+    }
+}
+
+template <int PS>
+int launch_photo(const float *imgL, const float *imgR, const float *disp, float *g_unit, float *partial, int *neg_flag,
+                 int B, int C, int H, int W, cudaStream_t s) {
+    void (*kern)(const float *, const float *, const float *, float *, float *, int *, int, int, float, float, float) =
+        C == 1 ? photo_l1_lean_kernel<1, PS> : C == 2 ? photo_l1_lean_kernel<2, PS>
+      : C == 3 ? photo_l1_lean_kernel<3, PS> : photo_l1_lean_kernel<4, PS>;
+    const size_t smem = (size_t)(C == 3 ? 4 : C) * 4 * PS * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "photometric_l1: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+    }
+    kern<<<dim3((unsigned)H, (unsigned)B), round_up(W / 4, 32), smem, s>>>(imgL, imgR, disp, g_unit, partial, neg_flag, H, W,
+                                                                           (float)W / 2.0f, 2.0f / (float)(W - 1), (float)H / 2.0f);
+    return check_launch("photometric_l1");
+}
+
 template <int PS, bool BORDER>
 int launch_fwd(const float *img, const float *disp, float *out, float *mask, int *neg_flag, int B, int C, int H, int W, cudaStream_t s) {
     void (*kern)(const float *, const float *, float *, float *, int *, int, int, float, float) =
@@ -498,6 +631,20 @@ int warp_bwd_lean_f32(const float *g, const float *img, const float *disp, float
     if (((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(disp) |
           reinterpret_cast<uintptr_t>(gV) | reinterpret_cast<uintptr_t>(g_disp)) & 15) != 0) return -1;
     DSSMD_LEAN_PICK(launch_bwd, g, img, disp, gV, g_disp, B, C, H, W, s);
+}
+
+// fused L1 photometric row sums + d/d(disp); -1 when the shape is not eligible
+int photometric_l1_lean_f32(const float *imgL, const float *imgR, const float *disp, float *g_unit, float *partial, int *neg_flag,
+                            int B, int C, int H, int W, cudaStream_t s) {
+    if (!eligible(B, C, H, W)) return -1;
+    if (((reinterpret_cast<uintptr_t>(imgL) | reinterpret_cast<uintptr_t>(imgR) | reinterpret_cast<uintptr_t>(disp) |
+          reinterpret_cast<uintptr_t>(g_unit)) & 15) != 0) return -1;
+    const int w4 = W / 4;
+    if (w4 + 2 <= 66) return launch_photo<66>(imgL, imgR, disp, g_unit, partial, neg_flag, B, C, H, W, s);
+    if (w4 + 2 <= 130) return launch_photo<130>(imgL, imgR, disp, g_unit, partial, neg_flag, B, C, H, W, s);
+    if (w4 + 2 <= 258) return launch_photo<258>(imgL, imgR, disp, g_unit, partial, neg_flag, B, C, H, W, s);
+    if (w4 + 2 <= 514) return launch_photo<514>(imgL, imgR, disp, g_unit, partial, neg_flag, B, C, H, W, s);
+    return launch_photo<1026>(imgL, imgR, disp, g_unit, partial, neg_flag, B, C, H, W, s);
 }
 
 #undef DSSMD_LEAN_PICK

@@ -123,6 +123,22 @@ DSSMD_API int dssmd_resize_bilinear_bwd(const void *g_out, void *g_in, int B, in
 DSSMD_API int dssmd_lrwarp_error_fwd(const void *imgL, const void *disp, const void *imgR, void *out, int *neg_flag,
                            int B, int C, int H0, int W0, int H, int W, int dtype, void *stream);
 
+/* ---- fused L1 photometric term on the warp residual --------------------------------
+ * The primitive of a photometric / reconstruction loss.  Upstream ships
+ * only LRwarp_error (utils/disparity_warper.py:109-115) and no loss that calls it; this entry point
+ * computes, for images already at disp's resolution,
+ *   err = imgR - warp(imgL, disp)                     ('border' padding, as LRwarp_error)
+ *   row_sums[b*H + y] = sum_{c,x} |err[b,c,y,x]|      (fp32, fixed summation order)
+ *   g_disp_unit[b,0,y,x] = d(sum |err|) / d(disp[b,0,y,x])        (may be NULL)
+ * in one pass and without writing err: sum(row_sums) / (B*C*H*W) is
+ * LRwarp_error(imgL, disp, imgR).abs().mean(), and g_disp_unit times the upstream scalar / (B*C*H*W)
+ * is its gradient w.r.t. disp (what autograd derives through aten::abs, the subtraction and
+ * grid_sampler_2d_backward).  The images carry no gradient.  `neg_flag` as in dssmd_warp_fwd.
+ * imgL, imgR: [B,C,H,W]; disp, g_disp_unit: [B,1,H,W]; row_sums: [B*H].  dtype: F32;
+ * DSSMD_ERR_UNSUPPORTED for shapes outside C <= 4, W % 4 == 0, H >= 2, 16-byte aligned tensors. */
+DSSMD_API int dssmd_photometric_l1_fwd(const void *imgL, const void *imgR, const void *disp, void *g_disp_unit, void *row_sums,
+                             int *neg_flag, int B, int C, int H, int W, int dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,6 +129,36 @@ def gen_lrwarp():
     print("lrwarp.npz:", len(lrwarp_cases()), "cases")
 
 
+def photo_cases():
+    # name, B, C, H0, W0, [(H, W) per scale], weights
+    return [
+        ("pyramid4", 2, 3, 16, 32, [(2, 4), (4, 8), (8, 16), (16, 32)], (0.6, 0.8, 1.0, 1.0)),
+        ("single", 1, 3, 12, 24, [(12, 24)], (1.0,)),
+        ("c1_half", 1, 1, 8, 40, [(4, 20)], (0.5,)),
+    ]
+
+
+def gen_photo():
+    """The photometric loss has no upstream caller; its definition in upstream terms is
+    sum_s w_s * LRwarp_error(imgL, disp_s, imgR).abs().mean()  (dssmd_b200/losses.py)."""
+    out = {}
+    for i, (name, B, C, H0, W0, sizes, weights) in enumerate(photo_cases()):
+        torch.manual_seed(SEED + 300 + i)
+        imgL, imgR = torch.rand(B, C, H0, W0), torch.rand(B, C, H0, W0)
+        disps = [(torch.rand(B, 1, h, w) * (w / 4.0)).requires_grad_(True) for h, w in sizes]
+        terms = [LRwarp_error(imgL, d, imgR).abs().mean() for d in disps]
+        total = sum(wt * t for wt, t in zip(weights, terms))
+        total.backward()
+        out.update({f"{name}.imgL": _np(imgL), f"{name}.imgR": _np(imgR), f"{name}.n": np.int32(len(sizes)),
+                    f"{name}.weights": np.asarray(weights, dtype=np.float64), f"{name}.total": np.float64(total.item()),
+                    f"{name}.terms": np.asarray([t.item() for t in terms], dtype=np.float64)})
+        for k, d in enumerate(disps):
+            out[f"{name}.disp{k}"] = _np(d)
+            out[f"{name}.g_disp{k}"] = _np(d.grad)
+    np.savez_compressed(os.path.join(OUT, "photo.npz"), **out)
+    print("photo.npz:", len(photo_cases()), "cases")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # fixed reduction order for the fixtures
@@ -136,3 +166,4 @@ if __name__ == "__main__":
     gen_corr()
     gen_warp()
     gen_lrwarp()
+    gen_photo()

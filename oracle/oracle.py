@@ -147,6 +147,20 @@ def lrwarp_error(imgL: np.ndarray, disp: np.ndarray, imgR: np.ndarray) -> np.nda
     return out
 
 
+def photometric_l1(imgL: np.ndarray, disp: np.ndarray, imgR: np.ndarray):
+    """LRwarp_error(imgL, disp, imgR).abs().mean() and its gradient w.r.t. disp, composed from the restated
+    pieces exactly as autograd composes upstream's: d|e|/de = sign(e), d(err)/d(warped) = -1, then the
+    backward of the 'border' warp of the (resized) left image.  Returns (loss as a Python float, g_disp)."""
+    err = lrwarp_error(imgL, disp, imgR)
+    n = err.size
+    loss = float(np.abs(err.astype(np.float64)).sum() / n)
+    H, W = disp.shape[-2:]
+    Ls = resize_bilinear(_c(imgL), (H, W)) if imgL.shape[-1] > W else _c(imgL)
+    g = (-np.sign(err) / n).astype(err.dtype)
+    _, g_disp = warp_bwd(g, Ls, _c(disp, err.dtype), "border")
+    return loss, g_disp
+
+
 # ---- bf16 helpers (the CUDA path takes bf16 I/O with fp32 accumulation) ----
 def bf16_round(a: np.ndarray) -> np.ndarray:
     """Round float32 values to the nearest bfloat16 (ties to even), kept as float32."""

@@ -423,3 +423,81 @@ def test_lrwarp_pyramid_vs_torch(ops, scale):
     rs = ops.resize_bilinear(imgL, disp.shape[-2:])
     rr = torch.nn.functional.interpolate(imgL, size=disp.shape[-2:], mode="bilinear", align_corners=False)
     assert rel_err(rs.cpu().numpy(), rr.cpu().numpy()) <= TOL_F32
+
+
+# ---------------------------------------------------------------- photometric L1
+PHOTO = load_cases("photo")
+
+
+@pytest.mark.parametrize("name", sorted(PHOTO))
+def test_photometric_golden(ops, name):
+    """sum_s w_s * LRwarp_error(imgL, disp_s, imgR).abs().mean() and d/d(disp_s), produced by upstream's functions."""
+    c = PHOTO[name]
+    L, R = cuda(c["imgL"]), cuda(c["imgR"])
+    disps = [cuda(c[f"disp{k}"]).requires_grad_(True) for k in range(int(c["n"]))]
+    total = ops.photometric_loss(L, R, disps, weights=[float(w) for w in c["weights"]])
+    total.backward()
+    assert abs(float(total.detach()) - float(c["total"])) <= TOL_F32 * abs(float(c["total"]))
+    for k, d in enumerate(disps):
+        assert rel_err(d.grad.cpu().numpy(), c[f"g_disp{k}"]) <= TOL_F32
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 40, 80, 1), (1, 3, 32, 64, 4), (1, 1, 2, 8, 1), (2, 4, 9, 260, 2), (1, 2, 3, 2064, 1),
+                                   (1, 3, 6, 30, 1),      # W % 4 != 0: composed from LRwarp_error
+                                   (1, 5, 6, 32, 1)],     # C > 4: composed
+                         ids=lambda s: "x".join(map(str, s)))
+def test_photometric_vs_oracle(ops, oracle, shape):
+    B, C, H, W, scale = shape
+    imgL, _ = images(B, C, H * scale, W * scale, 31, smooth=False)
+    imgR, _ = images(B, C, H * scale, W * scale, 32, smooth=False)
+    _, disp = images(B, C, H, W, 33)
+    disp.requires_grad_(True)
+    loss = ops.photometric_l1(imgL, disp, imgR)
+    (loss * 3.0).backward()
+    l_ref, g_ref = oracle.photometric_l1(imgL.cpu().numpy(), disp.detach().cpu().numpy(), imgR.cpu().numpy())
+    assert abs(float(loss) - l_ref) <= TOL_F32 * abs(l_ref)
+    assert rel_err(disp.grad.cpu().numpy(), 3.0 * g_ref) <= TOL_F32
+
+
+def test_photometric_pyramid_full_size_vs_composed(ops):
+    """cfg3's loss: 320x640 images, B8, the models' [1/8, 1/4, 1/2, 1] disparity pyramid.  The fused kernel against the
+    same loss composed from LRwarp_error (whose pieces are pinned above), value and gradient; run-to-run bit equality."""
+    B, H0, W0 = 8, 320, 640
+    imgL, _ = images(B, 3, H0, W0, 41)
+    imgR, _ = images(B, 3, H0, W0, 42)
+    pyr = [images(B, 3, H0 // s, W0 // s, 43 + s)[1].requires_grad_(True) for s in (8, 4, 2, 1)]
+    total = ops.photometric_loss(imgL, imgR, pyr)
+    total.backward()
+    got = [d.grad.clone() for d in pyr]
+    for d in pyr:
+        d.grad = None
+    ref = sum(w * ops.LRwarp_error(imgL, d, imgR).abs().mean() for w, d in zip(ops.losses.PYRAMID_WEIGHTS, pyr))
+    ref.backward()
+    assert abs(float(total) - float(ref)) <= TOL_F32 * abs(float(ref))
+    for g, d in zip(got, pyr):
+        # |err| is not differentiable at err = 0: where the two paths' samples differ in the last ulp and the residual
+        # is ~1e-8, sign(err) flips.  Isolated pixels may differ; everything else must agree to 1e-5.
+        diff = (g - d.grad).abs()
+        scale = float(d.grad.abs().max())
+        assert float((diff > TOL_F32 * scale).float().mean()) <= 2e-5
+        assert float(diff.mean()) <= 1e-6 * scale
+    again = ops.photometric_loss(imgL, imgR, [d.detach().requires_grad_(True) for d in pyr])
+    assert float(again) == float(total)
+
+
+def test_photometric_error_conventions(ops):
+    imgL, disp = images(1, 3, 8, 16, 51)
+    imgR, _ = images(1, 3, 8, 16, 52)
+    bad = disp.clone(); bad[0, 0, 3, 5] = -1.0
+    with pytest.raises(AssertionError):
+        ops.photometric_l1(imgL, bad, imgR)
+    with pytest.raises(RuntimeError):
+        ops.photometric_l1(imgL.cpu(), disp.cpu(), imgR.cpu())      # no CPU fallback
+    with pytest.raises(RuntimeError):
+        ops.photometric_l1(imgL, disp, imgR[:, :2])
+    with pytest.raises(ValueError):
+        ops.photometric_loss(imgL, imgR, [disp, disp], weights=[1.0])
+    # an image that needs a gradient takes upstream's composed graph
+    Lg = imgL.clone().requires_grad_(True)
+    ops.photometric_l1(Lg, disp, imgR).backward()
+    assert Lg.grad is not None and float(Lg.grad.abs().sum()) > 0

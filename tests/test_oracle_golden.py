@@ -100,3 +100,22 @@ def test_warp_invariants():
     # disp = 0 is still a resample, not the identity
     w0, _, _ = O.warp_fwd(img, np.zeros_like(disp))
     assert np.abs(w0 - img).max() > 0.05
+
+
+# ---- photometric L1 on the warp residual -------------
+PHOTO = load_cases("photo")
+
+
+@pytest.mark.parametrize("name", sorted(PHOTO))
+def test_photometric_l1_matches_reference(name):
+    """The fixture holds sum_s w_s * LRwarp_error(imgL, disp_s, imgR).abs().mean() and the autograd gradient of
+    every disparity map, produced by upstream's LRwarp_error (oracle/gen_golden.py: gen_photo)."""
+    c = PHOTO[name]
+    total = 0.0
+    for k in range(int(c["n"])):
+        loss, g_disp = O.photometric_l1(c["imgL"], c[f"disp{k}"], c["imgR"])
+        assert abs(loss - float(c["terms"][k])) <= TOL_F32 * abs(float(c["terms"][k]))
+        w = float(c["weights"][k])
+        assert rel_err(w * g_disp, c[f"g_disp{k}"]) <= TOL_F32
+        total += w * loss
+    assert abs(total - float(c["total"])) <= TOL_F32 * abs(float(c["total"]))
