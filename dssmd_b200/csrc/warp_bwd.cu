@@ -15,6 +15,8 @@
 namespace dssmd {
 
 // warp_lean.cu: instruction-lean horizontal-scatter kernel (K1) for image-like shapes; -1 = not eligible
+int warp_bwd_band_f32(const float *g, const float *img, const float *disp, float *g_img, float *g_disp,
+                      int B, int C, int H, int W, int border, cudaStream_t s);
 int warp_bwd_lean_f32(const float *g, const float *img, const float *disp, float *gV, float *g_disp,
                       int B, int C, int H, int W, int border, cudaStream_t s);
 
@@ -950,12 +952,16 @@ template <typename S>
 int warp_bwd_typed(const void *g, const void *img, const void *disp, void *g_img, void *g_disp,
                    void *workspace, size_t workspace_bytes,
                    int B, int C, int H, int W, int pad, cudaStream_t s) {
-    const int variant = env_int("DSSMD_WARP_BWD_VARIANT", 5);
+    const int variant = env_int("DSSMD_WARP_BWD_VARIANT", 6);
     if constexpr (sizeof(S) == 4) {
         const size_t smem = (size_t)2 * kCC * W * sizeof(int);
         const int border = pad == DSSMD_PAD_BORDER;
         const float *gp = (const float *)g, *ip = (const float *)img, *dp = (const float *)disp;
         float *gi = (float *)g_img, *gd = (float *)g_disp;
+        if (variant >= 6 && g_img) {   // one-pass band kernel: no workspace needed
+            const int rc = warp_bwd_band_f32(gp, ip, dp, gi, gd, B, C, H, W, border, s);
+            if (rc >= 0) return rc;
+        }
         const bool have_ws = workspace && workspace_bytes >= (size_t)B * C * H * W * sizeof(float);
         if (variant >= 4 && C <= 4 && W % 4 == 0 && W <= 4096 && H >= 2 && (long long)C * H * W < (1LL << 31) && (have_ws || !g_img) &&
             ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(disp) | reinterpret_cast<uintptr_t>(workspace) |

@@ -501,3 +501,43 @@ def test_photometric_error_conventions(ops):
     Lg = imgL.clone().requires_grad_(True)
     ops.photometric_l1(Lg, disp, imgR).backward()
     assert Lg.grad is not None and float(Lg.grad.abs().sum()) > 0
+
+
+# ---------------------------------------------------------------- warp backward, one-pass band kernel
+@pytest.mark.parametrize("pad", ["border", "zeros"])
+@pytest.mark.parametrize("rows", [1, 3, 4, 32])
+@pytest.mark.parametrize("shape", [(2, 3, 37, 96), (1, 4, 7, 520), (1, 1, 3, 8), (1, 2, 66, 1028)], ids=lambda s: "x".join(map(str, s)))
+def test_warp_bwd_band_rows(ops, oracle, shape, rows, pad, monkeypatch):
+    """The fused backward with forced band heights: bands of one row, bands that do not divide H, a band taller than
+    the image; every band boundary is a halo row scattered twice."""
+    monkeypatch.setenv("DSSMD_WARP_BWD_BAND_ROWS", str(rows))
+    B, C, H, W = shape
+    img, disp = images(B, C, H, W, 61, smooth=False)
+    img.requires_grad_(True); disp.requires_grad_(True)
+    g = feat((B, C, H, W), 62, False)
+    warped, _ = ops.disp_warp(img, disp, padding_mode=pad)
+    warped.backward(g)
+    gi_ref, gd_ref = oracle.warp_bwd(g.cpu().numpy(), img.detach().cpu().numpy(), disp.detach().cpu().numpy(), pad)
+    assert rel_err(img.grad.cpu().numpy(), gi_ref) <= TOL_F32
+    assert rel_err(disp.grad.cpu().numpy(), gd_ref) <= TOL_F32
+    # only the image needs a gradient: same g_img bits, no g_disp
+    img2 = img.detach().clone().requires_grad_(True)
+    w2, _ = ops.disp_warp(img2, disp.detach(), padding_mode=pad)
+    w2.backward(g)
+    assert torch.equal(img2.grad, img.grad)
+
+
+def test_warp_bwd_band_matches_two_kernel_path(ops, monkeypatch):
+    """Same fixed-point scales, same accumulation order: the one-pass kernel and the scatter + vertical-mix pair
+    must agree to rounding of the per-row |g| sums (<= 1e-6), at a full BASELINE size."""
+    img, disp = images(4, 3, 576, 960, 71)
+    g = feat((4, 3, 576, 960), 72, False)
+    outs = []
+    for variant in ("6", "5"):
+        monkeypatch.setenv("DSSMD_WARP_BWD_VARIANT", variant)
+        i2 = img.clone().requires_grad_(True); d2 = disp.clone().requires_grad_(True)
+        w, _ = ops.disp_warp(i2, d2)
+        w.backward(g)
+        outs.append((i2.grad.clone(), d2.grad.clone()))
+    assert rel_err(outs[0][0].cpu().numpy(), outs[1][0].cpu().numpy()) <= 1e-6
+    assert torch.equal(outs[0][1], outs[1][1])
