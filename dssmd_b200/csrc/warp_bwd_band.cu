@@ -29,8 +29,8 @@ warp_bwd_band_kernel(const float *__restrict__ g, const float *__restrict__ img,
                      float *__restrict__ g_img, float *__restrict__ g_disp, int H, int W, int R,
                      float halfW, float tscale, float halfH) {
     constexpr int P = PS + 6;                 // accumulator slots per plane (see warp_bwd_lean_kernel)
-    constexpr int ACH = 4 * P * 4;            // bytes of one accumulator channel [4][P]
-    constexpr int ABUF = NCT * ACH + 128;     // one accumulator buffer: int acc[NCT][4][P]; int sink[32]
+    constexpr int ACH = 4 * P * 4 + 128;      // bytes of one accumulator channel: int acc[4][P]; int sink[32]
+    constexpr int ABUF = NCT * ACH;           // one accumulator buffer
     constexpr int VW = NCT == 3 ? 4 : NCT;    // floats per difference cell
     constexpr int DBUF = 4 * PS * VW * 4;     // one difference row: float dvr[4][PS][VW] (cell p = k + 4)
     constexpr int NW = (PS - 2) / 32;         // warps per block (upper bound)
@@ -84,6 +84,7 @@ warp_bwd_band_kernel(const float *__restrict__ g, const float *__restrict__ img,
     float go[NCT][4];              // g of the row being scattered
     int k0[4];                     // its left-tap cells and weights
     float w0[4], w1[4], gmult[4];
+    unsigned cmask = 0u;           // 'border': bit j = pixel j is clamped onto the left border cell
     float pendA[NCT][4], pendB[NCT][4];   // partial g_img rows y-1 and y while row y is being read out
     float down_prev[NCT];          // fixed point -> float scale of the row to be read out
 #pragma unroll
@@ -96,19 +97,39 @@ warp_bwd_band_kernel(const float *__restrict__ g, const float *__restrict__ img,
     // ---- stage helpers ------------------------------------------------------------------------------------------
     // per-warp sums of |g| of a row -> s_part[buf]
     auto abs_sums = [&](const float (&gr)[NCT][4], int buf) {
+        float v[4];
 #pragma unroll
-        for (int c = 0; c < NCT; ++c) {
-            float asum = (fabsf(gr[c][0]) + fabsf(gr[c][1])) + (fabsf(gr[c][2]) + fabsf(gr[c][3]));
-            asum = active ? asum : 0.f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) asum += __shfl_xor_sync(0xffffffffu, asum, o);
-            if (lane == 0) s_part[buf][c][wid] = asum;
+        for (int c = 0; c < 4; ++c) {
+            const int cc = c < NCT ? c : 0;
+            const float a = (fabsf(gr[cc][0]) + fabsf(gr[cc][1])) + (fabsf(gr[cc][2]) + fabsf(gr[cc][3]));
+            v[c] = (c < NCT && active) ? a : 0.f;
         }
+        // transposed butterfly: each step halves the number of values a lane carries, so the 32-lane sums of all
+        // channels cost 6 shuffles instead of 5 per channel; channel c ends up in lanes 8c .. 8c+7 (fixed order)
+        const bool h16 = lane & 16, h8 = lane & 8;
+        float k0v, k1v;
+        if (NCT > 2) {
+            const float s0 = h16 ? v[0] : v[2], s1 = h16 ? v[1] : v[3];
+            k0v = (h16 ? v[2] : v[0]) + __shfl_xor_sync(0xffffffffu, s0, 16);
+            k1v = (h16 ? v[3] : v[1]) + __shfl_xor_sync(0xffffffffu, s1, 16);
+        } else {
+            k0v = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+            k1v = v[1] + __shfl_xor_sync(0xffffffffu, v[1], 16);
+        }
+        float r;
+        if (NCT > 1) r = (h8 ? k1v : k0v) + __shfl_xor_sync(0xffffffffu, h8 ? k0v : k1v, 8);
+        else r = k0v + __shfl_xor_sync(0xffffffffu, k0v, 8);
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        // lanes 8c hold channel c: NCT > 2: c = 2 * bit4 + bit3; NCT == 2: c = bit3 (both halves); NCT == 1: c = 0
+        const int c_of = NCT > 2 ? (lane >> 3) : NCT > 1 ? ((lane >> 3) & 1) : 0;
+        if ((lane & 7) == 0 && lane < 8 * NCT && c_of < NCT) s_part[buf][c_of][wid] = r;
     };
     // horizontal taps of a row from its disparities
     auto taps = [&](const float4 &d4) {
         const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
         const float xf0 = (float)xl;
+        cmask = 0u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float t = __fsub_rn(xf0 + (float)j, dd[j]);
@@ -116,6 +137,7 @@ warp_bwd_band_kernel(const float *__restrict__ g, const float *__restrict__ img,
             if (BORDER) {
                 gmult[j] = (ix > 0.0f && ix < wm1) ? halfW : 0.0f;   // clip_coordinates_set_grad
                 axis_border(ix, wm1, k0[j], w0[j], w1[j]);
+                if (ix <= 0.0f) cmask |= 1u << j;                    // clamped onto cell 0 (weights 1, 0)
             } else {
                 gmult[j] = halfW;
                 axis_zeros(ix, W, k0[j], w0[j], w1[j]);
@@ -256,6 +278,18 @@ warp_bwd_band_kernel(const float *__restrict__ g, const float *__restrict__ img,
             }
         }
 
+        // the two image rows that g_disp of row y + 1 differentiates: into L1 now, read by stage_diff at the end of
+        // the iteration (one of them is usually there already -- consecutive output rows share a source row)
+        if (nreal && g_disp && y + 1 >= yb0 && y + 1 < y_end && (lane & 7) == 0) {
+            const int yi0n = s_yi0[y + 1 - ys];
+            const int ya = min(max(yi0n, 0), H - 1), yb = min(max(yi0n + 1, 0), H - 1);
+#pragma unroll
+            for (int c = 0; c < NCT; ++c) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(ib + c * HW + (unsigned)(ya * W)));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(ib + c * HW + (unsigned)(yb * W)));
+            }
+        }
+
         if (y > ys) read_out(y - 1);
 
         float up[NCT];
@@ -293,25 +327,41 @@ warp_bwd_band_kernel(const float *__restrict__ g, const float *__restrict__ img,
                                        : (e < 127) ? __uint_as_float((unsigned)(127 - e) << 23) : __uint_as_float(0x00400000u);
             }
 
-            // scatter row y into acc[buf]
+            // scatter row y into acc[buf].  Taps that would pile onto one cell -- 'border': every pixel whose coordinate is
+            // clamped to the left edge adds to cell 0 (disparities up to 192 px clamp ~10 % of a row; same-address shared
+            // atomics of a warp serialise, 32 wavefronts per instruction); 'zeros': zero-weight taps outside the row --
+            // go to the lane's private sink word instead, and the clamped pixels' contributions are summed across the
+            // warp in integers (exact, order-free) and added to cell 0 once.
             const uint32_t ab = abase + (uint32_t)(buf * ABUF);
-            const uint32_t sink = ab + (uint32_t)(NCT * ACH) + 4u * (uint32_t)lane;
+            const uint32_t sink = ab + (uint32_t)(4 * P * 4) + 4u * (uint32_t)lane;   // + c * ACH: the sink of channel c
             uint32_t aL[4], aR[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                int kl = k0[j], kr = k0[j] + 1;
-                if (!BORDER) { kl = min(max(kl, 0), W); kr = min(max(kr, 0), W); }   // weight 0 outside [0, W)
-                const uint32_t p = (uint32_t)kl, q = (uint32_t)kr;
-                aL[j] = active ? ab + p + (p & 3u) * (uint32_t)(4 * P - 1) : sink;
-                aR[j] = active ? ab + q + (q & 3u) * (uint32_t)(4 * P - 1) : sink;
+                const uint32_t p = (uint32_t)k0[j], q = (uint32_t)(k0[j] + 1);
+                bool okL, okR;
+                if (BORDER) { okL = okR = active && !((cmask >> j) & 1u); }   // right tap at most cell W: inside the allocation, weight 0
+                else { okL = active && p < (uint32_t)W; okR = active && q < (uint32_t)W; }
+                aL[j] = okL ? ab + p + (p & 3u) * (uint32_t)(4 * P - 1) : sink;
+                aR[j] = okR ? ab + q + (q & 3u) * (uint32_t)(4 * P - 1) : sink;
             }
+            int qc[NCT];
 #pragma unroll
             for (int c = 0; c < NCT; ++c) {
+                qc[c] = 0;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float gs = go[c][j] * up[c];   // exact: power-of-two scale
-                    red_add(aL[j] + (uint32_t)(c * ACH), __float2int_rn(gs * w0[j]));
+                    const int qL = __float2int_rn(gs * w0[j]);
+                    red_add(aL[j] + (uint32_t)(c * ACH), qL);
                     red_add(aR[j] + (uint32_t)(c * ACH), __float2int_rn(gs * w1[j]));
+                    if (BORDER) qc[c] += ((cmask >> j) & 1u) ? qL : 0;
+                }
+            }
+            if (BORDER && __any_sync(0xffffffffu, active && cmask != 0u)) {
+#pragma unroll
+                for (int c = 0; c < NCT; ++c) {
+                    const int tot = __reduce_add_sync(0xffffffffu, active ? qc[c] : 0);
+                    if (lane == 0) red_add(ab + (uint32_t)(c * ACH), tot);   // cell 0
                 }
             }
         }
@@ -337,7 +387,7 @@ int launch_band(const float *g, const float *img, const float *disp, float *g_im
         C == 1 ? warp_bwd_band_kernel<1, PS, BORDER> : C == 2 ? warp_bwd_band_kernel<2, PS, BORDER>
       : C == 3 ? warp_bwd_band_kernel<3, PS, BORDER> : warp_bwd_band_kernel<4, PS, BORDER>;
     const int vw = C == 3 ? 4 : C;
-    const size_t smem = 2 * ((size_t)C * 4 * (PS + 6) * 4 + 128) + 2 * ((size_t)4 * PS * vw * 4);
+    const size_t smem = 2 * (size_t)C * (4 * (PS + 6) * 4 + 128) + 2 * ((size_t)4 * PS * vw * 4);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "warp_bwd(band): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
     const int threads = round_up(W / 4, 32);

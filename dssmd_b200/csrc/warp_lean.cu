@@ -158,9 +158,9 @@ __global__ void __launch_bounds__(PS - 2, 1024 / (PS - 2)) warp_bwd_lean_kernel(
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int P = PS + 6;          // accumulator slots per plane: >= W/4 + 1, and = 8 (mod 32) so that the four
                                        // planes start 8 banks apart (lanes whose taps straddle planes do not collide)
-    constexpr int ACH = 4 * P * 4;     // bytes of one accumulator channel [4][P]
+    constexpr int ACH = 4 * P * 4 + 128;   // bytes of one accumulator channel: int acc[4][P]; int sink[32]
     constexpr int VW = NCT == 3 ? 4 : NCT;   // floats per difference cell (all channels of a pixel)
-    // layout: int acc[NCT][4][P]; int sink[32]; float dvr[4][PS][VW] (cell p = k + 4)
+    // layout: { int acc[4][P]; int sink[32]; }[NCT]; float dvr[4][PS][VW] (cell p = k + 4)
     __shared__ float s_part[NCT][32];  // per-warp, per-channel sums of |g|
 
     const int W4 = W >> 2;
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(PS - 2, 1024 / (PS - 2)) warp_bwd_lean_kernel(
     const int xl = active ? x0 : W - 4;   // idle threads of the last warp re-read the last pixels (loads stay unconditional)
     const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
     const uint32_t abase = smem_u32(smem_raw);      // accumulators (for the RED instructions)
-    unsigned char *const dvr = smem_raw + NCT * ACH + 128;  // difference rows
+    unsigned char *const dvr = smem_raw + NCT * ACH;  // difference rows
     const unsigned orow = (unsigned)(y * W + xl);
 
     // output-row loads first
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(PS - 2, 1024 / (PS - 2)) warp_bwd_lean_kernel(
     {
         // cell addresses inside channel 0.  'border': the left tap is always inside, the right tap is at most cell W
         // (plane 0, one slot past the row: inside the allocation) and then has weight 0.
-        const uint32_t sink = abase + (uint32_t)(NCT * ACH) + 4u * (uint32_t)lane;
+        const uint32_t sink = abase + (uint32_t)(4 * P * 4) + 4u * (uint32_t)lane;   // + c * ACH: the sink of channel c
         uint32_t aL[4], aR[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -503,7 +503,7 @@ int launch_bwd(const float *g, const float *img, const float *disp, float *gV, f
     void (*kern)(const float *, const float *, const float *, float *, float *, int, int, float, float, float, int) =
         C == 1 ? warp_bwd_lean_kernel<1, PS, BORDER> : C == 2 ? warp_bwd_lean_kernel<2, PS, BORDER>
       : C == 3 ? warp_bwd_lean_kernel<3, PS, BORDER> : warp_bwd_lean_kernel<4, PS, BORDER>;
-    const size_t smem = ((size_t)C * 4 * (PS + 6) + 32 + (size_t)(C == 3 ? 4 : C) * 4 * PS) * sizeof(int);
+    const size_t smem = ((size_t)C * (4 * (PS + 6) + 32) + (size_t)(C == 3 ? 4 : C) * 4 * PS) * sizeof(int);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "warp_bwd: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));

@@ -506,7 +506,7 @@ def test_photometric_error_conventions(ops):
 # ---------------------------------------------------------------- warp backward, one-pass band kernel
 @pytest.mark.parametrize("pad", ["border", "zeros"])
 @pytest.mark.parametrize("rows", [1, 3, 4, 32])
-@pytest.mark.parametrize("shape", [(2, 3, 37, 96), (1, 4, 7, 520), (1, 1, 3, 8), (1, 2, 66, 1028)], ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("shape", [(2, 3, 37, 96), (1, 4, 7, 520), (1, 1, 3, 8), (1, 2, 66, 1028), (2, 3, 6, 512)], ids=lambda s: "x".join(map(str, s)))
 def test_warp_bwd_band_rows(ops, oracle, shape, rows, pad, monkeypatch):
     """The fused backward with forced band heights: bands of one row, bands that do not divide H, a band taller than
     the image; every band boundary is a halo row scattered twice."""
