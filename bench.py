@@ -219,6 +219,8 @@ def cpu_step_factory(w, batch):
         O.warp_fwd(img, disp, "border")
         O.warp_bwd(gi, img, disp, "border")
 
+    # all host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to every rank)
+    O.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     return step, O.num_threads()
 
 
@@ -443,7 +445,7 @@ def run_gpu(args, w):
                     "share_of_step": round(kern[dom]["us"] / sum(k["us"] for k in kern.values()), 3)}
         # CPU baseline: oracle port, bounded sample (one per-GPU batch, best of 2)
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # reported at N = 1 only (the host cores are shared by the ranks)
             stepf, cores = cpu_step_factory(w, B)
             stepf()
             best = 1e30

@@ -17,6 +17,8 @@
 // Accumulation order per output element: ascending source row, fma chain from 0 (the order of K2).  Deterministic.
 #include "warp_lean.cuh"
 
+#include <type_traits>
+
 namespace dssmd {
 
 namespace {
@@ -334,36 +336,38 @@ warp_bwd_band_kernel(const float *__restrict__ g, const float *__restrict__ img,
             // warp in integers (exact, order-free) and added to cell 0 once.
             const uint32_t ab = abase + (uint32_t)(buf * ABUF);
             const uint32_t sink = ab + (uint32_t)(4 * P * 4) + 4u * (uint32_t)lane;   // + c * ACH: the sink of channel c
-            uint32_t aL[4], aR[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t p = (uint32_t)k0[j], q = (uint32_t)(k0[j] + 1);
-                bool okL, okR;
-                if (BORDER) { okL = okR = active && !((cmask >> j) & 1u); }   // right tap at most cell W: inside the allocation, weight 0
-                else { okL = active && p < (uint32_t)W; okR = active && q < (uint32_t)W; }
-                aL[j] = okL ? ab + p + (p & 3u) * (uint32_t)(4 * P - 1) : sink;
-                aR[j] = okR ? ab + q + (q & 3u) * (uint32_t)(4 * P - 1) : sink;
-            }
-            int qc[NCT];
-#pragma unroll
-            for (int c = 0; c < NCT; ++c) {
-                qc[c] = 0;
+            // most warps have no clamped pixel: warp-uniform choice between the plain scatter and the one that diverts
+            auto scatter = [&](auto clamped_path) {
+                constexpr bool CL = decltype(clamped_path)::value;
+                uint32_t aL[4], aR[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float gs = go[c][j] * up[c];   // exact: power-of-two scale
-                    const int qL = __float2int_rn(gs * w0[j]);
-                    red_add(aL[j] + (uint32_t)(c * ACH), qL);
-                    red_add(aR[j] + (uint32_t)(c * ACH), __float2int_rn(gs * w1[j]));
-                    if (BORDER) qc[c] += ((cmask >> j) & 1u) ? qL : 0;
+                    const uint32_t p = (uint32_t)k0[j], q = (uint32_t)(k0[j] + 1);
+                    bool okL, okR;
+                    if (BORDER) { okL = okR = CL ? (active && !((cmask >> j) & 1u)) : active; }   // right tap at most cell W: allocated, weight 0
+                    else { okL = active && p < (uint32_t)W; okR = active && q < (uint32_t)W; }
+                    aL[j] = okL ? ab + p + (p & 3u) * (uint32_t)(4 * P - 1) : sink;
+                    aR[j] = okR ? ab + q + (q & 3u) * (uint32_t)(4 * P - 1) : sink;
                 }
-            }
-            if (BORDER && __any_sync(0xffffffffu, active && cmask != 0u)) {
 #pragma unroll
                 for (int c = 0; c < NCT; ++c) {
-                    const int tot = __reduce_add_sync(0xffffffffu, active ? qc[c] : 0);
-                    if (lane == 0) red_add(ab + (uint32_t)(c * ACH), tot);   // cell 0
+                    int qc = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float gs = go[c][j] * up[c];   // exact: power-of-two scale
+                        const int qL = __float2int_rn(gs * w0[j]);
+                        red_add(aL[j] + (uint32_t)(c * ACH), qL);
+                        red_add(aR[j] + (uint32_t)(c * ACH), __float2int_rn(gs * w1[j]));
+                        if (CL) qc += ((cmask >> j) & 1u) ? qL : 0;
+                    }
+                    if (CL) {
+                        const int tot = __reduce_add_sync(0xffffffffu, active ? qc : 0);
+                        if (lane == 0) red_add(ab + (uint32_t)(c * ACH), tot);   // cell 0
+                    }
                 }
-            }
+            };
+            if (BORDER && __any_sync(0xffffffffu, active && cmask != 0u)) scatter(std::true_type{});
+            else scatter(std::false_type{});
         }
 
         // stage row y + 1
