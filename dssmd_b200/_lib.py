@@ -31,6 +31,7 @@ SIGNATURES = {
     "dssmd_resize_bilinear_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "dssmd_lrwarp_error_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "dssmd_photometric_l1_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "dssmd_selftest_division": [_i, _i, _vp, _vp],
 }
 
 _lib = None

@@ -51,6 +51,7 @@ warp_bwd_band_kernel(const float *__restrict__ g, const float *__restrict__ img,
     const bool active = tid < W4;
     const int xl = active ? tid * 4 : W - 4;    // idle threads of the last warp re-read the last pixels
     const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+    const float rwm1 = div_rn_recip(wm1);
     const uint32_t abase = smem_u32(smem_raw);
     unsigned char *const dvr_base = smem_raw + 2 * ABUF;
     const int nwarps = (int)(blockDim.x >> 5);
@@ -135,7 +136,7 @@ warp_bwd_band_kernel(const float *__restrict__ g, const float *__restrict__ img,
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float t = __fsub_rn(xf0 + (float)j, dd[j]);
-            const float ix = unnorm_f(t, wm1, halfW);
+            const float ix = unnorm_f(t, wm1, rwm1, halfW);
             if (BORDER) {
                 gmult[j] = (ix > 0.0f && ix < wm1) ? halfW : 0.0f;   // clip_coordinates_set_grad
                 axis_border(ix, wm1, k0[j], w0[j], w1[j]);

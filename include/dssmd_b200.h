@@ -139,6 +139,16 @@ DSSMD_API int dssmd_lrwarp_error_fwd(const void *imgL, const void *disp, const v
 DSSMD_API int dssmd_photometric_l1_fwd(const void *imgL, const void *imgR, const void *disp, void *g_disp_unit, void *row_sums,
                              int *neg_flag, int B, int C, int H, int W, int dtype, void *stream);
 
+/* ---- self test ------------------------------------------------------------------------
+ * The lean warp kernels divide pixel coordinates by W - 1 with a reciprocal hoisted out of the pixel loop
+ * (csrc/warp_lean.cuh: div_rn_by) and rely on that being IEEE round-to-nearest division, bit for bit -- the
+ * validity mask is compared exactly with upstream's.  This entry point checks it on the device against
+ * __fdiv_rn for every divisor W - 1 with W in [W_lo, W_hi] and every numerator k / 64, k in [-16384, 64 * W_hi]
+ * (a superset of the x - disp values the kernels see at 1/64-pixel resolution), plus the same numerators
+ * perturbed by one ulp either way.  *mismatches (device or pinned-host memory, 8 bytes, zeroed by the
+ * caller) receives the number of differing quotients. */
+DSSMD_API int dssmd_selftest_division(int W_lo, int W_hi, unsigned long long *mismatches, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
