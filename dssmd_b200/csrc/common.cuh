@@ -8,6 +8,8 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <utility>
 
 #include "../../include/dssmd_b200.h"
 
@@ -58,6 +60,37 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 // streaming 128-bit global store (outputs are written once, never re-read here)
 __device__ __forceinline__ void st_global_cs(float4 *p, float4 v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------
+// The hot-path kernels are short (10-40 us) and follow each other on one stream, so the drain of one kernel and the
+// ramp of the next (block scheduling, shared-memory carve-out, barrier init, tensor-map fetch) are a measurable
+// share of the step.  Launched with programmatic stream serialization, a kernel's blocks may become resident while
+// the previous kernel on the stream is still draining; pdl_wait() (griddepcontrol.wait) then blocks until that
+// kernel has completed and its writes are visible, so stream order is preserved as long as no global memory is
+// touched before it.  pdl_launch_dependents() lets the NEXT kernel's blocks start their own ramp.
+// Both are no-ops for a kernel launched without the attribute.  DSSMD_PDL=0 disables the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+static inline bool pdl_enabled() {
+    const char *v = std::getenv("DSSMD_PDL");
+    return !(v && v[0] == '0');
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
 }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -70,6 +70,8 @@ __global__ void __launch_bounds__(PX == 4 ? 512 : 256) corr_bwd_reg_kernel(const
         fence_proxy_async();
     }
     __syncthreads();
+    pdl_launch_dependents();  // the next kernel on the stream may start its ramp
+    pdl_wait();               // nothing above touches global memory
 
     auto issue = [&](int it, int s) {  // one thread
         const int cb = it % p.NCB, rx = it / p.NCB;
@@ -234,7 +236,8 @@ int launch_reg(RegParams p, const CUtensorMap &mapIn, const CUtensorMap &mapG, i
     if (env_int_reg("DSSMD_CORR_DEBUG", 0))
         fprintf(stderr, "corr_bwd reg cfg: es=%d mode=%d PX=%d NH=%d WPR=%d TX=%d XT=%d CGW=%d CB=%d items=%d ipb=%d grid=%d (x%d/SM) threads=%d smem=%zu\n",
                 (int)sizeof(T), MODE, PX, p.NH, p.WPR, p.TX, p.XT, p.CGW, p.CB, p.nitems, p.ipb, grid, bps, threads, smem);
-    kern<<<(unsigned)grid, threads, smem, stream>>>(p, mapIn, mapG);
+    const cudaError_t le = launch_pdl(kern, dim3((unsigned)grid), dim3((unsigned)threads), smem, stream, p, mapIn, mapG);
+    if (le != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_bwd(reg): launch failed: %s", cudaGetErrorString(le));
     return check_launch(MODE == 0 ? "corr_bwd(gL, reg)" : "corr_bwd(gR, reg)");
 }
 

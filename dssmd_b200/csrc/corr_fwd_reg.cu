@@ -61,6 +61,8 @@ __global__ void __launch_bounds__(512) corr_fwd_reg_kernel(const FwdRegParams p,
         fence_proxy_async();
     }
     __syncthreads();
+    pdl_launch_dependents();  // the next kernel on the stream may start its ramp
+    pdl_wait();               // nothing above touches global memory
 
     auto issue = [&](int it, int s) {  // one thread
         const int cb = it % p.NCB, gx = it / p.NCB;
@@ -185,7 +187,8 @@ int launch_fwd_reg(FwdRegParams p, const CUtensorMap &mapL, const CUtensorMap &m
     if (env_int_fwd("DSSMD_CORR_DEBUG", 0))
         fprintf(stderr, "corr_fwd reg cfg: es=%d NH=%d WPR=%d TX=%d XT=%d CGW=%d CB=%d NCB=%d groups=%d gpb=%d grid=%d (x%d/SM) threads=%d smem=%zu\n",
                 (int)sizeof(T), p.NH, p.WPR, p.TX, p.XT, p.CGW, p.CB, p.NCB, p.ngroups, p.gpb, grid, bps, threads, smem);
-    kern<<<(unsigned)grid, threads, smem, stream>>>(p, mapL, mapR);
+    const cudaError_t le = launch_pdl(kern, dim3((unsigned)grid), dim3((unsigned)threads), smem, stream, p, mapL, mapR);
+    if (le != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_fwd(reg): launch failed: %s", cudaGetErrorString(le));
     return check_launch("corr_fwd(reg)");
 }
 

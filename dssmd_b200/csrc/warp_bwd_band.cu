@@ -249,6 +249,8 @@ warp_bwd_band_kernel(const float *__restrict__ g, const float *__restrict__ img,
 
     // ---- first row ------------------------------------------------------------------------------------------------
     __syncthreads();   // table visible
+    pdl_launch_dependents();
+    pdl_wait();        // nothing above touches global memory
     {
         const unsigned orow = (unsigned)(ys * W);
         const float4 d4 = __ldg(reinterpret_cast<const float4 *>(db + orow));
@@ -408,8 +410,9 @@ int launch_band(const float *g, const float *img, const float *disp, float *g_im
     }
     if (R > kMaxBandRows) R = kMaxBandRows;
     if (R > H) R = H;
-    kern<<<dim3((unsigned)ceil_div(H, R), (unsigned)B), threads, smem, s>>>(g, img, disp, g_img, g_disp, H, W, R, (float)W / 2.0f,
-                                                                             2.0f / (float)(W - 1), (float)H / 2.0f);
+    e = launch_pdl(kern, dim3((unsigned)ceil_div(H, R), (unsigned)B), dim3((unsigned)threads), smem, s, g, img, disp, g_img, g_disp, H, W, R,
+                   (float)W / 2.0f, 2.0f / (float)(W - 1), (float)H / 2.0f);
+    if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "warp_bwd(band): launch failed: %s", cudaGetErrorString(e));
     return check_launch("warp_bwd(band)");
 }
 

@@ -57,6 +57,9 @@ __global__ void __launch_bounds__(PS - 2, 1024 / (PS - 2)) warp_fwd_lean_kernel(
     if (BORDER) axis_border(iy_raw, hm1, yi0, yw0, yw1);
     else { yi0 = ymi0; yw0 = ymw0; yw1 = ymw1; }
 
+    pdl_launch_dependents();
+    pdl_wait();   // first global access below
+
     // source rows -> registers (in flight while the coordinates are computed).  Loads are unconditional (a
     // predicated load costs a branch): a tap row outside the image is read from the nearest row and has
     // weight 0, idle threads of the last warp re-read the last pixels.
@@ -497,7 +500,9 @@ int launch_fwd(const float *img, const float *disp, float *out, float *mask, int
         if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "warp_fwd: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
     }
     // W/2 and H/2: IEEE single divisions, the same values the device would compute
-    kern<<<dim3((unsigned)H, (unsigned)B), round_up(W / 4, 32), smem, s>>>(img, disp, out, mask, neg_flag, H, W, (float)W / 2.0f, (float)H / 2.0f);
+    const cudaError_t le = launch_pdl(kern, dim3((unsigned)H, (unsigned)B), dim3((unsigned)round_up(W / 4, 32)), smem, s, img, disp, out, mask, neg_flag, H, W,
+                                      (float)W / 2.0f, (float)H / 2.0f);
+    if (le != cudaSuccess) return fail(DSSMD_ERR_CUDA, "warp_fwd(lean): launch failed: %s", cudaGetErrorString(le));
     return check_launch("warp_fwd(lean)");
 }
 

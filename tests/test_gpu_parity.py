@@ -550,3 +550,36 @@ def test_hoisted_reciprocal_division_is_ieee(ops):
     bad = torch.zeros(1, dtype=torch.int64, device="cuda")
     _lib.check(_lib.lib().dssmd_selftest_division(4, 4096, _lib.ptr(bad), _lib.stream_ptr(bad.device)))
     assert int(bad.item()) == 0
+
+
+def test_back_to_back_dependent_launches(ops, oracle):
+    """The hot-path kernels are launched with programmatic stream serialization (a kernel may become resident while
+    its predecessor drains).  Stream order must still hold: chains in which each launch consumes the previous
+    launch's output directly, with no other kernel in between, repeated to give a race a chance to show."""
+    img, disp = images(2, 3, 96, 320, 81, smooth=False)
+    w_ref = img.cpu().numpy()
+    for _ in range(3):
+        w_ref, _, _ = oracle.warp_fwd(w_ref, disp.cpu().numpy(), "border")
+    L, R = feat((2, 64, 24, 80), 82), feat((2, 64, 24, 80), 83)
+    c_ref = oracle.corr_fwd(L.cpu().numpy(), R.cpu().numpy(), 64)
+    c_ref = oracle.corr_fwd(c_ref, c_ref, 16)
+    for _ in range(25):
+        w = img
+        for _ in range(3):
+            w, _ = ops.disp_warp(w, disp)
+        c = ops.build_corr(ops.build_corr(L, R, 64), ops.build_corr(L, R, 64), 16)
+        assert rel_err(w.cpu().numpy(), w_ref) <= TOL_F32
+        assert rel_err(c.cpu().numpy(), c_ref) <= TOL_F32
+    # backward chain: g_img of one warp is the upstream gradient of the next
+    g = feat((2, 3, 96, 320), 84, False)
+    gi_ref = g.cpu().numpy()
+    for _ in range(2):
+        gi_ref, _ = oracle.warp_bwd(gi_ref, img.cpu().numpy(), disp.cpu().numpy(), "border")
+    for _ in range(10):
+        x = img.clone().requires_grad_(True)
+        y, _ = ops.disp_warp(x, disp)
+        (gi1,) = torch.autograd.grad(y, x, g)
+        x2 = img.clone().requires_grad_(True)
+        y2, _ = ops.disp_warp(x2, disp)
+        (gi2,) = torch.autograd.grad(y2, x2, gi1)
+        assert rel_err(gi2.cpu().numpy(), gi_ref) <= TOL_F32
