@@ -46,11 +46,25 @@ warp_bwd_band_kernel(const float *__restrict__ g, const float *__restrict__ img,
     const int b = blockIdx.y;
     const int yb0 = blockIdx.x * R;             // owned rows [yb0, y_end)
     const int y_end = min(yb0 + R, H);
-    const int ys = max(yb0 - 1, 0);             // processed rows ys .. y_end (row H is virtual: contributes nothing)
+    // Processed rows ys .. y_end: the owned rows plus the neighbours whose vertical taps reach an owned row.  The taps of
+    // row y fall on rows {y-1, y} in the upper half of the image and on {y, y+1} in the lower half, so a band that does
+    // not straddle the middle needs only ONE of its two neighbours; the other is skipped (row above) or treated like
+    // the virtual row H that contributes nothing (row below).
+    const float hm1 = (float)(H - 1);
+    auto reaches = [&](int y, int r) {   // does output row y have a vertical tap on row r?  (same classification as the table)
+        int i0;
+        float a, b2;
+        const float iy_raw = unnorm_f((float)y, hm1, halfH);
+        if (BORDER) axis_border(iy_raw, hm1, i0, a, b2);
+        else axis_zeros(iy_raw, H, i0, a, b2);
+        return ((unsigned)i0 < (unsigned)H && i0 == r) || ((unsigned)(i0 + 1) < (unsigned)H && i0 + 1 == r);
+    };
+    const int ys = (yb0 > 0 && reaches(yb0 - 1, yb0)) ? yb0 - 1 : yb0;
+    const int y_real = (y_end < H && reaches(y_end, y_end - 1)) ? y_end + 1 : y_end;   // rows y < y_real are scattered
     const unsigned HW = (unsigned)(H * W);
     const bool active = tid < W4;
     const int xl = active ? tid * 4 : W - 4;    // idle threads of the last warp re-read the last pixels
-    const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+    const float wm1 = (float)(W - 1);
     const float rwm1 = div_rn_recip(wm1);
     const uint32_t abase = smem_u32(smem_raw);
     unsigned char *const dvr_base = smem_raw + 2 * ABUF;
@@ -199,7 +213,7 @@ warp_bwd_band_kernel(const float *__restrict__ g, const float *__restrict__ img,
     // emit g_img row y - 1
     auto read_out = [&](int y) {
         const int t = y - ys;
-        const bool real = y < H;
+        const bool real = y < y_real;
         const int yi0 = s_yi0[t];
         const float yw0 = s_yw0[t], yw1 = s_yw1[t];
         const bool in0 = (unsigned)yi0 < (unsigned)H, in1 = (unsigned)(yi0 + 1) < (unsigned)H;
@@ -266,8 +280,8 @@ warp_bwd_band_kernel(const float *__restrict__ g, const float *__restrict__ img,
     __syncthreads();
 
     for (int y = ys; y <= y_end; ++y) {
-        const bool real = y < H;
-        const bool nreal = y + 1 <= y_end && y + 1 < H;   // a next row exists and is a real one
+        const bool real = y < y_real;
+        const bool nreal = y + 1 < y_real;   // a next row exists and is scattered
         const int buf = y & 1;
 
         // loads of row y + 1, in flight while rows y - 1 and y are worked on
