@@ -283,7 +283,7 @@ def run_gpu(args, w):
     calls = [kernel_calls(torch, lib, _lib, w, s) for s in sets]
     names = list(calls[0].keys())
     # dssmd_warp_bwd is two kernels (horizontal scatter, vertical mix); the other calls are one each
-    launches_per_step = sum(2 if n == "warp_bwd" else 1 for n in names)
+    launches_per_step = len(names)   # one kernel per C-ABI call (the warp backward is a single band kernel at these shapes)
     set_bytes = sum(t.numel() * t.element_size() for t in sets[0].values())
 
     def eager_step(i):
