@@ -7,6 +7,7 @@ kernels.  No CPU fallback, no Triton, no multi-backend dispatch.
 from .cost_volume import CostVolume
 from .disparity_warper import LRwarp_error, disp_warp, meshgrid, normalize_coords, read_pfm
 from .functional import resize_bilinear, set_check_negative_disparity
+from .haze import convert_disp_to_depth, depth2trans, recover_haze_images, synthesize_haze
 from .install import install, uninstall
 from .losses import photometric_l1, photometric_loss
 from .stereo_op import print_tensor_shape
@@ -16,5 +17,6 @@ __all__ = [
     "build_corr", "CostVolume", "disp_warp", "LRwarp_error", "normalize_coords", "meshgrid",
     "read_pfm", "print_tensor_shape", "resize_bilinear", "set_check_negative_disparity",
     "install", "uninstall", "photometric_l1", "photometric_loss",
+    "convert_disp_to_depth", "depth2trans", "recover_haze_images", "synthesize_haze",
 ]
 __version__ = "0.1.0"

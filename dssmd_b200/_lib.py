@@ -32,6 +32,7 @@ SIGNATURES = {
     "dssmd_lrwarp_error_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "dssmd_photometric_l1_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "dssmd_selftest_division": [_i, _i, _vp, _vp],
+    "dssmd_haze_fwd": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
 }
 
 _lib = None

@@ -14,7 +14,7 @@ from __future__ import annotations
 import importlib
 import sys
 
-from . import cost_volume, disparity_warper, submoudles
+from . import cost_volume, disparity_warper, haze, submoudles
 
 # upstream module -> {attribute: replacement}
 _DEFINING = {
@@ -24,9 +24,15 @@ _DEFINING = {
                                   "LRwarp_error": disparity_warper.LRwarp_error},
     "utils.disparity_warper": {"disp_warp": disparity_warper.disp_warp,
                                "LRwarp_error": disparity_warper.LRwarp_error},
+    # haze synthesis on the input side of the training step (trainfiles/dssmd_traner_new.py:22, 250-256)
+    "DeBug.inference": {"convert_disp_to_depth": haze.convert_disp_to_depth, "depth2trans": haze.depth2trans,
+                        "recover_haze_images": haze.recover_haze_images},
 }
 # modules that copy those names into their own namespace at import time
-_IMPORTERS = ["models.DSSMD", "models.DSSMD_new", "models.SSMDNet", "models.SDNet"]
+_IMPORTERS = ["models.DSSMD", "models.DSSMD_new", "models.SSMDNet", "models.SDNet",
+              "trainfiles.dssmd_traner_new", "trainfiles.dssmd_trainer", "trainfiles.dssmd_disp_only",
+              "trainfiles.bidnet_trainer", "trainfiles.ffanet_trainer", "trainfiles.ffanet_trainer_kitti",
+              "trainfiles.ffanet_trainer_ddp", "DeBug.test_model", "DeBug.test_model_only"]
 
 _saved = {}
 
@@ -42,7 +48,7 @@ def install(import_missing: bool = True):
         if mod is None and import_missing:
             try:
                 mod = importlib.import_module(modname)
-            except ImportError:
+            except Exception:  # DeBug.inference needs skimage / matplotlib; patched only where it imports
                 mod = None
         if mod is None:
             continue

@@ -139,6 +139,20 @@ DSSMD_API int dssmd_lrwarp_error_fwd(const void *imgL, const void *disp, const v
 DSSMD_API int dssmd_photometric_l1_fwd(const void *imgL, const void *imgR, const void *disp, void *g_disp_unit, void *row_sums,
                              int *neg_flag, int B, int C, int H, int W, int dtype, void *stream);
 
+/* ---- haze synthesis (input side of the training step) ----------------------------
+ * One launch for the elementwise chain upstream runs per batch (trainfiles/dssmd_traner_new.py:250-256):
+ *   convert_disp_to_depth  DeBug/inference.py:57-64    depth = (focal_length * baseline) / disp
+ *   depth2trans            DeBug/inference.py:126-134  trans = exp((-depth) * beta)
+ *   recover_haze_images    DeBug/inference.py:95-112   haze  = (clear * trans) + airlight * (1 - trans)
+ * src: [B,1,H,W], a disparity map (src_is_disparity != 0) or a depth map (then baseline / focal_length are unused);
+ * clear, haze: [B,C,H,W]; trans, depth: [B,1,H,W]; baseline, focal_length, beta, airlight: [B] device arrays of the
+ * compute dtype.  Any of haze / trans / depth may be NULL (not wanted).  clear and src have image_dtype, the outputs
+ * compute_dtype -- upstream's type promotion: (F32, F32), (F32, F64) (float32 images with the float64 scalars the data
+ * loaders produce), (F64, F64).  Every operation is rounded individually, in upstream's order. */
+DSSMD_API int dssmd_haze_fwd(const void *clear, const void *src, int src_is_disparity, const void *baseline, const void *focal_length,
+                   const void *beta, const void *airlight, void *haze, void *trans, void *depth,
+                   int B, int C, int H, int W, int image_dtype, int compute_dtype, void *stream);
+
 /* ---- self test ------------------------------------------------------------------------
  * The lean warp kernels divide pixel coordinates by W - 1 with a reciprocal hoisted out of the pixel loop
  * (csrc/warp_lean.cuh: div_rn_by) and rely on that being IEEE round-to-nearest division, bit for bit -- the

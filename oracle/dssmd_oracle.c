@@ -11,6 +11,7 @@
  *   CostVolume.correlation models/UtilsNet/cost_volume.py:39-47
  *   disp_warp             utils/disparity_warper.py:83-106 (== models/UtilsNet/stereo_op.py:41-63)
  *   LRwarp_error          utils/disparity_warper.py:109-115
+ *   convert_disp_to_depth / depth2trans / recover_haze_images   DeBug/inference.py:57-64, 126-134, 95-112
  * and the autograd backward of each.  The arithmetic of the upstream functions
  * lives in PyTorch (aten::mul/mean, aten::grid_sampler_2d,
  * aten::upsample_bilinear2d; torch 2.11.0 in this project's image, upstream
@@ -34,6 +35,7 @@
 #define FLOOR floorf
 #define FMIN fminf
 #define FMAX fmaxf
+#define EXP expf
 #include "dssmd_oracle_impl.h"
 #undef REAL
 #undef SUF
@@ -41,6 +43,7 @@
 #undef FLOOR
 #undef FMIN
 #undef FMAX
+#undef EXP
 
 #define REAL double
 #define SUF f64
@@ -48,6 +51,7 @@
 #define FLOOR floor
 #define FMIN fmin
 #define FMAX fmax
+#define EXP exp
 #include "dssmd_oracle_impl.h"
 #undef REAL
 #undef SUF
@@ -55,6 +59,7 @@
 #undef FLOOR
 #undef FMIN
 #undef FMAX
+#undef EXP
 
 #ifdef _OPENMP
 #include <omp.h>

@@ -316,6 +316,50 @@ int FN(oracle_lrwarp_error)(const REAL *imgL, const REAL *disp, const REAL *imgR
     return bad;
 }
 
+
+/* ------------------------------------------------------------------------
+ * Haze synthesis (input side of the training step).
+ * Restates, operation for operation and with upstream's rounding points,
+ *   convert_disp_to_depth  DeBug/inference.py:57-64    depth = (focal * baseline) / disp
+ *   depth2trans            DeBug/inference.py:126-134  trans = exp((-depth) * beta)
+ *   recover_haze_images    DeBug/inference.py:95-112   haze  = (clear * trans) + A * (1 - trans)
+ * as called per batch by trainfiles/dssmd_traner_new.py:250-256.  src is the
+ * disparity (src_is_disp != 0) or the depth itself.  The per-sample scalars
+ * are REAL; the image-side element type is given by in_is_f32 (upstream's
+ * type promotion: float32 images with the float64 scalars of the data loaders
+ * compute in float64).  Any of haze / trans / depth may be NULL.
+ * ---------------------------------------------------------------------- */
+void FN(oracle_haze_fwd)(const void *clear, const void *src, int src_is_disp, int in_is_f32,
+                         const REAL *baseline, const REAL *focal, const REAL *beta, const REAL *airlight,
+                         REAL *haze, REAL *trans, REAL *depth, int B, int C, long HW)
+{
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; ++b) {
+        const REAL fb = src_is_disp ? focal[b] * baseline[b] : (REAL)0;
+        const REAL be = (haze || trans) ? beta[b] : (REAL)0;
+        const REAL A = haze ? airlight[b] : (REAL)0;
+        for (long i = 0; i < HW; ++i) {
+            const long p = (long)b * HW + i;
+            const REAL s = in_is_f32 ? (REAL)((const float *)src)[p] : (REAL)((const double *)src)[p];
+            const REAL dep = src_is_disp ? fb / s : s;
+            if (depth) depth[p] = dep;
+            if (!(haze || trans)) continue;
+            const REAL nd = -dep;
+            const REAL t = EXP(nd * be);
+            if (trans) trans[p] = t;
+            if (haze) {
+                const REAL a = A * ((REAL)1 - t);
+                for (int c = 0; c < C; ++c) {
+                    const long pc = ((long)b * C + c) * HW + i;
+                    const REAL J = in_is_f32 ? (REAL)((const float *)clear)[pc] : (REAL)((const double *)clear)[pc];
+                    const REAL jt = J * t;
+                    haze[pc] = jt + a;
+                }
+            }
+        }
+    }
+}
+
 #undef FN
 #undef CAT
 #undef CAT_

@@ -25,6 +25,13 @@ from models.UtilsNet.submoudles import build_corr  # noqa: E402
 from models.UtilsNet.stereo_op import disp_warp as disp_warp_stereo_op  # noqa: E402
 from utils.disparity_warper import LRwarp_error, disp_warp  # noqa: E402
 
+# DeBug/inference.py imports skimage / matplotlib (absent here) for dataset I/O and plotting only: empty stubs let
+# the module import unmodified
+import types  # noqa: E402
+for _m in ("skimage", "skimage.io", "skimage.transform", "matplotlib", "matplotlib.pyplot"):
+    sys.modules.setdefault(_m, types.ModuleType(_m))
+from DeBug.inference import convert_disp_to_depth, depth2trans, recover_haze_images  # noqa: E402
+
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
 SEED = 1024
 
@@ -159,6 +166,38 @@ def gen_photo():
     print("photo.npz:", len(photo_cases()), "cases")
 
 
+def haze_cases():
+    # name, B, H, W, image dtype, scalar dtype, (baseline, focal), beta range, airlight range
+    return [
+        ("sceneflow_f64_scalars", 2, 12, 20, torch.float32, torch.float64, (0.1, 1050.0), (0.02, 0.30), (0.8, 1.0)),
+        ("kitti_f64_scalars", 2, 6, 31, torch.float32, torch.float64, (0.54, 721.277), (0.008, 0.06), (0.85, 1.0)),
+        ("all_f32", 3, 5, 16, torch.float32, torch.float32, (0.1, 1050.0), (0.02, 0.30), (0.8, 1.0)),
+        ("all_f64", 1, 4, 9, torch.float64, torch.float64, (0.54, 721.277), (0.008, 0.06), (0.85, 1.0)),
+    ]
+
+
+def gen_haze():
+    """The per-batch chain of trainfiles/dssmd_traner_new.py:250-256 on the dtypes the data loaders hand over."""
+    out = {}
+    for i, (name, B, H, W, idt, sdt, (bl, fl), brange, arange) in enumerate(haze_cases()):
+        torch.manual_seed(SEED + 400 + i)
+        clear = torch.rand(B, 3, H, W).to(idt)
+        disp = (0.5 + torch.rand(B, 1, H, W) * 191.5 * W / 960.0 * 8).to(idt)
+        baseline = torch.full((B,), bl, dtype=sdt)
+        focal = torch.full((B,), fl, dtype=sdt)
+        beta = (brange[0] + torch.rand(B, dtype=torch.float64) * (brange[1] - brange[0])).to(sdt)
+        A = (arange[0] + torch.rand(B, dtype=torch.float64) * (arange[1] - arange[0])).to(sdt)
+        depth = convert_disp_to_depth(baseline=baseline, focal_length=focal, disp=disp)
+        trans = depth2trans(depth, beta=beta)
+        haze = recover_haze_images(clean_images=clear, beta=beta, A=A, depth=depth)
+        keep = lambda t: t.detach().contiguous().numpy()  # noqa: E731  (dtype preserved: float64 results stay float64)
+        out.update({f"{name}.clear": keep(clear), f"{name}.disp": keep(disp), f"{name}.baseline": keep(baseline),
+                    f"{name}.focal": keep(focal), f"{name}.beta": keep(beta), f"{name}.airlight": keep(A),
+                    f"{name}.depth": keep(depth), f"{name}.trans": keep(trans), f"{name}.haze": keep(haze)})
+    np.savez_compressed(os.path.join(OUT, "haze.npz"), **out)
+    print("haze.npz:", len(haze_cases()), "cases")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # fixed reduction order for the fixtures
@@ -167,3 +206,4 @@ if __name__ == "__main__":
     gen_warp()
     gen_lrwarp()
     gen_photo()
+    gen_haze()

@@ -161,6 +161,39 @@ def photometric_l1(imgL: np.ndarray, disp: np.ndarray, imgR: np.ndarray):
     return loss, g_disp
 
 
+def haze(clear, src, src_is_disp, baseline, focal, beta, airlight, want=("haze", "trans", "depth")):
+    """convert_disp_to_depth -> depth2trans -> recover_haze_images (DeBug/inference.py:57-64, 126-134, 95-112) in
+    upstream's operation order and type promotion: the result dtype is float64 as soon as any image or scalar is.
+    `src` is the disparity (src_is_disp) or the depth, [B,1,H,W]; scalars are [B] arrays or None when unused.
+    Returns a dict with the requested outputs."""
+    src = _c(src)
+    arrs = [a for a in (clear, src, baseline, focal, beta, airlight) if a is not None]
+    cdt = np.float64 if any(np.asarray(a).dtype == np.float64 for a in arrs) else np.float32
+    idt = np.float64 if any(np.asarray(a).dtype == np.float64 for a in (clear, src) if a is not None) else np.float32
+    src = _c(src, idt)
+    B = src.shape[0]
+    HW = int(np.prod(src.shape[1:]))
+    C = 0
+    if clear is not None:
+        clear = _c(clear, idt)
+        C = clear.shape[1]
+        assert src.shape[1] == 1 and clear.shape[0] == B and clear.shape[2:] == src.shape[2:]
+    sc = [None if a is None else _c(np.asarray(a).reshape(B), cdt) for a in (baseline, focal, beta, airlight)]
+    out = {}
+    if "haze" in want:
+        out["haze"] = np.empty(clear.shape, dtype=cdt)
+    if "trans" in want:
+        out["trans"] = np.empty(src.shape, dtype=cdt)
+    if "depth" in want:
+        out["depth"] = np.empty(src.shape, dtype=cdt)
+    null = ctypes.c_void_p(None)
+    pp = lambda a: null if a is None else _p(a)  # noqa: E731
+    fn = getattr(lib(), "oracle_haze_fwd_" + ("f64" if cdt == np.float64 else "f32"))
+    fn(pp(clear), _p(src), _I(1 if src_is_disp else 0), _I(1 if idt == np.float32 else 0), pp(sc[0]), pp(sc[1]), pp(sc[2]),
+       pp(sc[3]), pp(out.get("haze")), pp(out.get("trans")), pp(out.get("depth")), _I(B), _I(C), ctypes.c_long(HW))
+    return out
+
+
 # ---- bf16 helpers (the CUDA path takes bf16 I/O with fp32 accumulation) ----
 def bf16_round(a: np.ndarray) -> np.ndarray:
     """Round float32 values to the nearest bfloat16 (ties to even), kept as float32."""

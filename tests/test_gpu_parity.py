@@ -583,3 +583,67 @@ def test_back_to_back_dependent_launches(ops, oracle):
         y2, _ = ops.disp_warp(x2, disp)
         (gi2,) = torch.autograd.grad(y2, x2, gi1)
         assert rel_err(gi2.cpu().numpy(), gi_ref) <= TOL_F32
+
+
+# ------------------------------------------------------------------ haze synthesis
+HAZE = load_cases("haze")
+
+
+def _haze_tol(a):
+    return TOL_F32 if a.dtype == np.float32 else 1e-13
+
+
+@pytest.mark.parametrize("name", sorted(HAZE))
+def test_haze_golden(ops, name):
+    """Upstream's convert_disp_to_depth / depth2trans / recover_haze_images on the loaders' dtypes (float64 scalars with
+    float32 images promote to float64), one by one and as the single fused launch."""
+    c = HAZE[name]
+    t = {k: torch.from_numpy(c[k]).cuda() for k in ("clear", "disp", "baseline", "focal", "beta", "airlight")}
+    depth = ops.convert_disp_to_depth(baseline=t["baseline"], focal_length=t["focal"], disp=t["disp"])
+    trans = ops.depth2trans(depth, beta=t["beta"])
+    haze = ops.recover_haze_images(clean_images=t["clear"], beta=t["beta"], A=t["airlight"], depth=depth)
+    fh, ft, fd = ops.synthesize_haze(t["clear"], t["disp"], t["baseline"], t["focal"], t["beta"], t["airlight"])
+    for got, fused, key in ((depth, fd, "depth"), (trans, ft, "trans"), (haze, fh, "haze")):
+        ref = c[key]
+        assert got.shape == ref.shape and got.is_contiguous() and str(got.dtype).endswith(str(ref.dtype)), key
+        assert rel_err(got.cpu().numpy(), ref) <= _haze_tol(ref), key
+        assert torch.equal(got, fused), key                     # same arithmetic, same bits
+
+
+@pytest.mark.parametrize("shape,idt,sdt", [((4, 576, 960), torch.float32, torch.float64),
+                                           ((8, 320, 640), torch.float32, torch.float32),
+                                           ((2, 37, 53), torch.float32, torch.float64),
+                                           ((1, 5, 7), torch.float64, torch.float64)])
+def test_haze_vs_oracle(ops, oracle, shape, idt, sdt):
+    B, H, W = shape
+    g = torch.Generator(device="cuda").manual_seed(1024 + H)
+    clear = torch.rand(B, 3, H, W, generator=g, device="cuda").to(idt)
+    disp = (0.5 + torch.rand(B, 1, H, W, generator=g, device="cuda") * 191.5).to(idt)
+    baseline = torch.full((B,), 0.1, dtype=sdt, device="cuda")
+    focal = torch.full((B,), 1050.0, dtype=sdt, device="cuda")
+    beta = (0.02 + 0.28 * torch.rand(B, generator=g, device="cuda")).to(sdt)
+    A = (0.8 + 0.2 * torch.rand(B, generator=g, device="cuda")).to(sdt)
+    haze, trans, depth = ops.synthesize_haze(clear, disp, baseline, focal, beta, A)
+    n = lambda x: x.cpu().numpy()  # noqa: E731
+    ref = oracle.haze(n(clear), n(disp), True, n(baseline), n(focal), n(beta), n(A))
+    for got, key in ((haze, "haze"), (trans, "trans"), (depth, "depth")):
+        assert n(got).dtype == ref[key].dtype, key
+        assert rel_err(n(got), ref[key]) <= _haze_tol(ref[key]), key
+    # size-independent properties: transmission in (0, 1], haze between the clear image and the airlight,
+    # depth * disp == f * b, and the ASM inverse recovers the clear image where the transmission is not tiny
+    assert bool(((trans > 0) & (trans <= 1)).all())
+    Ab = A.view(B, 1, 1, 1).to(haze.dtype)
+    assert bool((haze >= torch.minimum(clear.to(haze.dtype), Ab) - 1e-6).all())
+    assert bool((haze <= torch.maximum(clear.to(haze.dtype), Ab) + 1e-6).all())
+    assert rel_err(n(depth * disp), np.full(n(depth).shape, 105.0)) <= TOL_F32
+    ok = trans > 0.05
+    back = (haze - Ab * (1 - trans)) / trans
+    assert float(((back - clear).abs() * ok).max()) <= 1e-4
+
+
+def test_haze_needs_grad_uses_upstream_expression(ops):
+    disp = (torch.rand(2, 1, 8, 16, device="cuda") + 1).requires_grad_(True)
+    one = torch.ones(2, device="cuda")
+    depth = ops.convert_disp_to_depth(one * 0.1, one * 1050, disp)
+    depth.sum().backward()
+    assert rel_err(disp.grad.cpu().numpy(), (-105.0 / disp.detach() ** 2).cpu().numpy()) <= TOL_F32

@@ -121,3 +121,48 @@ def test_install_rebinds_defining_and_importing_modules():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_haze_signatures_and_errors_follow_upstream():
+    from dssmd_b200 import haze
+    assert str(inspect.signature(haze.convert_disp_to_depth)) == "(baseline, focal_length, disp)"
+    assert str(inspect.signature(haze.depth2trans)) == "(depth, beta)"
+    assert str(inspect.signature(haze.recover_haze_images)) == "(clean_images, beta, A, depth)"
+    disp = torch.rand(2, 1, 4, 8) + 1
+    with pytest.raises(AssertionError):                       # upstream: assert baseline.shape[0] == b
+        haze.convert_disp_to_depth(torch.ones(3), torch.ones(2), disp)
+    with pytest.raises(AssertionError):
+        haze.depth2trans(disp, torch.ones(1))
+    with pytest.raises(AssertionError):
+        haze.recover_haze_images(torch.rand(2, 3, 4, 8), torch.ones(2), torch.ones(5), disp)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        haze.convert_disp_to_depth(torch.ones(2), torch.ones(2), disp)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        haze.synthesize_haze(torch.rand(2, 3, 4, 8), disp, torch.ones(2), torch.ones(2), torch.ones(2), torch.ones(2))
+
+
+def test_install_rebinds_haze_functions_in_trainers():
+    names = ["DeBug", "DeBug.inference", "trainfiles", "trainfiles.dssmd_traner_new"]
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        ups = {k: (lambda *a, _k=k, **kw: _k) for k in ("convert_disp_to_depth", "depth2trans", "recover_haze_images", "recover_depth")}
+        up = ups["depth2trans"]
+        for n in names:
+            sys.modules[n] = types.ModuleType(n)
+        for n in ("DeBug.inference", "trainfiles.dssmd_traner_new"):
+            sys.modules[n].__dict__.update(ups)
+        dssmd_b200.install(import_missing=False)
+        tr = sys.modules["trainfiles.dssmd_traner_new"]
+        assert tr.convert_disp_to_depth is dssmd_b200.convert_disp_to_depth
+        assert tr.depth2trans is dssmd_b200.depth2trans
+        assert tr.recover_haze_images is dssmd_b200.recover_haze_images
+        assert tr.recover_depth is ups["recover_depth"]            # not on the path: untouched
+        dssmd_b200.uninstall()
+        assert tr.depth2trans is up
+    finally:
+        dssmd_b200.uninstall()
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

@@ -119,3 +119,39 @@ def test_photometric_l1_matches_reference(name):
         assert rel_err(w * g_disp, c[f"g_disp{k}"]) <= TOL_F32
         total += w * loss
     assert abs(total - float(c["total"])) <= TOL_F32 * abs(float(c["total"]))
+
+
+# ---- haze synthesis ----------------------------------
+HAZE = load_cases("haze")
+
+
+@pytest.mark.parametrize("name", sorted(HAZE))
+def test_haze_chain_matches_reference(name):
+    """Fixtures: upstream's convert_disp_to_depth -> depth2trans -> recover_haze_images (DeBug/inference.py) on the dtypes
+    the data loaders hand over (oracle/gen_golden.py: gen_haze).  Result dtype follows upstream's type promotion."""
+    c = HAZE[name]
+    out = O.haze(c["clear"], c["disp"], True, c["baseline"], c["focal"], c["beta"], c["airlight"])
+    for k in ("depth", "trans", "haze"):
+        assert out[k].dtype == c[k].dtype and out[k].shape == c[k].shape, k
+        assert rel_err(out[k], c[k]) <= (TOL_F32 if c[k].dtype == np.float32 else 1e-14), k
+    # the three upstream entry points one by one (depth given instead of disparity)
+    t = O.haze(None, c["depth"], False, None, None, c["beta"], None, want=("trans",))["trans"]
+    assert rel_err(t, c["trans"]) <= (TOL_F32 if c["trans"].dtype == np.float32 else 1e-14)
+    h = O.haze(c["clear"], c["depth"], False, None, None, c["beta"], c["airlight"], want=("haze",))["haze"]
+    assert rel_err(h, c["haze"]) <= (TOL_F32 if c["haze"].dtype == np.float32 else 1e-14)
+
+
+def test_haze_invariants():
+    rng = np.random.default_rng(5)
+    clear = rng.random((2, 3, 6, 8), dtype=np.float32)
+    disp = (0.5 + rng.random((2, 1, 6, 8), dtype=np.float32) * 50).astype(np.float32)
+    one = np.ones(2, np.float32)
+    # beta = 0: transmission 1, the hazy image is the clear image
+    o = O.haze(clear, disp, True, one * 0.1, one * 1050, one * 0, one * 0.9)
+    assert np.all(o["trans"] == 1) and np.array_equal(o["haze"], clear)
+    # transmission in (0, 1], hazy image between the clear image and the airlight
+    o = O.haze(clear, disp, True, one * 0.1, one * 1050, one * 0.05, one * 0.9)
+    assert np.all((o["trans"] > 0) & (o["trans"] <= 1))
+    lo, hi = np.minimum(clear, 0.9), np.maximum(clear, 0.9)
+    assert np.all((o["haze"] >= lo - 1e-6) & (o["haze"] <= hi + 1e-6))
+    assert rel_err(o["depth"] * disp, np.full_like(disp, 105.0)) <= TOL_F32
