@@ -32,6 +32,10 @@ SIGNATURES = {
     "dssmd_lrwarp_error_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "dssmd_photometric_l1_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "dssmd_selftest_division": [_i, _i, _vp, _vp],
+    "dssmd_corr_fwd_cat": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "dssmd_corr_bwd_cat": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "dssmd_asm_recovered_l1_blocks": [_i, _i, _i],
+    "dssmd_asm_recovered_l1_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "dssmd_haze_fwd": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
 }
 

@@ -24,7 +24,7 @@
 namespace dssmd {
 
 // corr_bwd_reg.cu: fp32 fast path (g slab in registers); -1 = shape not eligible
-int corr_bwd_reg(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, int dtype, cudaStream_t stream);
+int corr_bwd_reg(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, long long gbs, int dtype, cudaStream_t stream);
 
 namespace {
 
@@ -37,6 +37,7 @@ struct CorrBwdParams {
     const void *g;
     const void *In;   // R (mode 0) or L (mode 1)
     void *out;        // gL (mode 0) or gR (mode 1)
+    long long GBS;    // elements between two images of g (D*H*W, or the channel count of a concat gradient * H*W)
     int B, C, H, W, D;
     int NR;     // B*H rows
     int TX;     // tile width (multiple of 8)
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(256) corr_bwd_kernel(const CorrBwdParams p) {
         if (row < p.NR) {
             const int b = row / p.H, y = row - b * p.H;
             bi = (long long)b * p.C * HW + (long long)y * p.W;
-            bg = (long long)b * p.D * HW + (long long)y * p.W;
+            bg = (long long)b * p.GBS + (long long)y * p.W;
         }
         s_rowbase_in[tid] = bi;
         s_rowbase_g[tid] = bg;
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(256) corr_bwd_kernel(const CorrBwdParams p) {
 
 // ---- fp64: plain gather kernels (arbiter precision, not a hot path) ---------------
 __global__ void corr_bwd_f64_kernel(const double *g, const double *L, const double *R, double *gL, double *gR,
-                                    int B, int C, int H, int W, int D) {
+                                    int B, int C, int H, int W, int D, long long gbs) {
     const long long n = (long long)B * C * H * W;
     const long long HW = (long long)H * W;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
@@ -277,7 +278,7 @@ __global__ void corr_bwd_f64_kernel(const double *g, const double *L, const doub
         const int x = (int)(i % W);
         const int y = (int)((i / W) % H);
         const int b = (int)(i / (HW * C));
-        const double *gr = g + (long long)b * D * HW + (long long)y * W;
+        const double *gr = g + (long long)b * gbs + (long long)y * W;
         const long long rowoff = i - x;
         double a = 0.0, r = 0.0;
         for (int d = 0; d < D && d <= x; ++d) a += (gr[d * HW + x] / (double)C) * R[rowoff + x - d];
@@ -293,14 +294,14 @@ int env_int(const char *name, int dflt) {
 }
 
 template <typename T, int MODE>
-int launch_mode(const void *g, const void *In, void *out, int B, int C, int H, int W, int D, cudaStream_t stream) {
+int launch_mode(const void *g, const void *In, void *out, int B, int C, int H, int W, int D, long long gbs, cudaStream_t stream) {
     if (env_int("DSSMD_CORR_BWD_VARIANT", 1) >= 1) {
         constexpr int dtype = sizeof(T) == 4 ? DSSMD_F32 : std::is_same<T, __nv_bfloat16>::value ? DSSMD_BF16 : DSSMD_F16;
-        const int rc = corr_bwd_reg(g, In, out, MODE, B, C, H, W, D, dtype, stream);
+        const int rc = corr_bwd_reg(g, In, out, MODE, B, C, H, W, D, gbs, dtype, stream);
         if (rc >= 0) return rc;
     }
     CorrBwdParams p{};
-    p.g = g; p.In = In; p.out = out;
+    p.g = g; p.In = In; p.out = out; p.GBS = gbs;
     p.B = B; p.C = C; p.H = H; p.W = W; p.D = D;
     p.NR = B * H;
     p.c_pow2 = (C & (C - 1)) == 0;
@@ -386,13 +387,13 @@ int launch_mode(const void *g, const void *In, void *out, int B, int C, int H, i
 
 template <typename T>
 int launch_typed(const void *g, const void *L, const void *R, void *gL, void *gR,
-                 int B, int C, int H, int W, int D, cudaStream_t stream) {
+                 int B, int C, int H, int W, int D, long long gbs, cudaStream_t stream) {
     if (gL) {
-        const int rc = launch_mode<T, 0>(g, R, gL, B, C, H, W, D, stream);
+        const int rc = launch_mode<T, 0>(g, R, gL, B, C, H, W, D, gbs, stream);
         if (rc) return rc;
     }
     if (gR) {
-        const int rc = launch_mode<T, 1>(g, L, gR, B, C, H, W, D, stream);
+        const int rc = launch_mode<T, 1>(g, L, gR, B, C, H, W, D, gbs, stream);
         if (rc) return rc;
     }
     return DSSMD_OK;
@@ -402,6 +403,29 @@ int launch_typed(const void *g, const void *L, const void *R, void *gL, void *gR
 
 }  // namespace dssmd
 
+namespace dssmd {
+namespace {
+int corr_bwd_entry(const void *g, const void *L, const void *R, void *gL, void *gR, int B, int C, int H, int W, int D, long long gbs,
+                   int dtype, cudaStream_t s) {
+    switch (dtype) {
+        case DSSMD_F32: return launch_typed<float>(g, L, R, gL, gR, B, C, H, W, D, gbs, s);
+        case DSSMD_BF16: return launch_typed<__nv_bfloat16>(g, L, R, gL, gR, B, C, H, W, D, gbs, s);
+        case DSSMD_F16: return launch_typed<__half>(g, L, R, gL, gR, B, C, H, W, D, gbs, s);
+        case DSSMD_F64: {
+            const long long n = (long long)B * C * H * W;
+            const int nt = 256;
+            long long nb = (n + nt - 1) / nt;
+            if (nb > 148LL * 32) nb = 148LL * 32;
+            corr_bwd_f64_kernel<<<(unsigned)nb, nt, 0, s>>>((const double *)g, (const double *)L, (const double *)R,
+                                                            (double *)gL, (double *)gR, B, C, H, W, D, gbs);
+            return check_launch("corr_bwd_f64");
+        }
+        default: return fail(DSSMD_ERR_INVALID_ARGUMENT, "corr_bwd: unknown dtype %d", dtype);
+    }
+}
+}  // namespace
+}  // namespace dssmd
+
 extern "C" int dssmd_corr_bwd(const void *g, const void *L, const void *R, void *gL, void *gR,
                               int B, int C, int H, int W, int D, int dtype, void *stream) {
     using namespace dssmd;
@@ -409,20 +433,20 @@ extern "C" int dssmd_corr_bwd(const void *g, const void *L, const void *R, void 
     DSSMD_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0, "corr_bwd: sizes must be positive (B=%d C=%d H=%d W=%d D=%d)", B, C, H, W, D);
     DSSMD_REQUIRE((long long)B * H < (1LL << 31), "corr_bwd: B*H too large");
     if (!gL && !gR) return DSSMD_OK;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    switch (dtype) {
-        case DSSMD_F32: return launch_typed<float>(g, L, R, gL, gR, B, C, H, W, D, s);
-        case DSSMD_BF16: return launch_typed<__nv_bfloat16>(g, L, R, gL, gR, B, C, H, W, D, s);
-        case DSSMD_F16: return launch_typed<__half>(g, L, R, gL, gR, B, C, H, W, D, s);
-        case DSSMD_F64: {
-            const long long n = (long long)B * C * H * W;
-            const int nt = 256;
-            long long nb = (n + nt - 1) / nt;
-            if (nb > 148LL * 32) nb = 148LL * 32;
-            corr_bwd_f64_kernel<<<(unsigned)nb, nt, 0, s>>>((const double *)g, (const double *)L, (const double *)R,
-                                                            (double *)gL, (double *)gR, B, C, H, W, D);
-            return check_launch("corr_bwd_f64");
-        }
-        default: return fail(DSSMD_ERR_INVALID_ARGUMENT, "corr_bwd: unknown dtype %d", dtype);
-    }
+    return corr_bwd_entry(g, L, R, gL, gR, B, C, H, W, D, (long long)D * H * W, dtype, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dssmd_corr_bwd_cat(const void *g_cat, const void *L, const void *R, void *gL, void *gR,
+                                  int B, int C, int H, int W, int D, int cat_channels, int channel_offset, int dtype, void *stream) {
+    using namespace dssmd;
+    DSSMD_REQUIRE(g_cat && L && R, "corr_bwd_cat: null input pointer");
+    DSSMD_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0, "corr_bwd_cat: sizes must be positive (B=%d C=%d H=%d W=%d D=%d)", B, C, H, W, D);
+    DSSMD_REQUIRE((long long)B * H < (1LL << 31), "corr_bwd_cat: B*H too large");
+    DSSMD_REQUIRE(channel_offset >= 0 && cat_channels >= channel_offset + D,
+                  "corr_bwd_cat: channels [%d, %d) do not fit a gradient of %d channels", channel_offset, channel_offset + D, cat_channels);
+    DSSMD_REQUIRE(dtype == DSSMD_F32 || dtype == DSSMD_BF16 || dtype == DSSMD_F16 || dtype == DSSMD_F64, "corr_bwd_cat: unknown dtype %d", dtype);
+    if (!gL && !gR) return DSSMD_OK;
+    const int es = dtype == DSSMD_F64 ? 8 : dtype == DSSMD_F32 ? 4 : 2;
+    const char *gp = static_cast<const char *>(g_cat) + (size_t)channel_offset * H * W * es;
+    return corr_bwd_entry(gp, L, R, gL, gR, B, C, H, W, D, (long long)cat_channels * H * W, dtype, static_cast<cudaStream_t>(stream));
 }

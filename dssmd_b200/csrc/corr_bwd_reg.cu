@@ -246,7 +246,7 @@ int launch_reg(RegParams p, const CUtensorMap &mapIn, const CUtensorMap &mapG, i
 namespace {
 
 template <typename T>
-int corr_bwd_reg_typed(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, CUtensorMapDataType tmtype,
+int corr_bwd_reg_typed(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, long long gbs, CUtensorMapDataType tmtype,
                        cudaStream_t stream) {
     constexpr int ES = (int)sizeof(T);
     constexpr int EPV = 16 / ES;                    // elements per 16 bytes: rows and boxes are multiples of it
@@ -322,7 +322,7 @@ int corr_bwd_reg_typed(const void *g, const void *in, void *out, int mode, int B
     }
     {
         const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
-        const cuuint64_t strides[3] = {(cuuint64_t)W * ES, (cuuint64_t)H * W * ES, (cuuint64_t)D * H * W * ES};
+        const cuuint64_t strides[3] = {(cuuint64_t)W * ES, (cuuint64_t)H * W * ES, (cuuint64_t)gbs * ES};
         const cuuint32_t box[4] = {(cuuint32_t)p.GW, 1, (cuuint32_t)D, 1};
         if (!make_tmap(&mapG, tmtype, g, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
     }
@@ -352,11 +352,11 @@ int corr_bwd_reg_typed(const void *g, const void *in, void *out, int mode, int B
 
 // mode 0: out = gL, in = R;  mode 1: out = gR, in = L.  dtype: DSSMD_F32 / BF16 / F16 (all tensors).  Returns -1 when
 // the shape is not eligible (the caller falls back to the generic kernel), else a DSSMD_* code.
-int corr_bwd_reg(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, int dtype, cudaStream_t stream) {
+int corr_bwd_reg(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, long long gbs, int dtype, cudaStream_t stream) {
     switch (dtype) {
-        case DSSMD_F32: return corr_bwd_reg_typed<float>(g, in, out, mode, B, C, H, W, D, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, stream);
-        case DSSMD_BF16: return corr_bwd_reg_typed<__nv_bfloat16>(g, in, out, mode, B, C, H, W, D, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, stream);
-        case DSSMD_F16: return corr_bwd_reg_typed<__half>(g, in, out, mode, B, C, H, W, D, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, stream);
+        case DSSMD_F32: return corr_bwd_reg_typed<float>(g, in, out, mode, B, C, H, W, D, gbs, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, stream);
+        case DSSMD_BF16: return corr_bwd_reg_typed<__nv_bfloat16>(g, in, out, mode, B, C, H, W, D, gbs, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, stream);
+        case DSSMD_F16: return corr_bwd_reg_typed<__half>(g, in, out, mode, B, C, H, W, D, gbs, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, stream);
         default: return -1;
     }
 }

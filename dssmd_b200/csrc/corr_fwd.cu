@@ -26,9 +26,9 @@
 namespace dssmd {
 
 // tensor-core path (corr_fwd_umma.cu); returns -1 when the shape is outside its limits
-int corr_fwd_umma_f32(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, cudaStream_t stream);
+int corr_fwd_umma_f32(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, long long obs, cudaStream_t stream);
 // register-blocked, TMA-staged FFMA path (corr_fwd_reg.cu), fp32 / bf16 / fp16; -1 when the shape is not eligible
-int corr_fwd_reg(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, int dtype, cudaStream_t stream);
+int corr_fwd_reg(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, long long obs, int dtype, cudaStream_t stream);
 
 namespace {
 
@@ -41,6 +41,7 @@ struct CorrFwdParams {
     const void *L;
     const void *R;
     void *out;
+    long long OBS;  // elements between two images of `out` (D*H*W, or the channel count of a concat buffer * H*W)
     int B, C, H, W, D;
     int NR;     // B*H image rows
     int TX;     // tile width in pixels (multiple of 8)
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(256) corr_fwd_kernel(const CorrFwdParams p) {
     const int xg = X0 + xs;
     const float Cf = (float)p.C;
     const float invC = 1.0f / Cf;
-    T *ob = static_cast<T *>(p.out) + ((long long)b * p.D * p.H + y) * p.W + xg;
+    T *ob = static_cast<T *>(p.out) + (long long)b * p.OBS + (long long)y * p.W + xg;
     const bool vec = (sizeof(T) == 4) && ((p.W & 3) == 0) && (xg + kPix <= p.W) &&
                      ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
 #pragma unroll
@@ -440,7 +441,7 @@ __global__ void __maxnreg__(96) corr_fwd_d4_kernel(const CorrFwdParams p) {
     const int xg = X0 + xs;
     const float Cf = (float)p.C;
     const float invC = 1.0f / Cf;
-    T *ob = static_cast<T *>(p.out) + ((long long)b * p.D * p.H + y) * p.W + xg;
+    T *ob = static_cast<T *>(p.out) + (long long)b * p.OBS + (long long)y * p.W + xg;
     const bool vec = (sizeof(T) == 4) && ((p.W & 3) == 0) && (xg + kPix <= p.W) &&
                      ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
 #pragma unroll
@@ -467,7 +468,7 @@ __global__ void __maxnreg__(96) corr_fwd_d4_kernel(const CorrFwdParams p) {
 
 // ---- fp64: plain one-thread-per-output kernel (arbiter precision, not a hot path) ----
 __global__ void corr_fwd_f64_kernel(const double *L, const double *R, double *out,
-                                    int B, int C, int H, int W, int D) {
+                                    int B, int C, int H, int W, int D, long long obs) {
     const long long n = (long long)B * D * H * W;
     const long long HW = (long long)H * W;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
@@ -483,7 +484,7 @@ __global__ void corr_fwd_f64_kernel(const double *L, const double *R, double *ou
             for (int c = 0; c < C; ++c) s += l[c * HW] * r[c * HW];
             s /= (double)C;
         }
-        out[i] = s;
+        out[(long long)b * obs + (i - (long long)b * HW * D)] = s;
     }
 }
 
@@ -522,9 +523,9 @@ int launch_d4_cs(CorrFwdParams &p, size_t smem_bytes, dim3 grid, int threads, cu
 
 // narrow-tile path; returns -1 when the shape is outside its limits (caller falls back)
 template <typename T>
-int launch_d4(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, cudaStream_t stream) {
+int launch_d4(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, long long obs, cudaStream_t stream) {
     CorrFwdParams p{};
-    p.L = L; p.R = R; p.out = out;
+    p.L = L; p.R = R; p.out = out; p.OBS = obs;
     p.B = B; p.C = C; p.H = H; p.W = W; p.D = D;
     p.NR = B * H;
     p.c_pow2 = (C & (C - 1)) == 0;
@@ -588,7 +589,7 @@ int launch_d4(const void *L, const void *R, void *out, int B, int C, int H, int 
 }
 
 template <typename T>
-int launch_typed(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, cudaStream_t stream) {
+int launch_typed(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, long long obs, cudaStream_t stream) {
     // 0 wide FFMA tile, 1 register-blocked / narrow FFMA tile, 2 tcgen05 (3xTF32); unset = by size: the persistent
     // tensor-core kernel needs several 128-pixel tiles per SM to amortise its pipeline fill, and its work grows with
     // 128 + D per tile where the FFMA kernels' grows with D (measured, C256 D41 800 tiles: 87 vs 108 us;
@@ -597,21 +598,21 @@ int launch_typed(const void *L, const void *R, void *out, int B, int C, int H, i
     if (variant < 0) variant = (sizeof(T) == 4 && C >= 64 && D >= 32 && (long)B * H * W / 128 >= 3L * sm_count()) ? 2 : 1;
     if constexpr (sizeof(T) == 4) {
         if (variant == 2) {
-            const int rc = corr_fwd_umma_f32(L, R, out, B, C, H, W, D, stream);
+            const int rc = corr_fwd_umma_f32(L, R, out, B, C, H, W, D, obs, stream);
             if (rc >= 0) return rc;
         }
     }
     if (variant >= 1 && env_int("DSSMD_CORR_FWD_REG", 1) != 0) {
         constexpr int dtype = sizeof(T) == 4 ? DSSMD_F32 : std::is_same<T, __nv_bfloat16>::value ? DSSMD_BF16 : DSSMD_F16;
-        const int rc = corr_fwd_reg(L, R, out, B, C, H, W, D, dtype, stream);
+        const int rc = corr_fwd_reg(L, R, out, B, C, H, W, D, obs, dtype, stream);
         if (rc >= 0) return rc;
     }
     if (variant >= 1 && D <= 64) {
-        const int rc = launch_d4<T>(L, R, out, B, C, H, W, D, stream);
+        const int rc = launch_d4<T>(L, R, out, B, C, H, W, D, obs, stream);
         if (rc >= 0) return rc;
     }
     CorrFwdParams p{};
-    p.L = L; p.R = R; p.out = out;
+    p.L = L; p.R = R; p.out = out; p.OBS = obs;
     p.B = B; p.C = C; p.H = H; p.W = W; p.D = D;
     p.NR = B * H;
     p.c_pow2 = (C & (C - 1)) == 0;
@@ -717,25 +718,46 @@ int launch_typed(const void *L, const void *R, void *out, int B, int C, int H, i
 
 }  // namespace dssmd
 
+namespace dssmd {
+namespace {
+int corr_fwd_entry(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, long long obs, int dtype, cudaStream_t s) {
+    switch (dtype) {
+        case DSSMD_F32: return launch_typed<float>(L, R, out, B, C, H, W, D, obs, s);
+        case DSSMD_BF16: return launch_typed<__nv_bfloat16>(L, R, out, B, C, H, W, D, obs, s);
+        case DSSMD_F16: return launch_typed<__half>(L, R, out, B, C, H, W, D, obs, s);
+        case DSSMD_F64: {
+            const long long n = (long long)B * D * H * W;
+            const int nt = 256;
+            long long nb = (n + nt - 1) / nt;
+            if (nb > 148LL * 32) nb = 148LL * 32;
+            corr_fwd_f64_kernel<<<(unsigned)nb, nt, 0, s>>>((const double *)L, (const double *)R, (double *)out, B, C, H, W, D, obs);
+            return check_launch("corr_fwd_f64");
+        }
+        default: return fail(DSSMD_ERR_INVALID_ARGUMENT, "corr_fwd: unknown dtype %d", dtype);
+    }
+}
+int dtype_size(int dtype) { return dtype == DSSMD_F64 ? 8 : dtype == DSSMD_F32 ? 4 : 2; }
+}  // namespace
+}  // namespace dssmd
+
 extern "C" int dssmd_corr_fwd(const void *L, const void *R, void *out, int B, int C, int H, int W, int D,
                               int dtype, void *stream) {
     using namespace dssmd;
     DSSMD_REQUIRE(L && R && out, "corr_fwd: null pointer");
     DSSMD_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0, "corr_fwd: sizes must be positive (B=%d C=%d H=%d W=%d D=%d)", B, C, H, W, D);
     DSSMD_REQUIRE((long long)B * H < (1LL << 31), "corr_fwd: B*H too large");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    switch (dtype) {
-        case DSSMD_F32: return launch_typed<float>(L, R, out, B, C, H, W, D, s);
-        case DSSMD_BF16: return launch_typed<__nv_bfloat16>(L, R, out, B, C, H, W, D, s);
-        case DSSMD_F16: return launch_typed<__half>(L, R, out, B, C, H, W, D, s);
-        case DSSMD_F64: {
-            const long long n = (long long)B * D * H * W;
-            const int nt = 256;
-            long long nb = (n + nt - 1) / nt;
-            if (nb > 148LL * 32) nb = 148LL * 32;
-            corr_fwd_f64_kernel<<<(unsigned)nb, nt, 0, s>>>((const double *)L, (const double *)R, (double *)out, B, C, H, W, D);
-            return check_launch("corr_fwd_f64");
-        }
-        default: return fail(DSSMD_ERR_INVALID_ARGUMENT, "corr_fwd: unknown dtype %d", dtype);
-    }
+    return corr_fwd_entry(L, R, out, B, C, H, W, D, (long long)D * H * W, dtype, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int dssmd_corr_fwd_cat(const void *L, const void *R, void *cat, int B, int C, int H, int W, int D,
+                                  int cat_channels, int channel_offset, int dtype, void *stream) {
+    using namespace dssmd;
+    DSSMD_REQUIRE(L && R && cat, "corr_fwd_cat: null pointer");
+    DSSMD_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0, "corr_fwd_cat: sizes must be positive (B=%d C=%d H=%d W=%d D=%d)", B, C, H, W, D);
+    DSSMD_REQUIRE((long long)B * H < (1LL << 31), "corr_fwd_cat: B*H too large");
+    DSSMD_REQUIRE(channel_offset >= 0 && cat_channels >= channel_offset + D,
+                  "corr_fwd_cat: channels [%d, %d) do not fit a buffer of %d channels", channel_offset, channel_offset + D, cat_channels);
+    DSSMD_REQUIRE(dtype == DSSMD_F32 || dtype == DSSMD_BF16 || dtype == DSSMD_F16 || dtype == DSSMD_F64, "corr_fwd_cat: unknown dtype %d", dtype);
+    char *o = static_cast<char *>(cat) + (size_t)channel_offset * H * W * dtype_size(dtype);
+    return corr_fwd_entry(L, R, o, B, C, H, W, D, (long long)cat_channels * H * W, dtype, static_cast<cudaStream_t>(stream));
 }

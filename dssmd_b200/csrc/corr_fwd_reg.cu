@@ -25,6 +25,7 @@ namespace {
 
 struct FwdRegParams {
     void *out;
+    long long OBS;  // elements between two images of `out`
     int C, H, W, D;
     int NH;         // lanes per pixel group (power of two), D <= 12*NH
     int WPR;        // warps side by side along x
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(512) corr_fwd_reg_kernel(const FwdRegParams p,
             const int xt = gx % p.XT, row = gx / p.XT;
             const int b = row / p.H, y = row - b * p.H;
             const int x = xt * p.TX + xl;
-            T *o = reinterpret_cast<T *>(p.out) + (size_t)b * p.D * HW + (size_t)y * p.W + x;
+            T *o = reinterpret_cast<T *>(p.out) + (size_t)b * p.OBS + (size_t)y * p.W + x;
             if (p.CGW == 1) {
                 if (x < p.W) {
 #pragma unroll
@@ -193,14 +194,14 @@ int launch_fwd_reg(FwdRegParams p, const CUtensorMap &mapL, const CUtensorMap &m
 }
 
 template <typename T>
-int corr_fwd_reg_typed(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, CUtensorMapDataType tmtype, cudaStream_t stream) {
+int corr_fwd_reg_typed(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, long long obs, CUtensorMapDataType tmtype, cudaStream_t stream) {
     constexpr int ES = (int)sizeof(T);
     constexpr int EPV = 16 / ES;  // elements per 16 bytes: rows and boxes are multiples of it
     if (W % EPV != 0 || D > kDP * 16) return -1;
     if (((reinterpret_cast<uintptr_t>(L) | reinterpret_cast<uintptr_t>(R) | reinterpret_cast<uintptr_t>(out)) & 15) != 0) return -1;
     if ((long long)B * H * 64 >= (1LL << 31)) return -1;
     FwdRegParams p{};
-    p.out = out;
+    p.out = out; p.OBS = obs;
     p.C = C; p.H = H; p.W = W; p.D = D;
     p.invC = 1.0f / (float)C;
     int nh = 1, lognh = 0;
@@ -275,11 +276,11 @@ int corr_fwd_reg_typed(const void *L, const void *R, void *out, int B, int C, in
 
 // dtype: DSSMD_F32 / BF16 / F16 (all tensors).  Returns -1 when the shape is not eligible (the caller falls back to the
 // cp.async kernels), else a DSSMD_* code.
-int corr_fwd_reg(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, int dtype, cudaStream_t stream) {
+int corr_fwd_reg(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, long long obs, int dtype, cudaStream_t stream) {
     switch (dtype) {
-        case DSSMD_F32: return corr_fwd_reg_typed<float>(L, R, out, B, C, H, W, D, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, stream);
-        case DSSMD_BF16: return corr_fwd_reg_typed<__nv_bfloat16>(L, R, out, B, C, H, W, D, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, stream);
-        case DSSMD_F16: return corr_fwd_reg_typed<__half>(L, R, out, B, C, H, W, D, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, stream);
+        case DSSMD_F32: return corr_fwd_reg_typed<float>(L, R, out, B, C, H, W, D, obs, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, stream);
+        case DSSMD_BF16: return corr_fwd_reg_typed<__nv_bfloat16>(L, R, out, B, C, H, W, D, obs, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, stream);
+        case DSSMD_F16: return corr_fwd_reg_typed<__half>(L, R, out, B, C, H, W, D, obs, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, stream);
         default: return -1;
     }
 }

@@ -63,6 +63,7 @@ struct UmmaParams {
     const float *L;
     const float *R;
     float *out;
+    long long OBS;  // elements between two images of `out`
     int B, C, H, W, D;
     int P;        // B*H*W pixels (< 2^31)
     int tpi;      // tiles per batch image = ceil(H*W / 128)
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fwd_umma_kernel(const UmmaPa
                 if (mine) {
                     const int x = sg.xa + (m - sg.m0);
                     const int b = sg.row / p.H, y = sg.row - b * p.H;
-                    float *o = p.out + ((long long)b * p.D * p.H + y) * p.W + x;
+                    float *o = p.out + (long long)b * p.OBS + (long long)y * p.W + x;
 #pragma unroll
                     for (int k = 0; k < 16 * NW16 - 38; ++k) {
                         const int d = p.D - 1 - k;
@@ -380,7 +381,7 @@ namespace {
 }  // namespace
 
 // Returns -1 when the shape is outside this kernel's limits (caller falls back to FFMA).
-int corr_fwd_umma_f32(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, cudaStream_t stream) {
+int corr_fwd_umma_f32(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, long long obs, cudaStream_t stream) {
     if (W % 4 != 0 || W < 43 || D < 2 || D > 58) return -1;
     if (((reinterpret_cast<uintptr_t>(L) | reinterpret_cast<uintptr_t>(R)) & 15) != 0) return -1;
     if (C % kKC != 0) return -1;
@@ -406,7 +407,7 @@ int corr_fwd_umma_f32(const void *L, const void *R, void *out, int B, int C, int
     const int nmma = kBoxX * maxbox;
     if (nmma > 256 || nmma < 16) return -1;
     UmmaParams p{};
-    p.L = (const float *)L; p.R = (const float *)R; p.out = (float *)out;
+    p.L = (const float *)L; p.R = (const float *)R; p.out = (float *)out; p.OBS = obs;
     p.B = B; p.C = C; p.H = H; p.W = W; p.D = D;
     p.P = B * H * W;
     p.tpi = (H * W + kTileM - 1) / kTileM;

@@ -68,6 +68,61 @@ class CorrelationFn(torch.autograd.Function):
         return gL, gR, None
 
 
+class CorrelationCatFn(torch.autograd.Function):
+    """cat((head, build_corr(left, right, max_disp)), dim=1) with the correlation kernel writing its channels directly
+    into the concat buffer, and the backward reading them out of the concat gradient in place (no volume round trip,
+    no slice copy).  Upstream pattern: models/DSSMD.py:129-131."""
+
+    @staticmethod
+    def forward(ctx, head, left, right, max_disp):
+        _lib.require_cuda("build_corr_cat", head, left, right)
+        for t in (head, left, right):
+            _check4("build_corr_cat", t)
+        if left.shape != right.shape:
+            raise RuntimeError(f"build_corr_cat: left {tuple(left.shape)} and right {tuple(right.shape)} differ")
+        if left.dtype != right.dtype or head.dtype != left.dtype:
+            raise RuntimeError(f"build_corr_cat: dtypes differ ({head.dtype}, {left.dtype}, {right.dtype})")
+        B, C, H, W = left.shape
+        if head.shape[0] != B or tuple(head.shape[2:]) != (H, W):   # torch.cat's own requirement
+            raise RuntimeError(f"build_corr_cat: Sizes of tensors must match except in dimension 1 "
+                               f"(head {tuple(head.shape)}, features {tuple(left.shape)})")
+        D = max(int(max_disp), 0)
+        Ch = head.shape[1]
+        L, R = left.contiguous(), right.contiguous()
+        out = torch.empty((B, Ch + D, H, W), dtype=L.dtype, device=L.device)
+        out[:, :Ch].copy_(head)
+        if D > 0 and out.numel() > 0 and C > 0:
+            with torch.cuda.device(L.device):
+                _lib.check(_lib.lib().dssmd_corr_fwd_cat(_lib.ptr(L), _lib.ptr(R), _lib.ptr(out), B, C, H, W, D, Ch + D, Ch,
+                                                         _lib.dtype_code(L), _lib.stream_ptr(L.device)))
+        elif D > 0 and out.numel() > 0:
+            out[:, Ch:].fill_(float("nan"))  # mean over zero channels
+        ctx.save_for_backward(L, R)
+        ctx.D, ctx.Ch = D, Ch
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L, R = ctx.saved_tensors
+        B, C, H, W = L.shape
+        D, Ch = ctx.D, ctx.Ch
+        need_h, need_l, need_r = ctx.needs_input_grad[:3]
+        g = g.contiguous()
+        g_head = g[:, :Ch] if need_h else None
+        gL = torch.empty_like(L) if need_l else None
+        gR = torch.empty_like(R) if need_r else None
+        if (need_l or need_r) and L.numel() > 0:
+            if D == 0:
+                for t in (gL, gR):
+                    if t is not None:
+                        t.zero_()
+            else:
+                with torch.cuda.device(L.device):
+                    _lib.check(_lib.lib().dssmd_corr_bwd_cat(_lib.ptr(g), _lib.ptr(L), _lib.ptr(R), _lib.ptr(gL), _lib.ptr(gR),
+                                                             B, C, H, W, D, Ch + D, Ch, _lib.dtype_code(L), _lib.stream_ptr(L.device)))
+        return g_head, gL, gR, None
+
+
 def _pad_code(padding_mode):
     if padding_mode not in ("zeros", "border", "reflection"):
         raise ValueError(f"nn.functional.grid_sample(): expected padding_mode to be 'zeros', 'border', or "

@@ -19,7 +19,8 @@ import torch
 from . import _lib
 from .functional import LRWarpErrorFn, _check4, _new_flag, _raise_if_flag, resize_bilinear
 
-__all__ = ["photometric_l1", "photometric_loss", "PYRAMID_WEIGHTS"]
+__all__ = ["photometric_l1", "photometric_loss", "PYRAMID_WEIGHTS", "RecoveredCleanImagesLoss", "RecoveredCleanImagesLossV2",
+           "recovered_clean_l1"]
 
 PYRAMID_WEIGHTS = (0.6, 0.8, 1.0, 1.0)  # upstream's weights for the [1/8, 1/4, 1/2, 1] disparity pyramid
 
@@ -99,3 +100,82 @@ def photometric_loss(imgL, imgR, disp_pyramid, weights=None):
         term = photometric_l1(imgL, d, imgR) * float(w)
         total = term if total is None else total + term
     return total
+
+
+# ---- ASM reconstruction loss -------------------------------------------------------------------
+class _RecoveredCleanL1Fn(torch.autograd.Function):
+    """mean |clamp((haze_s - A (1 - t)) / t, 0, 1) - clean_s| with d/dt and d/dA computed in the forward launch."""
+
+    @staticmethod
+    def forward(ctx, trans, airlight, haze, clean):
+        B, C, H0, W0 = haze.shape
+        h, w = trans.shape[-2:]
+        T, A = trans.contiguous(), airlight.reshape(B).contiguous()
+        Hz, Cl = haze.contiguous(), clean.contiguous()
+        lib = _lib.lib()
+        nblk = int(lib.dssmd_asm_recovered_l1_blocks(B, h, w))
+        partial = torch.empty((B, nblk, 2), dtype=torch.float32, device=T.device)
+        need_t = ctx.needs_input_grad[0]
+        g_unit = torch.empty_like(T) if need_t else None
+        with torch.cuda.device(T.device):
+            _lib.check(lib.dssmd_asm_recovered_l1_fwd(_lib.ptr(T), _lib.ptr(A), _lib.ptr(Hz), _lib.ptr(Cl), _lib.ptr(g_unit),
+                                                      _lib.ptr(partial), B, C, H0, W0, h, w, _lib.dtype_code(T), _lib.stream_ptr(T.device)))
+        sums = partial.sum(dim=1)                      # [B, 2], fixed order
+        ctx.n = float(B * C * h * w)
+        ctx.a_shape = tuple(airlight.shape)
+        ctx.save_for_backward(g_unit, sums[:, 1])
+        return sums[:, 0].sum() / ctx.n
+
+    @staticmethod
+    def backward(ctx, g):
+        g_unit, ga = ctx.saved_tensors
+        scale = g / ctx.n
+        g_t = g_unit * scale if ctx.needs_input_grad[0] else None
+        g_a = (ga * scale).reshape(ctx.a_shape) if ctx.needs_input_grad[1] else None
+        return g_t, g_a, None, None
+
+
+def recovered_clean_l1(transmission_map, airlight, haze_image, clean_image):
+    """One level of upstream's reconstruction loss (losses/DSSMDLoss.py:87-111) as one kernel launch: the clean image is
+    recovered through the atmospheric scattering model from the predicted transmission [B,1,h,w] and airlight (B values),
+    clamped to [0, 1] and compared (L1 mean) with the clean image, both images bilinearly downsampled to the
+    transmission map's size first.  Gradients flow to the transmission map and the airlight."""
+    _lib.require_cuda("RecoveredCleanImagesLoss", transmission_map, airlight, haze_image, clean_image)
+    _check4("RecoveredCleanImagesLoss", transmission_map)
+    _check4("RecoveredCleanImagesLoss", haze_image)
+    _check4("RecoveredCleanImagesLoss", clean_image)
+    B, C, H0, W0 = haze_image.shape
+    h, w = transmission_map.shape[-2:]
+    if tuple(transmission_map.shape) != (B, 1, h, w):
+        raise RuntimeError(f"RecoveredCleanImagesLoss: transmission map must be [B,1,h,w], got {tuple(transmission_map.shape)}")
+    if clean_image.shape != haze_image.shape:
+        raise RuntimeError(f"RecoveredCleanImagesLoss: haze {tuple(haze_image.shape)} and clean {tuple(clean_image.shape)} images differ")
+    if airlight.numel() != B or airlight.shape[0] != B:
+        raise RuntimeError(f"RecoveredCleanImagesLoss: airlight must hold one value per sample, got {tuple(airlight.shape)}")
+    if any(t.dtype != torch.float32 for t in (transmission_map, airlight, haze_image, clean_image)):
+        raise NotImplementedError("RecoveredCleanImagesLoss: only float32 is implemented")
+    if haze_image.requires_grad or clean_image.requires_grad:
+        raise NotImplementedError("RecoveredCleanImagesLoss: gradients w.r.t. the images are not implemented "
+                                  "(upstream feeds the synthesised hazy input and the ground-truth clean image)")
+    scale = W0 // w if w else 0
+    if scale < 1 or W0 != w * scale or H0 != h * scale:
+        raise NotImplementedError(f"RecoveredCleanImagesLoss: images {H0}x{W0} must be an integer multiple of the "
+                                  f"transmission map {h}x{w}")
+    return _RecoveredCleanL1Fn.apply(transmission_map, airlight, haze_image, clean_image)
+
+
+class RecoveredCleanImagesLoss(torch.nn.Module):
+    """Same constructor and forward signature as upstream's losses/DSSMDLoss.py:81-111 (airlight: [B,1])."""
+
+    def __init__(self, type='normal'):  # noqa: A002  (upstream's argument name)
+        super().__init__()
+        self.loss_type = type
+
+    def forward(self, transmission_map, airlight, haze_image, clean_image):
+        if self.loss_type != 'normal':   # upstream: `loss` is unbound for any other type
+            raise UnboundLocalError("local variable 'loss' referenced before assignment")
+        return recovered_clean_l1(transmission_map, airlight, haze_image, clean_image)
+
+
+class RecoveredCleanImagesLossV2(RecoveredCleanImagesLoss):
+    """losses/DSSMDLoss.py:115-145: as above, the airlight already broadcastable ([B,1,1,1])."""

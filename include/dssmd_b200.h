@@ -74,6 +74,17 @@ DSSMD_API int dssmd_corr_fwd(const void *L, const void *R, void *out,
 DSSMD_API int dssmd_corr_bwd(const void *g, const void *L, const void *R, void *gL, void *gR,
                    int B, int C, int H, int W, int D, int dtype, void *stream);
 
+/* Correlation written straight into / read straight out of the concat buffer of its consumer.
+ * Upstream: in_conv3b = torch.cat((conv_redir(conv3_l), build_corr(conv3_l, conv3_r, max_disp // 8)), dim=1),
+ * models/DSSMD.py:129-131 (same pattern models/DSSMD_new.py, SSMDNet.py, SDNet.py).
+ * cat / g_cat: [B, cat_channels, H, W]; the D correlation channels are channels
+ * [channel_offset, channel_offset + D) of it; every other channel is left untouched (fwd) / ignored (bwd).
+ * Same arithmetic, kernels and results as dssmd_corr_fwd / dssmd_corr_bwd. */
+DSSMD_API int dssmd_corr_fwd_cat(const void *L, const void *R, void *cat, int B, int C, int H, int W, int D,
+                       int cat_channels, int channel_offset, int dtype, void *stream);
+DSSMD_API int dssmd_corr_bwd_cat(const void *g_cat, const void *L, const void *R, void *gL, void *gR,
+                       int B, int C, int H, int W, int D, int cat_channels, int channel_offset, int dtype, void *stream);
+
 /* ---- disparity warp -----------------------------------------------------------
  * Replaces disp_warp(img, disp, padding_mode), utils/disparity_warper.py:83-106
  * (byte-identical copy at models/UtilsNet/stereo_op.py:41-63), including its
@@ -152,6 +163,22 @@ DSSMD_API int dssmd_photometric_l1_fwd(const void *imgL, const void *imgR, const
 DSSMD_API int dssmd_haze_fwd(const void *clear, const void *src, int src_is_disparity, const void *baseline, const void *focal_length,
                    const void *beta, const void *airlight, void *haze, void *trans, void *depth,
                    int B, int C, int H, int W, int image_dtype, int compute_dtype, void *stream);
+
+/* ---- ASM reconstruction loss ------------------------------------------------------
+ * Replaces RecoveredCleanImagesLoss.forward(transmission_map, airlight, haze_image, clean_image),
+ * losses/DSSMDLoss.py:81-111 (V2 :115-145), called per level of the transmission pyramid by
+ * trainfiles/dssmd_traner_new.py:298-302, together with its autograd backward:
+ *   rec = (haze_s - A * (1 - t)) / t;   loss = mean | clamp(rec, 0, 1) - clean_s |
+ * with haze_s / clean_s the bilinear (align_corners=False) downsample of the images to the size of t when they are
+ * W0 / w times larger (integer factor, H0 == h * W0 / w).
+ * trans: [B,1,h,w]; airlight: [B]; haze, clean: [B,C,H0,W0]; g_trans_unit: [B,1,h,w] = d(sum |diff|)/d(trans), may be
+ * NULL; partial: [B, nblocks, 2] floats with nblocks = dssmd_asm_recovered_l1_blocks(B, h, w): per block the sum of
+ * |diff| and of d|diff|/d(airlight).  loss = sum(partial[..., 0]) / (B*C*h*w); d loss / d airlight[b] =
+ * sum(partial[b, :, 1]) / (B*C*h*w).  One launch, deterministic. */
+DSSMD_API int dssmd_asm_recovered_l1_blocks(int B, int h, int w);
+DSSMD_API int dssmd_asm_recovered_l1_fwd(const void *trans, const void *airlight, const void *haze, const void *clean,
+                               void *g_trans_unit, void *partial, int B, int C, int H0, int W0, int h, int w,
+                               int dtype, void *stream);
 
 /* ---- self test ------------------------------------------------------------------------
  * The lean warp kernels divide pixel coordinates by W - 1 with a reciprocal hoisted out of the pixel loop

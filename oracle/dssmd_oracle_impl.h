@@ -360,6 +360,57 @@ void FN(oracle_haze_fwd)(const void *clear, const void *src, int src_is_disp, in
     }
 }
 
+/* ------------------------------------------------------------------------
+ * ASM reconstruction loss, value and gradients.
+ * Restates RecoveredCleanImagesLoss.forward, losses/DSSMDLoss.py:87-111 (the
+ * `transmission_map.min==0` test compares a method with 0: always the else
+ * branch), and the backward autograd derives from it, node by node:
+ *   om = 1 - t;  am = A * om;  num = haze_s - am;  rec = num / t
+ *   rc = clamp(rec, 0, 1);  diff = rc - clean_s;  loss = mean |diff|
+ *   g_diff = sign(diff) / n;  g_rec = g_diff on 0 <= rec <= 1 else 0
+ *   g_num = g_rec / t;  g_t += -g_rec * (rec / t)          (div backward)
+ *   g_am = -g_num;  g_A += g_am * om;  g_om = g_am * A;  g_t += -g_om
+ * haze_s / clean_s: the images at the size of t (resized by the caller with
+ * oracle_resize_bilinear when larger).  Sums are accumulated in double.
+ * Returns the loss; g_t: [B,1,h,w], g_A: [B] (either may be NULL).
+ * ---------------------------------------------------------------------- */
+double FN(oracle_recovered_l1)(const REAL *trans, const REAL *airlight, const REAL *haze_s, const REAL *clean_s,
+                               REAL *g_t, REAL *g_A, int B, int C, long hw)
+{
+    const double n = (double)B * C * (double)hw;
+    double total = 0.0;
+    for (int b = 0; b < B; ++b) {
+        const REAL A = airlight[b];
+        double ga = 0.0;
+        for (long i = 0; i < hw; ++i) {
+            const REAL t = trans[(long)b * hw + i];
+            const REAL om = (REAL)1 - t;
+            const REAL am = A * om;
+            double gt = 0.0;
+            for (int c = 0; c < C; ++c) {
+                const long pc = ((long)b * C + c) * hw + i;
+                const REAL num = haze_s[pc] - am;
+                const REAL rec = num / t;
+                const REAL rc = FMIN(FMAX(rec, (REAL)0), (REAL)1);
+                const REAL diff = rc - clean_s[pc];
+                total += diff < 0 ? -(double)diff : (double)diff;
+                const REAL sg = diff > 0 ? (REAL)1 : (diff < 0 ? (REAL)-1 : (REAL)0);
+                const REAL g_rec = (rec >= 0 && rec <= 1) ? (REAL)(sg / n) : (REAL)0;
+                const REAL g_num = g_rec / t;
+                const REAL q = rec / t;
+                gt += (double)(-g_rec * q);
+                const REAL g_am = -g_num;
+                ga += (double)(g_am * om);
+                const REAL g_om = g_am * A;
+                gt += (double)(-g_om);
+            }
+            if (g_t) g_t[(long)b * hw + i] = (REAL)gt;
+        }
+        if (g_A) g_A[b] = (REAL)ga;
+    }
+    return total / n;
+}
+
 #undef FN
 #undef CAT
 #undef CAT_

@@ -30,6 +30,7 @@ from utils.disparity_warper import LRwarp_error, disp_warp  # noqa: E402
 import types  # noqa: E402
 for _m in ("skimage", "skimage.io", "skimage.transform", "matplotlib", "matplotlib.pyplot"):
     sys.modules.setdefault(_m, types.ModuleType(_m))
+from losses.DSSMDLoss import RecoveredCleanImagesLoss, RecoveredCleanImagesLossV2  # noqa: E402
 from DeBug.inference import convert_disp_to_depth, depth2trans, recover_haze_images  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
@@ -198,6 +199,41 @@ def gen_haze():
     print("haze.npz:", len(haze_cases()), "cases")
 
 
+def asm_cases():
+    # name, B, C, H0, W0, scale, V2?
+    return [
+        ("full", 2, 3, 8, 16, 1, False),
+        ("half", 2, 3, 8, 16, 2, False),
+        ("quarter_v2", 1, 3, 16, 32, 4, True),
+        ("eighth", 2, 3, 16, 32, 8, False),
+        ("ragged_full", 1, 3, 5, 7, 1, False),
+    ]
+
+
+def gen_asm():
+    """RecoveredCleanImagesLoss (losses/DSSMDLoss.py:81-145) on a synthesised hazy image, a perturbed transmission map and a
+    perturbed airlight, so that the clamp is active on both sides for part of the pixels."""
+    out = {}
+    for i, (name, B, C, H0, W0, scale, v2) in enumerate(asm_cases()):
+        torch.manual_seed(SEED + 500 + i)
+        h, w = H0 // scale, W0 // scale
+        clean = torch.rand(B, C, H0, W0)
+        t_true = 0.15 + 0.8 * torch.rand(B, 1, H0, W0)
+        A_true = 0.8 + 0.2 * torch.rand(B, 1)
+        haze = clean * t_true + A_true.view(B, 1, 1, 1) * (1 - t_true)
+        t_small = torch.nn.functional.interpolate(t_true, size=(h, w), mode="bilinear", align_corners=False) if scale > 1 else t_true
+        trans = (t_small * (0.7 + 0.6 * torch.rand(B, 1, h, w))).clamp(0.05, 1.0).requires_grad_(True)
+        A = (A_true + 0.2 * (torch.rand(B, 1) - 0.5)).requires_grad_(True)
+        mod = (RecoveredCleanImagesLossV2 if v2 else RecoveredCleanImagesLoss)(type="normal")
+        loss = mod(trans, A.view(B, 1, 1, 1) if v2 else A, haze, clean)
+        loss.backward()
+        out.update({f"{name}.trans": _np(trans), f"{name}.airlight": _np(A), f"{name}.haze": _np(haze), f"{name}.clean": _np(clean),
+                    f"{name}.v2": np.bool_(v2), f"{name}.loss": np.float64(loss.item()),
+                    f"{name}.g_trans": _np(trans.grad), f"{name}.g_airlight": _np(A.grad)})
+    np.savez_compressed(os.path.join(OUT, "asm.npz"), **out)
+    print("asm.npz:", len(asm_cases()), "cases")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # fixed reduction order for the fixtures
@@ -207,3 +243,4 @@ if __name__ == "__main__":
     gen_lrwarp()
     gen_photo()
     gen_haze()
+    gen_asm()

@@ -194,6 +194,23 @@ def haze(clear, src, src_is_disp, baseline, focal, beta, airlight, want=("haze",
     return out
 
 
+def recovered_clean_l1(trans, airlight, haze_img, clean_img):
+    """RecoveredCleanImagesLoss.forward (losses/DSSMDLoss.py:87-111) and its autograd gradients:
+    returns (loss, g_trans [B,1,h,w], g_airlight [B])."""
+    trans = _c(trans)
+    haze_img = _c(haze_img, trans.dtype); clean_img = _c(clean_img, trans.dtype)
+    B, C, H0, W0 = haze_img.shape
+    h, w = trans.shape[-2:]
+    if W0 // w != 1:
+        haze_img, clean_img = resize_bilinear(haze_img, (h, w)), resize_bilinear(clean_img, (h, w))
+    A = _c(np.asarray(airlight).reshape(B), trans.dtype)
+    g_t = np.empty_like(trans); g_A = np.empty_like(A)
+    fn = getattr(lib(), "oracle_recovered_l1_" + _suffix(trans))
+    fn.restype = ctypes.c_double
+    loss = fn(_p(trans), _p(A), _p(haze_img), _p(clean_img), _p(g_t), _p(g_A), _I(B), _I(C), ctypes.c_long(h * w))
+    return float(loss), g_t, g_A
+
+
 # ---- bf16 helpers (the CUDA path takes bf16 I/O with fp32 accumulation) ----
 def bf16_round(a: np.ndarray) -> np.ndarray:
     """Round float32 values to the nearest bfloat16 (ties to even), kept as float32."""

@@ -647,3 +647,166 @@ def test_haze_needs_grad_uses_upstream_expression(ops):
     depth = ops.convert_disp_to_depth(one * 0.1, one * 1050, disp)
     depth.sum().backward()
     assert rel_err(disp.grad.cpu().numpy(), (-105.0 / disp.detach() ** 2).cpu().numpy()) <= TOL_F32
+
+
+# ------------------------------------------------------------------ correlation into the concat buffer
+CAT_SHAPES = [
+    # B, C, H, W, D, head channels, dtype, env
+    (4, 128, 72, 120, 24, 32, torch.float32, {}),                                   # model shape (cfg5), register-blocked TMA kernels
+    (2, 128, 40, 80, 24, 32, torch.float32, {}),                                    # cfg1 / cfg3
+    (2, 64, 12, 64, 41, 7, torch.float32, {"DSSMD_CORR_FWD_VARIANT": "2"}),         # tcgen05 forward forced
+    (2, 64, 12, 64, 24, 5, torch.float32, {"DSSMD_CORR_FWD_VARIANT": "1", "DSSMD_CORR_FWD_REG": "0", "DSSMD_CORR_BWD_VARIANT": "0"}),  # cp.async kernels
+    (2, 64, 12, 64, 24, 5, torch.float32, {"DSSMD_CORR_FWD_VARIANT": "0", "DSSMD_CORR_BWD_VARIANT": "0"}),  # wide-tile forward
+    (2, 20, 5, 37, 11, 3, torch.float32, {}),                                       # ragged W: scalar paths
+    (2, 64, 8, 48, 12, 16, torch.bfloat16, {}),
+    (1, 64, 8, 48, 12, 1, torch.float16, {}),
+    (1, 16, 4, 12, 5, 2, torch.float64, {}),
+    (1, 16, 3, 6, 9, 4, torch.float32, {}),                                         # D > W
+]
+
+
+@pytest.mark.parametrize("B,C,H,W,D,Ch,dt,env", CAT_SHAPES)
+def test_corr_cat_equals_cat_of_corr(ops, monkeypatch, B, C, H, W, D, Ch, dt, env):
+    """build_corr_cat(head, L, R, D) == torch.cat((head, build_corr(L, R, D)), 1), forward and all three gradients, to
+    the bit: same kernels, only the batch stride of the volume differs (upstream models/DSSMD.py:129-131)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    L0, R0 = feat((B, C, H, W), 31, dtype=dt), feat((B, C, H, W), 32, dtype=dt)
+    h0 = feat((B, Ch, H, W), 33, relu=False, dtype=dt)
+    g = feat((B, Ch + D, H, W), 34, relu=False, dtype=dt)
+    outs = []
+    for fused in (False, True):
+        L, R, h = (t.clone().requires_grad_(True) for t in (L0, R0, h0))
+        out = ops.build_corr_cat(h, L, R, D) if fused else torch.cat((h, ops.build_corr(L, R, D)), dim=1)
+        assert out.shape == (B, Ch + D, H, W) and out.is_contiguous() and out.dtype == dt
+        out.backward(g)
+        outs.append((out.detach(), h.grad, L.grad, R.grad))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert torch.equal(outs[1][1], g[:, :Ch])
+
+
+def test_corr_cat_vs_oracle(ops, oracle):
+    B, C, H, W, D, Ch = 2, 128, 40, 80, 24, 32
+    L, R = feat((B, C, H, W), 41), feat((B, C, H, W), 42)
+    h = feat((B, Ch, H, W), 43)
+    out = ops.build_corr_cat(h, L, R, D)
+    ref = oracle.corr_fwd(L.cpu().numpy(), R.cpu().numpy(), D)
+    assert torch.equal(out[:, :Ch], h)
+    assert rel_err(out[:, Ch:].cpu().numpy(), ref) <= TOL_F32
+
+
+def test_corr_cat_errors(ops):
+    L = feat((1, 8, 4, 8), 1)
+    with pytest.raises(RuntimeError, match="Sizes of tensors must match"):
+        ops.build_corr_cat(feat((1, 4, 5, 8), 2), L, L, 3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.build_corr_cat(torch.zeros(1, 4, 4, 8), L.cpu(), L.cpu(), 3)
+    from dssmd_b200 import _lib
+    vp = _lib.ptr
+    out = torch.empty(1, 6, 4, 8, device="cuda")
+    rc = _lib.lib().dssmd_corr_fwd_cat(vp(L), vp(L), vp(out), 1, 8, 4, 8, 3, 5, 3, 0, None)
+    assert rc == 1 and b"do not fit" in _lib.lib().dssmd_last_error()
+
+
+# ------------------------------------------------------------------ ASM reconstruction loss (SURVEY.md section 8f-3)
+ASM = load_cases("asm")
+
+
+@pytest.mark.parametrize("name", sorted(ASM))
+def test_recovered_clean_loss_golden(ops, name):
+    c = ASM[name]
+    v2 = bool(c["v2"])
+    B = c["airlight"].shape[0]
+    trans = cuda(c["trans"]).requires_grad_(True)
+    A = cuda(c["airlight"]).requires_grad_(True)
+    mod = (ops.RecoveredCleanImagesLossV2 if v2 else ops.RecoveredCleanImagesLoss)(type="normal")
+    loss = mod(trans, A.view(B, 1, 1, 1) if v2 else A, cuda(c["haze"]), cuda(c["clean"]))
+    loss.backward()
+    assert abs(float(loss.detach()) - float(c["loss"])) <= TOL_F32 * abs(float(c["loss"]))
+    assert rel_err(trans.grad.cpu().numpy(), c["g_trans"]) <= TOL_F32
+    assert A.grad.shape == A.shape
+    assert rel_err(A.grad.cpu().numpy(), c["g_airlight"]) <= TOL_F32
+
+
+def _asm_inputs(B, H0, W0, scale, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    r = lambda *s: torch.rand(*s, generator=g, device="cuda")  # noqa: E731
+    h, w = H0 // scale, W0 // scale
+    clean = r(B, 3, H0, W0)
+    t_true = 0.15 + 0.8 * r(B, 1, H0, W0)
+    A_true = 0.8 + 0.2 * r(B, 1)
+    haze = clean * t_true + A_true.view(B, 1, 1, 1) * (1 - t_true)
+    t_small = torch.nn.functional.avg_pool2d(t_true, scale) if scale > 1 else t_true
+    trans = (t_small * (0.7 + 0.6 * r(B, 1, h, w))).clamp(0.05, 1.0)
+    A = A_true + 0.2 * (r(B, 1) - 0.5)
+    return trans, A, haze, clean
+
+
+@pytest.mark.parametrize("B,H0,W0,scale", [(4, 576, 960, 1), (8, 320, 640, 1), (8, 320, 640, 2), (8, 320, 640, 4),
+                                            (8, 320, 640, 8), (2, 37, 53, 1), (1, 30, 42, 3)])
+def test_recovered_clean_loss_vs_oracle(ops, oracle, B, H0, W0, scale):
+    trans, A, haze, clean = _asm_inputs(B, H0, W0, scale, 1024 + scale)
+    tr, Ar = trans.clone().requires_grad_(True), A.clone().requires_grad_(True)
+    loss = ops.recovered_clean_l1(tr, Ar, haze, clean)
+    loss.backward()
+    n = lambda x: x.detach().cpu().numpy()  # noqa: E731
+    l_ref, gt_ref, ga_ref = oracle.recovered_clean_l1(n(trans), n(A), n(haze), n(clean))
+    assert abs(float(loss.detach()) - l_ref) <= TOL_F32 * abs(l_ref)
+    assert rel_err(n(tr.grad), gt_ref) <= TOL_F32
+    assert rel_err(n(Ar.grad).reshape(-1), ga_ref) <= 5 * TOL_F32       # a sum of ~1e5..1e6 signed fp32 terms per sample
+    # run-to-run bit equality (fixed reduction order)
+    tr2, Ar2 = trans.clone().requires_grad_(True), A.clone().requires_grad_(True)
+    loss2 = ops.recovered_clean_l1(tr2, Ar2, haze, clean)
+    loss2.backward()
+    assert torch.equal(loss2.detach(), loss.detach()) and torch.equal(tr2.grad, tr.grad) and torch.equal(Ar2.grad, Ar.grad)
+
+
+def test_recovered_clean_loss_pyramid_matches_upstream_expression(ops):
+    """The trainer's loop (trainfiles/dssmd_traner_new.py:298-302) over the 4-level transmission pyramid against upstream's
+    expression evaluated with torch ops on the same GPU, value and gradients; zero loss for the true parameters."""
+    B, H0, W0 = 4, 320, 640
+    weights = [0.6, 0.8, 1.0, 1.0]
+    pyr = [_asm_inputs(B, H0, W0, s, 77 + s) for s in (8, 4, 2, 1)]
+    haze, clean, A0 = pyr[-1][2], pyr[-1][3], pyr[-1][1]
+
+    def upstream(t, A):
+        s = haze.shape[-1] // t.shape[-1]
+        hz, cl = haze, clean
+        if s != 1:
+            hz = torch.nn.functional.interpolate(hz, scale_factor=1. / s, mode='bilinear', align_corners=False)
+            cl = torch.nn.functional.interpolate(cl, scale_factor=1. / s, mode='bilinear', align_corners=False)
+        a = A.unsqueeze(-1).unsqueeze(-1)
+        rec = torch.clamp((hz - a * (1 - t)) / t, min=0, max=1.0)
+        return torch.nn.functional.l1_loss(rec, cl)
+
+    res = []
+    for fn in (lambda t, A: ops.RecoveredCleanImagesLoss()(t, A, haze, clean), upstream):
+        ts = [p[0].clone().requires_grad_(True) for p in pyr]
+        A = A0.clone().requires_grad_(True)
+        total = sum(fn(t, A) * wt for t, wt in zip(ts, weights))
+        total.backward()
+        res.append((total.detach(), [t.grad for t in ts], A.grad))
+    assert abs(float(res[0][0]) - float(res[1][0])) <= TOL_F32 * abs(float(res[1][0]))
+    for a, b in zip(res[0][1], res[1][1]):
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= TOL_F32
+    assert rel_err(res[0][2].cpu().numpy(), res[1][2].cpu().numpy()) <= 5 * TOL_F32
+    # the true transmission and airlight recover the clean image: zero loss
+    t_true = 0.2 + 0.7 * torch.rand(B, 1, H0, W0, device="cuda")
+    A_true = torch.full((B, 1), 0.9, device="cuda")
+    hz = clean * t_true + 0.9 * (1 - t_true)
+    assert float(ops.recovered_clean_l1(t_true, A_true, hz, clean)) <= 1e-6
+
+
+def test_recovered_clean_loss_errors(ops):
+    t = torch.rand(2, 1, 8, 16, device="cuda") + 0.1
+    A = torch.rand(2, 1, device="cuda")
+    img = torch.rand(2, 3, 16, 32, device="cuda")
+    with pytest.raises(NotImplementedError, match="integer multiple"):
+        ops.recovered_clean_l1(t, A, torch.rand(2, 3, 17, 32, device="cuda"), torch.rand(2, 3, 17, 32, device="cuda"))
+    with pytest.raises(RuntimeError, match="one value per sample"):
+        ops.recovered_clean_l1(t, torch.rand(3, 1, device="cuda"), img, img)
+    with pytest.raises(NotImplementedError, match="float32"):
+        ops.recovered_clean_l1(t.double(), A.double(), img.double(), img.double())
+    with pytest.raises(UnboundLocalError):
+        ops.RecoveredCleanImagesLoss(type="other")(t, A, img, img)

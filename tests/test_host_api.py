@@ -166,3 +166,18 @@ def test_install_rebinds_haze_functions_in_trainers():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_asm_loss_signature_and_no_cpu_fallback():
+    from dssmd_b200 import losses
+    assert str(inspect.signature(losses.RecoveredCleanImagesLoss.__init__)) == "(self, type='normal')"
+    assert str(inspect.signature(losses.RecoveredCleanImagesLoss.forward)) == "(self, transmission_map, airlight, haze_image, clean_image)"
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        losses.RecoveredCleanImagesLoss()(torch.rand(1, 1, 4, 8), torch.rand(1, 1), torch.rand(1, 3, 4, 8), torch.rand(1, 3, 4, 8))
+
+
+def test_build_corr_cat_signature_and_no_cpu_fallback():
+    assert str(inspect.signature(submoudles.build_corr_cat)) == "(head, img_left, img_right, max_disp=40)"
+    x = torch.rand(1, 4, 3, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dssmd_b200.build_corr_cat(x, x, x, 3)

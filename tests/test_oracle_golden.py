@@ -155,3 +155,28 @@ def test_haze_invariants():
     lo, hi = np.minimum(clear, 0.9), np.maximum(clear, 0.9)
     assert np.all((o["haze"] >= lo - 1e-6) & (o["haze"] <= hi + 1e-6))
     assert rel_err(o["depth"] * disp, np.full_like(disp, 105.0)) <= TOL_F32
+
+
+# ---- ASM reconstruction loss -------------------------
+ASM = load_cases("asm")
+
+
+@pytest.mark.parametrize("name", sorted(ASM))
+def test_recovered_clean_loss_matches_reference(name):
+    """Fixtures: upstream's RecoveredCleanImagesLoss / V2 (losses/DSSMDLoss.py:81-145) and its autograd gradients w.r.t.
+    the transmission map and the airlight (oracle/gen_golden.py: gen_asm)."""
+    c = ASM[name]
+    loss, g_t, g_a = O.recovered_clean_l1(c["trans"], c["airlight"], c["haze"], c["clean"])
+    assert abs(loss - float(c["loss"])) <= TOL_F32 * abs(float(c["loss"]))
+    assert rel_err(g_t, c["g_trans"]) <= TOL_F32
+    assert rel_err(g_a.reshape(c["g_airlight"].shape), c["g_airlight"]) <= TOL_F32
+
+
+def test_recovered_clean_loss_is_zero_for_the_true_parameters():
+    rng = np.random.default_rng(3)
+    clean = rng.random((2, 3, 6, 8), dtype=np.float32) * 0.9 + 0.05
+    t = (0.3 + 0.6 * rng.random((2, 1, 6, 8), dtype=np.float32)).astype(np.float32)
+    A = np.array([0.9, 0.8], np.float32)
+    haze = clean * t + A.reshape(2, 1, 1, 1) * (1 - t)
+    loss, _, _ = O.recovered_clean_l1(t, A, haze, clean)
+    assert loss <= 1e-6
