@@ -125,9 +125,99 @@ __global__ void __launch_bounds__(kThreads) asm_recovered_l1_kernel(const float 
     }
 }
 
+// Even integer scale S (the pyramid levels 1/2, 1/4, 1/8): with align_corners=False the source coordinate of output pixel x
+// is S*x + S/2 - 1/2, i.e. exactly between source pixels S*x + S/2 - 1 and S*x + S/2, both weights 1/2 -- no coordinate
+// arithmetic, and the taps come as vector loads: S == 2: a thread owns 2 output pixels = one float4 per source row;
+// S == 4: one output pixel = the middle of one float4; S == 8: two scalars.  Same operations, in the same order, as
+// resize_at() performs for these weights.
+template <int S>
+__global__ void __launch_bounds__(kThreads) asm_recovered_l1_even_kernel(const float *__restrict__ trans, const float *__restrict__ airlight,
+                                                                         const float *__restrict__ haze, const float *__restrict__ clean,
+                                                                         float *__restrict__ g_t_unit, float *__restrict__ partial,
+                                                                         int C, int H0, int W0, int h, int w) {
+    using N = Num<float>;
+    pdl_launch_dependents();
+    pdl_wait();
+    constexpr int OPX = S == 2 ? 2 : 1;        // output pixels per thread
+    const int b = blockIdx.y;
+    const long long hw = (long long)h * w, HW0 = (long long)H0 * W0;
+    const float A = airlight[b];
+    const float *tb = trans + (size_t)b * hw;
+    const float *hb = haze + (size_t)b * C * HW0, *cb = clean + (size_t)b * C * HW0;
+    const int wq = w / OPX;
+    const long long nq = (long long)h * wq;
+    float s_abs = 0.f, s_ga = 0.f;
+    auto down = [&](float a, float b2, float c2, float d2) {   // rows (a b) over (c d), all weights 1/2
+        const float top = N::add(N::mul(0.5f, a), N::mul(0.5f, b2));
+        const float bot = N::add(N::mul(0.5f, c2), N::mul(0.5f, d2));
+        return N::add(N::mul(0.5f, top), N::mul(0.5f, bot));
+    };
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nq; i += (long long)gridDim.x * kThreads) {
+        const int y = (int)(i / wq), xq = (int)(i - (long long)y * wq);
+        const int x = xq * OPX;
+        const size_t r0 = (size_t)(S * y + S / 2 - 1) * W0, r1 = r0 + W0;
+        float t[OPX];
+        if constexpr (OPX == 2) {
+            const float2 tv = __ldg(reinterpret_cast<const float2 *>(tb + (size_t)y * w + x));
+            t[0] = tv.x; t[1] = tv.y;
+        } else {
+            t[0] = __ldg(tb + (size_t)y * w + x);
+        }
+        PixelOut acc[OPX];
+#pragma unroll
+        for (int j = 0; j < OPX; ++j) acc[j] = PixelOut{0.f, 0.f, 0.f};
+        for (int k = 0; k < C; ++k) {
+            const float *hp = hb + (size_t)k * HW0, *cp = cb + (size_t)k * HW0;
+            float hh[OPX], cc[OPX];
+            if constexpr (S == 2) {
+                const float4 h0 = __ldg(reinterpret_cast<const float4 *>(hp + r0 + 2 * x)), h1 = __ldg(reinterpret_cast<const float4 *>(hp + r1 + 2 * x));
+                const float4 c0 = __ldg(reinterpret_cast<const float4 *>(cp + r0 + 2 * x)), c1 = __ldg(reinterpret_cast<const float4 *>(cp + r1 + 2 * x));
+                hh[0] = down(h0.x, h0.y, h1.x, h1.y); hh[1] = down(h0.z, h0.w, h1.z, h1.w);
+                cc[0] = down(c0.x, c0.y, c1.x, c1.y); cc[1] = down(c0.z, c0.w, c1.z, c1.w);
+            } else if constexpr (S == 4) {
+                const float4 h0 = __ldg(reinterpret_cast<const float4 *>(hp + r0 + 4 * x)), h1 = __ldg(reinterpret_cast<const float4 *>(hp + r1 + 4 * x));
+                const float4 c0 = __ldg(reinterpret_cast<const float4 *>(cp + r0 + 4 * x)), c1 = __ldg(reinterpret_cast<const float4 *>(cp + r1 + 4 * x));
+                hh[0] = down(h0.y, h0.z, h1.y, h1.z);
+                cc[0] = down(c0.y, c0.z, c1.y, c1.z);
+            } else {
+                const size_t o = (size_t)S * x + S / 2 - 1;
+                hh[0] = down(__ldg(hp + r0 + o), __ldg(hp + r0 + o + 1), __ldg(hp + r1 + o), __ldg(hp + r1 + o + 1));
+                cc[0] = down(__ldg(cp + r0 + o), __ldg(cp + r0 + o + 1), __ldg(cp + r1 + o), __ldg(cp + r1 + o + 1));
+            }
+#pragma unroll
+            for (int j = 0; j < OPX; ++j) {
+                PixelOut o1;
+                asm_pixel(t[j], A, &hh[j], &cc[j], 1, o1);
+                acc[j].abs_sum += o1.abs_sum; acc[j].ga += o1.ga; acc[j].gt += o1.gt;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < OPX; ++j) { s_abs += acc[j].abs_sum; s_ga += acc[j].ga; }
+        if (g_t_unit) {
+            float *gp = g_t_unit + (size_t)b * hw + (size_t)y * w + x;
+            if constexpr (OPX == 2) *reinterpret_cast<float2 *>(gp) = make_float2(acc[0].gt, acc[1].gt);
+            else *gp = acc[0].gt;
+        }
+    }
+    __shared__ float red[2][kThreads / 32];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        s_abs += __shfl_xor_sync(0xffffffffu, s_abs, off);
+        s_ga += __shfl_xor_sync(0xffffffffu, s_ga, off);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s_abs; red[1][threadIdx.x >> 5] = s_ga; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, g = 0.f;
+        for (int k = 0; k < kThreads / 32; ++k) { a += red[0][k]; g += red[1][k]; }
+        float *p = partial + ((size_t)b * gridDim.x + blockIdx.x) * 2;
+        p[0] = a; p[1] = g;
+    }
+}
+
 int asm_blocks(int h, int w, int B) {
     const long long hw = (long long)h * w;
-    long long nb = (hw / 4 + kThreads - 1) / kThreads;           // one 4-pixel vector per thread
+    long long nb = (hw + kThreads - 1) / kThreads;               // at most one pixel per thread; the cap makes the big levels loop
     const long long cap = ((long long)sm_count() * 8 + B - 1) / B;   // ~8 resident blocks per SM over the whole batch
     if (nb > cap) nb = cap;
     if (nb < 1) nb = 1;
@@ -162,7 +252,12 @@ extern "C" int dssmd_asm_recovered_l1_fwd(const void *trans, const void *airligh
     cudaError_t e;
 #define DSSMD_ASM_ARGS (const float *)trans, (const float *)airlight, (const float *)haze, (const float *)clean, (float *)g_trans_unit, \
                        (float *)partial, C, H0, W0, h, w
-    if (full && C == 3) e = launch_pdl(asm_recovered_l1_kernel<3, true>, grid, dim3(kThreads), 0, s, DSSMD_ASM_ARGS);
+    const int scale = W0 / w;
+    const bool even_ok = (W0 % 4 == 0) && (w % 2 == 0) && (all & 15) == 0;   // float4 rows of the images, float2 pairs of t / g_t
+    if (scale == 2 && even_ok) e = launch_pdl(asm_recovered_l1_even_kernel<2>, grid, dim3(kThreads), 0, s, DSSMD_ASM_ARGS);
+    else if (scale == 4 && even_ok) e = launch_pdl(asm_recovered_l1_even_kernel<4>, grid, dim3(kThreads), 0, s, DSSMD_ASM_ARGS);
+    else if (scale == 8) e = launch_pdl(asm_recovered_l1_even_kernel<8>, grid, dim3(kThreads), 0, s, DSSMD_ASM_ARGS);
+    else if (full && C == 3) e = launch_pdl(asm_recovered_l1_kernel<3, true>, grid, dim3(kThreads), 0, s, DSSMD_ASM_ARGS);
     else if (full && C == 1) e = launch_pdl(asm_recovered_l1_kernel<1, true>, grid, dim3(kThreads), 0, s, DSSMD_ASM_ARGS);
     else e = launch_pdl(asm_recovered_l1_kernel<0, false>, grid, dim3(kThreads), 0, s, DSSMD_ASM_ARGS);
 #undef DSSMD_ASM_ARGS
