@@ -245,14 +245,20 @@ int launch_reg(RegParams p, const CUtensorMap &mapIn, const CUtensorMap &mapG, i
 
 namespace {
 
+// -1 = not eligible; with DSSMD_CORR_DEBUG set, says which test rejected the shape
+int reg_reject(int where) {
+    if (env_int_reg("DSSMD_CORR_DEBUG", 0)) fprintf(stderr, "corr_bwd reg: not eligible (test %d), generic kernel instead\n", where);
+    return -1;
+}
+
 template <typename T>
 int corr_bwd_reg_typed(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, long long gbs, CUtensorMapDataType tmtype,
                        cudaStream_t stream) {
     constexpr int ES = (int)sizeof(T);
     constexpr int EPV = 16 / ES;                    // elements per 16 bytes: rows and boxes are multiples of it
-    if (W % EPV != 0 || D > kDP * 16) return -1;
-    if (((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) != 0) return -1;
-    if ((long long)B * H * 64 >= (1LL << 31)) return -1;
+    if (W % EPV != 0 || D > kDP * 16) return reg_reject(1);
+    if (((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) != 0) return reg_reject(2);
+    if ((long long)B * H * 64 >= (1LL << 31)) return reg_reject(3);
     RegParams p{};
     p.out = out;
     p.C = C; p.H = H; p.W = W; p.D = D;
@@ -273,7 +279,7 @@ int corr_bwd_reg_typed(const void *g, const void *in, void *out, int mode, int B
     // x tile: the operand box (tile + halo) must fit a 256-element TMA box
     int wpr = ceil_div(W, pxw);
     while (wpr > 1 && wpr * pxw + p.HALO > 256) wpr = (wpr + 1) / 2;
-    if (wpr * pxw + p.HALO > 256) return -1;
+    if (wpr * pxw + p.HALO > 256) return reg_reject(4);
     p.WPR = wpr;
     p.TX = wpr * pxw;
     p.XT = ceil_div(W, p.TX);
@@ -283,7 +289,7 @@ int corr_bwd_reg_typed(const void *g, const void *in, void *out, int mode, int B
     if (cgw < 1) cgw = 8 / wpr;
     if (cgw < 1) cgw = 1;
     const int max_warps = px == 4 ? 16 : 8;   // __launch_bounds__ of the kernel
-    if (wpr > max_warps) return -1;
+    if (wpr > max_warps) return reg_reject(5);
     while (cgw > 1 && wpr * cgw > max_warps) --cgw;
     if (cgw > C) cgw = C;
     p.CGW = cgw;
@@ -301,7 +307,7 @@ int corr_bwd_reg_typed(const void *g, const void *in, void *out, int mode, int B
     {
         const size_t gbytes = (size_t)D * p.GW * ES + 128, rowb = (size_t)p.WP * ES;
         const size_t budget = (size_t)env_int_reg("DSSMD_CORR_BWD_SMEM_KB2", 100) * 1024 / 2;
-        if (gbytes + rowb * cgw > budget) return -1;
+        if (gbytes + rowb * cgw > budget) return reg_reject(6);
         while (cb > cgw && gbytes + rowb * cb + 128 > budget) cb -= cgw;
     }
     p.CB = cb;
@@ -310,7 +316,7 @@ int corr_bwd_reg_typed(const void *g, const void *in, void *out, int mode, int B
     p.g_bytes = (uint32_t)((size_t)D * p.GW * ES);
     const size_t stage = (size_t)((p.op_bytes + 127u) & ~127u) + ((p.g_bytes + 127u) & ~127u);
     const size_t smem = 2 * stage + 128;
-    if (smem > 200 * 1024) return -1;
+    if (smem > 200 * 1024) return reg_reject(7);
     p.nitems = B * H * p.XT * p.NCB;
     const int threads = wpr * cgw * 32;
     CUtensorMap mapIn, mapG;
@@ -318,13 +324,13 @@ int corr_bwd_reg_typed(const void *g, const void *in, void *out, int mode, int B
         const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
         const cuuint64_t strides[3] = {(cuuint64_t)W * ES, (cuuint64_t)H * W * ES, (cuuint64_t)C * H * W * ES};
         const cuuint32_t box[4] = {(cuuint32_t)p.WP, 1, (cuuint32_t)cb, 1};
-        if (!make_tmap(&mapIn, tmtype, in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
+        if (!make_tmap(&mapIn, tmtype, in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return reg_reject(8);
     }
     {
         const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
         const cuuint64_t strides[3] = {(cuuint64_t)W * ES, (cuuint64_t)H * W * ES, (cuuint64_t)gbs * ES};
         const cuuint32_t box[4] = {(cuuint32_t)p.GW, 1, (cuuint32_t)D, 1};
-        if (!make_tmap(&mapG, tmtype, g, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
+        if (!make_tmap(&mapG, tmtype, g, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return reg_reject(9);
     }
 #define DSSMD_REG_LAUNCH(M)                                                                     \
     if constexpr (ES == 4) {                                                                    \

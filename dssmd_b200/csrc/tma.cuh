@@ -61,9 +61,18 @@ inline bool make_tmap(CUtensorMap *m, CUtensorMapDataType dtype, const void *bas
     EncodeTiledFn fn = encode_tiled();
     if (!fn) return false;
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    return fn(m, dtype, (cuuint32_t)rank, const_cast<void *>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    auto encode = [&] {
+        return fn(m, dtype, (cuuint32_t)rank, const_cast<void *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    if (encode()) return true;
+    // The encoder is a driver entry point and wants the calling thread to have a current context.  A thread that has
+    // only set its device (an autograd worker on its first backward, a fresh nn.DataParallel replica thread --
+    // trainfiles/dssmd_traner_new.py:131-135) may not have one bound yet: measured, the first call from such a thread
+    // fails and every later one succeeds.  cudaFree(0) makes the runtime bind the primary context; then try again.
+    cudaFree(nullptr);
+    return encode();
 }
 inline bool make_tmap_f32(CUtensorMap *m, const void *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides,
                           const cuuint32_t *box, CUtensorMapSwizzle swizzle) {

@@ -810,3 +810,37 @@ def test_recovered_clean_loss_errors(ops):
         ops.recovered_clean_l1(t.double(), A.double(), img.double(), img.double())
     with pytest.raises(UnboundLocalError):
         ops.RecoveredCleanImagesLoss(type="other")(t, A, img, img)
+
+
+def test_fast_paths_are_taken_from_fresh_threads():
+    """The TMA-staged kernels need tensor maps, and the driver's encoder needs a current context in the calling thread.
+    An autograd worker on its first backward and every nn.DataParallel replica thread (trainfiles/dssmd_traner_new.py:131-135)
+    start without one: the first call from such a thread must still get the fast kernels (DSSMD_CORR_DEBUG prints the chosen
+    configuration), not the generic fallback.  Runs in a subprocess so that the threads are really fresh."""
+    import os
+    import subprocess
+    import sys
+    from helpers import ROOT
+    code = r'''
+import sys, threading
+sys.path.insert(0, %r)
+import torch, dssmd_b200
+L = torch.randn(2, 128, 36, 120, device="cuda").relu().requires_grad_(True)
+R = torch.randn(2, 128, 36, 120, device="cuda").relu().requires_grad_(True)
+torch.cuda.synchronize()
+def worker():
+    with torch.cuda.device(0):
+        out = dssmd_b200.build_corr(L, R, 24)      # forward from a fresh replica thread
+    box.append(out)
+box = []
+t = threading.Thread(target=worker); t.start(); t.join()
+box[0].sum().backward()                           # backward on the autograd worker's first call
+torch.cuda.synchronize()
+print("done")
+''' % ROOT
+    env = dict(os.environ, DSSMD_CORR_DEBUG="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "done" in r.stdout, r.stderr[-2000:]
+    assert "corr_fwd reg cfg" in r.stderr, r.stderr[-2000:]
+    assert r.stderr.count("corr_bwd reg cfg") == 2, r.stderr[-2000:]
+    assert "not eligible" not in r.stderr, r.stderr[-2000:]
