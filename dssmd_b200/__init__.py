@@ -11,12 +11,13 @@ from .haze import convert_disp_to_depth, depth2trans, recover_haze_images, synth
 from .install import install, uninstall
 from .losses import RecoveredCleanImagesLoss, RecoveredCleanImagesLossV2, photometric_l1, photometric_loss, recovered_clean_l1
 from .stereo_op import print_tensor_shape
+from .sttm import STTM_Single, epipolar_attention
 from .submoudles import build_corr, build_corr_cat
 
 __all__ = [
     "build_corr", "build_corr_cat", "CostVolume", "disp_warp", "LRwarp_error", "normalize_coords", "meshgrid",
     "read_pfm", "print_tensor_shape", "resize_bilinear", "set_check_negative_disparity",
     "install", "uninstall", "photometric_l1", "photometric_loss", "RecoveredCleanImagesLoss", "RecoveredCleanImagesLossV2", "recovered_clean_l1",
-    "convert_disp_to_depth", "depth2trans", "recover_haze_images", "synthesize_haze",
+    "STTM_Single", "epipolar_attention", "convert_disp_to_depth", "depth2trans", "recover_haze_images", "synthesize_haze",
 ]
 __version__ = "0.1.0"

@@ -14,7 +14,7 @@ from __future__ import annotations
 import importlib
 import sys
 
-from . import cost_volume, disparity_warper, haze, submoudles
+from . import cost_volume, disparity_warper, haze, sttm, submoudles
 
 # upstream module -> {attribute: replacement}
 _DEFINING = {
@@ -25,6 +25,8 @@ _DEFINING = {
     "utils.disparity_warper": {"disp_warp": disparity_warper.disp_warp,
                                "LRwarp_error": disparity_warper.LRwarp_error},
     # haze synthesis on the input side of the training step (trainfiles/dssmd_traner_new.py:22, 250-256)
+    # attention along the epipolar line (models/BidNet/BidNet.py:6, 115)
+    "models.BidNet.STTM_Simple": {"STTM_Single": sttm.STTM_Single},
     "DeBug.inference": {"convert_disp_to_depth": haze.convert_disp_to_depth, "depth2trans": haze.depth2trans,
                         "recover_haze_images": haze.recover_haze_images},
 }
@@ -32,7 +34,7 @@ _DEFINING = {
 _IMPORTERS = ["models.DSSMD", "models.DSSMD_new", "models.SSMDNet", "models.SDNet",
               "trainfiles.dssmd_traner_new", "trainfiles.dssmd_trainer", "trainfiles.dssmd_disp_only",
               "trainfiles.bidnet_trainer", "trainfiles.ffanet_trainer", "trainfiles.ffanet_trainer_kitti",
-              "trainfiles.ffanet_trainer_ddp", "DeBug.test_model", "DeBug.test_model_only"]
+              "trainfiles.ffanet_trainer_ddp", "DeBug.test_model", "DeBug.test_model_only", "models.BidNet.BidNet"]
 
 _saved = {}
 

@@ -180,6 +180,21 @@ DSSMD_API int dssmd_asm_recovered_l1_fwd(const void *trans, const void *airlight
                                void *g_trans_unit, void *partial, int B, int C, int H0, int W0, int h, int w,
                                int dtype, void *stream);
 
+/* ---- attention along the epipolar line ---------------------------------------------
+ * Replaces the core of STTM_Single.forward, models/BidNet/STTM_Simple.py:43-57 (q, k, v are the outputs of its three
+ * 1x1 convolutions; used at full resolution by models/BidNet/BidNet.py:115, 239-240):
+ *   out[b,c,y,x] = sum_x' softmax_x'( scale * sum_c' q[b,c',y,x] k[b,c',y,x'] ) * v[b,c,y,x']
+ * q, k, v, out: [B,C,H,W] NCHW fp32 (no permutes, the [B*H, W, W] attention matrix is never written);
+ * lse: [B*H, W] row log-sum-exp of the scaled scores, saved for the backward (may be NULL for inference).
+ * C in {16, 32, 64, 128}, W % 4 == 0, B*H <= 65535, 16-byte aligned tensors; anything else: DSSMD_ERR_UNSUPPORTED. */
+DSSMD_API int dssmd_epipolar_attn_fwd(const void *q, const void *k, const void *v, void *out, void *lse,
+                            int B, int C, int H, int W, float scale, int dtype, void *stream);
+/* Backward of the above: g_q, g_k, g_v: [B,C,H,W] (g_q may be NULL, g_k / g_v only together); delta: [B*H, W] scratch
+ * (sum_c g_out * out, written by the first of the three launches).  Deterministic, no atomics. */
+DSSMD_API int dssmd_epipolar_attn_bwd(const void *q, const void *k, const void *v, const void *out, const void *g_out,
+                            const void *lse, void *delta, void *g_q, void *g_k, void *g_v,
+                            int B, int C, int H, int W, float scale, int dtype, void *stream);
+
 /* ---- self test ------------------------------------------------------------------------
  * The lean warp kernels divide pixel coordinates by W - 1 with a reciprocal hoisted out of the pixel loop
  * (csrc/warp_lean.cuh: div_rn_by) and rely on that being IEEE round-to-nearest division, bit for bit -- the

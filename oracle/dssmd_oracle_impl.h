@@ -411,6 +411,75 @@ double FN(oracle_recovered_l1)(const REAL *trans, const REAL *airlight, const RE
     return total / n;
 }
 
+/* ------------------------------------------------------------------------
+ * Attention along the epipolar line, forward and backward.
+ * Restates the core of STTM_Single.forward, models/BidNet/STTM_Simple.py:43-57:
+ *   per image row (b, y):  dots[x][x'] = scale * sum_c q[c][x] k[c][x']
+ *   attn = softmax(dots, over x');  out[c][x] = sum_x' attn[x][x'] v[c][x']
+ * on NCHW tensors (upstream permutes to [B*H, W, C] first; same numbers), and
+ * the backward autograd derives from it (matmul, softmax, matmul):
+ *   dattn = g^T v;  ddots = attn o (dattn - rowsum(attn o dattn));  g_q = scale * ddots k;
+ *   g_k = scale * ddots^T q;  g_v = attn^T g.
+ * g == NULL: forward only.  scratch: 3 * W * threads REALs are taken from the heap.
+ * ---------------------------------------------------------------------- */
+#include <stdlib.h>
+void FN(oracle_epipolar_attn)(const REAL *q, const REAL *k, const REAL *v, REAL *out, const REAL *g,
+                              REAL *g_q, REAL *g_k, REAL *g_v, int B, int C, int H, int W, REAL scale)
+{
+    const long HW = (long)H * W;
+#pragma omp parallel
+    {
+        REAL *attn = (REAL *)malloc(sizeof(REAL) * (size_t)W * 2);
+        REAL *dat = attn + W;
+#pragma omp for collapse(2) schedule(static)
+        for (int b = 0; b < B; ++b)
+            for (int y = 0; y < H; ++y) {
+                const long ro = (long)b * C * HW + (long)y * W;
+                if (g)
+                    for (int c = 0; c < C; ++c)
+                        for (int x = 0; x < W; ++x) { g_k[ro + c * HW + x] = 0; g_v[ro + c * HW + x] = 0; }
+                for (int x = 0; x < W; ++x) {
+                    REAL mx = 0;
+                    for (int j = 0; j < W; ++j) {
+                        REAL d = 0;
+                        for (int c = 0; c < C; ++c) d += q[ro + c * HW + x] * k[ro + c * HW + j];
+                        d *= scale;
+                        attn[j] = d;
+                        if (j == 0 || d > mx) mx = d;
+                    }
+                    REAL sum = 0;
+                    for (int j = 0; j < W; ++j) { attn[j] = EXP(attn[j] - mx); sum += attn[j]; }
+                    for (int j = 0; j < W; ++j) attn[j] /= sum;
+                    for (int c = 0; c < C; ++c) {
+                        REAL o = 0;
+                        for (int j = 0; j < W; ++j) o += attn[j] * v[ro + c * HW + j];
+                        out[ro + c * HW + x] = o;
+                    }
+                    if (!g) continue;
+                    REAL rs = 0;
+                    for (int j = 0; j < W; ++j) {
+                        REAL d = 0;
+                        for (int c = 0; c < C; ++c) d += g[ro + c * HW + x] * v[ro + c * HW + j];
+                        dat[j] = d;
+                        rs += attn[j] * d;
+                    }
+                    for (int j = 0; j < W; ++j) dat[j] = attn[j] * (dat[j] - rs);   /* ddots */
+                    for (int c = 0; c < C; ++c) {
+                        REAL a = 0;
+                        const REAL qc = q[ro + c * HW + x], gc = g[ro + c * HW + x];
+                        for (int j = 0; j < W; ++j) {
+                            a += dat[j] * k[ro + c * HW + j];
+                            g_k[ro + c * HW + j] += scale * dat[j] * qc;
+                            g_v[ro + c * HW + j] += attn[j] * gc;
+                        }
+                        g_q[ro + c * HW + x] = scale * a;
+                    }
+                }
+            }
+        free(attn);
+    }
+}
+
 #undef FN
 #undef CAT
 #undef CAT_

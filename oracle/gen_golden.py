@@ -31,6 +31,7 @@ import types  # noqa: E402
 for _m in ("skimage", "skimage.io", "skimage.transform", "matplotlib", "matplotlib.pyplot"):
     sys.modules.setdefault(_m, types.ModuleType(_m))
 from losses.DSSMDLoss import RecoveredCleanImagesLoss, RecoveredCleanImagesLossV2  # noqa: E402
+from models.BidNet.STTM_Simple import STTM_Single  # noqa: E402
 from DeBug.inference import convert_disp_to_depth, depth2trans, recover_haze_images  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
@@ -234,6 +235,62 @@ def gen_asm():
     print("asm.npz:", len(asm_cases()), "cases")
 
 
+def attn_cases():
+    # name, B, dim, heads, dim_head, H, W
+    return [
+        ("bidnet_like", 1, 32, 1, 32, 2, 72),        # BidNet's configuration (models/BidNet/BidNet.py:115), W not a multiple of 64
+        ("two_tiles", 1, 16, 1, 16, 2, 128),
+        ("short_row", 2, 16, 2, 8, 2, 20),
+        ("c64", 1, 64, 2, 32, 2, 40),                # to_out takes 2 * inner_dim channels: dim == heads * dim_head
+        ("c128", 1, 128, 4, 32, 1, 68),               # upstream's own example shape class (STTM_Simple.py:73)
+    ]
+
+
+def gen_attn():
+    """STTM_Single (models/BidNet/STTM_Simple.py) run unmodified: the fixtures hold the outputs of its three 1x1 convolutions
+    (forward hooks), the attention output it concatenates to the left features (input of to_out), the gradient arriving
+    there and the gradients autograd returns to q, k, v -- plus the module's weights, inputs and final output for the
+    drop-in module test."""
+    out = {}
+    for i, (name, B, dim, heads, dh, H, W) in enumerate(attn_cases()):
+        torch.manual_seed(SEED + 600 + i)
+        mod = STTM_Single(dim=dim, heads=heads, dim_head=dh, out_dim=dim).train()
+        left, right = 2 * torch.randn(B, dim, H, W), 2 * torch.randn(B, dim, H, W)
+        kept = {}
+
+        def keep(key):
+            def hook(_m, _inp, o):
+                o.retain_grad()
+                kept[key] = o
+            return hook
+        hs = [mod.q.register_forward_hook(keep("q")), mod.k.register_forward_hook(keep("k")), mod.v.register_forward_hook(keep("v"))]
+
+        def pre(_m, inp):
+            inp[0].retain_grad()
+            kept["cat"] = inp[0]
+        hs.append(mod.to_out[0].register_forward_pre_hook(pre))
+        left_r, right_r = left.clone().requires_grad_(True), right.clone().requires_grad_(True)
+        y = mod(left_r, right_r)
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        for h in hs:
+            h.remove()
+        inner = heads * dh
+        out.update({f"{name}.q": _np(kept["q"]), f"{name}.k": _np(kept["k"]), f"{name}.v": _np(kept["v"]),
+                    f"{name}.scale": np.float64(mod.scale), f"{name}.out": _np(kept["cat"][:, dim:]),
+                    f"{name}.g_out": _np(kept["cat"].grad[:, dim:]), f"{name}.g_q": _np(kept["q"].grad),
+                    f"{name}.g_k": _np(kept["k"].grad), f"{name}.g_v": _np(kept["v"].grad),
+                    f"{name}.cfg": np.asarray([dim, heads, dh, dim], dtype=np.int32)})
+        assert kept["q"].shape == (B, inner, H, W)
+        if name in ("bidnet_like", "short_row"):   # the whole module, for the drop-in test (kept to two cases: fixture size)
+            out.update({f"{name}.left": _np(left), f"{name}.right": _np(right), f"{name}.y": _np(y), f"{name}.g_y": _np(gy),
+                        f"{name}.g_left": _np(left_r.grad), f"{name}.g_right": _np(right_r.grad)})
+            for k_, t in mod.state_dict().items():
+                out[f"{name}.w:{k_}"] = t.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "attn.npz"), **out)
+    print("attn.npz:", len(attn_cases()), "cases")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # fixed reduction order for the fixtures
@@ -244,3 +301,4 @@ if __name__ == "__main__":
     gen_photo()
     gen_haze()
     gen_asm()
+    gen_attn()

@@ -211,6 +211,24 @@ def recovered_clean_l1(trans, airlight, haze_img, clean_img):
     return float(loss), g_t, g_A
 
 
+def epipolar_attention(q, k, v, scale, g=None):
+    """Core of STTM_Single.forward (models/BidNet/STTM_Simple.py:43-57) on NCHW tensors: out, and with an upstream
+    gradient g also (g_q, g_k, g_v)."""
+    q = _c(q); k = _c(k, q.dtype); v = _c(v, q.dtype)
+    B, C, H, W = q.shape
+    out = np.empty_like(q)
+    null = ctypes.c_void_p(None)
+    fn = getattr(lib(), "oracle_epipolar_attn_" + _suffix(q))
+    sc = ctypes.c_float(scale) if q.dtype == np.float32 else ctypes.c_double(scale)
+    if g is None:
+        fn(_p(q), _p(k), _p(v), _p(out), null, null, null, null, _I(B), _I(C), _I(H), _I(W), sc)
+        return out
+    g = _c(g, q.dtype)
+    gq, gk, gv = np.empty_like(q), np.empty_like(q), np.empty_like(q)
+    fn(_p(q), _p(k), _p(v), _p(out), _p(g), _p(gq), _p(gk), _p(gv), _I(B), _I(C), _I(H), _I(W), sc)
+    return out, gq, gk, gv
+
+
 # ---- bf16 helpers (the CUDA path takes bf16 I/O with fp32 accumulation) ----
 def bf16_round(a: np.ndarray) -> np.ndarray:
     """Round float32 values to the nearest bfloat16 (ties to even), kept as float32."""

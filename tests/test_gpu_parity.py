@@ -844,3 +844,91 @@ print("done")
     assert "corr_fwd reg cfg" in r.stderr, r.stderr[-2000:]
     assert r.stderr.count("corr_bwd reg cfg") == 2, r.stderr[-2000:]
     assert "not eligible" not in r.stderr, r.stderr[-2000:]
+
+
+# ------------------------------------------------------------------ attention along the epipolar line
+ATTN = load_cases("attn")
+
+
+@pytest.mark.parametrize("name", sorted(ATTN))
+def test_epipolar_attention_golden(ops, name):
+    c = ATTN[name]
+    q, k, v = (cuda(c[n]).requires_grad_(True) for n in ("q", "k", "v"))
+    out = ops.epipolar_attention(q, k, v, float(c["scale"]))
+    assert out.shape == q.shape and out.is_contiguous()
+    out.backward(cuda(c["g_out"]))
+    assert rel_err(out.detach().cpu().numpy(), c["out"]) <= TOL_F32
+    assert rel_err(q.grad.cpu().numpy(), c["g_q"]) <= TOL_F32
+    assert rel_err(k.grad.cpu().numpy(), c["g_k"]) <= TOL_F32
+    assert rel_err(v.grad.cpu().numpy(), c["g_v"]) <= TOL_F32
+
+
+@pytest.mark.parametrize("name", ["bidnet_like", "short_row"])
+def test_sttm_single_module_drop_in(ops, name):
+    """dssmd_b200.STTM_Single loads upstream's state_dict unchanged and reproduces the module's output and input gradients
+    (train mode: BatchNorm uses batch statistics, as in the fixture)."""
+    c = ATTN[name]
+    dim, heads, dh, out_dim = (int(t) for t in c["cfg"])
+    mod = ops.STTM_Single(dim=dim, heads=heads, dim_head=dh, out_dim=out_dim).cuda().train()
+    sd = {k_[2:]: torch.from_numpy(np.ascontiguousarray(c[k_])) for k_ in c if k_.startswith("w:")}
+    mod.load_state_dict(sd)                       # strict: same parameter and buffer names as upstream
+    left, right = cuda(c["left"]).requires_grad_(True), cuda(c["right"]).requires_grad_(True)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False       # the 1x1 convolutions around the kernel: fp32 like the CPU fixture
+    try:
+        y = mod(left, right)
+        y.backward(cuda(c["g_y"]))
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert rel_err(y.detach().cpu().numpy(), c["y"]) <= 2 * TOL_F32
+    assert rel_err(left.grad.cpu().numpy(), c["g_left"]) <= 1e-4     # through cuDNN convolutions and BatchNorm on either side
+    assert rel_err(right.grad.cpu().numpy(), c["g_right"]) <= 1e-4
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 32, 6, 640), (1, 32, 4, 1280), (2, 128, 5, 80), (1, 64, 3, 160), (2, 16, 3, 44), (1, 32, 2, 4)])
+def test_epipolar_attention_vs_torch_and_oracle(ops, oracle, B, C, H, W):
+    """BidNet's full-resolution widths against upstream's expression with torch ops on the same GPU (fp32 matmul) and, for the
+    small cases, the C oracle; rows independent; deterministic."""
+    g = torch.Generator(device="cuda").manual_seed(100 + W)
+    q, k, v, go = (torch.randn(B, C, H, W, generator=g, device="cuda") for _ in range(4))
+    scale = 32 ** -0.5
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        res = []
+        for fused in (True, False):
+            qq, kk, vv = (t.clone().requires_grad_(True) for t in (q, k, v))
+            if fused:
+                out = ops.epipolar_attention(qq, kk, vv, scale)
+            else:                                   # models/BidNet/STTM_Simple.py:43-57
+                b, c, h, w = qq.shape
+                q2, k2, v2 = (t.permute(0, 2, 3, 1).reshape(b * h, w, c).contiguous() for t in (qq, kk, vv))
+                attn = torch.softmax(torch.matmul(q2, k2.transpose(-1, -2)) * scale, dim=-1)
+                out = torch.matmul(attn, v2).view(b, h, w, c).contiguous().permute(0, 3, 1, 2)
+            out.backward(go)
+            res.append([t.detach().cpu().numpy() for t in (out, qq.grad, kk.grad, vv.grad)])
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    for a, b_ in zip(*res):
+        assert rel_err(a, b_) <= TOL_F32
+    if B * H * W * W * C <= 2e8:
+        ref = oracle.epipolar_attention(*(t.cpu().numpy() for t in (q, k, v)), scale, go.cpu().numpy())
+        for a, b_ in zip(res[0], ref):
+            assert rel_err(a, b_) <= TOL_F32
+    out2 = ops.epipolar_attention(q, k, v, scale)
+    assert torch.equal(out2, torch.from_numpy(res[0][0]).cuda())
+    k3 = k.clone(); k3[:, :, 0] += 1.0               # row 0 of k only touches row 0 of the output
+    out3 = ops.epipolar_attention(q, k3, v, scale)
+    assert torch.equal(out3[:, :, 1:], out2[:, :, 1:]) and not torch.equal(out3[:, :, 0], out2[:, :, 0])
+
+
+def test_epipolar_attention_errors(ops):
+    x = torch.randn(1, 32, 2, 8, device="cuda")
+    with pytest.raises(NotImplementedError, match="needs C in"):
+        ops.epipolar_attention(x[:, :24], x[:, :24], x[:, :24], 1.0)
+    with pytest.raises(NotImplementedError, match="needs C in"):
+        ops.epipolar_attention(x[..., :6], x[..., :6], x[..., :6], 1.0)
+    with pytest.raises(NotImplementedError, match="float32"):
+        ops.epipolar_attention(x.half(), x.half(), x.half(), 1.0)
+    with pytest.raises(RuntimeError, match="differ"):
+        ops.epipolar_attention(x, x[:, :16], x, 1.0)

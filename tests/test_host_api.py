@@ -181,3 +181,15 @@ def test_build_corr_cat_signature_and_no_cpu_fallback():
     x = torch.rand(1, 4, 3, 8)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         dssmd_b200.build_corr_cat(x, x, x, 3)
+
+
+def test_sttm_single_signature_state_dict_and_no_cpu_fallback():
+    from dssmd_b200 import sttm
+    assert str(inspect.signature(sttm.STTM_Single.__init__)) == "(self, dim, heads=8, dim_head=64, out_dim=256)"
+    assert str(inspect.signature(sttm.STTM_Single.forward)) == "(self, left_feat, right_feat)"
+    m = sttm.STTM_Single(dim=32, heads=1, dim_head=32, out_dim=32)
+    keys = list(m.state_dict().keys())
+    for k in ("q.weight", "k.weight", "v.weight", "norm.weight", "norm.bias", "to_out.0.weight", "to_out.1.running_mean", "to_out.3.weight"):
+        assert k in keys
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(1, 32, 2, 8), torch.randn(1, 32, 2, 8))

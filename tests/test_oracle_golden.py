@@ -180,3 +180,36 @@ def test_recovered_clean_loss_is_zero_for_the_true_parameters():
     haze = clean * t + A.reshape(2, 1, 1, 1) * (1 - t)
     loss, _, _ = O.recovered_clean_l1(t, A, haze, clean)
     assert loss <= 1e-6
+
+
+# ---- attention along the epipolar line -----------------
+ATTN = load_cases("attn")
+
+
+@pytest.mark.parametrize("name", sorted(ATTN))
+def test_epipolar_attention_matches_reference(name):
+    """Fixtures: upstream's STTM_Single (models/BidNet/STTM_Simple.py) run unmodified, q / k / v and the attention output
+    captured with hooks, gradients from its autograd graph (oracle/gen_golden.py: gen_attn)."""
+    c = ATTN[name]
+    out, gq, gk, gv = O.epipolar_attention(c["q"], c["k"], c["v"], float(c["scale"]), c["g_out"])
+    assert rel_err(out, c["out"]) <= TOL_F32
+    assert rel_err(gq, c["g_q"]) <= TOL_F32
+    assert rel_err(gk, c["g_k"]) <= TOL_F32
+    assert rel_err(gv, c["g_v"]) <= TOL_F32
+    assert np.array_equal(O.epipolar_attention(c["q"], c["k"], c["v"], float(c["scale"])), out)
+
+
+def test_epipolar_attention_invariants():
+    rng = np.random.default_rng(11)
+    q = rng.standard_normal((1, 16, 2, 12)).astype(np.float32)
+    k = rng.standard_normal((1, 16, 2, 12)).astype(np.float32)
+    v = rng.standard_normal((1, 16, 2, 12)).astype(np.float32)
+    # scale 0: uniform attention, the output is the row mean of v
+    out = O.epipolar_attention(q, k, v, 0.0)
+    assert rel_err(out, np.broadcast_to(v.mean(-1, keepdims=True), v.shape)) <= TOL_F32
+    # the output is a convex combination of the row's values
+    out = O.epipolar_attention(q, k, v, 0.25)
+    assert np.all(out <= v.max(-1, keepdims=True) + 1e-6) and np.all(out >= v.min(-1, keepdims=True) - 1e-6)
+    # rows are independent: changing row 1 of k leaves row 0 of the output alone
+    k2 = k.copy(); k2[:, :, 1] += 1.0
+    assert np.array_equal(O.epipolar_attention(q, k2, v, 0.25)[:, :, 0], out[:, :, 0])
