@@ -14,7 +14,7 @@ from __future__ import annotations
 import importlib
 import sys
 
-from . import cost_volume, disparity_warper, haze, sttm, submoudles
+from . import cost_volume, disparity_warper, haze, losses, sttm, submoudles
 
 # upstream module -> {attribute: replacement}
 _DEFINING = {
@@ -27,6 +27,9 @@ _DEFINING = {
     # haze synthesis on the input side of the training step (trainfiles/dssmd_traner_new.py:22, 250-256)
     # attention along the epipolar line (models/BidNet/BidNet.py:6, 115)
     "models.BidNet.STTM_Simple": {"STTM_Single": sttm.STTM_Single},
+    # ASM reconstruction loss (trainfiles/dssmd_traner_new.py:23, 175, 298-302)
+    "losses.DSSMDLoss": {"RecoveredCleanImagesLoss": losses.RecoveredCleanImagesLoss,
+                         "RecoveredCleanImagesLossV2": losses.RecoveredCleanImagesLossV2},
     "DeBug.inference": {"convert_disp_to_depth": haze.convert_disp_to_depth, "depth2trans": haze.depth2trans,
                         "recover_haze_images": haze.recover_haze_images},
 }

@@ -142,7 +142,7 @@ def test_haze_signatures_and_errors_follow_upstream():
 
 
 def test_install_rebinds_haze_functions_in_trainers():
-    names = ["DeBug", "DeBug.inference", "trainfiles", "trainfiles.dssmd_traner_new"]
+    names = ["DeBug", "DeBug.inference", "trainfiles", "trainfiles.dssmd_traner_new", "losses", "losses.DSSMDLoss"]
     saved = {k: sys.modules.get(k) for k in names}
     try:
         ups = {k: (lambda *a, _k=k, **kw: _k) for k in ("convert_disp_to_depth", "depth2trans", "recover_haze_images", "recover_depth")}
@@ -151,8 +151,13 @@ def test_install_rebinds_haze_functions_in_trainers():
             sys.modules[n] = types.ModuleType(n)
         for n in ("DeBug.inference", "trainfiles.dssmd_traner_new"):
             sys.modules[n].__dict__.update(ups)
+        class UpLoss:
+            pass
+        sys.modules["losses.DSSMDLoss"].RecoveredCleanImagesLoss = UpLoss
+        sys.modules["trainfiles.dssmd_traner_new"].RecoveredCleanImagesLoss = UpLoss
         dssmd_b200.install(import_missing=False)
         tr = sys.modules["trainfiles.dssmd_traner_new"]
+        assert tr.RecoveredCleanImagesLoss is dssmd_b200.RecoveredCleanImagesLoss
         assert tr.convert_disp_to_depth is dssmd_b200.convert_disp_to_depth
         assert tr.depth2trans is dssmd_b200.depth2trans
         assert tr.recover_haze_images is dssmd_b200.recover_haze_images
