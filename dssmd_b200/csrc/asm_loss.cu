@@ -47,8 +47,8 @@ __device__ __forceinline__ void asm_pixel(float t, float A, const float *h, cons
 
 // grid = (blocks over the h*w plane, B); block partial sums -> partial[(b * gridDim.x + blockIdx.x) * 2 + {0, 1}]
 template <int C, bool FULL>
-__global__ void __launch_bounds__(kThreads) asm_recovered_l1_kernel(const float *__restrict__ trans, const float *__restrict__ airlight,
-                                                                    const float *__restrict__ haze, const float *__restrict__ clean,
+__global__ void __launch_bounds__(kThreads) asm_recovered_l1_kernel(const float *trans, const float *airlight,
+                                                                    const float *haze, const float *clean,
                                                                     float *__restrict__ g_t_unit, float *__restrict__ partial,
                                                                     int Cdyn, int H0, int W0, int h, int w) {
     pdl_launch_dependents();
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kThreads) asm_recovered_l1_kernel(const float 
     const int b = blockIdx.y;
     const int CC = C > 0 ? C : Cdyn;
     const long long hw = (long long)h * w, HW0 = (long long)H0 * W0;
-    const float A = airlight[b];
+    const float A = ld_cg(airlight + b);
     const float *tb = trans + (size_t)b * hw;
     const float *hb = haze + (size_t)b * CC * HW0, *cb = clean + (size_t)b * CC * HW0;
     float s_abs = 0.f, s_ga = 0.f;
@@ -64,12 +64,12 @@ __global__ void __launch_bounds__(kThreads) asm_recovered_l1_kernel(const float 
         // scale 1, w % 4 == 0, 16-byte aligned tensors: 4 pixels per thread, 128-bit loads
         const long long nv = hw / 4;
         for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nv; i += (long long)gridDim.x * kThreads) {
-            const float4 tv = __ldg(reinterpret_cast<const float4 *>(tb) + i);
+            const float4 tv = ld_cg(reinterpret_cast<const float4 *>(tb) + i);
             float4 hv[C], cv[C];
 #pragma unroll
             for (int k = 0; k < C; ++k) {
-                hv[k] = __ldg(reinterpret_cast<const float4 *>(hb + (size_t)k * HW0) + i);
-                cv[k] = __ldg(reinterpret_cast<const float4 *>(cb + (size_t)k * HW0) + i);
+                hv[k] = ld_cg(reinterpret_cast<const float4 *>(hb + (size_t)k * HW0) + i);
+                cv[k] = ld_cg(reinterpret_cast<const float4 *>(cb + (size_t)k * HW0) + i);
             }
             const float tt[4] = {tv.x, tv.y, tv.z, tv.w};
             float gt[4];
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kThreads) asm_recovered_l1_kernel(const float 
             const Src<float> ys = src_index<float>(y, H0, h), xs = src_index<float>(x, W0, w);
             float hh[8], cc[8];
             PixelOut acc{0.f, 0.f, 0.f};
-            const float t = __ldg(tb + i);
+            const float t = ld_cg(tb + i);
             for (int k0 = 0; k0 < CC; k0 += 8) {   // channels in groups of 8 (images have 3)
                 const int kc = CC - k0 < 8 ? CC - k0 : 8;
                 for (int k = 0; k < kc; ++k) {
@@ -131,8 +131,8 @@ __global__ void __launch_bounds__(kThreads) asm_recovered_l1_kernel(const float 
 // S == 4: one output pixel = the middle of one float4; S == 8: two scalars.  Same operations, in the same order, as
 // resize_at() performs for these weights.
 template <int S>
-__global__ void __launch_bounds__(kThreads) asm_recovered_l1_even_kernel(const float *__restrict__ trans, const float *__restrict__ airlight,
-                                                                         const float *__restrict__ haze, const float *__restrict__ clean,
+__global__ void __launch_bounds__(kThreads) asm_recovered_l1_even_kernel(const float *trans, const float *airlight,
+                                                                         const float *haze, const float *clean,
                                                                          float *__restrict__ g_t_unit, float *__restrict__ partial,
                                                                          int C, int H0, int W0, int h, int w) {
     using N = Num<float>;
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kThreads) asm_recovered_l1_even_kernel(const f
     constexpr int OPX = S == 2 ? 2 : 1;        // output pixels per thread
     const int b = blockIdx.y;
     const long long hw = (long long)h * w, HW0 = (long long)H0 * W0;
-    const float A = airlight[b];
+    const float A = ld_cg(airlight + b);
     const float *tb = trans + (size_t)b * hw;
     const float *hb = haze + (size_t)b * C * HW0, *cb = clean + (size_t)b * C * HW0;
     const int wq = w / OPX;
@@ -158,10 +158,10 @@ __global__ void __launch_bounds__(kThreads) asm_recovered_l1_even_kernel(const f
         const size_t r0 = (size_t)(S * y + S / 2 - 1) * W0, r1 = r0 + W0;
         float t[OPX];
         if constexpr (OPX == 2) {
-            const float2 tv = __ldg(reinterpret_cast<const float2 *>(tb + (size_t)y * w + x));
+            const float2 tv = ld_cg(reinterpret_cast<const float2 *>(tb + (size_t)y * w + x));
             t[0] = tv.x; t[1] = tv.y;
         } else {
-            t[0] = __ldg(tb + (size_t)y * w + x);
+            t[0] = ld_cg(tb + (size_t)y * w + x);
         }
         PixelOut acc[OPX];
 #pragma unroll
@@ -170,19 +170,19 @@ __global__ void __launch_bounds__(kThreads) asm_recovered_l1_even_kernel(const f
             const float *hp = hb + (size_t)k * HW0, *cp = cb + (size_t)k * HW0;
             float hh[OPX], cc[OPX];
             if constexpr (S == 2) {
-                const float4 h0 = __ldg(reinterpret_cast<const float4 *>(hp + r0 + 2 * x)), h1 = __ldg(reinterpret_cast<const float4 *>(hp + r1 + 2 * x));
-                const float4 c0 = __ldg(reinterpret_cast<const float4 *>(cp + r0 + 2 * x)), c1 = __ldg(reinterpret_cast<const float4 *>(cp + r1 + 2 * x));
+                const float4 h0 = ld_cg(reinterpret_cast<const float4 *>(hp + r0 + 2 * x)), h1 = ld_cg(reinterpret_cast<const float4 *>(hp + r1 + 2 * x));
+                const float4 c0 = ld_cg(reinterpret_cast<const float4 *>(cp + r0 + 2 * x)), c1 = ld_cg(reinterpret_cast<const float4 *>(cp + r1 + 2 * x));
                 hh[0] = down(h0.x, h0.y, h1.x, h1.y); hh[1] = down(h0.z, h0.w, h1.z, h1.w);
                 cc[0] = down(c0.x, c0.y, c1.x, c1.y); cc[1] = down(c0.z, c0.w, c1.z, c1.w);
             } else if constexpr (S == 4) {
-                const float4 h0 = __ldg(reinterpret_cast<const float4 *>(hp + r0 + 4 * x)), h1 = __ldg(reinterpret_cast<const float4 *>(hp + r1 + 4 * x));
-                const float4 c0 = __ldg(reinterpret_cast<const float4 *>(cp + r0 + 4 * x)), c1 = __ldg(reinterpret_cast<const float4 *>(cp + r1 + 4 * x));
+                const float4 h0 = ld_cg(reinterpret_cast<const float4 *>(hp + r0 + 4 * x)), h1 = ld_cg(reinterpret_cast<const float4 *>(hp + r1 + 4 * x));
+                const float4 c0 = ld_cg(reinterpret_cast<const float4 *>(cp + r0 + 4 * x)), c1 = ld_cg(reinterpret_cast<const float4 *>(cp + r1 + 4 * x));
                 hh[0] = down(h0.y, h0.z, h1.y, h1.z);
                 cc[0] = down(c0.y, c0.z, c1.y, c1.z);
             } else {
                 const size_t o = (size_t)S * x + S / 2 - 1;
-                hh[0] = down(__ldg(hp + r0 + o), __ldg(hp + r0 + o + 1), __ldg(hp + r1 + o), __ldg(hp + r1 + o + 1));
-                cc[0] = down(__ldg(cp + r0 + o), __ldg(cp + r0 + o + 1), __ldg(cp + r1 + o), __ldg(cp + r1 + o + 1));
+                hh[0] = down(ld_cg(hp + r0 + o), ld_cg(hp + r0 + o + 1), ld_cg(hp + r1 + o), ld_cg(hp + r1 + o + 1));
+                cc[0] = down(ld_cg(cp + r0 + o), ld_cg(cp + r0 + o + 1), ld_cg(cp + r1 + o), ld_cg(cp + r1 + o + 1));
             }
 #pragma unroll
             for (int j = 0; j < OPX; ++j) {

@@ -73,6 +73,16 @@ __device__ __forceinline__ void st_global_cs(float4 *p, float4 v) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Loads in a kernel that may FOLLOW one of our own kernels on the stream: launched with programmatic stream serialization it
+// can become resident while that predecessor is still writing the tensors it reads after griddepcontrol.wait, so they are
+// not read-only for the kernel's lifetime and the non-coherent path (ld.global.nc -- __ldg, and what nvcc picks by itself
+// for const __restrict__ pointers) is off limits: measured, a consumer on some boxes read stale lines (the attention
+// backward reading `delta` from the launch before it).  ld.global.cg caches in L2 only and is always coherent.
+__device__ __forceinline__ float ld_cg(const float *p) { return __ldcg(p); }
+__device__ __forceinline__ double ld_cg(const double *p) { return __ldcg(p); }
+__device__ __forceinline__ float2 ld_cg(const float2 *p) { return __ldcg(p); }
+__device__ __forceinline__ float4 ld_cg(const float4 *p) { return __ldcg(p); }
+
 static inline bool pdl_enabled() {
     const char *v = std::getenv("DSSMD_PDL");
     return !(v && v[0] == '0');

@@ -35,7 +35,7 @@ __device__ __forceinline__ void load_tile(float *dst, const float *rowbase, size
         const int c = idx >> 4, f = idx & 15;
         const int x = x0 + 4 * f;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (x < W) v = __ldg(reinterpret_cast<const float4 *>(rowbase + (size_t)c * HW + x));
+        if (x < W) v = ld_cg(reinterpret_cast<const float4 *>(rowbase + (size_t)c * HW + x));
         *reinterpret_cast<float4 *>(dst + c * kLD + 4 * f) = v;
     }
 }
@@ -102,8 +102,8 @@ __device__ __forceinline__ float row_sum16(float v) {
 
 // ---- forward: grid (query tiles, B*H) ---------------------------------------------------------------------------------
 template <int CH>
-__global__ void __launch_bounds__(kThreads) epipolar_attn_fwd_kernel(const float *__restrict__ q, const float *__restrict__ k,
-                                                                     const float *__restrict__ v, float *__restrict__ out,
+__global__ void __launch_bounds__(kThreads) epipolar_attn_fwd_kernel(const float *q, const float *k,
+                                                                     const float *v, float *__restrict__ out,
                                                                      float *__restrict__ lse, int H, int W, float scale) {
     constexpr int C = 16 * CH;
     extern __shared__ __align__(16) float smem[];
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kThreads) epipolar_attn_fwd_kernel(const float
 }
 
 // ---- delta[r, x] = sum_c dO[b,c,y,x] * O[b,c,y,x] -------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) epipolar_attn_delta_kernel(const float *__restrict__ g_out, const float *__restrict__ out,
+__global__ void __launch_bounds__(256) epipolar_attn_delta_kernel(const float *g_out, const float *out,
                                                                   float *__restrict__ delta, int C, int H, int W, long long n) {
     pdl_launch_dependents();
     pdl_wait();
@@ -172,16 +172,16 @@ __global__ void __launch_bounds__(256) epipolar_attn_delta_kernel(const float *_
         const long long b = i / (long long)HW, p = i - b * (long long)HW;
         const float *a = g_out + (size_t)b * C * HW + p, *o = out + (size_t)b * C * HW + p;
         float s = 0.f;
-        for (int c = 0; c < C; ++c) s = fmaf(__ldg(a + (size_t)c * HW), __ldg(o + (size_t)c * HW), s);
+        for (int c = 0; c < C; ++c) s = fmaf(ld_cg(a + (size_t)c * HW), ld_cg(o + (size_t)c * HW), s);
         delta[i] = s;   // [B*H, W] is the same linear index as [B, H, W]
     }
 }
 
 // ---- backward: grid (row tiles, B*H).  KEYMAJOR = false: rows = queries, writes dQ.  true: rows = keys, writes dK, dV ----
 template <int CH, bool KEYMAJOR>
-__global__ void __launch_bounds__(kThreads) epipolar_attn_bwd_kernel(const float *__restrict__ q, const float *__restrict__ k,
-                                                                     const float *__restrict__ v, const float *__restrict__ g_out,
-                                                                     const float *__restrict__ lse, const float *__restrict__ delta,
+__global__ void __launch_bounds__(kThreads) epipolar_attn_bwd_kernel(const float *q, const float *k,
+                                                                     const float *v, const float *g_out,
+                                                                     const float *lse, const float *delta,
                                                                      float *__restrict__ g1, float *__restrict__ g2, int H, int W, float scale) {
     constexpr int C = 16 * CH;
     extern __shared__ __align__(16) float smem[];
@@ -213,8 +213,8 @@ __global__ void __launch_bounds__(kThreads) epipolar_attn_bwd_kernel(const float
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int x = x0 + 4 * ty + i;
-            rl[i] = x < W ? __ldg(lrow + x) : 0.f;
-            rd[i] = x < W ? __ldg(drow + x) : 0.f;
+            rl[i] = x < W ? ld_cg(lrow + x) : 0.f;
+            rd[i] = x < W ? ld_cg(drow + x) : 0.f;
         }
     }
     for (int j0 = 0; j0 < W; j0 += kT) {
@@ -230,8 +230,8 @@ __global__ void __launch_bounds__(kThreads) epipolar_attn_bwd_kernel(const float
         if (KEYMAJOR) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                cl[j] = jb + j < W ? __ldg(lrow + jb + j) : 0.f;
-                cd[j] = jb + j < W ? __ldg(drow + jb + j) : 0.f;
+                cl[j] = jb + j < W ? ld_cg(lrow + jb + j) : 0.f;
+                cd[j] = jb + j < W ? ld_cg(drow + jb + j) : 0.f;
             }
         }
 #pragma unroll

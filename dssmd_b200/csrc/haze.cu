@@ -7,6 +7,8 @@
 // order (no FMA contraction), in the dtype upstream's type promotion computes in: the data loaders hand over the
 // scalars as float64 (np.array(float), dataloader/ComplexSceneflowLoader.py:112-119), so with float32 images upstream
 // computes and returns float64 -- template <I = image / disparity element, S = compute and output element>.
+// Inputs are read with ld.global.cg and are not __restrict__ (see ld_cg in common.cuh: a predecessor launched with
+// programmatic serialization may still be writing them when this kernel becomes resident).
 // HBM-bound: (C + 1) * sizeof(I) read, (C + 2) * sizeof(S) written per pixel when everything is requested.
 #include "common.cuh"
 
@@ -34,12 +36,12 @@ template <typename T, int V> struct Vec { T v[V]; };
 template <typename T, int V>
 __device__ __forceinline__ Vec<T, V> ldv(const T *p) {
     Vec<T, V> r;
-    if constexpr (V == 1) r.v[0] = __ldg(p);
+    if constexpr (V == 1) r.v[0] = ld_cg(p);
     else if constexpr (sizeof(T) * V == 16) {
-        const float4 q = __ldg(reinterpret_cast<const float4 *>(p));
+        const float4 q = ld_cg(reinterpret_cast<const float4 *>(p));
         r = *reinterpret_cast<const Vec<T, V> *>(&q);
     } else {  // 32 bytes: 4 doubles
-        const float4 q0 = __ldg(reinterpret_cast<const float4 *>(p)), q1 = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+        const float4 q0 = ld_cg(reinterpret_cast<const float4 *>(p)), q1 = ld_cg(reinterpret_cast<const float4 *>(p) + 1);
         float4 *d = reinterpret_cast<float4 *>(&r);
         d[0] = q0; d[1] = q1;
     }
@@ -58,19 +60,19 @@ __device__ __forceinline__ void stv(T *p, const Vec<T, V> &r) {
 
 // grid = (chunks of the H*W plane, B); thread = V consecutive pixels, all channels
 template <typename I, typename S, int V>
-__global__ void __launch_bounds__(256) haze_kernel(const I *__restrict__ clear, const I *__restrict__ src, int src_is_disp,
-                                                   const S *__restrict__ baseline, const S *__restrict__ focal,
-                                                   const S *__restrict__ beta, const S *__restrict__ airlight,
+__global__ void __launch_bounds__(256) haze_kernel(const I *clear, const I *src, int src_is_disp,
+                                                   const S *baseline, const S *focal,
+                                                   const S *beta, const S *airlight,
                                                    S *__restrict__ haze, S *__restrict__ trans, S *__restrict__ depth,
                                                    int C, long long HW) {
     using N = HNum<S>;
     pdl_launch_dependents();
     pdl_wait();
     const int b = blockIdx.y;
-    const S fb = src_is_disp ? N::mul(focal[b], baseline[b]) : (S)0;
+    const S fb = src_is_disp ? N::mul(ld_cg(focal + b), ld_cg(baseline + b)) : (S)0;
     const bool need_t = haze || trans;
-    const S be = need_t ? beta[b] : (S)0;
-    const S A = haze ? airlight[b] : (S)0;
+    const S be = need_t ? ld_cg(beta + b) : (S)0;
+    const S A = haze ? ld_cg(airlight + b) : (S)0;
     const long long nvec = HW / V;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
         const long long o = i * V;

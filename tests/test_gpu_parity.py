@@ -563,26 +563,32 @@ def test_back_to_back_dependent_launches(ops, oracle):
     L, R = feat((2, 64, 24, 80), 82), feat((2, 64, 24, 80), 83)
     c_ref = oracle.corr_fwd(L.cpu().numpy(), R.cpu().numpy(), 64)
     c_ref = oracle.corr_fwd(c_ref, c_ref, 16)
-    for _ in range(25):
-        w = img
+    for it in range(25):
+        # a different power-of-two scale per iteration (exact in both ops, so the references just scale): the buffers of one
+        # iteration are recycled by the next with DIFFERENT contents, and a consumer that read a stale cache line of its
+        # predecessor's output would show
+        sc = float(2 ** (it % 5 - 2))
+        w = img * sc
         for _ in range(3):
             w, _ = ops.disp_warp(w, disp)
-        c = ops.build_corr(ops.build_corr(L, R, 64), ops.build_corr(L, R, 64), 16)
-        assert rel_err(w.cpu().numpy(), w_ref) <= TOL_F32
-        assert rel_err(c.cpu().numpy(), c_ref) <= TOL_F32
+        Ls = L * sc
+        c = ops.build_corr(ops.build_corr(Ls, R, 64), ops.build_corr(Ls, R, 64), 16)
+        assert rel_err(w.cpu().numpy(), w_ref * sc) <= TOL_F32
+        assert rel_err(c.cpu().numpy(), c_ref * sc * sc) <= TOL_F32
     # backward chain: g_img of one warp is the upstream gradient of the next
     g = feat((2, 3, 96, 320), 84, False)
     gi_ref = g.cpu().numpy()
     for _ in range(2):
         gi_ref, _ = oracle.warp_bwd(gi_ref, img.cpu().numpy(), disp.cpu().numpy(), "border")
-    for _ in range(10):
+    for it in range(10):
+        sc = float(2 ** (it % 5 - 2))
         x = img.clone().requires_grad_(True)
         y, _ = ops.disp_warp(x, disp)
-        (gi1,) = torch.autograd.grad(y, x, g)
+        (gi1,) = torch.autograd.grad(y, x, g * sc)
         x2 = img.clone().requires_grad_(True)
         y2, _ = ops.disp_warp(x2, disp)
         (gi2,) = torch.autograd.grad(y2, x2, gi1)
-        assert rel_err(gi2.cpu().numpy(), gi_ref) <= TOL_F32
+        assert rel_err(gi2.cpu().numpy(), gi_ref * sc) <= TOL_F32
 
 
 # ------------------------------------------------------------------ haze synthesis
@@ -932,3 +938,17 @@ def test_epipolar_attention_errors(ops):
         ops.epipolar_attention(x.half(), x.half(), x.half(), 1.0)
     with pytest.raises(RuntimeError, match="differ"):
         ops.epipolar_attention(x, x[:, :16], x, 1.0)
+
+
+def test_epipolar_attention_repeated_with_changing_data(ops, oracle):
+    """The backward is three dependent launches (delta -> dQ -> dK, dV) whose buffers the allocator recycles from call to call:
+    new data every iteration, every result checked (a consumer reading a stale line of its predecessor's output would show)."""
+    B, C, H, W = 1, 16, 2, 128
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for it in range(12):
+        q, k, v, go = (torch.randn(B, C, H, W, generator=g, device="cuda").requires_grad_(True) for _ in range(4))
+        out = ops.epipolar_attention(q, k, v, 0.25)
+        out.backward(go.detach())
+        ref = oracle.epipolar_attention(*(t.detach().cpu().numpy() for t in (q, k, v)), 0.25, go.detach().cpu().numpy())
+        for a, b_ in zip((out, q.grad, k.grad, v.grad), ref):
+            assert rel_err(a.detach().cpu().numpy(), b_) <= TOL_F32, it
