@@ -78,6 +78,10 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // not read-only for the kernel's lifetime and the non-coherent path (ld.global.nc -- __ldg, and what nvcc picks by itself
 // for const __restrict__ pointers) is off limits: measured, a consumer on some boxes read stale lines (the attention
 // backward reading `delta` from the launch before it).  ld.global.cg caches in L2 only and is always coherent.
+// ld.global.ca: coherent as well (ordered by griddepcontrol.wait under the memory model) and cached in L1, for the kernels
+// that re-read rows (the warp kernels)
+__device__ __forceinline__ float ld_ca(const float *p) { return __ldca(p); }
+__device__ __forceinline__ float4 ld_ca(const float4 *p) { return __ldca(p); }
 __device__ __forceinline__ float ld_cg(const float *p) { return __ldcg(p); }
 __device__ __forceinline__ double ld_cg(const double *p) { return __ldcg(p); }
 __device__ __forceinline__ float2 ld_cg(const float2 *p) { return __ldcg(p); }

@@ -27,7 +27,7 @@ constexpr int kMaxBandRows = 32;  // owned rows per band (R) upper bound; the ta
 
 template <int NCT, int PS, bool BORDER>
 __global__ void __launch_bounds__(PS - 2, (512 / (PS - 2)) > 0 ? (512 / (PS - 2)) : 1)
-warp_bwd_band_kernel(const float *__restrict__ g, const float *__restrict__ img, const float *__restrict__ disp,
+warp_bwd_band_kernel(const float *g, const float *img, const float *disp,
                      float *__restrict__ g_img, float *__restrict__ g_disp, int H, int W, int R,
                      float halfW, float tscale, float halfH) {
     constexpr int P = PS + 6;                 // accumulator slots per plane (see warp_bwd_lean_kernel)
@@ -171,10 +171,10 @@ warp_bwd_band_kernel(const float *__restrict__ g, const float *__restrict__ img,
         float n0[NCT], n1[NCT];
 #pragma unroll
         for (int c = 0; c < NCT; ++c) {
-            r0[c] = __ldg(reinterpret_cast<const float4 *>(ib + c * HW + (unsigned)(ya * W)));
-            r1[c] = __ldg(reinterpret_cast<const float4 *>(ib + c * HW + (unsigned)(yb * W)));
-            n0[c] = __ldg(ib + c * HW + (unsigned)(ya * W + nx));
-            n1[c] = __ldg(ib + c * HW + (unsigned)(yb * W + nx));
+            r0[c] = ld_ca(reinterpret_cast<const float4 *>(ib + c * HW + (unsigned)(ya * W)));
+            r1[c] = ld_ca(reinterpret_cast<const float4 *>(ib + c * HW + (unsigned)(yb * W)));
+            n0[c] = ld_ca(ib + c * HW + (unsigned)(ya * W + nx));
+            n1[c] = ld_ca(ib + c * HW + (unsigned)(yb * W + nx));
         }
         if (active) {
             unsigned char *const dvr = dvr_base + buf * DBUF;
@@ -267,10 +267,10 @@ warp_bwd_band_kernel(const float *__restrict__ g, const float *__restrict__ img,
     pdl_wait();        // nothing above touches global memory
     {
         const unsigned orow = (unsigned)(ys * W);
-        const float4 d4 = __ldg(reinterpret_cast<const float4 *>(db + orow));
+        const float4 d4 = ld_ca(reinterpret_cast<const float4 *>(db + orow));
 #pragma unroll
         for (int c = 0; c < NCT; ++c) {
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(gb + c * HW + orow));
+            const float4 v = ld_ca(reinterpret_cast<const float4 *>(gb + c * HW + orow));
             go[c][0] = v.x; go[c][1] = v.y; go[c][2] = v.z; go[c][3] = v.w;
         }
         if (g_disp && ys >= yb0) stage_diff(ys, ys & 1);
@@ -289,10 +289,10 @@ warp_bwd_band_kernel(const float *__restrict__ g, const float *__restrict__ img,
         float4 dn = make_float4(0.f, 0.f, 0.f, 0.f);
         if (nreal) {
             const unsigned nrow = (unsigned)((y + 1) * W);
-            dn = __ldg(reinterpret_cast<const float4 *>(db + nrow));
+            dn = ld_ca(reinterpret_cast<const float4 *>(db + nrow));
 #pragma unroll
             for (int c = 0; c < NCT; ++c) {
-                const float4 v = __ldg(reinterpret_cast<const float4 *>(gb + c * HW + nrow));
+                const float4 v = ld_ca(reinterpret_cast<const float4 *>(gb + c * HW + nrow));
                 gn[c][0] = v.x; gn[c][1] = v.y; gn[c][2] = v.z; gn[c][3] = v.w;
             }
         }

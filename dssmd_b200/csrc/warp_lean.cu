@@ -34,7 +34,7 @@ namespace {
 // 4 scalar LDS and 4 FMAs per channel.
 // ---------------------------------------------------------------------------------
 template <int NCT, int PS, bool BORDER>
-__global__ void __launch_bounds__(PS - 2, 1024 / (PS - 2)) warp_fwd_lean_kernel(const float *__restrict__ img, const float *__restrict__ disp,
+__global__ void __launch_bounds__(PS - 2, 1024 / (PS - 2)) warp_fwd_lean_kernel(const float *img, const float *disp,
                                                                                 float *__restrict__ out, float *__restrict__ mask,
                                                                                 int *neg_flag, int H, int W, float halfW, float halfH) {
     constexpr int VW = NCT == 3 ? 4 : NCT;
@@ -70,12 +70,12 @@ __global__ void __launch_bounds__(PS - 2, 1024 / (PS - 2)) warp_fwd_lean_kernel(
         const float *ib = img + (size_t)b * NCT * HW + xl;
 #pragma unroll
         for (int c = 0; c < NCT; ++c) {
-            st[c][0] = __ldg(reinterpret_cast<const float4 *>(ib + c * HW + (unsigned)(ya * W)));
-            st[c][1] = __ldg(reinterpret_cast<const float4 *>(ib + c * HW + (unsigned)(yb * W)));
+            st[c][0] = ld_ca(reinterpret_cast<const float4 *>(ib + c * HW + (unsigned)(ya * W)));
+            st[c][1] = ld_ca(reinterpret_cast<const float4 *>(ib + c * HW + (unsigned)(yb * W)));
         }
     }
     const unsigned orow = (unsigned)(y * W + x0);
-    const float4 d4 = __ldg(reinterpret_cast<const float4 *>(disp + (size_t)b * HW + (unsigned)(y * W + xl)));
+    const float4 d4 = ld_ca(reinterpret_cast<const float4 *>(disp + (size_t)b * HW + (unsigned)(y * W + xl)));
     const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
 
     uint32_t a0[4], a1[4];  // byte offset of the low / high x tap
@@ -156,8 +156,8 @@ __global__ void __launch_bounds__(PS - 2, 1024 / (PS - 2)) warp_fwd_lean_kernel(
 // ---------------------------------------------------------------------------------
 
 template <int NCT, int PS, bool BORDER>
-__global__ void __launch_bounds__(PS - 2, 1024 / (PS - 2)) warp_bwd_lean_kernel(const float *__restrict__ g, const float *__restrict__ img,
-                                                                                const float *__restrict__ disp, float *__restrict__ gV,
+__global__ void __launch_bounds__(PS - 2, 1024 / (PS - 2)) warp_bwd_lean_kernel(const float *g, const float *img,
+                                                                                const float *disp, float *__restrict__ gV,
                                                                                 float *__restrict__ g_disp, int H, int W,
                                                                                 float halfW, float tscale, float halfH, int dbg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -182,13 +182,13 @@ __global__ void __launch_bounds__(PS - 2, 1024 / (PS - 2)) warp_bwd_lean_kernel(
     const unsigned orow = (unsigned)(y * W + xl);
 
     // output-row loads first
-    const float4 d4 = __ldg(reinterpret_cast<const float4 *>(disp + (size_t)b * HW + orow));
+    const float4 d4 = ld_ca(reinterpret_cast<const float4 *>(disp + (size_t)b * HW + orow));
     float go[NCT][4];
     {
         const float *gb = g + (size_t)b * NCT * HW + orow;
 #pragma unroll
         for (int c = 0; c < NCT; ++c) {
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(gb + c * HW));
+            const float4 v = ld_ca(reinterpret_cast<const float4 *>(gb + c * HW));
             go[c][0] = v.x; go[c][1] = v.y; go[c][2] = v.z; go[c][3] = v.w;
         }
     }
@@ -209,10 +209,10 @@ __global__ void __launch_bounds__(PS - 2, 1024 / (PS - 2)) warp_bwd_lean_kernel(
         float n0[NCT], n1[NCT];
 #pragma unroll
         for (int c = 0; c < NCT; ++c) {
-            r0[c] = __ldg(reinterpret_cast<const float4 *>(ib + c * HW + (unsigned)(ya * W)));
-            r1[c] = __ldg(reinterpret_cast<const float4 *>(ib + c * HW + (unsigned)(yb * W)));
-            n0[c] = __ldg(ib + c * HW + (unsigned)(ya * W + nx));
-            n1[c] = __ldg(ib + c * HW + (unsigned)(yb * W + nx));
+            r0[c] = ld_ca(reinterpret_cast<const float4 *>(ib + c * HW + (unsigned)(ya * W)));
+            r1[c] = ld_ca(reinterpret_cast<const float4 *>(ib + c * HW + (unsigned)(yb * W)));
+            n0[c] = ld_ca(ib + c * HW + (unsigned)(ya * W + nx));
+            n1[c] = ld_ca(ib + c * HW + (unsigned)(yb * W + nx));
         }
         if (active) {
             const uint32_t sa = (uint32_t)(VW * 4) * ((uint32_t)tid + 1u);  // cells 4*tid+4 .. +7: slot tid + 1 of planes 0..3
@@ -367,8 +367,8 @@ __global__ void __launch_bounds__(PS - 2, 1024 / (PS - 2)) warp_bwd_lean_kernel(
 // gradient here).  Row sums are reduced in a fixed order: deterministic.
 // ---------------------------------------------------------------------------------
 template <int NCT, int PS>
-__global__ void __launch_bounds__(PS - 2, 1024 / (PS - 2)) photo_l1_lean_kernel(const float *__restrict__ imgL, const float *__restrict__ imgR,
-                                                                                const float *__restrict__ disp, float *__restrict__ g_unit,
+__global__ void __launch_bounds__(PS - 2, 1024 / (PS - 2)) photo_l1_lean_kernel(const float *imgL, const float *imgR,
+                                                                                const float *disp, float *__restrict__ g_unit,
                                                                                 float *__restrict__ partial, int *neg_flag, int H, int W,
                                                                                 float halfW, float tscale, float halfH) {
     constexpr int VW = NCT == 3 ? 4 : NCT;
@@ -395,12 +395,12 @@ __global__ void __launch_bounds__(PS - 2, 1024 / (PS - 2)) photo_l1_lean_kernel(
         const float *rb = imgR + (size_t)b * NCT * HW + (unsigned)(y * W + xl);
 #pragma unroll
         for (int c = 0; c < NCT; ++c) {
-            st[c][0] = __ldg(reinterpret_cast<const float4 *>(ib + c * HW + (unsigned)(ya * W)));
-            st[c][1] = __ldg(reinterpret_cast<const float4 *>(ib + c * HW + (unsigned)(yb * W)));
-            rr[c] = __ldg(reinterpret_cast<const float4 *>(rb + c * HW));
+            st[c][0] = ld_ca(reinterpret_cast<const float4 *>(ib + c * HW + (unsigned)(ya * W)));
+            st[c][1] = ld_ca(reinterpret_cast<const float4 *>(ib + c * HW + (unsigned)(yb * W)));
+            rr[c] = ld_ca(reinterpret_cast<const float4 *>(rb + c * HW));
         }
     }
-    const float4 d4 = __ldg(reinterpret_cast<const float4 *>(disp + (size_t)b * HW + (unsigned)(y * W + xl)));
+    const float4 d4 = ld_ca(reinterpret_cast<const float4 *>(disp + (size_t)b * HW + (unsigned)(y * W + xl)));
     const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
 
     uint32_t a0[4], a1[4];
