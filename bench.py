@@ -190,6 +190,105 @@ def capture(torch, fn):
     return g
 
 
+def aux_kernels(torch, lib, _lib, w, device, peak, nsets=4, rounds=10):
+    """Kernels either side of the hot path, timed like the per-call numbers above (CUDA events
+    around graph replays, inputs rotating over `nsets` sets): haze synthesis, the ASM reconstruction loss per pyramid level,
+    the correlation written into / read out of the 56-channel concat buffer, and the epipolar attention at BidNet's shape.
+    Not part of the metric's step; reported so that the driver's own run holds measured numbers for these rows."""
+    B, C, Hf, Wf, D, H, W = (w[k] for k in ("B", "C", "Hf", "Wf", "D", "H", "W"))
+    F32, F64 = 0, 3
+    vp = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)  # noqa: E731
+    st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)  # noqa: E731
+    chk = _lib.check
+    g = torch.Generator(device=device).manual_seed(1024)
+    rnd = lambda *shape: torch.rand(*shape, generator=g, device=device)  # noqa: E731
+
+    def timed(calls):
+        def one_round():
+            for c in calls:
+                c()
+        one_round()
+        torch.cuda.synchronize()
+        gr = capture(torch, one_round)
+        for _ in range(3):
+            gr.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(rounds):
+            gr.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / (rounds * len(calls))
+
+    out = {}
+
+    def put(name, us, nbytes=None, flop=None):
+        d = {"us": round(us, 2)}
+        if nbytes is not None:
+            d.update({"algorithmic_bytes": int(nbytes), "GBps": round(nbytes / us / 1e3, 1), "frac_of_peak": round(nbytes / us / 1e3 / peak, 4)})
+        if flop is not None:
+            d.update({"flop": float(flop), "TFLOPps": round(flop / us / 1e6, 2)})
+        out[name] = d
+
+    # ---- haze synthesis of one view (trainfiles/dssmd_traner_new.py:250-256)
+    px = B * H * W
+    for name, sdt, code, es in (("haze_f32_scalars", torch.float32, F32, 4), ("haze_f64_scalars", torch.float64, F64, 8)):
+        calls = []
+        for _ in range(nsets):
+            clear, disp = rnd(B, 3, H, W), 0.5 + 191.5 * rnd(B, 1, H, W)
+            sc = [torch.full((B,), v, dtype=sdt, device=device) for v in (0.1, 1050.0, 0.1, 0.9)]
+            o = [torch.empty(B, 3, H, W, dtype=sdt, device=device), torch.empty(B, 1, H, W, dtype=sdt, device=device),
+                 torch.empty(B, 1, H, W, dtype=sdt, device=device)]
+            calls.append(lambda clear=clear, disp=disp, sc=sc, o=o, code=code: chk(lib.dssmd_haze_fwd(
+                vp(clear), vp(disp), 1, vp(sc[0]), vp(sc[1]), vp(sc[2]), vp(sc[3]), vp(o[0]), vp(o[1]), vp(o[2]), B, 3, H, W, F32, code, st())))
+        put(name, timed(calls), px * (4 * 4 + 5 * es))
+        del calls
+    # ---- ASM reconstruction loss, one launch per level of the transmission pyramid (:298-302)
+    imgs = [(rnd(B, 3, H, W), rnd(B, 3, H, W)) for _ in range(nsets)]
+    for scale in (1, 2, 4, 8):
+        h, ww = H // scale, W // scale
+        nblk = int(lib.dssmd_asm_recovered_l1_blocks(B, h, ww))
+        calls = []
+        for hz, cl in imgs:
+            t, A = 0.1 + 0.9 * rnd(B, 1, h, ww), 0.8 + 0.2 * rnd(B)
+            gt, part = torch.empty_like(t), torch.empty(B, nblk, 2, device=device)
+            calls.append(lambda t=t, A=A, hz=hz, cl=cl, gt=gt, part=part, h=h, ww=ww: chk(lib.dssmd_asm_recovered_l1_fwd(
+                vp(t), vp(A), vp(hz), vp(cl), vp(gt), vp(part), B, 3, H, W, h, ww, F32, st())))
+        touched = 1 if scale == 1 else min(4, scale * scale)      # source pixels read per output pixel and plane
+        put(f"asm_l1_level_1/{scale}", timed(calls), B * h * ww * 4 * (2 + 6 * touched))
+        del calls
+    del imgs
+    # ---- correlation into / out of the 56-channel concat buffer (models/DSSMD.py:129-131)
+    Ch = 32
+    fw, bw = [], []
+    for _ in range(nsets):
+        L, R = torch.randn(B, C, Hf, Wf, generator=g, device=device).relu(), torch.randn(B, C, Hf, Wf, generator=g, device=device).relu()
+        cat, gcat = torch.empty(B, Ch + D, Hf, Wf, device=device), torch.randn(B, Ch + D, Hf, Wf, generator=g, device=device)
+        gL, gR = torch.empty_like(L), torch.empty_like(R)
+        fw.append(lambda L=L, R=R, cat=cat: chk(lib.dssmd_corr_fwd_cat(vp(L), vp(R), vp(cat), B, C, Hf, Wf, D, Ch + D, Ch, F32, st())))
+        bw.append(lambda L=L, R=R, gcat=gcat, gL=gL, gR=gR: chk(lib.dssmd_corr_bwd_cat(vp(gcat), vp(L), vp(R), vp(gL), vp(gR), B, C, Hf, Wf, D,
+                                                                                  Ch + D, Ch, F32, st())))
+    feat, vol = B * C * Hf * Wf * 4, B * D * Hf * Wf * 4
+    put("corr_fwd_cat", timed(fw), 2 * feat + vol)
+    put("corr_bwd_cat_gL+gR", timed(bw), vol + 4 * feat)
+    del fw, bw
+    # ---- attention along the epipolar line at BidNet's shape (models/BidNet/BidNet.py:115: B8, 32 channels, 320 x 640)
+    Ba, Ca, Ha, Wa = 8, 32, 320, 640
+    q, k, v, go = (torch.randn(Ba, Ca, Ha, Wa, generator=g, device=device) for _ in range(4))
+    o, lse, dl = torch.empty_like(q), torch.empty(Ba * Ha, Wa, device=device), torch.empty(Ba * Ha, Wa, device=device)
+    gq, gk, gv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+    scale = Ca ** -0.5
+    unit = 2.0 * Ba * Ha * Wa * Wa * Ca      # one W x W x C product per row
+    rounds = 3
+    put("epipolar_attn_fwd", timed([lambda: chk(lib.dssmd_epipolar_attn_fwd(vp(q), vp(k), vp(v), vp(o), vp(lse), Ba, Ca, Ha, Wa, scale, F32, st()))]),
+        flop=2 * unit)
+    put("epipolar_attn_bwd", timed([lambda: chk(lib.dssmd_epipolar_attn_bwd(vp(q), vp(k), vp(v), vp(o), vp(go), vp(lse), vp(dl), vp(gq), vp(gk), vp(gv),
+                                                                            Ba, Ca, Ha, Wa, scale, F32, st()))]), flop=7 * unit)
+    out["epipolar_attn_fwd"]["shape"] = out["epipolar_attn_bwd"]["shape"] = [Ba, Ca, Ha, Wa]
+    return out
+
+
 def shard_batch(global_batch: int, world_size: int, rank: int):
     """[begin, end) of the stereo pairs rank `rank` owns (batch-partitioned, no halo)."""
     per, extra = divmod(global_batch, world_size)
@@ -453,6 +552,11 @@ def run_gpu(args, w):
                 t0 = time.perf_counter(); stepf(); best = min(best, time.perf_counter() - t0)
             cpu = {"value": B / best, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"one per-GPU batch (B={B}) of {args.workload}, all four ops, best of 2 after 1 warm-up"}
+        aux = None
+        if not args.no_aux and not args.no_graph and world == 1:
+            del sets
+            torch.cuda.empty_cache()
+            aux = aux_kernels(torch, lib, _lib, w, device, peak)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -466,7 +570,7 @@ def run_gpu(args, w):
                     "path": "dssmd_b200.build_corr/.backward + disp_warp/.backward on pinned host tensors; "
                             "upload / compute / download streams, device inputs and host outputs double-buffered"},
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "kernels": kern, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roofline, "kernels": kern, "aux_kernels": aux, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if distributed:
@@ -484,6 +588,7 @@ def main():
     ap.add_argument("--sets", type=int, default=4, help="input/output sets rotated through to defeat L2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-aux", action="store_true", help="skip the timings of the kernels either side of the hot path (aux_kernels)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
