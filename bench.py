@@ -26,6 +26,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+QUIET = None   # QuietStdout, set by main()
 METRIC = "stereo_pairs_per_s@576x960"
 UNIT = "pairs/s"
 
@@ -289,6 +290,23 @@ def aux_kernels(torch, lib, _lib, w, device, peak, nsets=4, rounds=10):
     return out
 
 
+class QuietStdout:
+    """File descriptor 1 points at stderr while the job runs, so that nothing but the ONE JSON line reaches stdout (NCCL
+    prints its version banner to stdout from C when NCCL_DEBUG is set on the box); emit() writes the line to the real
+    stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        print(text, flush=True)
+        os.dup2(2, 1)
+
+
 def shard_batch(global_batch: int, world_size: int, rank: int):
     """[begin, end) of the stereo pairs rank `rank` owns (batch-partitioned, no halo)."""
     per, extra = divmod(global_batch, world_size)
@@ -347,7 +365,7 @@ def run_reference(args, w):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    QUIET.emit(json.dumps(line))
     return 0
 
 
@@ -572,7 +590,7 @@ def run_gpu(args, w):
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "kernels": kern, "aux_kernels": aux, "cpu_baseline": cpu, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        QUIET.emit(json.dumps(line))
     if distributed:
         dist.destroy_process_group()
     return 0
@@ -590,6 +608,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-aux", action="store_true", help="skip the timings of the kernels either side of the hot path (aux_kernels)")
     args = ap.parse_args()
+    global QUIET
+    QUIET = QuietStdout()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, w)
