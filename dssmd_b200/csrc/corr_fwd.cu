@@ -29,6 +29,8 @@ namespace dssmd {
 int corr_fwd_umma_f32(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, long long obs, cudaStream_t stream);
 // register-blocked, TMA-staged FFMA path (corr_fwd_reg.cu), fp32 / bf16 / fp16; -1 when the shape is not eligible
 int corr_fwd_reg(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, long long obs, int dtype, cudaStream_t stream);
+// tensor-core path for 16-bit tensors (corr_fwd_mma16.cu); -1 when the shape is outside its limits
+int corr_fwd_mma16(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, long long obs, int dtype, cudaStream_t stream);
 
 namespace {
 
@@ -595,6 +597,13 @@ int launch_typed(const void *L, const void *R, void *out, int B, int C, int H, i
     // 128 + D per tile where the FFMA kernels' grows with D (measured, C256 D41 800 tiles: 87 vs 108 us;
     // C128 D24 960 tiles: 50 vs 42 us; 270 tiles: 21 vs 13 us)
     int variant = env_int("DSSMD_CORR_FWD_VARIANT", -1);
+    if constexpr (sizeof(T) == 2) {
+        // 16-bit tensors: mma.sync on the banded row GEMM unless a variant is forced
+        if (variant < 0) {
+            const int rc = corr_fwd_mma16(L, R, out, B, C, H, W, D, obs, std::is_same<T, __nv_bfloat16>::value ? DSSMD_BF16 : DSSMD_F16, stream);
+            if (rc >= 0) return rc;
+        }
+    }
     if (variant < 0) variant = (sizeof(T) == 4 && C >= 64 && D >= 32 && (long)B * H * W / 128 >= 3L * sm_count()) ? 2 : 1;
     if constexpr (sizeof(T) == 4) {
         if (variant == 2) {

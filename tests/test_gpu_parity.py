@@ -288,7 +288,7 @@ def test_warp_vs_oracle(ops, oracle, shape, pad):
     assert set(np.unique(m)) <= {0.0, 1.0}
 
 
-@pytest.mark.parametrize("cfg", [("cfg3", 8, 320, 640), ("cfg4", 2, 384, 1280), ("cfg5", 4, 576, 960)], ids=lambda c: c[0])
+@pytest.mark.parametrize("cfg", [("cfg3", 8, 320, 640), ("cfg4", 2, 384, 1280), ("cfg4_1248", 1, 384, 1248), ("cfg5", 4, 576, 960)], ids=lambda c: c[0])
 def test_warp_full_size_vs_torch(ops, cfg):
     """Full BASELINE sizes.  The parity reference is the torch restatement run on
     the CPU (that is what upstream's functions do there, and what the golden
@@ -952,3 +952,45 @@ def test_epipolar_attention_repeated_with_changing_data(ops, oracle):
         ref = oracle.epipolar_attention(*(t.detach().cpu().numpy() for t in (q, k, v)), 0.25, go.detach().cpu().numpy())
         for a, b_ in zip((out, q.grad, k.grad, v.grad), ref):
             assert rel_err(a.detach().cpu().numpy(), b_) <= TOL_F32, it
+
+
+# ------------------------------------------------------------------ 16-bit correlation forward on the tensor cores (mma.sync)
+MMA16_SHAPES = [
+    # B, C, H, W, D
+    (2, 128, 6, 120, 24),      # model shape (cfg5): 8 warps, the last one half empty
+    (1, 256, 4, 160, 41),      # cfg2: 10 warps, 4 column-tile pairs
+    (2, 128, 5, 80, 24),       # cfg1 / cfg3
+    (1, 64, 3, 80, 5),
+    (1, 40, 2, 48, 12),        # channels not a multiple of the 32-channel stage
+    (1, 64, 2, 264, 64),       # two x tiles per row
+    (1, 32, 2, 64, 81),        # largest D it takes, D > W
+    (1, 16, 2, 16, 1),         # D = 1: no halo
+    (1, 48, 3, 1000, 40),      # four x tiles, ragged last tile
+]
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", MMA16_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_corr_fwd_mma16(ops, oracle, shape, dt, monkeypatch, capfd):
+    """bf16 / fp16 forward: the banded row GEMM on mma.sync.m16n8k16 (fp32 accumulation) against the oracle on the rounded inputs,
+    and against the FFMA kernels it replaces (DSSMD_CORR_FWD_MMA16=0); also through the concat buffer."""
+    B, C, H, W, D = shape
+    L, R = feat((B, C, H, W), 11, True, dt), feat((B, C, H, W), 12, False, dt)
+    monkeypatch.setenv("DSSMD_CORR_DEBUG", "1")
+    out = ops.build_corr(L, R, D)
+    torch.cuda.synchronize()
+    assert "corr_fwd mma16 cfg" in capfd.readouterr().err
+    monkeypatch.delenv("DSSMD_CORR_DEBUG")
+    assert out.dtype == dt and out.is_contiguous()
+    ref = oracle.corr_fwd(L.float().cpu().numpy(), R.float().cpu().numpy(), D)
+    assert rel_err(out.float().cpu().numpy(), ref) <= TOL_BF16
+    for d in range(min(D, W)):
+        assert bool((out[:, d, :, :d] == 0).all())            # the zero left border is exact
+    assert bool((out[:, W:] == 0).all())                       # channels d >= W
+    monkeypatch.setenv("DSSMD_CORR_FWD_MMA16", "0")
+    old = ops.build_corr(L, R, D)
+    monkeypatch.delenv("DSSMD_CORR_FWD_MMA16")
+    # both accumulate exact products in fp32 and round once: they agree to an ulp of the 16-bit result
+    assert rel_err(out.float().cpu().numpy(), old.float().cpu().numpy()) <= (2 ** -7 if dt == torch.bfloat16 else 2 ** -10)
+    head = feat((B, 3, H, W), 13, False, dt)
+    assert torch.equal(ops.build_corr_cat(head, L, R, D), torch.cat((head, out), dim=1))
