@@ -25,6 +25,8 @@ namespace dssmd {
 
 // corr_bwd_reg.cu: fp32 fast path (g slab in registers); -1 = shape not eligible
 int corr_bwd_reg(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, long long gbs, int dtype, cudaStream_t stream);
+// corr_bwd_mma16.cu: 16-bit tensors on the tensor cores; -1 = shape not eligible
+int corr_bwd_mma16(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, long long gbs, int dtype, cudaStream_t stream);
 
 namespace {
 
@@ -295,6 +297,12 @@ int env_int(const char *name, int dflt) {
 
 template <typename T, int MODE>
 int launch_mode(const void *g, const void *In, void *out, int B, int C, int H, int W, int D, long long gbs, cudaStream_t stream) {
+    if constexpr (sizeof(T) == 2) {
+        if (env_int("DSSMD_CORR_BWD_VARIANT", -1) < 0) {   // no variant forced: mma.sync on the banded row GEMM
+            const int rc = corr_bwd_mma16(g, In, out, MODE, B, C, H, W, D, gbs, std::is_same<T, __nv_bfloat16>::value ? DSSMD_BF16 : DSSMD_F16, stream);
+            if (rc >= 0) return rc;
+        }
+    }
     if (env_int("DSSMD_CORR_BWD_VARIANT", 1) >= 1) {
         constexpr int dtype = sizeof(T) == 4 ? DSSMD_F32 : std::is_same<T, __nv_bfloat16>::value ? DSSMD_BF16 : DSSMD_F16;
         const int rc = corr_bwd_reg(g, In, out, MODE, B, C, H, W, D, gbs, dtype, stream);

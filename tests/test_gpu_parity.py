@@ -994,3 +994,42 @@ def test_corr_fwd_mma16(ops, oracle, shape, dt, monkeypatch, capfd):
     assert rel_err(out.float().cpu().numpy(), old.float().cpu().numpy()) <= (2 ** -7 if dt == torch.bfloat16 else 2 ** -10)
     head = feat((B, 3, H, W), 13, False, dt)
     assert torch.equal(ops.build_corr_cat(head, L, R, D), torch.cat((head, out), dim=1))
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", MMA16_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_corr_bwd_mma16(ops, oracle, shape, dt, monkeypatch, capfd):
+    """bf16 / fp16 backward: both gradients as banded row GEMMs on mma.sync.m16n8k16 (the band operand built once per warp from
+    the staged g tile) against the oracle on the rounded inputs and against the FFMA kernels (DSSMD_CORR_BWD_MMA16=0), and
+    through the concat gradient."""
+    B, C, H, W, D = shape
+    L0, R0 = feat((B, C, H, W), 21, True, dt), feat((B, C, H, W), 22, False, dt)
+    g = feat((B, D, H, W), 23, False, dt)
+    res = []
+    for new in (True, False):
+        if new:
+            monkeypatch.setenv("DSSMD_CORR_DEBUG", "1")
+        else:
+            monkeypatch.setenv("DSSMD_CORR_BWD_MMA16", "0")
+        L, R = L0.clone().requires_grad_(True), R0.clone().requires_grad_(True)
+        ops.build_corr(L, R, D).backward(g)
+        torch.cuda.synchronize()
+        if new:
+            err = capfd.readouterr().err
+            assert err.count("corr_bwd mma16 cfg") == 2, err
+            monkeypatch.delenv("DSSMD_CORR_DEBUG")
+        else:
+            monkeypatch.delenv("DSSMD_CORR_BWD_MMA16")
+        res.append((L.grad, R.grad))
+    gL, gR = oracle.corr_bwd(g.float().cpu().numpy(), L0.float().cpu().numpy(), R0.float().cpu().numpy())
+    assert rel_err(res[0][0].float().cpu().numpy(), gL) <= TOL_BF16
+    assert rel_err(res[0][1].float().cpu().numpy(), gR) <= TOL_BF16
+    ulp = 2 ** -7 if dt == torch.bfloat16 else 2 ** -10
+    assert rel_err(res[0][0].float().cpu().numpy(), res[1][0].float().cpu().numpy()) <= ulp
+    assert rel_err(res[0][1].float().cpu().numpy(), res[1][1].float().cpu().numpy()) <= ulp
+    # the concat gradient read in place
+    head = feat((B, 3, H, W), 24, False, dt).requires_grad_(True)
+    L, R = L0.clone().requires_grad_(True), R0.clone().requires_grad_(True)
+    gcat = torch.cat((feat((B, 3, H, W), 25, False, dt), g), dim=1)
+    ops.build_corr_cat(head, L, R, D).backward(gcat)
+    assert torch.equal(L.grad, res[0][0]) and torch.equal(R.grad, res[0][1])
