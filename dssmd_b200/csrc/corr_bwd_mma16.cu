@@ -53,6 +53,9 @@ __device__ __forceinline__ void mma16816b(float (&c)[4], const uint32_t (&a)[4],
     }
 }
 
+__device__ __forceinline__ void store_pair(__nv_bfloat16 *o, float a, float b) { *reinterpret_cast<__nv_bfloat162 *>(o) = __floats2bfloat162_rn(a, b); }
+__device__ __forceinline__ void store_pair(__half *o, float a, float b) { *reinterpret_cast<__half2 *>(o) = __floats2half2_rn(a, b); }
+
 template <typename T, int MODE, int NP>
 __global__ void __launch_bounds__(kMaxWarps * 32) corr_bwd_mma16_kernel(const BwdMma16Params p) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -70,6 +73,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_bwd_mma16_kernel(const Bw
     const int xin0 = MODE == 0 ? X0 - p.HALO : X0;        // position of operand column 0
     const int nck = (p.C + kCK - 1) / kCK;
 
+    // flat chunk index over the block: every LDGSTS warp instruction carries 32 chunks (see corr_fwd_mma16.cu)
     auto stage_in = [&](int c0, int s) {
         const uint32_t rs = sbase + g_bytes + (uint32_t)s * stage_bytes;
         for (int i = tid; i < kCK * rchunks; i += blockDim.x) {
@@ -92,11 +96,15 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_bwd_mma16_kernel(const Bw
     const int g8 = lane >> 2, tq = lane & 3;
     const int wx = warp * 16;
     uint32_t afr[NP][4];          // the banded operand G of this warp's 16 pixels, all K steps
-    // B (16 channels x 16 positions): matrices (n 0-7, k 0-7), (n 0-7, k 8-15), (n 8-15, k 0-7), (n 8-15, k 8-15)
+    // The product is issued transposed -- channels as the M dimension, pixels as N -- so that an accumulator register pair holds two
+    // NEIGHBOURING pixels of one channel (one packed 4-byte store, four lanes = 16 contiguous bytes of a channel row):
+    //   A (16 channels x 16 positions) = the staged rows as they lie: matrices (m 0-7, k 0-7), (m 8-15, k 0-7), (m 0-7, k 8-15), (m 8-15, k 8-15)
+    //   B (16 positions x 8 pixels)    = G^T: the "col" fragment (k = 2 tq .., n = g8) is G[pixel g8][k ..], i.e. afr[q][0], afr[q][2] for
+    //                                    pixels 0-7 and afr[q][1], afr[q][3] for pixels 8-15
     const int j = lane >> 3, r8 = lane & 7;
-    const uint32_t b_off = (uint32_t)(((j >> 1) * 8 + r8) * p.RS + (wx + (j & 1) * 8) * 2);
+    const uint32_t a_off = (uint32_t)(((j & 1) * 8 + r8) * p.RS + (wx + (j >> 1) * 8) * 2);
     T *const ob = static_cast<T *>(p.out) + (size_t)b * p.C * HW + (size_t)y * p.W + X0 + wx;
-    const bool st0 = X0 + wx + g8 < p.W, st1 = X0 + wx + g8 + 8 < p.W;
+    const bool st0 = X0 + wx + 2 * tq < p.W, st1 = X0 + wx + 8 + 2 * tq < p.W;   // W % 8 == 0: a pixel pair is in or out together
 
     for (int ck = 0; ck < nck; ++ck) {
         const int s = ck & 1;
@@ -135,23 +143,21 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_bwd_mma16_kernel(const Bw
                 for (int k = 0; k < 4; ++k) acc[t][k] = 0.f;
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
-                uint32_t b0, b1, b2, b3;
-                ldmatrix_x4(rs + (uint32_t)(n16 * 16 * p.RS) + b_off + (uint32_t)(q * 32), b0, b1, b2, b3);
-                mma16816b<T>(acc[0], afr[q], b0, b1);
-                mma16816b<T>(acc[1], afr[q], b2, b3);
+                uint32_t a[4];
+                ldmatrix_x4(rs + (uint32_t)(n16 * 16 * p.RS) + a_off + (uint32_t)(q * 32), a[0], a[1], a[2], a[3]);
+                mma16816b<T>(acc[0], a, afr[q][0], afr[q][2]);
+                mma16816b<T>(acc[1], a, afr[q][1], afr[q][3]);
             }
-            // acc[t]: c0/c1 = (pixel g8, channels 2 tq, 2 tq + 1), c2/c3 = (pixel g8 + 8, ...) of channel tile t
+            // acc[t]: c0/c1 = (channel g8, pixels 8 t + 2 tq, + 1), c2/c3 = (channel g8 + 8, same pixels)
 #pragma unroll
-            for (int t = 0; t < 2; ++t)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int c = c0 + n16 * 16 + t * 8 + 2 * tq + e;
-                    if (c < p.C) {
-                        T *o = ob + (size_t)c * HW;
-                        if (st0) o[g8] = from_f32<T>(acc[t][e] * p.invC);
-                        if (st1) o[g8 + 8] = from_f32<T>(acc[t][2 + e] * p.invC);
-                    }
+            for (int hh = 0; hh < 2; ++hh) {
+                const int c = c0 + n16 * 16 + hh * 8 + g8;
+                if (c < p.C) {
+                    T *o = ob + (size_t)c * HW + 2 * tq;
+                    if (st0) store_pair(o, acc[0][2 * hh] * p.invC, acc[0][2 * hh + 1] * p.invC);
+                    if (st1) store_pair(o + 8, acc[1][2 * hh] * p.invC, acc[1][2 * hh + 1] * p.invC);
                 }
+            }
         }
         __syncthreads();
     }
@@ -177,6 +183,7 @@ template <typename T, int MODE>
 int corr_bwd_mma16_typed(const void *g, const void *in, void *out, int B, int C, int H, int W, int D, long long gbs, cudaStream_t stream) {
     if (W % 8 != 0 || D > 81 || C < 16) return -1;
     if (((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(in)) & 15) != 0 || (gbs % 8) != 0) return -1;
+    if ((reinterpret_cast<uintptr_t>(out) & 3) != 0) return -1;   // packed 4-byte stores
     BwdMma16Params p{};
     p.g = g; p.In = in; p.out = out; p.GBS = gbs;
     p.C = C; p.H = H; p.W = W; p.D = D;
@@ -185,7 +192,9 @@ int corr_bwd_mma16_typed(const void *g, const void *in, void *out, int B, int C,
     const int np = ceil_div(p.HALO + 16, 16);
     if (np < 1 || np > 6) return -1;
     int warps = ceil_div(W, 16);
-    p.XT = ceil_div(warps, kMaxWarps);
+    int maxw = env_int_bm16("DSSMD_MMA16_MAXW", 8);
+    if (maxw < 1 || maxw > kMaxWarps) maxw = kMaxWarps;
+    p.XT = ceil_div(warps, maxw);
     warps = ceil_div(warps, p.XT);
     p.TX = warps * 16;
     p.RW = p.TX + 16 * np - 16;

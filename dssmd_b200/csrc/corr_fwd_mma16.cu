@@ -74,6 +74,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_fwd_mma16_kernel(const Mm
     const int nck = (p.C + kCK - 1) / kCK;
 
     // stage `s` <- channels [c0, c0 + kCK): L columns X0 .. X0 + TX, R columns X0 - HALO .. X0 - HALO + RW
+    // stage `s` <- channels [c0, c0 + kCK): L columns X0 .. X0 + TX, R columns X0 - HALO .. X0 - HALO + RW.  Flat chunk index over
+    // the block: every LDGSTS warp instruction carries 32 chunks (measured: a warp-per-row mapping with 20-27 of 32 lanes busy is
+    // 1.7x slower -- the copy path is bound by LDGSTS issue, ~20 cycles per warp instruction)
     auto stage_in = [&](int c0, int s) {
         const uint32_t ls = sbase + (uint32_t)s * stage_bytes, rs = ls + (uint32_t)kCK * (uint32_t)p.LS;
         for (int i = tid; i < kCK * lchunks; i += blockDim.x) {
@@ -175,7 +178,9 @@ int corr_fwd_mma16_typed(const void *L, const void *R, void *out, int B, int C, 
     const int np = ceil_div(p.HALO + 16, 16);            // pairs of 8-column tiles per warp
     if (np < 1 || np > 6) return -1;
     int warps = ceil_div(W, 16);
-    p.XT = ceil_div(warps, kMaxWarps);
+    int maxw = env_int_m16("DSSMD_MMA16_MAXW", 8);   // measured: two 80-pixel tiles per 160-pixel row beat one (39.8 vs 43.7 us at cfg2)
+    if (maxw < 1 || maxw > kMaxWarps) maxw = kMaxWarps;
+    p.XT = ceil_div(warps, maxw);
     warps = ceil_div(warps, p.XT);                       // balance the tiles of a row
     p.TX = warps * 16;
     p.RW = p.TX + 16 * np - 16;
