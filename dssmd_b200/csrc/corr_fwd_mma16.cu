@@ -17,6 +17,7 @@
 // stride of an odd number of 16-byte chunks keeps its 8 row addresses on distinct banks.  Epilogue: the accumulator
 // fragments scatter their band elements into a per-warp [D][16] staging tile, which goes out as 32-byte row segments.
 #include "common.cuh"
+#include "tma.cuh"
 
 #include <type_traits>
 
@@ -58,9 +59,13 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
 }
 
 // NP = pairs of 8-column tiles per warp (16 * NP >= HALO + 16)
-template <typename T, int NP>
-__global__ void __launch_bounds__(kMaxWarps * 32) corr_fwd_mma16_kernel(const Mma16Params p) {
-    extern __shared__ __align__(16) unsigned char smem[];
+// TMA = true: the two tiles of a stage arrive as one tensor-map box each (the boxes are an odd number of 16-byte chunks wide, so the
+// dense box rows are the conflict-free stride; out-of-range columns / channels are zero-filled by the TMA unit); false: cp.async.
+template <typename T, int NP, bool TMA>
+__global__ void __launch_bounds__(kMaxWarps * 32) corr_fwd_mma16_kernel(const Mma16Params p, const __grid_constant__ CUtensorMap mapL,
+                                                                        const __grid_constant__ CUtensorMap mapR) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long s_bar[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int row = blockIdx.x / p.XT, xt = blockIdx.x - row * p.XT;
     const int b = row / p.H, y = row - b * p.H;
@@ -100,7 +105,25 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_fwd_mma16_kernel(const Mm
 #pragma unroll
         for (int k = 0; k < 4; ++k) acc[n][k] = 0.f;
 
-    stage_in(0, 0);
+    auto issue = [&](int c0, int s) {   // one thread
+        const uint32_t ls = sbase + (uint32_t)s * stage_bytes, rs = ls + (uint32_t)kCK * (uint32_t)p.LS;
+        const uint32_t bar = smem_u32(&s_bar[s]);
+        fence_proxy_async();   // the stage was read through the generic proxy before the block barrier
+        mbar_arrive_expect_tx(bar, stage_bytes);
+        tma_load_4d(ls, &mapL, X0, y, c0, b, bar);
+        tma_load_4d(rs, &mapR, X0 - p.HALO, y, c0, b, bar);
+    };
+    if constexpr (TMA) {
+        if (tid == 0) {
+            mbar_init(smem_u32(&s_bar[0]), 1);
+            mbar_init(smem_u32(&s_bar[1]), 1);
+            fence_proxy_async();
+        }
+        __syncthreads();
+        if (tid == 0) issue(0, 0);
+    } else {
+        stage_in(0, 0);
+    }
     // ldmatrix row addresses of this lane: matrix j = lane / 8, row r = lane % 8
     const int j = lane >> 3, r8 = lane & 7;
     const int wx = warp * 16;                              // this warp's first pixel inside the block tile
@@ -111,9 +134,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_fwd_mma16_kernel(const Mm
 
     for (int ck = 0; ck < nck; ++ck) {
         const int s = ck & 1;
-        if (ck + 1 < nck) { stage_in((ck + 1) * kCK, s ^ 1); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        __syncthreads();
+        if constexpr (TMA) {
+            if (tid == 0 && ck + 1 < nck) issue((ck + 1) * kCK, s ^ 1);   // stage s^1 was released by the barrier ending iteration ck-1
+            mbar_wait(smem_u32(&s_bar[s]), (uint32_t)((ck >> 1) & 1));
+        } else {
+            if (ck + 1 < nck) { stage_in((ck + 1) * kCK, s ^ 1); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+            __syncthreads();
+        }
         const uint32_t ls = sbase + (uint32_t)s * stage_bytes, rs = ls + (uint32_t)kCK * (uint32_t)p.LS;
 #pragma unroll
         for (int k16 = 0; k16 < kCK / 16; ++k16) {
@@ -155,15 +183,20 @@ int env_int_m16(const char *name, int dflt) {
     return (v && *v) ? std::atoi(v) : dflt;
 }
 
-template <typename T, int NP>
-int launch_np(const Mma16Params &p, int grid, int threads, size_t smem, cudaStream_t stream) {
-    auto kern = corr_fwd_mma16_kernel<T, NP>;
+template <typename T, int NP, bool TMA>
+int launch_np2(const Mma16Params &p, const CUtensorMap &mapL, const CUtensorMap &mapR, int grid, int threads, size_t smem, cudaStream_t stream) {
+    auto kern = corr_fwd_mma16_kernel<T, NP, TMA>;
     if (smem > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_fwd(mma16): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
     }
-    kern<<<grid, threads, smem, stream>>>(p);
+    kern<<<grid, threads, smem, stream>>>(p, mapL, mapR);
     return check_launch("corr_fwd(mma16)");
+}
+
+template <typename T, int NP>
+int launch_np(const Mma16Params &p, bool tma, const CUtensorMap &mapL, const CUtensorMap &mapR, int grid, int threads, size_t smem, cudaStream_t stream) {
+    return tma ? launch_np2<T, NP, true>(p, mapL, mapR, grid, threads, smem, stream) : launch_np2<T, NP, false>(p, mapL, mapR, grid, threads, smem, stream);
 }
 
 template <typename T>
@@ -187,6 +220,17 @@ int corr_fwd_mma16_typed(const void *L, const void *R, void *out, int B, int C, 
     auto odd16 = [](int bytes) { int c = (bytes + 15) / 16; if ((c & 1) == 0) ++c; return c * 16; };
     p.LS = odd16(p.TX * 2);
     p.RS = odd16(p.RW * 2);
+    // TMA staging: boxes as wide as the padded rows (<= 256 elements), rows of W*2 bytes a multiple of 16 (W % 8 == 0)
+    CUtensorMap mapL{}, mapR{};
+    bool tma = env_int_m16("DSSMD_MMA16_TMA", 1) != 0 && p.LS / 2 <= 256 && p.RS / 2 <= 256 && (reinterpret_cast<uintptr_t>(out) & 1) == 0;
+    if (tma) {
+        const CUtensorMapDataType tmt = std::is_same<T, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+        const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+        const cuuint64_t strides[3] = {(cuuint64_t)W * 2, (cuuint64_t)H * W * 2, (cuuint64_t)C * H * W * 2};
+        const cuuint32_t boxl[4] = {(cuuint32_t)(p.LS / 2), 1, (cuuint32_t)kCK, 1}, boxr[4] = {(cuuint32_t)(p.RS / 2), 1, (cuuint32_t)kCK, 1};
+        tma = make_tmap(&mapL, tmt, L, 4, dims, strides, boxl, CU_TENSOR_MAP_SWIZZLE_NONE) &&
+              make_tmap(&mapR, tmt, R, 4, dims, strides, boxr, CU_TENSOR_MAP_SWIZZLE_NONE);
+    }
     size_t smem = 2 * (size_t)kCK * (size_t)(p.LS + p.RS);
     const size_t epi = (size_t)warps * D * 17 * sizeof(float);
     if (epi > smem) smem = epi;
@@ -194,15 +238,15 @@ int corr_fwd_mma16_typed(const void *L, const void *R, void *out, int B, int C, 
     const long long blocks = (long long)B * H * p.XT;
     if (blocks >= (1LL << 31)) return -1;
     if (env_int_m16("DSSMD_CORR_DEBUG", 0))
-        fprintf(stderr, "corr_fwd mma16 cfg: NP=%d HALO=%d TX=%d XT=%d RW=%d LS=%d RS=%d warps=%d grid=%lld smem=%zu\n", np, p.HALO, p.TX, p.XT,
-                p.RW, p.LS, p.RS, warps, blocks, smem);
+        fprintf(stderr, "corr_fwd mma16 cfg: NP=%d HALO=%d TX=%d XT=%d RW=%d LS=%d RS=%d warps=%d grid=%lld smem=%zu tma=%d\n", np, p.HALO, p.TX, p.XT,
+                p.RW, p.LS, p.RS, warps, blocks, smem, (int)tma);
     switch (np) {
-        case 1: return launch_np<T, 1>(p, (int)blocks, warps * 32, smem, stream);
-        case 2: return launch_np<T, 2>(p, (int)blocks, warps * 32, smem, stream);
-        case 3: return launch_np<T, 3>(p, (int)blocks, warps * 32, smem, stream);
-        case 4: return launch_np<T, 4>(p, (int)blocks, warps * 32, smem, stream);
-        case 5: return launch_np<T, 5>(p, (int)blocks, warps * 32, smem, stream);
-        default: return launch_np<T, 6>(p, (int)blocks, warps * 32, smem, stream);
+        case 1: return launch_np<T, 1>(p, tma, mapL, mapR, (int)blocks, warps * 32, smem, stream);
+        case 2: return launch_np<T, 2>(p, tma, mapL, mapR, (int)blocks, warps * 32, smem, stream);
+        case 3: return launch_np<T, 3>(p, tma, mapL, mapR, (int)blocks, warps * 32, smem, stream);
+        case 4: return launch_np<T, 4>(p, tma, mapL, mapR, (int)blocks, warps * 32, smem, stream);
+        case 5: return launch_np<T, 5>(p, tma, mapL, mapR, (int)blocks, warps * 32, smem, stream);
+        default: return launch_np<T, 6>(p, tma, mapL, mapR, (int)blocks, warps * 32, smem, stream);
     }
 }
 
