@@ -14,6 +14,7 @@
 // accumulation is fp32.  Block = one image row x a tile of up to 256 pixels, a warp per 16 pixels; operand rows staged by
 // cp.async (zero fill outside the row = the x-d < 0 / x'+d >= W limits of the sums), two stages of 32 channels.
 #include "common.cuh"
+#include "tma.cuh"
 
 #include <type_traits>
 
@@ -56,9 +57,13 @@ __device__ __forceinline__ void mma16816b(float (&c)[4], const uint32_t (&a)[4],
 __device__ __forceinline__ void store_pair(__nv_bfloat16 *o, float a, float b) { *reinterpret_cast<__nv_bfloat162 *>(o) = __floats2bfloat162_rn(a, b); }
 __device__ __forceinline__ void store_pair(__half *o, float a, float b) { *reinterpret_cast<__half2 *>(o) = __floats2half2_rn(a, b); }
 
-template <typename T, int MODE, int NP>
-__global__ void __launch_bounds__(kMaxWarps * 32) corr_bwd_mma16_kernel(const BwdMma16Params p) {
-    extern __shared__ __align__(16) unsigned char smem[];
+// TMA = true: the g tile and the operand rows of a stage arrive as tensor-map boxes (dense rows of an odd number of 16-byte chunks,
+// zero fill outside the row); false: cp.async
+template <typename T, int MODE, int NP, bool TMA>
+__global__ void __launch_bounds__(kMaxWarps * 32) corr_bwd_mma16_kernel(const BwdMma16Params p, const __grid_constant__ CUtensorMap mapIn,
+                                                                        const __grid_constant__ CUtensorMap mapG) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long s_bar[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row = blockIdx.x / p.XT, xt = blockIdx.x - row * p.XT;
     const int b = row / p.H, y = row - b * p.H;
@@ -67,6 +72,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_bwd_mma16_kernel(const Bw
     const T *Gg = static_cast<const T *>(p.g) + (size_t)b * p.GBS + (size_t)y * p.W;
     const T *Ig = static_cast<const T *>(p.In) + (size_t)b * p.C * HW + (size_t)y * p.W;
     const uint32_t g_bytes = (uint32_t)p.D * (uint32_t)p.GS;
+    const uint32_t g_pad = (g_bytes + 127u) & ~127u;      // the operand stages behind the g tile stay 128-byte aligned (TMA)
     const uint32_t stage_bytes = (uint32_t)kCK * (uint32_t)p.RS;
     const uint32_t sbase = smem_u32(smem);                 // g tile | stage 0 | stage 1
     const int rchunks = p.RW / 8, gchunks = p.GWD / 8;
@@ -75,7 +81,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_bwd_mma16_kernel(const Bw
 
     // flat chunk index over the block: every LDGSTS warp instruction carries 32 chunks (see corr_fwd_mma16.cu)
     auto stage_in = [&](int c0, int s) {
-        const uint32_t rs = sbase + g_bytes + (uint32_t)s * stage_bytes;
+        const uint32_t rs = sbase + g_pad + (uint32_t)s * stage_bytes;
         for (int i = tid; i < kCK * rchunks; i += blockDim.x) {
             const int c = i / rchunks, ch = i - c * rchunks;
             const int x = xin0 + 8 * ch;
@@ -84,14 +90,32 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_bwd_mma16_kernel(const Bw
         }
         cp_async_commit();
     };
-    // g tile: D rows of columns X0 .. X0 + GWD (zero past the row end), in the first cp.async group together with stage 0
-    for (int i = tid; i < p.D * gchunks; i += blockDim.x) {
-        const int d = i / gchunks, ch = i - d * gchunks;
-        const int x = X0 + 8 * ch;
-        const bool ok = x < p.W;
-        cp_async16(sbase + (uint32_t)(d * p.GS + 16 * ch), ok ? (const void *)(Gg + (size_t)d * HW + x) : (const void *)Gg, ok ? 16 : 0);
+    auto issue = [&](int c0, int s, bool with_g) {   // one thread
+        const uint32_t rs = sbase + g_pad + (uint32_t)s * stage_bytes;
+        const uint32_t bar = smem_u32(&s_bar[s]);
+        fence_proxy_async();
+        mbar_arrive_expect_tx(bar, stage_bytes + (with_g ? g_bytes : 0u));
+        tma_load_4d(rs, &mapIn, xin0, y, c0, b, bar);
+        if (with_g) tma_load_4d(sbase, &mapG, X0, y, 0, b, bar);
+    };
+    if constexpr (TMA) {
+        if (tid == 0) {
+            mbar_init(smem_u32(&s_bar[0]), 1);
+            mbar_init(smem_u32(&s_bar[1]), 1);
+            fence_proxy_async();
+        }
+        __syncthreads();
+        if (tid == 0) issue(0, 0, true);
+    } else {
+        // g tile: D rows of columns X0 .. X0 + GWD (zero past the row end), in the first cp.async group together with stage 0
+        for (int i = tid; i < p.D * gchunks; i += blockDim.x) {
+            const int d = i / gchunks, ch = i - d * gchunks;
+            const int x = X0 + 8 * ch;
+            const bool ok = x < p.W;
+            cp_async16(sbase + (uint32_t)(d * p.GS + 16 * ch), ok ? (const void *)(Gg + (size_t)d * HW + x) : (const void *)Gg, ok ? 16 : 0);
+        }
+        stage_in(0, 0);
     }
-    stage_in(0, 0);
 
     const int g8 = lane >> 2, tq = lane & 3;
     const int wx = warp * 16;
@@ -108,9 +132,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_bwd_mma16_kernel(const Bw
 
     for (int ck = 0; ck < nck; ++ck) {
         const int s = ck & 1;
-        if (ck + 1 < nck) { stage_in((ck + 1) * kCK, s ^ 1); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        __syncthreads();
+        if constexpr (TMA) {
+            if (tid == 0 && ck + 1 < nck) issue((ck + 1) * kCK, s ^ 1, false);
+            mbar_wait(smem_u32(&s_bar[s]), (uint32_t)((ck >> 1) & 1));
+        } else {
+            if (ck + 1 < nck) { stage_in((ck + 1) * kCK, s ^ 1); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+            __syncthreads();
+        }
         if (ck == 0) {
             // A fragments from the g tile: a0 (m = g8, k = 2 tq ..), a1 (m = g8 + 8), a2 (k + 8), a3 (m + 8, k + 8)
             const unsigned short *gt = reinterpret_cast<const unsigned short *>(smem);
@@ -132,7 +161,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_bwd_mma16_kernel(const Bw
                     afr[q][i] = v;
                 }
         }
-        const uint32_t rs = sbase + g_bytes + (uint32_t)s * stage_bytes;
+        const uint32_t rs = sbase + g_pad + (uint32_t)s * stage_bytes;
         const int c0 = ck * kCK;
 #pragma unroll
         for (int n16 = 0; n16 < kCK / 16; ++n16) {
@@ -168,15 +197,21 @@ int env_int_bm16(const char *name, int dflt) {
     return (v && *v) ? std::atoi(v) : dflt;
 }
 
-template <typename T, int MODE, int NP>
-int launch_bnp(const BwdMma16Params &p, int grid, int threads, size_t smem, cudaStream_t stream) {
-    auto kern = corr_bwd_mma16_kernel<T, MODE, NP>;
+template <typename T, int MODE, int NP, bool TMA>
+int launch_bnp2(const BwdMma16Params &p, const CUtensorMap &mapIn, const CUtensorMap &mapG, int grid, int threads, size_t smem, cudaStream_t stream) {
+    auto kern = corr_bwd_mma16_kernel<T, MODE, NP, TMA>;
     if (smem > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_bwd(mma16): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
     }
-    kern<<<grid, threads, smem, stream>>>(p);
+    kern<<<grid, threads, smem, stream>>>(p, mapIn, mapG);
     return check_launch(MODE == 0 ? "corr_bwd(gL, mma16)" : "corr_bwd(gR, mma16)");
+}
+
+template <typename T, int MODE, int NP>
+int launch_bnp(const BwdMma16Params &p, bool tma, const CUtensorMap &mapIn, const CUtensorMap &mapG, int grid, int threads, size_t smem, cudaStream_t stream) {
+    return tma ? launch_bnp2<T, MODE, NP, true>(p, mapIn, mapG, grid, threads, smem, stream)
+               : launch_bnp2<T, MODE, NP, false>(p, mapIn, mapG, grid, threads, smem, stream);
 }
 
 template <typename T, int MODE>
@@ -202,20 +237,33 @@ int corr_bwd_mma16_typed(const void *g, const void *in, void *out, int B, int C,
     auto odd16 = [](int bytes) { int c = (bytes + 15) / 16; if ((c & 1) == 0) ++c; return c * 16; };
     p.RS = odd16(p.RW * 2);
     p.GS = odd16(p.GWD * 2);
-    const size_t smem = (size_t)D * p.GS + 2 * (size_t)kCK * p.RS;
+    CUtensorMap mapIn{}, mapG{};
+    bool tma = env_int_bm16("DSSMD_MMA16_TMA", 1) != 0 && p.RS / 2 <= 256 && p.GS / 2 <= 256;
+    if (tma) {
+        const CUtensorMapDataType tmt = std::is_same<T, __nv_bfloat16>::value ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+        const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+        const cuuint64_t strides[3] = {(cuuint64_t)W * 2, (cuuint64_t)H * W * 2, (cuuint64_t)C * H * W * 2};
+        const cuuint32_t box[4] = {(cuuint32_t)(p.RS / 2), 1, (cuuint32_t)kCK, 1};
+        const cuuint64_t gdims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+        const cuuint64_t gstrides[3] = {(cuuint64_t)W * 2, (cuuint64_t)H * W * 2, (cuuint64_t)gbs * 2};
+        const cuuint32_t gbox[4] = {(cuuint32_t)(p.GS / 2), 1, (cuuint32_t)D, 1};
+        tma = make_tmap(&mapIn, tmt, in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE) &&
+              make_tmap(&mapG, tmt, g, 4, gdims, gstrides, gbox, CU_TENSOR_MAP_SWIZZLE_NONE);
+    }
+    const size_t smem = (((size_t)D * p.GS + 127) & ~(size_t)127) + 2 * (size_t)kCK * p.RS;
     if (smem > 200 * 1024) return -1;
     const long long blocks = (long long)B * H * p.XT;
     if (blocks >= (1LL << 31)) return -1;
     if (env_int_bm16("DSSMD_CORR_DEBUG", 0))
-        fprintf(stderr, "corr_bwd mma16 cfg: mode=%d NP=%d HALO=%d TX=%d XT=%d RW=%d RS=%d GS=%d warps=%d grid=%lld smem=%zu\n", MODE, np, p.HALO,
-                p.TX, p.XT, p.RW, p.RS, p.GS, warps, blocks, smem);
+        fprintf(stderr, "corr_bwd mma16 cfg: mode=%d NP=%d HALO=%d TX=%d XT=%d RW=%d RS=%d GS=%d warps=%d grid=%lld smem=%zu tma=%d\n", MODE, np, p.HALO,
+                p.TX, p.XT, p.RW, p.RS, p.GS, warps, blocks, smem, (int)tma);
     switch (np) {
-        case 1: return launch_bnp<T, MODE, 1>(p, (int)blocks, warps * 32, smem, stream);
-        case 2: return launch_bnp<T, MODE, 2>(p, (int)blocks, warps * 32, smem, stream);
-        case 3: return launch_bnp<T, MODE, 3>(p, (int)blocks, warps * 32, smem, stream);
-        case 4: return launch_bnp<T, MODE, 4>(p, (int)blocks, warps * 32, smem, stream);
-        case 5: return launch_bnp<T, MODE, 5>(p, (int)blocks, warps * 32, smem, stream);
-        default: return launch_bnp<T, MODE, 6>(p, (int)blocks, warps * 32, smem, stream);
+        case 1: return launch_bnp<T, MODE, 1>(p, tma, mapIn, mapG, (int)blocks, warps * 32, smem, stream);
+        case 2: return launch_bnp<T, MODE, 2>(p, tma, mapIn, mapG, (int)blocks, warps * 32, smem, stream);
+        case 3: return launch_bnp<T, MODE, 3>(p, tma, mapIn, mapG, (int)blocks, warps * 32, smem, stream);
+        case 4: return launch_bnp<T, MODE, 4>(p, tma, mapIn, mapG, (int)blocks, warps * 32, smem, stream);
+        case 5: return launch_bnp<T, MODE, 5>(p, tma, mapIn, mapG, (int)blocks, warps * 32, smem, stream);
+        default: return launch_bnp<T, MODE, 6>(p, tma, mapIn, mapG, (int)blocks, warps * 32, smem, stream);
     }
 }
 
