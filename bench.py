@@ -270,10 +270,25 @@ def aux_kernels(torch, lib, _lib, w, device, peak, nsets=4, rounds=10):
         fw.append(lambda L=L, R=R, cat=cat: chk(lib.dssmd_corr_fwd_cat(vp(L), vp(R), vp(cat), B, C, Hf, Wf, D, Ch + D, Ch, F32, st())))
         bw.append(lambda L=L, R=R, gcat=gcat, gL=gL, gR=gR: chk(lib.dssmd_corr_bwd_cat(vp(gcat), vp(L), vp(R), vp(gL), vp(gR), B, C, Hf, Wf, D,
                                                                                   Ch + D, Ch, F32, st())))
-    feat, vol = B * C * Hf * Wf * 4, B * D * Hf * Wf * 4
-    put("corr_fwd_cat", timed(fw), 2 * feat + vol)
-    put("corr_bwd_cat_gL+gR", timed(bw), vol + 4 * feat)
+    feat, vol_bytes = B * C * Hf * Wf * 4, B * D * Hf * Wf * 4
+    put("corr_fwd_cat", timed(fw), 2 * feat + vol_bytes)
+    put("corr_bwd_cat_gL+gR", timed(bw), vol_bytes + 4 * feat)
     del fw, bw
+    # ---- the correlation on 16-bit tensors (BASELINE config 2 asks for fp32 / bf16): mma.sync kernels, same shapes as the step
+    BF16 = 1
+    fw, bl, br = [], [], []
+    for _ in range(nsets):
+        L = torch.randn(B, C, Hf, Wf, generator=g, device=device).relu().bfloat16()
+        R = torch.randn(B, C, Hf, Wf, generator=g, device=device).relu().bfloat16()
+        gv = torch.randn(B, D, Hf, Wf, generator=g, device=device).bfloat16()
+        vol, gL, gR = torch.empty_like(gv), torch.empty_like(L), torch.empty_like(R)
+        fw.append(lambda L=L, R=R, vol=vol: chk(lib.dssmd_corr_fwd(vp(L), vp(R), vp(vol), B, C, Hf, Wf, D, BF16, st())))
+        bl.append(lambda L=L, R=R, gv=gv, gL=gL: chk(lib.dssmd_corr_bwd(vp(gv), vp(L), vp(R), vp(gL), vp(None), B, C, Hf, Wf, D, BF16, st())))
+        br.append(lambda L=L, R=R, gv=gv, gR=gR: chk(lib.dssmd_corr_bwd(vp(gv), vp(L), vp(R), vp(None), vp(gR), B, C, Hf, Wf, D, BF16, st())))
+    put("corr_fwd_bf16", timed(fw), (2 * feat + vol_bytes) // 2)
+    put("corr_bwd_gL_bf16", timed(bl), (2 * feat + vol_bytes) // 2)
+    put("corr_bwd_gR_bf16", timed(br), (2 * feat + vol_bytes) // 2)
+    del fw, bl, br
     # ---- attention along the epipolar line at BidNet's shape (models/BidNet/BidNet.py:115: B8, 32 channels, 320 x 640)
     Ba, Ca, Ha, Wa = 8, 32, 320, 640
     q, k, v, go = (torch.randn(Ba, Ca, Ha, Wa, generator=g, device=device) for _ in range(4))
