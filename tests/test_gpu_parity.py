@@ -1033,3 +1033,37 @@ def test_corr_bwd_mma16(ops, oracle, shape, dt, monkeypatch, capfd):
     gcat = torch.cat((feat((B, 3, H, W), 25, False, dt), g), dim=1)
     ops.build_corr_cat(head, L, R, D).backward(gcat)
     assert torch.equal(L.grad, res[0][0]) and torch.equal(R.grad, res[0][1])
+
+
+# ------------------------------------------------------------------ fp32 forward on mma.sync with 3xTF32 splitting
+MMA32_SHAPES = [
+    (2, 128, 6, 120, 24),      # cfg5
+    (1, 256, 4, 160, 41),      # cfg2
+    (2, 128, 5, 80, 24),       # cfg1 / cfg3
+    (1, 64, 3, 156, 24),       # 384x1248 / 8: W % 8 != 0
+    (1, 20, 2, 44, 12),        # channels not a multiple of the 16-channel stage
+    (1, 64, 2, 264, 64),       # three x tiles per row
+    (1, 32, 2, 64, 81),        # largest D, D > W
+    (1, 16, 2, 16, 1),         # D = 1
+]
+
+
+@pytest.mark.parametrize("relu", [True, False])
+@pytest.mark.parametrize("shape", MMA32_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_corr_fwd_mma32(ops, oracle, shape, relu, monkeypatch, capfd):
+    """DSSMD_CORR_FWD_VARIANT=3: the banded row GEMM on mma.sync.m16n8k8 with every fp32 operand split into tf32 hi + lo (three
+    products per step) must meet the fp32 bar (1e-5) on post-ReLU features and on zero-mean ones (cancellation)."""
+    B, C, H, W, D = shape
+    L, R = feat((B, C, H, W), 31, relu), feat((B, C, H, W), 32, relu)
+    monkeypatch.setenv("DSSMD_CORR_FWD_VARIANT", "3")
+    monkeypatch.setenv("DSSMD_CORR_DEBUG", "1")
+    out = ops.build_corr(L, R, D)
+    torch.cuda.synchronize()
+    assert "corr_fwd mma32 cfg" in capfd.readouterr().err
+    ref = oracle.corr_fwd(L.cpu().numpy(), R.cpu().numpy(), D)
+    assert rel_err(out.cpu().numpy(), ref) <= TOL_F32
+    for d in range(min(D, W)):
+        assert bool((out[:, d, :, :d] == 0).all())
+    assert bool((out[:, W:] == 0).all())
+    head = feat((B, 3, H, W), 33, False)
+    assert torch.equal(ops.build_corr_cat(head, L, R, D), torch.cat((head, out), dim=1))
