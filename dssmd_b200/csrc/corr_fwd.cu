@@ -607,7 +607,13 @@ int launch_typed(const void *L, const void *R, void *out, int B, int C, int H, i
         }
     }
     if constexpr (sizeof(T) == 4) {
-        if (variant == 3) {   // opt-in while it is being measured
+        // 3 = mma.sync with 3xTF32 splitting.  Unset: taken where it measured faster than the other fp32 kernels -- rows that fill the
+        // register-blocked kernel's 128-pixel tiles badly (W = 80: 12.9 vs 18.5 us at 320x640 / 8) and problems of several thousand
+        // 16-pixel warp tiles (cfg2 73.8 vs 86.2 us on tcgen05, KITTI 35.6 vs 41.6 us); the register-blocked kernel keeps the small
+        // well-fitting shapes (cfg5, W = 120: 12.9 vs 14.4 us)
+        const long warp_tiles = (long)B * H * ceil_div(W, 16);
+        const bool fills_reg_tiles = (double)W >= 0.75 * (double)(ceil_div(W, 128) * 128);
+        if (variant == 3 || (variant < 0 && (!fills_reg_tiles || warp_tiles >= 4000))) {
             const int rc = corr_fwd_mma32(L, R, out, B, C, H, W, D, obs, stream);
             if (rc >= 0) return rc;
         }

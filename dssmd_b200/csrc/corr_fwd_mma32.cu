@@ -19,7 +19,7 @@ namespace dssmd {
 
 namespace {
 
-constexpr int kCK = 16;          // channels per stage (two k8 steps)
+constexpr int kCK = 16;          // channels per stage (two k8 steps; 32 is slower at three of the four bench shapes)
 constexpr int kMaxWarps = 8;     // 128 pixels per block
 
 struct Mma32Params {
