@@ -25,6 +25,8 @@ namespace dssmd {
 
 // corr_bwd_reg.cu: fp32 fast path (g slab in registers); -1 = shape not eligible
 int corr_bwd_reg(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, long long gbs, int dtype, cudaStream_t stream);
+// corr_bwd_mma32.cu: fp32 on mma.sync with 3xTF32 splitting; -1 = shape not eligible
+int corr_bwd_mma32(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, long long gbs, cudaStream_t stream);
 // corr_bwd_mma16.cu: 16-bit tensors on the tensor cores; -1 = shape not eligible
 int corr_bwd_mma16(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, long long gbs, int dtype, cudaStream_t stream);
 
@@ -300,6 +302,18 @@ int launch_mode(const void *g, const void *In, void *out, int B, int C, int H, i
     if constexpr (sizeof(T) == 2) {
         if (env_int("DSSMD_CORR_BWD_VARIANT", -1) < 0) {   // no variant forced: mma.sync on the banded row GEMM
             const int rc = corr_bwd_mma16(g, In, out, MODE, B, C, H, W, D, gbs, std::is_same<T, __nv_bfloat16>::value ? DSSMD_BF16 : DSSMD_F16, stream);
+            if (rc >= 0) return rc;
+        }
+    }
+    if constexpr (sizeof(T) == 4) {
+        // 3 = mma.sync with 3xTF32 splitting.  Unset: taken where it measured faster than the register-blocked FFMA kernel -- problems of
+        // several thousand 16-pixel warp tiles (cfg2 117 / 123 -> 81 / 77 us, KITTI 45 / 46 -> 37 / 38 us), rows that fill the FFMA
+        // kernel's tiles badly (W = 80: 16.7 / 17.8 -> 15.4 / 14.9 us), and gL everywhere (cfg5 14.9 -> 13.9 us; gR there 15.4 vs 17.0)
+        const int forced = env_int("DSSMD_CORR_BWD_VARIANT", -1);
+        const long warp_tiles = (long)B * H * ceil_div(W, 16);
+        const bool fills_reg_tiles = (double)W >= 0.75 * (double)(ceil_div(W, 128) * 128);
+        if (forced == 3 || (forced < 0 && (MODE == 0 || !fills_reg_tiles || warp_tiles >= 4000))) {
+            const int rc = corr_bwd_mma32(g, In, out, MODE, B, C, H, W, D, gbs, stream);
             if (rc >= 0) return rc;
         }
     }

@@ -1,0 +1,219 @@
+// corr_bwd_mma32.cu -- fp32 backward of the correlation volume on the warp-level tensor instructions with 3xTF32 splitting.
+//
+//   gL[c,x ] = (1/C) * sum_d g[d,x]    * R[c,x-d]        (MODE 0)
+//   gR[c,x'] = (1/C) * sum_d g[d,x'+d] * L[c,x'+d]       (MODE 1)       (the graph autograd builds from submoudles.py:304-308)
+//
+// The formulation of corr_bwd_mma16.cu (a banded operand G built once per warp from the staged g tile, the product issued
+// transposed: channels as M, the 16 pixels of the warp as two N tiles) on mma.sync.m16n8k8.tf32, with both operands split in
+// registers into hi = tf32(v) and lo = tf32(v - hi) and three products per step (lo*hi, hi*lo, hi*hi; fp32 accumulate):
+//   MODE 0:  gL[c][x0+m] = sum_k R[c][x0 - HALO + k] * G[m][k],   G[m][k] = g[m + HALO - k][x0 + m]    (0 outside 0 <= d < D)
+//   MODE 1:  gR[c][x0+m] = sum_k L[c][x0 + k]        * G[m][k],   G[m][k] = g[k - m][x0 + k]
+// HALO = D - 1 rounded up to 4, K = HALO + 16 rounded up to 8.  The split G fragments (2 x 4 x K/8 registers) stay in
+// registers for the whole block, like the g slab of corr_bwd_reg.cu.  Operand rows and the g tile arrive by TMA; the operand
+// box is 4 (mod 32) floats wide so that the scalar A-fragment loads (row = channel g / g + 8, column = position tq / tq + 4) hit
+// 32 distinct banks.  An accumulator pair is two neighbouring pixels of one channel: 8-byte stores, 32 contiguous bytes per
+// four lanes.
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace dssmd {
+
+namespace {
+
+constexpr int kCK = 32;          // channels per stage (two 16-channel M tiles)
+constexpr int kMaxWarps = 8;     // 128 pixels per block
+
+struct BwdMma32Params {
+    float *out;
+    int C, H, W, D;
+    int HALO;        // D - 1 rounded up to a multiple of 4
+    int TX, XT;      // pixels per block tile (multiple of 16), tiles per row
+    int RW;          // staged operand row width in floats (= box width, 4 mod 32)
+    int GW;          // staged g row width in floats (= box width, multiple of 4)
+    float invC;
+};
+
+__device__ __forceinline__ void split_tf32b(float v, uint32_t &hi, uint32_t &lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+    const float r = v - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+
+__device__ __forceinline__ void mma1688b(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// NK = k8 steps (8 * NK >= HALO + 16)
+template <int MODE, int NK>
+__global__ void __launch_bounds__(kMaxWarps * 32) corr_bwd_mma32_kernel(const BwdMma32Params p, const __grid_constant__ CUtensorMap mapIn,
+                                                                        const __grid_constant__ CUtensorMap mapG) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row = blockIdx.x / p.XT, xt = blockIdx.x - row * p.XT;
+    const int b = row / p.H, y = row - b * p.H;
+    const int X0 = xt * p.TX;
+    const size_t HW = (size_t)p.H * p.W;
+    const uint32_t g_bytes = (uint32_t)p.D * (uint32_t)p.GW * 4u;
+    const uint32_t g_pad = (g_bytes + 127u) & ~127u;
+    const uint32_t stage_bytes = (uint32_t)kCK * (uint32_t)p.RW * 4u;
+    const uint32_t sbase = smem_u32(smem);                 // g tile | stage 0 | stage 1
+    const int xin0 = MODE == 0 ? X0 - p.HALO : X0;        // position of operand column 0
+    const int nck = (p.C + kCK - 1) / kCK;
+
+    auto issue = [&](int c0, int s, bool with_g) {   // one thread
+        const uint32_t rs = sbase + g_pad + (uint32_t)s * stage_bytes;
+        const uint32_t bar = smem_u32(&s_bar[s]);
+        fence_proxy_async();
+        mbar_arrive_expect_tx(bar, stage_bytes + (with_g ? g_bytes : 0u));
+        tma_load_4d(rs, &mapIn, xin0, y, c0, b, bar);
+        if (with_g) tma_load_4d(sbase, &mapG, X0, y, 0, b, bar);
+    };
+    if (tid == 0) {
+        mbar_init(smem_u32(&s_bar[0]), 1);
+        mbar_init(smem_u32(&s_bar[1]), 1);
+        fence_proxy_async();
+    }
+    __syncthreads();
+    pdl_launch_dependents();
+    pdl_wait();            // nothing above touches global memory
+    if (tid == 0) issue(0, 0, true);
+
+    const int g8 = lane >> 2, tq = lane & 3;
+    const int wx = warp * 16;
+    uint32_t gh[NK][2][2], gl[NK][2][2];     // G^T "col" fragments (k = tq / tq + 4, pixel 8 t + g8) of every k8 step, hi and lo
+    const int a_idx = g8 * p.RW + wx + tq;   // A fragment: (channel g8 / g8 + 8, position tq / tq + 4) of each k8 step
+    float *const ob = p.out + (size_t)b * p.C * HW + (size_t)y * p.W + X0 + wx + 2 * tq;
+    const bool st0 = X0 + wx + 2 * tq < p.W, st1 = X0 + wx + 8 + 2 * tq < p.W;   // W % 4 == 0 and even offsets: a pixel pair is in or out together
+
+    for (int ck = 0; ck < nck; ++ck) {
+        const int s = ck & 1;
+        if (tid == 0 && ck + 1 < nck) issue((ck + 1) * kCK, s ^ 1, false);   // stage s^1 was released by the barrier ending iteration ck-1
+        mbar_wait(smem_u32(&s_bar[s]), (uint32_t)((ck >> 1) & 1));
+        if (ck == 0) {
+            const float *gt = reinterpret_cast<const float *>(smem);
+#pragma unroll
+            for (int q = 0; q < NK; ++q)
+#pragma unroll
+                for (int t = 0; t < 2; ++t)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int m = 8 * t + g8, k = 8 * q + tq + 4 * e;
+                        const int d = MODE == 0 ? m + p.HALO - k : k - m;
+                        const int xc = MODE == 0 ? wx + m : wx + k;
+                        const float v = (d >= 0 && d < p.D) ? gt[d * p.GW + xc] : 0.f;
+                        split_tf32b(v, gh[q][t][e], gl[q][t][e]);
+                    }
+        }
+        const float *Rs = reinterpret_cast<const float *>(smem + g_pad + (size_t)s * stage_bytes);
+        const int c0 = ck * kCK;
+#pragma unroll
+        for (int mt = 0; mt < kCK / 16; ++mt) {
+            float acc[2][4];
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[t][k] = 0.f;
+            const float *ra = Rs + mt * 16 * p.RW + a_idx;
+#pragma unroll
+            for (int q = 0; q < NK; ++q) {
+                uint32_t ah[4], al[4];
+                split_tf32b(ra[8 * q], ah[0], al[0]);
+                split_tf32b(ra[8 * p.RW + 8 * q], ah[1], al[1]);
+                split_tf32b(ra[8 * q + 4], ah[2], al[2]);
+                split_tf32b(ra[8 * p.RW + 8 * q + 4], ah[3], al[3]);
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    mma1688b(acc[t], al, gh[q][t][0], gh[q][t][1]);     // small terms first
+                    mma1688b(acc[t], ah, gl[q][t][0], gl[q][t][1]);
+                    mma1688b(acc[t], ah, gh[q][t][0], gh[q][t][1]);
+                }
+            }
+            // acc[t]: c0/c1 = (channel g8, pixels 8 t + 2 tq, + 1), c2/c3 = (channel g8 + 8, same pixels)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int c = c0 + mt * 16 + hh * 8 + g8;
+                if (c < p.C) {
+                    float *o = ob + (size_t)c * HW;
+                    if (st0) *reinterpret_cast<float2 *>(o) = make_float2(acc[0][2 * hh] * p.invC, acc[0][2 * hh + 1] * p.invC);
+                    if (st1) *reinterpret_cast<float2 *>(o + 8) = make_float2(acc[1][2 * hh] * p.invC, acc[1][2 * hh + 1] * p.invC);
+                }
+            }
+        }
+        __syncthreads();   // stage s may be refilled by the next iteration's TMA
+    }
+}
+
+int env_int_bm32(const char *name, int dflt) {
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
+template <int MODE, int NK>
+int launch_bnk(const BwdMma32Params &p, const CUtensorMap &mapIn, const CUtensorMap &mapG, int grid, int threads, size_t smem, cudaStream_t stream) {
+    auto kern = corr_bwd_mma32_kernel<MODE, NK>;
+    if (smem > 48 * 1024) {
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_bwd(mma32): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+    }
+    const cudaError_t le = launch_pdl(kern, dim3((unsigned)grid), dim3((unsigned)threads), smem, stream, p, mapIn, mapG);
+    if (le != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_bwd(mma32): launch failed: %s", cudaGetErrorString(le));
+    return check_launch(MODE == 0 ? "corr_bwd(gL, mma32)" : "corr_bwd(gR, mma32)");
+}
+
+template <int MODE>
+int corr_bwd_mma32_mode(const void *g, const void *in, void *out, int B, int C, int H, int W, int D, long long gbs, cudaStream_t stream) {
+    if (W % 4 != 0 || D > 81 || C < 8) return -1;
+    if (((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(in)) & 15) != 0 || (gbs % 4) != 0) return -1;
+    if ((reinterpret_cast<uintptr_t>(out) & 7) != 0) return -1;   // 8-byte stores
+    BwdMma32Params p{};
+    p.out = static_cast<float *>(out);
+    p.C = C; p.H = H; p.W = W; p.D = D;
+    p.invC = 1.0f / (float)C;
+    p.HALO = round_up(D - 1, 4);
+    const int nk = ceil_div(p.HALO + 16, 8);
+    if (nk < 2 || nk > 12) return -1;
+    int warps = ceil_div(W, 16);
+    int maxw = env_int_bm32("DSSMD_MMA32_MAXW", kMaxWarps);
+    if (maxw < 1 || maxw > kMaxWarps) maxw = kMaxWarps;
+    p.XT = ceil_div(warps, maxw);
+    warps = ceil_div(warps, p.XT);
+    p.TX = warps * 16;
+    const int need = p.TX + 8 * nk - 16;                  // operand positions a block touches
+    p.RW = ((need + 27) / 32) * 32 + 4;                   // smallest value >= need that is 4 (mod 32)
+    p.GW = MODE == 0 ? p.TX : round_up(need, 4);
+    if (p.RW > 256 || p.GW > 256) return -1;
+    const size_t smem = (((size_t)D * p.GW * 4 + 127) & ~(size_t)127) + 2 * (size_t)kCK * p.RW * 4;
+    if (smem > 200 * 1024) return -1;
+    const long long blocks = (long long)B * H * p.XT;
+    if (blocks >= (1LL << 31)) return -1;
+    CUtensorMap mapIn, mapG;
+    const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)p.RW, 1, (cuuint32_t)kCK, 1};
+    const cuuint64_t gdims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+    const cuuint64_t gstrides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)gbs * 4};
+    const cuuint32_t gbox[4] = {(cuuint32_t)p.GW, 1, (cuuint32_t)D, 1};
+    if (!make_tmap_f32(&mapIn, in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE) ||
+        !make_tmap_f32(&mapG, g, 4, gdims, gstrides, gbox, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
+    if (env_int_bm32("DSSMD_CORR_DEBUG", 0))
+        fprintf(stderr, "corr_bwd mma32 cfg: mode=%d NK=%d HALO=%d TX=%d XT=%d RW=%d GW=%d warps=%d grid=%lld smem=%zu\n", MODE, nk, p.HALO, p.TX, p.XT,
+                p.RW, p.GW, warps, blocks, smem);
+#define DSSMD_BNK_CASE(n) case n: return launch_bnk<MODE, n>(p, mapIn, mapG, (int)blocks, warps * 32, smem, stream);
+    switch (nk) {
+        DSSMD_BNK_CASE(2) DSSMD_BNK_CASE(3) DSSMD_BNK_CASE(4) DSSMD_BNK_CASE(5) DSSMD_BNK_CASE(6) DSSMD_BNK_CASE(7)
+        DSSMD_BNK_CASE(8) DSSMD_BNK_CASE(9) DSSMD_BNK_CASE(10) DSSMD_BNK_CASE(11)
+        default: return launch_bnk<MODE, 12>(p, mapIn, mapG, (int)blocks, warps * 32, smem, stream);
+    }
+#undef DSSMD_BNK_CASE
+}
+
+}  // namespace
+
+// fp32 tensors.  mode 0: out = gL, in = R;  mode 1: out = gR, in = L.  -1 = not eligible (caller falls back).
+int corr_bwd_mma32(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, long long gbs, cudaStream_t stream) {
+    return mode == 0 ? corr_bwd_mma32_mode<0>(g, in, out, B, C, H, W, D, gbs, stream) : corr_bwd_mma32_mode<1>(g, in, out, B, C, H, W, D, gbs, stream);
+}
+
+}  // namespace dssmd

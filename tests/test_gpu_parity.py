@@ -1067,3 +1067,28 @@ def test_corr_fwd_mma32(ops, oracle, shape, relu, monkeypatch, capfd):
     assert bool((out[:, W:] == 0).all())
     head = feat((B, 3, H, W), 33, False)
     assert torch.equal(ops.build_corr_cat(head, L, R, D), torch.cat((head, out), dim=1))
+
+
+@pytest.mark.parametrize("relu", [True, False])
+@pytest.mark.parametrize("shape", MMA32_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_corr_bwd_mma32(ops, oracle, shape, relu, monkeypatch, capfd):
+    """DSSMD_CORR_BWD_VARIANT=3: both gradients on mma.sync.m16n8k8 with 3xTF32 splitting of the operand rows and of the banded g
+    operand, at the fp32 bar, plain and through the concat gradient."""
+    B, C, H, W, D = shape
+    L0, R0 = feat((B, C, H, W), 41, relu), feat((B, C, H, W), 42, relu)
+    g = feat((B, D, H, W), 43, False)
+    monkeypatch.setenv("DSSMD_CORR_BWD_VARIANT", "3")
+    monkeypatch.setenv("DSSMD_CORR_DEBUG", "1")
+    L, R = L0.clone().requires_grad_(True), R0.clone().requires_grad_(True)
+    ops.build_corr(L, R, D).backward(g)
+    torch.cuda.synchronize()
+    err = capfd.readouterr().err
+    assert err.count("corr_bwd mma32 cfg") == 2, err
+    gL, gR = oracle.corr_bwd(g.cpu().numpy(), L0.cpu().numpy(), R0.cpu().numpy())
+    assert rel_err(L.grad.cpu().numpy(), gL) <= TOL_F32
+    assert rel_err(R.grad.cpu().numpy(), gR) <= TOL_F32
+    head = feat((B, 3, H, W), 44, False).requires_grad_(True)
+    L2, R2 = L0.clone().requires_grad_(True), R0.clone().requires_grad_(True)
+    gcat = torch.cat((feat((B, 3, H, W), 45, False), g), dim=1)
+    ops.build_corr_cat(head, L2, R2, D).backward(gcat)
+    assert torch.equal(L2.grad, L.grad) and torch.equal(R2.grad, R.grad)
