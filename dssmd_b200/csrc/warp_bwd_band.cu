@@ -418,8 +418,16 @@ int launch_band(const float *g, const float *img, const float *disp, float *g_im
         int occ = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
         if (e != cudaSuccess || occ < 1) occ = 1;
+        // A band costs R + 1 row passes (one halo row) and the grid runs in ceil(blocks / slots) waves: take the R that minimises
+        // waves * (R + 1).  (The rule "one wave" picked R = 32 at 384x1280 x16 -- 192 blocks on 148 one-block SMs, a second wave 30 %
+        // full: 179 us; R = 24 gives 256 blocks in two full-ish waves of 25 passes.)
         const long long slots = (long long)occ * sm_count();
-        R = (int)(((long long)B * H + slots - 1) / slots);
+        long long best = -1;
+        for (int r = 4; r <= kMaxBandRows && r <= (H > 4 ? H : 4); ++r) {
+            const long long blocks = (long long)ceil_div(H, r) * B;
+            const long long cost = ((blocks + slots - 1) / slots) * (r + 1);
+            if (best < 0 || cost <= best) { best = cost; R = r; }   // ties: the larger R (fewer halo rows)
+        }
         if (R < 4) R = 4;
     }
     if (R > kMaxBandRows) R = kMaxBandRows;
