@@ -15,8 +15,8 @@ prof = os.path.join(root, "profiles")
 
 # bench-level call -> kernel-name substrings launched by it
 CALLS = {"corr_fwd": ["corr_fwd"],
-         "corr_bwd_gL": ["corr_bwd_reg_kernel<0", "corr_bwd_reg_kernel<float, 0", "corr_bwd_kernel<float, 0"],
-         "corr_bwd_gR": ["corr_bwd_reg_kernel<1", "corr_bwd_reg_kernel<float, 1", "corr_bwd_kernel<float, 1"], "warp_fwd": ["warp_fwd"],
+         "corr_bwd_gL": ["corr_bwd_reg_kernel<0", "corr_bwd_reg_kernel<float, 0", "corr_bwd_kernel<float, 0", "corr_bwd_mma32_kernel<0"],
+         "corr_bwd_gR": ["corr_bwd_reg_kernel<1", "corr_bwd_reg_kernel<float, 1", "corr_bwd_kernel<float, 1", "corr_bwd_mma32_kernel<1"], "warp_fwd": ["warp_fwd"],
          "warp_bwd": ["warp_bwd"]}
 
 
