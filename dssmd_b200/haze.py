@@ -10,9 +10,10 @@ Mirrors, name for name, the functions upstream's trainers import from DeBug/infe
 each as ONE kernel launch instead of 2 / 3 / 8 ATen kernels, plus `synthesize_haze`, which does the whole chain
 (disparity -> depth -> transmission -> hazy image) in one launch.  Results follow upstream's type promotion: the data
 loaders hand the per-sample scalars over as float64, so float32 images give float64 results (upstream then calls
-`.float()`).  Upstream's `assert x.shape[0] == b` checks are kept (AssertionError).  When an input requires a gradient
-the upstream expression itself is evaluated with torch ops on the GPU (the kernels are forward-only; upstream calls
-these functions on `requires_grad=False` data).
+`.float()`).  Upstream's `assert x.shape[0] == b` checks are kept (AssertionError).  The kernels are forward-only
+(upstream calls these functions on `requires_grad=False` data): an input that requires a gradient raises
+NotImplementedError here.  `install()` binds `guarded(kernel_fn, upstream_fn)` in upstream's modules, which hands such
+calls (and non-CUDA / non-fp32/fp64 tensors) to upstream's own saved function instead.
 """
 from __future__ import annotations
 
@@ -20,11 +21,44 @@ import torch
 
 from . import _lib
 
-__all__ = ["convert_disp_to_depth", "depth2trans", "recover_haze_images", "synthesize_haze"]
+__all__ = ["convert_disp_to_depth", "depth2trans", "recover_haze_images", "synthesize_haze", "kernel_supports", "guarded"]
 
 
 def _needs_grad(*ts):
     return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in ts)
+
+
+def _no_grad_path(name, *ts):
+    if _needs_grad(*ts):
+        raise NotImplementedError(f"{name}: the kernel is forward-only and an input requires a gradient "
+                                  "(upstream calls it on requires_grad=False data)")
+
+
+def kernel_supports(*tensors):
+    """True when `dssmd_haze_fwd` takes these arguments: CUDA float32 / float64 tensors that carry no gradient."""
+    ts = [t for t in tensors if isinstance(t, torch.Tensor)]
+    return (len(ts) == len(tensors) and all(t.is_cuda and t.dtype in (torch.float32, torch.float64) for t in ts)
+            and not _needs_grad(*ts))
+
+
+def guarded(kernel_fn, upstream_fn):
+    """What install() binds in upstream's modules: the kernel for arguments it takes, upstream's saved function otherwise."""
+    import functools
+    import inspect
+    sig = inspect.signature(kernel_fn)   # same parameter names as upstream's: the trainers call these with keywords
+
+    @functools.wraps(kernel_fn)
+    def fn(*args, **kwargs):
+        try:
+            bound = sig.bind(*args, **kwargs).args
+        except TypeError:
+            return upstream_fn(*args, **kwargs)   # upstream raises its own error
+        if not kernel_supports(*bound):
+            return upstream_fn(*args, **kwargs)
+        return kernel_fn(*bound)
+    fn.__wrapped_upstream__ = upstream_fn
+    fn.__kernel__ = kernel_fn
+    return fn
 
 
 def _compute_dtype(name, images, scalars):
@@ -86,8 +120,7 @@ def convert_disp_to_depth(baseline, focal_length, disp):
     b = disp.shape[0]
     assert baseline.shape[0] == b
     assert focal_length.shape[0] == b
-    if _needs_grad(baseline, focal_length, disp):
-        return focal_length.view(b, 1, 1, 1) * baseline.view(b, 1, 1, 1) / disp
+    _no_grad_path("convert_disp_to_depth", baseline, focal_length, disp)
     return _launch("convert_disp_to_depth", None, disp, True, baseline, focal_length, None, None, False, False, True)[2]
 
 
@@ -95,8 +128,7 @@ def depth2trans(depth, beta):
     """transmission = exp(-depth * beta)  (DeBug/inference.py:126-134)."""
     b = depth.shape[0]
     assert beta.shape[0] == b
-    if _needs_grad(depth, beta):
-        return torch.exp(-depth * beta.view(b, 1, 1, 1))
+    _no_grad_path("depth2trans", depth, beta)
     return _launch("depth2trans", None, depth, False, None, None, beta, None, False, True, False)[1]
 
 
@@ -105,9 +137,7 @@ def recover_haze_images(clean_images, beta, A, depth):
     b = clean_images.shape[0]
     assert beta.shape[0] == b
     assert A.shape[0] == b
-    if _needs_grad(clean_images, beta, A, depth):
-        t = torch.exp(-depth.repeat(1, 3, 1, 1) * beta.view(b, 1, 1, 1))
-        return (clean_images * t) + A.view(b, 1, 1, 1) * (1 - t)
+    _no_grad_path("recover_haze_images", clean_images, beta, A, depth)
     return _launch("recover_haze_images", clean_images, depth, False, None, None, beta, A, True, False, False)[0]
 
 
@@ -116,7 +146,5 @@ def synthesize_haze(clean_images, disp, baseline, focal_length, beta, A):
     returns (haze, transmission, depth) for one view."""
     b = clean_images.shape[0]
     assert baseline.shape[0] == b and focal_length.shape[0] == b and beta.shape[0] == b and A.shape[0] == b
-    if _needs_grad(clean_images, disp, baseline, focal_length, beta, A):
-        depth = convert_disp_to_depth(baseline, focal_length, disp)
-        return recover_haze_images(clean_images, beta, A, depth), depth2trans(depth, beta), depth
+    _no_grad_path("synthesize_haze", clean_images, disp, baseline, focal_length, beta, A)
     return _launch("synthesize_haze", clean_images, disp, True, baseline, focal_length, beta, A, True, True, True)

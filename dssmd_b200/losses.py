@@ -20,7 +20,7 @@ from . import _lib
 from .functional import LRWarpErrorFn, _check4, _new_flag, _raise_if_flag, resize_bilinear
 
 __all__ = ["photometric_l1", "photometric_loss", "PYRAMID_WEIGHTS", "RecoveredCleanImagesLoss", "RecoveredCleanImagesLossV2",
-           "recovered_clean_l1"]
+           "recovered_clean_l1", "asm_kernel_supports", "guarded_asm_forward"]
 
 PYRAMID_WEIGHTS = (0.6, 0.8, 1.0, 1.0)  # upstream's weights for the [1/8, 1/4, 1/2, 1] disparity pyramid
 
@@ -113,11 +113,11 @@ class _RecoveredCleanL1Fn(torch.autograd.Function):
         T, A = trans.contiguous(), airlight.reshape(B).contiguous()
         Hz, Cl = haze.contiguous(), clean.contiguous()
         lib = _lib.lib()
-        nblk = int(lib.dssmd_asm_recovered_l1_blocks(B, h, w))
-        partial = torch.empty((B, nblk, 2), dtype=torch.float32, device=T.device)
         need_t = ctx.needs_input_grad[0]
         g_unit = torch.empty_like(T) if need_t else None
-        with torch.cuda.device(T.device):
+        with torch.cuda.device(T.device):   # the block count depends on the SM count of the tensors' device
+            nblk = int(lib.dssmd_asm_recovered_l1_blocks(B, h, w))
+            partial = torch.empty((B, nblk, 2), dtype=torch.float32, device=T.device)
             _lib.check(lib.dssmd_asm_recovered_l1_fwd(_lib.ptr(T), _lib.ptr(A), _lib.ptr(Hz), _lib.ptr(Cl), _lib.ptr(g_unit),
                                                       _lib.ptr(partial), B, C, H0, W0, h, w, _lib.dtype_code(T), _lib.stream_ptr(T.device)))
         sums = partial.sum(dim=1)                      # [B, 2], fixed order
@@ -133,6 +133,35 @@ class _RecoveredCleanL1Fn(torch.autograd.Function):
         g_t = g_unit * scale if ctx.needs_input_grad[0] else None
         g_a = (ga * scale).reshape(ctx.a_shape) if ctx.needs_input_grad[1] else None
         return g_t, g_a, None, None
+
+
+def asm_kernel_supports(transmission_map, airlight, haze_image, clean_image):
+    """True when `dssmd_asm_recovered_l1_fwd` takes this level: CUDA float32 tensors, no gradient into the images, image
+    size an integer multiple of the transmission map's."""
+    ts = (transmission_map, airlight, haze_image, clean_image)
+    if not all(isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 for t in ts) or torch.is_autocast_enabled():
+        return False
+    if transmission_map.dim() != 4 or haze_image.dim() != 4 or clean_image.shape != haze_image.shape:
+        return False
+    if torch.is_grad_enabled() and (haze_image.requires_grad or clean_image.requires_grad):
+        return False
+    B, _, H0, W0 = haze_image.shape
+    h, w = transmission_map.shape[-2:]
+    if tuple(transmission_map.shape) != (B, 1, h, w) or airlight.numel() != B or airlight.shape[0] != B or w == 0 or h == 0:
+        return False
+    scale = W0 // w
+    return scale >= 1 and W0 == w * scale and H0 == h * scale
+
+
+def guarded_asm_forward(upstream_forward):
+    """The `forward` install() puts on upstream's RecoveredCleanImagesLoss / V2: the fused launch for levels the kernel
+    takes, upstream's saved forward for everything else (other dtypes, AMP, image gradients, non-integer scales)."""
+    def forward(self, transmission_map, airlight, haze_image, clean_image):
+        if self.loss_type != 'normal' or not asm_kernel_supports(transmission_map, airlight, haze_image, clean_image):
+            return upstream_forward(self, transmission_map, airlight, haze_image, clean_image)
+        return recovered_clean_l1(transmission_map, airlight, haze_image, clean_image)
+    forward.__wrapped_upstream__ = upstream_forward
+    return forward
 
 
 def recovered_clean_l1(transmission_map, airlight, haze_image, clean_image):

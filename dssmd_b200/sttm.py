@@ -6,7 +6,9 @@ and returns `softmax(q k^T * scale) v` per image row in NCHW: no permute / resha
 [B*H, W, W] attention matrix (two 4.2 GB fp32 intermediates at BidNet's B8 x 32 x 320 x 640).  `STTM_Single` is
 upstream's module with the same constructor, parameter names (state_dicts load unchanged) and forward signature, its
 attention core swapped for the kernel.  fp32, C in {16, 32, 64, 128}, W % 4 == 0; anything else raises
-NotImplementedError -- there is no fallback.
+NotImplementedError -- there is no fallback in this package.  `install()` does not replace upstream's class: it patches
+the class's `forward` with `guarded_forward`, which takes the kernel for inputs inside those limits and hands everything
+else to upstream's own, saved `forward`.
 """
 from __future__ import annotations
 
@@ -16,7 +18,35 @@ import torch.nn as nn
 from . import _lib
 from .functional import _check4
 
-__all__ = ["epipolar_attention", "STTM_Single"]
+__all__ = ["epipolar_attention", "STTM_Single", "kernel_supports", "guarded_forward"]
+
+_CHANNELS = (16, 32, 64, 128)
+
+
+def kernel_supports(channels, left_feat, right_feat):
+    """True when `dssmd_epipolar_attn_*` takes the attention of these features (after 1x1 convolutions to `channels`)."""
+    if not (isinstance(left_feat, torch.Tensor) and isinstance(right_feat, torch.Tensor)):
+        return False
+    if not (left_feat.is_cuda and right_feat.is_cuda) or left_feat.device != right_feat.device:
+        return False
+    if left_feat.dtype != torch.float32 or right_feat.dtype != torch.float32 or torch.is_autocast_enabled():
+        return False
+    if left_feat.dim() != 4 or left_feat.shape != right_feat.shape:
+        return False
+    B, _, H, W = left_feat.shape
+    return channels in _CHANNELS and W % 4 == 0 and B * H <= 65535
+
+
+def guarded_forward(upstream_forward):
+    """The `forward` install() puts on upstream's STTM_Single: upstream's projections and output head, the attention core
+    on the kernel; inputs outside the kernel's limits run upstream's saved forward unchanged."""
+    def forward(self, left_feat, right_feat):
+        if not kernel_supports(self.q.out_channels, left_feat, right_feat):
+            return upstream_forward(self, left_feat, right_feat)
+        out = epipolar_attention(self.q(left_feat), self.k(right_feat), self.v(right_feat), self.scale)
+        return self.to_out(torch.cat((left_feat, out), dim=1))
+    forward.__wrapped_upstream__ = upstream_forward
+    return forward
 
 
 class EpipolarAttentionFn(torch.autograd.Function):
@@ -64,7 +94,7 @@ def epipolar_attention(q, k, v, scale):
     if any(t.dtype != torch.float32 for t in (q, k, v)):
         raise NotImplementedError("epipolar_attention: only float32 is implemented")
     B, C, H, W = q.shape
-    if C not in (16, 32, 64, 128) or W % 4 != 0 or B * H > 65535:
+    if C not in _CHANNELS or W % 4 != 0 or B * H > 65535:
         raise NotImplementedError(f"epipolar_attention: needs C in (16, 32, 64, 128), W % 4 == 0 and B*H <= 65535, got {tuple(q.shape)}")
     return EpipolarAttentionFn.apply(q, k, v, scale)
 

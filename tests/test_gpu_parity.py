@@ -647,12 +647,25 @@ def test_haze_vs_oracle(ops, oracle, shape, idt, sdt):
     assert float(((back - clear).abs() * ok).max()) <= 1e-4
 
 
-def test_haze_needs_grad_uses_upstream_expression(ops):
+def test_haze_needs_grad_raises_and_guarded_wrapper_hands_it_to_upstream(ops):
+    """The kernels are forward-only: no eager-torch branch inside the package.  What install() binds in upstream's
+    modules (haze.guarded) sends such a call to upstream's own function instead."""
+    from dssmd_b200 import haze
     disp = (torch.rand(2, 1, 8, 16, device="cuda") + 1).requires_grad_(True)
     one = torch.ones(2, device="cuda")
-    depth = ops.convert_disp_to_depth(one * 0.1, one * 1050, disp)
+    with pytest.raises(NotImplementedError, match="forward-only"):
+        ops.convert_disp_to_depth(one * 0.1, one * 1050, disp)
+
+    def upstream(baseline, focal_length, disp):       # DeBug/inference.py:57-64
+        b = disp.shape[0]
+        return focal_length.view(b, 1, 1, 1) * baseline.view(b, 1, 1, 1) / disp
+    g = haze.guarded(haze.convert_disp_to_depth, upstream)
+    depth = g(baseline=one * 0.1, focal_length=one * 1050, disp=disp)   # the trainers call with keywords
     depth.sum().backward()
     assert rel_err(disp.grad.cpu().numpy(), (-105.0 / disp.detach() ** 2).cpu().numpy()) <= TOL_F32
+    with torch.no_grad():                                                # no gradient wanted: the kernel
+        k = g(one * 0.1, one * 1050, disp)
+    assert rel_err(k.cpu().numpy(), depth.detach().cpu().numpy()) <= TOL_F32
 
 
 # ------------------------------------------------------------------ correlation into the concat buffer (SURVEY.md section 8f-2)

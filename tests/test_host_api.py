@@ -12,6 +12,8 @@ from dssmd_b200 import cost_volume, disparity_warper, stereo_op, submoudles
 
 
 def test_signatures_match_upstream():
+    # upstream's signatures as literals, for boxes without an upstream checkout; tests/test_upstream_dropin.py compares
+    # with inspect.signature of the real upstream functions where the tree is present
     assert str(inspect.signature(submoudles.build_corr)) == "(img_left, img_right, max_disp=40)"
     assert str(inspect.signature(disparity_warper.disp_warp)) == "(img, disp, padding_mode='border')"
     assert str(inspect.signature(disparity_warper.LRwarp_error)) == "(imgL, disp, imgR)"
@@ -152,18 +154,26 @@ def test_install_rebinds_haze_functions_in_trainers():
         for n in ("DeBug.inference", "trainfiles.dssmd_traner_new"):
             sys.modules[n].__dict__.update(ups)
         class UpLoss:
-            pass
+            loss_type = 'normal'
+            def forward(self, transmission_map, airlight, haze_image, clean_image):
+                return "upstream"
+        up_forward = UpLoss.forward
         sys.modules["losses.DSSMDLoss"].RecoveredCleanImagesLoss = UpLoss
         sys.modules["trainfiles.dssmd_traner_new"].RecoveredCleanImagesLoss = UpLoss
         dssmd_b200.install(import_missing=False)
         tr = sys.modules["trainfiles.dssmd_traner_new"]
-        assert tr.RecoveredCleanImagesLoss is dssmd_b200.RecoveredCleanImagesLoss
-        assert tr.convert_disp_to_depth is dssmd_b200.convert_disp_to_depth
-        assert tr.depth2trans is dssmd_b200.depth2trans
-        assert tr.recover_haze_images is dssmd_b200.recover_haze_images
+        # guarded patches: upstream's class keeps its identity, its forward takes the kernel where the kernel applies
+        assert tr.RecoveredCleanImagesLoss is UpLoss and UpLoss.forward.__wrapped_upstream__ is up_forward
+        cpu = [torch.rand(1, 1, 4, 8), torch.rand(1, 1), torch.rand(1, 3, 4, 8), torch.rand(1, 3, 4, 8)]
+        assert UpLoss().forward(*cpu) == "upstream"                # CPU tensors: outside the kernel's limits -> upstream's code
+        for n in ("convert_disp_to_depth", "depth2trans", "recover_haze_images"):
+            assert getattr(tr, n).__kernel__ is getattr(dssmd_b200, n) and getattr(tr, n).__wrapped_upstream__ is ups[n]
+        assert tr.depth2trans(torch.rand(2, 1, 4, 8), torch.ones(2)) == "depth2trans"   # CPU -> upstream's function
         assert tr.recover_depth is ups["recover_depth"]            # not on the path: untouched
+        dssmd_b200.install(import_missing=False)                   # idempotent: no double wrapping
+        assert UpLoss.forward.__wrapped_upstream__ is up_forward
         dssmd_b200.uninstall()
-        assert tr.depth2trans is up
+        assert tr.depth2trans is up and UpLoss.forward is up_forward
     finally:
         dssmd_b200.uninstall()
         for k, v in saved.items():
