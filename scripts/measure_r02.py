@@ -1,0 +1,234 @@
+#!/usr/bin/env python
+"""The measurements BASELINE.json names beside the headline, written as one JSON document:
+
+  d_sweep              cfg5 max_disp sweep at kernel level on the model's 1/8 feature shape [4,128,72,120]:
+                       model-faithful D = max_disp // 8 in {5, 12, 24} and stress D = max_disp in {40, 96, 192}
+  kitti_b1             cfg4 batch 1 (corr [1,128,48,160] D=24, warp [1,3,384,1280]): per-call latency with hot L2 (one
+                       input set) and cold L2 (sets rotating over > 2x L2), graph replay; and the eager public-API call
+  reference_torch_cuda the torch restatement of upstream's ops (tests/ref_torch.py: the op sequence upstream's build_corr /
+                       disp_warp issue) timed on the same GPU -- "what users run today"
+  api                  the cfg5 step through build_corr/.backward + disp_warp/.backward on DEVICE tensors: eager, and the
+                       raw C-ABI step eager and graph-replayed (host cost of the public API)
+
+    python scripts/measure_r02.py [--out gpurun_out/r02_measure.json] [--only d_sweep,kitti_b1,...]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from dssmd_b200 import _lib  # noqa: E402
+
+DEV = torch.device("cuda", 0)
+L2_BYTES = 126e6
+
+
+def time_graph(fn_round, per_round, rounds=20):
+    fn_round()
+    torch.cuda.synchronize()
+    g = bench.capture(torch, fn_round)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(rounds):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (rounds * per_round)
+
+
+def sets_for(w, cold):
+    one = sum(t.numel() * t.element_size() for t in bench.make_set(torch, w, DEV, 1).values())
+    n = max(4, int(2.5 * L2_BYTES / one) + 1) if cold else 1
+    return [bench.make_set(torch, w, DEV, 1024 + i) for i in range(n)], one
+
+
+def per_call(w, cold=True, names=None):
+    lib = _lib.lib()
+    sets, one = sets_for(w, cold)
+    calls = [bench.kernel_calls(torch, lib, _lib, w, s) for s in sets]
+    peak, _ = bench.measured_peak()
+    ab = bench.algorithmic_bytes(w)
+    out = {}
+    for n in (names or list(calls[0].keys())):
+        def rnd(n=n):
+            for c in calls:
+                c[n]()
+        reps = len(calls) if cold else 1
+        if not cold:
+            def rnd(n=n):   # noqa: F811  (hot: the same set 8 times per replay)
+                for _ in range(8):
+                    calls[0][n]()
+            reps = 8
+        us = time_graph(rnd, reps)
+        out[n] = {"us": round(us, 2), "algorithmic_MB": round(ab[n] / 1e6, 2), "GBps": round(ab[n] / us / 1e3, 1),
+                  "frac_of_peak": round(ab[n] / us / 1e3 / peak, 4)}
+    out["_sets"] = len(sets)
+    out["_set_MB"] = round(one / 1e6, 1)
+    del sets, calls
+    torch.cuda.empty_cache()
+    return out
+
+
+def d_sweep():
+    res = {"shape": [4, 128, 72, 120], "note": "model-faithful D = max_disp // 8 (5, 12, 24) and stress D = max_disp (40, 96, 192); "
+           "D = 192 > W = 120: 72 all-zero channels are still output bytes", "rows": {}}
+    base = bench.WORKLOADS["sceneflow_576x960"]
+    for D in (5, 12, 24, 40, 96, 192):
+        w = dict(base, D=D)
+        w = dict(w, H=64, W=64)   # the warp tensors of a set are not used here
+        res["rows"][str(D)] = per_call(w, cold=True, names=["corr_fwd", "corr_bwd_gL", "corr_bwd_gR"])
+    return res
+
+
+def kitti_b1():
+    w = dict(bench.WORKLOADS["kitti_384x1280"], B=1)
+    res = {"corr": [1, 128, 48, 160, 24], "warp": [1, 3, 384, 1280], "cold_l2": per_call(w, cold=True), "hot_l2": per_call(w, cold=False)}
+    for k in ("cold_l2", "hot_l2"):
+        res[k]["step_us"] = round(sum(v["us"] for n, v in res[k].items() if not n.startswith("_")), 2)
+        res[k]["pairs_per_s"] = round(1e6 / res[k]["step_us"], 1)
+    # eager public API, one pair: wall-clock per call incl. the host side (Python -> ctypes -> launch, autograd node)
+    import dssmd_b200
+    s = bench.make_set(torch, w, DEV, 5)
+    L, R = s["L"].requires_grad_(True), s["R"].requires_grad_(True)
+    img, disp = s["img"].requires_grad_(True), s["disp"].requires_grad_(True)
+
+    def api_step():
+        L.grad = R.grad = img.grad = disp.grad = None
+        dssmd_b200.build_corr(L, R, 24).backward(s["g_vol"])
+        warped, _ = dssmd_b200.disp_warp(img, disp)
+        warped.backward(s["g_img"])
+    for chk in (True, False):
+        dssmd_b200.set_check_negative_disparity(chk)
+        for _ in range(5):
+            api_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(50):
+            api_step()
+        torch.cuda.synchronize()
+        res["api_eager_step_us" + ("" if chk else "_no_negative_check")] = round((time.perf_counter() - t0) * 1e6 / 50, 1)
+    dssmd_b200.set_check_negative_disparity(True)
+    return res
+
+
+def reference_torch_cuda():
+    import ref_torch
+
+    def timeit(fn, reps=10):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / reps
+
+    out = {"what": "tests/ref_torch.py (the op sequence of upstream's build_corr / disp_warp, autograd backward) on CUDA tensors"}
+    for wname, w in bench.WORKLOADS.items():
+        s = bench.make_set(torch, w, DEV, 1024)
+        L, R = s["L"].clone().requires_grad_(True), s["R"].clone().requires_grad_(True)
+        img, disp = s["img"].clone().requires_grad_(True), s["disp"].clone().requires_grad_(True)
+
+        def corr_fb():
+            L.grad = R.grad = None
+            ref_torch.corr_ref(L, R, w["D"]).backward(s["g_vol"])
+
+        def warp_fb():
+            img.grad = disp.grad = None
+            ref_torch.warp_ref(img, disp)[0].backward(s["g_img"])
+        r = {"corr_fwd_bwd_us": timeit(corr_fb), "warp_fwd_bwd_us": timeit(warp_fb)}
+        r["step_us"] = r["corr_fwd_bwd_us"] + r["warp_fwd_bwd_us"]
+        r["pairs_per_s"] = w["B"] / (r["step_us"] * 1e-6)
+        out[wname] = {k: round(v, 1) for k, v in r.items()}
+        del s
+        torch.cuda.empty_cache()
+    return out
+
+
+def api():
+    """Host cost of the public API at cfg5 on device-resident tensors."""
+    import dssmd_b200
+    w = bench.WORKLOADS["sceneflow_576x960"]
+    lib = _lib.lib()
+    nsets = 4
+    sets = [bench.make_set(torch, w, DEV, 1024 + i) for i in range(nsets)]
+    calls = [bench.kernel_calls(torch, lib, _lib, w, s) for s in sets]
+    names = list(calls[0].keys())
+
+    def raw(i):
+        for n in names:
+            calls[i % nsets][n]()
+
+    def wall(fn, reps=200):
+        for i in range(10):
+            fn(i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(reps):
+            fn(i)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e6 / reps
+
+    res = {"workload": "sceneflow_576x960", "raw_abi_eager_us": round(wall(raw), 1)}
+    res["raw_abi_graph_us"] = round(time_graph(lambda: [raw(i) for i in range(nsets)], nsets), 1)
+    leaves = [{k: s[k].detach().requires_grad_(True) for k in ("L", "R", "img", "disp")} for s in sets]
+
+    def api_step(i, D=w["D"]):
+        s, lv = sets[i % nsets], leaves[i % nsets]
+        for t in lv.values():
+            t.grad = None
+        dssmd_b200.build_corr(lv["L"], lv["R"], D).backward(s["g_vol"])
+        warped, _ = dssmd_b200.disp_warp(lv["img"], lv["disp"])
+        warped.backward(s["g_img"])
+    for chk in (True, False):
+        dssmd_b200.set_check_negative_disparity(chk)
+        res["api_eager_us" + ("" if chk else "_no_negative_check")] = round(wall(api_step), 1)
+    # graph capture of the public API (no host read-back of the flag while capturing)
+    try:
+        dssmd_b200.set_check_negative_disparity(False)
+        res["api_graph_us"] = round(time_graph(lambda: [api_step(i) for i in range(nsets)], nsets), 1)
+    except Exception as e:  # noqa: BLE001
+        res["api_graph_us"] = None
+        res["api_graph_error"] = f"{type(e).__name__}: {e}"[:200]
+    dssmd_b200.set_check_negative_disparity(True)
+    res["eager_over_graph"] = round(res["api_eager_us"] / res["raw_abi_graph_us"], 2)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "r02_measure.json"))
+    ap.add_argument("--only", default="d_sweep,kitti_b1,reference_torch_cuda,api")
+    a = ap.parse_args()
+    peak, src = bench.measured_peak()
+    doc = {"device": torch.cuda.get_device_name(0), "hbm_peak_GBps": peak, "peak_source": src,
+           "timing": "CUDA events around graph replays on the launch stream; cold = input/output sets rotating over > 2.5x the 126 MB L2"}
+    for name in a.only.split(","):
+        t0 = time.time()
+        try:
+            doc[name] = globals()[name]()
+        except Exception as e:  # noqa: BLE001
+            doc[name] = {"error": f"{type(e).__name__}: {e}"}
+        print(f"[{name}] {time.time() - t0:.1f} s", file=sys.stderr, flush=True)
+    os.makedirs(os.path.dirname(os.path.abspath(a.out)), exist_ok=True)
+    with open(a.out, "w") as f:
+        json.dump(doc, f, indent=1)
+    print(json.dumps(doc))
+
+
+if __name__ == "__main__":
+    main()
