@@ -17,6 +17,9 @@ namespace dssmd {
 // warp_lean.cu: instruction-lean horizontal-scatter kernel (K1) for image-like shapes; -1 = not eligible
 int warp_bwd_band_f32(const float *g, const float *img, const float *disp, float *g_img, float *g_disp,
                       int B, int C, int H, int W, int border, cudaStream_t s);
+// warp_bwd_band2.cu: the band kernel rewritten around its instruction count (default); -1 = not eligible
+int warp_bwd_band2_f32(const float *g, const float *img, const float *disp, float *g_img, float *g_disp,
+                       int B, int C, int H, int W, int border, cudaStream_t s);
 int warp_bwd_lean_f32(const float *g, const float *img, const float *disp, float *gV, float *g_disp,
                       int B, int C, int H, int W, int border, cudaStream_t s);
 
@@ -952,13 +955,17 @@ template <typename S>
 int warp_bwd_typed(const void *g, const void *img, const void *disp, void *g_img, void *g_disp,
                    void *workspace, size_t workspace_bytes,
                    int B, int C, int H, int W, int pad, cudaStream_t s) {
-    const int variant = env_int("DSSMD_WARP_BWD_VARIANT", 6);
+    const int variant = env_int("DSSMD_WARP_BWD_VARIANT", 7);   // 7: band2 (default), 6: first band kernel, 5: scatter + vertical mix, ...
     if constexpr (sizeof(S) == 4) {
         const size_t smem = (size_t)2 * kCC * W * sizeof(int);
         const int border = pad == DSSMD_PAD_BORDER;
         const float *gp = (const float *)g, *ip = (const float *)img, *dp = (const float *)disp;
         float *gi = (float *)g_img, *gd = (float *)g_disp;
-        if (variant >= 6 && g_img) {   // one-pass band kernel: no workspace needed
+        if (variant >= 7 && g_img) {   // one-pass band kernel, lean instruction stream: no workspace needed
+            const int rc = warp_bwd_band2_f32(gp, ip, dp, gi, gd, B, C, H, W, border, s);
+            if (rc >= 0) return rc;
+        }
+        if (variant >= 6 && g_img) {   // first one-pass band kernel
             const int rc = warp_bwd_band_f32(gp, ip, dp, gi, gd, B, C, H, W, border, s);
             if (rc >= 0) return rc;
         }
