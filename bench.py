@@ -51,7 +51,8 @@ def algorithmic_bytes(w, esize=4, cimg=3):
     px = B * H * W * 4
     return {
         "corr_fwd": 2 * feat + vol,
-        "corr_bwd_gL": vol + 2 * feat,
+        "corr_bwd": vol + 4 * feat,          # g, L, R in; gL, gR out: one call, as autograd issues it
+        "corr_bwd_gL": vol + 2 * feat,       # single-gradient calls (development sweeps; not part of the step)
         "corr_bwd_gR": vol + 2 * feat,
         "warp_fwd": px * (cimg + 1 + cimg + cimg),
         "warp_bwd": px * (cimg + cimg + 1 + cimg + 1),
@@ -164,9 +165,10 @@ def make_set(torch, w, device, seed):
     return s
 
 
-def kernel_calls(torch, lib, _lib, w, s):
-    """The five launches of one step, as closures over the C ABI.  Each launches on
-    torch's current stream (so they can be captured into a CUDA graph)."""
+def kernel_calls(torch, lib, _lib, w, s, split_bwd=False):
+    """The four C-ABI calls of one step (correlation fwd, correlation bwd with both gradients, warp fwd, warp bwd), as
+    closures.  Each launches on torch's current stream (so they can be captured into a CUDA graph).  split_bwd adds the
+    single-gradient correlation backward calls (development sweeps)."""
     B, C, Hf, Wf, D, H, W = (w[k] for k in ("B", "C", "Hf", "Wf", "D", "H", "W"))
     p = {k: ctypes.c_void_p(t.data_ptr()) for k, t in s.items()}
     null = ctypes.c_void_p(0)
@@ -174,13 +176,16 @@ def kernel_calls(torch, lib, _lib, w, s):
     chk = _lib.check
     st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
-    return {
+    calls = {
         "corr_fwd": lambda: chk(lib.dssmd_corr_fwd(p["L"], p["R"], p["vol"], B, C, Hf, Wf, D, F32, st())),
-        "corr_bwd_gL": lambda: chk(lib.dssmd_corr_bwd(p["g_vol"], p["L"], p["R"], p["gL"], null, B, C, Hf, Wf, D, F32, st())),
-        "corr_bwd_gR": lambda: chk(lib.dssmd_corr_bwd(p["g_vol"], p["L"], p["R"], null, p["gR"], B, C, Hf, Wf, D, F32, st())),
+        "corr_bwd": lambda: chk(lib.dssmd_corr_bwd(p["g_vol"], p["L"], p["R"], p["gL"], p["gR"], B, C, Hf, Wf, D, F32, st())),
         "warp_fwd": lambda: chk(lib.dssmd_warp_fwd(p["img"], p["disp"], p["warped"], p["mask"], null, B, 3, H, W, BORDER, F32, st())),
         "warp_bwd": lambda: chk(lib.dssmd_warp_bwd(p["g_img"], p["img"], p["disp"], p["d_img"], p["d_disp"], p["ws"], ctypes.c_size_t(s["ws"].numel() * 4), B, 3, H, W, BORDER, F32, st())),
     }
+    if split_bwd:
+        calls["corr_bwd_gL"] = lambda: chk(lib.dssmd_corr_bwd(p["g_vol"], p["L"], p["R"], p["gL"], null, B, C, Hf, Wf, D, F32, st()))
+        calls["corr_bwd_gR"] = lambda: chk(lib.dssmd_corr_bwd(p["g_vol"], p["L"], p["R"], null, p["gR"], B, C, Hf, Wf, D, F32, st()))
+    return calls
 
 
 def capture(torch, fn):
@@ -414,8 +419,7 @@ def run_gpu(args, w):
     stream = torch.cuda.current_stream(device)
     calls = [kernel_calls(torch, lib, _lib, w, s) for s in sets]
     names = list(calls[0].keys())
-    # dssmd_warp_bwd is two kernels (horizontal scatter, vertical mix); the other calls are one each
-    launches_per_step = len(names)   # one kernel per C-ABI call (the warp backward is a single band kernel at these shapes)
+    launches_per_step = len(names)   # one kernel per C-ABI call at these shapes (fused correlation backward, band warp backward)
     set_bytes = sum(t.numel() * t.element_size() for t in sets[0].values())
 
     def eager_step(i):

@@ -27,6 +27,9 @@ namespace dssmd {
 int corr_bwd_reg(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, long long gbs, int dtype, cudaStream_t stream);
 // corr_bwd_mma32.cu: fp32 on mma.sync with 3xTF32 splitting; -1 = shape not eligible
 int corr_bwd_mma32(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, long long gbs, cudaStream_t stream);
+// corr_bwd_fused.cu: both gradients of an fp32 correlation in one launch; -1 = not eligible
+int corr_bwd_fused_f32(const void *g, const void *L, const void *R, void *gL, void *gR, int B, int C, int H, int W, int D, long long gbs,
+                       cudaStream_t stream);
 // corr_bwd_mma16.cu: 16-bit tensors on the tensor cores; -1 = shape not eligible
 int corr_bwd_mma16(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, long long gbs, int dtype, cudaStream_t stream);
 
@@ -410,6 +413,14 @@ int launch_mode(const void *g, const void *In, void *out, int B, int C, int H, i
 template <typename T>
 int launch_typed(const void *g, const void *L, const void *R, void *gL, void *gR,
                  int B, int C, int H, int W, int D, long long gbs, cudaStream_t stream) {
+    if constexpr (sizeof(T) == 4) {
+        // both gradients wanted (the autograd case): one fused launch where the shape is eligible (corr_bwd_fused.cu).  A forced
+        // per-gradient variant (DSSMD_CORR_BWD_VARIANT) keeps the two-launch path; DSSMD_CORR_BWD_FUSED=0 disables the fusion.
+        if (gL && gR && env_int("DSSMD_CORR_BWD_VARIANT", -1) < 0) {
+            const int rc = corr_bwd_fused_f32(g, L, R, gL, gR, B, C, H, W, D, gbs, stream);
+            if (rc >= 0) return rc;
+        }
+    }
     if (gL) {
         const int rc = launch_mode<T, 0>(g, R, gL, B, C, H, W, D, gbs, stream);
         if (rc) return rc;

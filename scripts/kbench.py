@@ -46,6 +46,7 @@ def main():
     sweeps = {
         "corr_fwd": [("DSSMD_CORR_FWD_XT", ["", "1", "2", "3", "4"]), ("DSSMD_CORR_FWD_CS", ["1", "2", "4"]),
                      ("DSSMD_CORR_FWD_CK", ["8", "16"])],
+        "corr_bwd": [("DSSMD_CORR_BWD_FUSED", ["1", "0"])],
         "corr_bwd_gL": [("DSSMD_CORR_BWD_CG", ["", "1", "2", "4", "8"]), ("DSSMD_CORR_BWD_ROWS", ["", "1", "2", "4"]),
                         ("DSSMD_CORR_BWD_SMEM_KB", ["", "40", "100"])],
         "corr_bwd_gR": [("DSSMD_CORR_BWD_CG", ["", "1", "2", "4", "8"]), ("DSSMD_CORR_BWD_ROWS", ["", "1", "2", "4"]),
@@ -60,7 +61,7 @@ def main():
         w = bench.WORKLOADS[wname]
         nsets = 4
         sets = [bench.make_set(torch, w, dev, 1024 + i) for i in range(nsets)]
-        calls = [bench.kernel_calls(torch, lib, _lib, w, s) for s in sets]
+        calls = [bench.kernel_calls(torch, lib, _lib, w, s, split_bwd=True) for s in sets]
         ab = bench.algorithmic_bytes(w)[which]
         print(f"== {wname} {which}: algorithmic {ab/1e6:.1f} MB, floor {ab/peak/1e3:.1f} us @ {peak:.0f} GB/s", flush=True)
         # one-at-a-time sweep around the defaults

@@ -56,11 +56,11 @@ def sets_for(w, cold):
 def per_call(w, cold=True, names=None):
     lib = _lib.lib()
     sets, one = sets_for(w, cold)
-    calls = [bench.kernel_calls(torch, lib, _lib, w, s) for s in sets]
+    calls = [bench.kernel_calls(torch, lib, _lib, w, s, split_bwd=True) for s in sets]
     peak, _ = bench.measured_peak()
     ab = bench.algorithmic_bytes(w)
     out = {}
-    for n in (names or list(calls[0].keys())):
+    for n in (names or [k for k in calls[0] if k not in ("corr_bwd_gL", "corr_bwd_gR")]):
         def rnd(n=n):
             for c in calls:
                 c[n]()
@@ -87,7 +87,7 @@ def d_sweep():
     for D in (5, 12, 24, 40, 96, 192):
         w = dict(base, D=D)
         w = dict(w, H=64, W=64)   # the warp tensors of a set are not used here
-        res["rows"][str(D)] = per_call(w, cold=True, names=["corr_fwd", "corr_bwd_gL", "corr_bwd_gR"])
+        res["rows"][str(D)] = per_call(w, cold=True, names=["corr_fwd", "corr_bwd", "corr_bwd_gL", "corr_bwd_gR"])
     return res
 
 

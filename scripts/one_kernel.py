@@ -18,7 +18,7 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 dev = torch.device("cuda", 0)
 w = bench.WORKLOADS[wname]
 sets = [bench.make_set(torch, w, dev, 1024 + i) for i in range(2)]
-calls = [bench.kernel_calls(torch, _lib.lib(), _lib, w, s) for s in sets]
+calls = [bench.kernel_calls(torch, _lib.lib(), _lib, w, s, split_bwd=True) for s in sets]
 for i in range(reps):
     for n in name.split(","):
         calls[i % 2][n]()
