@@ -327,6 +327,15 @@ class QuietStdout:
         os.dup2(2, 1)
 
 
+def config_dict(args, w, world):
+    """`config` of the JSON line: the same dict from both arms (the driver compares them), nothing arm-specific in it."""
+    B = w["B"]
+    return {"workload": args.workload, "desc": w["desc"], "per_gpu_batch": B, "global_batch": B * world,
+            "corr": [B, w["C"], w["Hf"], w["Wf"], w["D"]], "warp": [B, 3, w["H"], w["W"]],
+            "ops": ["corr_fwd", "corr_bwd", "warp_fwd", "warp_bwd"],
+            "parallelism": f"batch-sharded x{world}, no data-path collective"}
+
+
 def shard_batch(global_batch: int, world_size: int, rank: int):
     """[begin, end) of the stereo pairs rank `rank` owns (batch-partitioned, no halo)."""
     per, extra = divmod(global_batch, world_size)
@@ -378,7 +387,7 @@ def run_reference(args, w):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": w["desc"], "per_gpu_batch": w["B"]},
+        "config": config_dict(args, w, int(os.environ.get("WORLD_SIZE", "1"))),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "note": "upstream is pure PyTorch (no compiled code of its own); the C/OpenMP oracle port "
                                  "of its algorithm is timed on all host cores"},
@@ -387,6 +396,90 @@ def run_reference(args, w):
     }
     QUIET.emit(json.dumps(line))
     return 0
+
+
+def pin_to_gpu_numa_node(torch, local_rank):
+    """Bind this rank's threads to the CPUs of the NUMA node its GPU hangs off, so that the pinned staging buffers
+    (first touch) and the copy-issuing thread are local to the GPU's PCIe root.  Best effort: returns what it did."""
+    try:
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"node": node, "bound": False, "why": "no NUMA information for the device"}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return {"node": node, "bound": False, "why": "node's CPUs are outside this process's affinity mask"}
+        os.sched_setaffinity(0, allowed)
+        return {"node": node, "bound": True, "cpus": len(allowed)}
+    except Exception as e:  # noqa: BLE001
+        return {"node": None, "bound": False, "why": f"{type(e).__name__}: {e}"[:120]}
+
+
+def api_timings(torch, dssmd_b200, w, sets, nsets, device, graph_ms):
+    """The step through the PUBLIC API (build_corr / disp_warp + autograd backward) on device-resident tensors: eager
+    (wall clock around K steps with one sync), and captured into CUDA graphs (device time).  Against `ms_per_step`
+    (graph replay of the raw C-ABI calls) this is what the Python / autograd layer costs."""
+    leaves = [{k: s[k].detach().requires_grad_(True) for k in ("L", "R", "img", "disp")} for s in sets]
+
+    def api_step(i):
+        s, lv = sets[i % nsets], leaves[i % nsets]
+        for t in lv.values():
+            t.grad = None
+        dssmd_b200.build_corr(lv["L"], lv["R"], w["D"]).backward(s["g_vol"])
+        warped, _ = dssmd_b200.disp_warp(lv["img"], lv["disp"])
+        warped.backward(s["g_img"])
+
+    out = {"what": "build_corr(L, R, D).backward(g) + disp_warp(img, disp)[0].backward(g) on device tensors, us per step"}
+    for mode, key in ((True, "eager_us"), ("deferred", "eager_deferred_check_us"), (False, "eager_no_check_us")):
+        dssmd_b200.set_check_negative_disparity(mode)
+        for i in range(10):
+            api_step(i)
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        for i in range(100):
+            api_step(i)
+        torch.cuda.synchronize(device)
+        out[key] = round((time.perf_counter() - t0) * 1e6 / 100, 1)
+    dssmd_b200.check_negative_disparity_now()
+    try:
+        dssmd_b200.set_check_negative_disparity(False)
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        graphs = []
+        with torch.cuda.stream(side):
+            for i in range(nsets):
+                api_step(i)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    api_step(i)
+                graphs.append(g)
+        torch.cuda.current_stream(device).wait_stream(side)
+        for g in graphs:
+            g.replay()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(25):
+            for g in graphs:
+                g.replay()
+        e1.record()
+        torch.cuda.synchronize(device)
+        out["graph_us"] = round(e0.elapsed_time(e1) * 1e3 / (25 * nsets), 1)
+    except Exception as e:  # noqa: BLE001
+        out["graph_us"] = None
+        out["graph_error"] = f"{type(e).__name__}: {e}"[:160]
+    dssmd_b200.set_check_negative_disparity(True)
+    out["raw_abi_graph_us"] = round(graph_ms * 1e3, 1)
+    out["eager_over_raw_graph"] = round(out["eager_deferred_check_us"] / (graph_ms * 1e3), 2)
+    return out
 
 
 # ----------------------------------------------------------------------------------
@@ -413,7 +506,10 @@ def run_gpu(args, w):
     from dssmd_b200 import _lib
     lib = _lib.lib()
 
-    B = w["B"]
+    # the global batch (per-GPU batch x ranks: BASELINE's "batch 32 split across 8 B200") is partitioned by stereo pair
+    b0, b1 = shard_batch(w["B"] * world, world, rank)
+    B = b1 - b0
+    assert B == w["B"]
     nsets = args.sets
     sets = [make_set(torch, w, device, 1024 + 97 * rank + i) for i in range(nsets)]
     stream = torch.cuda.current_stream(device)
@@ -494,32 +590,48 @@ def run_gpu(args, w):
                        "frac_of_peak": round(gbs / peak, 4)}
     barrier()
 
+    # ---- the public API on device-resident tensors: what the Python / autograd layer costs --------------------------------
+    api = None
+    if rank == 0 and not args.no_api:
+        api = api_timings(torch, dssmd_b200, w, sets, nsets, device, ms_step)
+    barrier()
+
     # ---- end-to-end through the public Python API with HOST buffers ---------------------
     # Every step copies ALL of its inputs from pinned host memory and reads ALL of its
     # outputs (volume, both feature gradients, warped image, mask, image/disparity
     # gradients) back to pinned host memory.  Staged the way a loader feeding this path
     # would be: one upload stream, one compute stream, one download stream, device input
-    # and host output buffers double-buffered, so PCIe carries both directions at once
-    # and step i only waits for step i-2.  (Copies issued from the compute streams
-    # themselves serialise H2D behind D2H on this platform -- scripts/e2e_timeline.py.)
-    dssmd_b200.set_check_negative_disparity(True)
-    in_w, in_c = ("img", "disp", "g_img"), ("L", "R", "g_vol")
-    h = {k: sets[0][k].cpu().pin_memory() for k in in_w + in_c}
+    # and host output buffers triple-buffered, so PCIe carries both directions at once
+    # and step i only waits for step i-3.  The inputs of a step travel as ONE copy (one
+    # pinned host slab, one device slab, the tensors are views).  The disp >= 0 check runs
+    # in "deferred" mode: no host wait inside the step, a violation surfaces a step late.
+    numa = pin_to_gpu_numa_node(torch, local_rank)     # before the pinned buffers are touched
+    dssmd_b200.set_check_negative_disparity("deferred")
+    in_keys = ("img", "disp", "g_img", "L", "R", "g_vol")
     out_keys = ("vol", "gL", "gR", "warped", "mask", "d_img", "d_disp")
-    depth = 2
+    depth = 3
+
+    def slab(keys, like, dev, pinned=False):
+        """one contiguous buffer holding `keys` (256-byte aligned), and the tensors as views of it"""
+        offs, n = {}, 0
+        for k in keys:
+            offs[k] = n
+            n += (like[k].numel() * 4 + 255) // 256 * 256
+        buf = torch.empty(n, dtype=torch.uint8, device=dev)
+        if pinned:
+            buf = buf.pin_memory()
+        views = {k: buf[offs[k]:offs[k] + like[k].numel() * 4].view(torch.float32).view(like[k].shape) for k in keys}
+        return buf, views
+
+    h_buf, h = slab(in_keys, sets[0], "cpu", pinned=True)
+    for k in in_keys:
+        h[k].copy_(sets[0][k])
+    dins = [slab(in_keys, sets[0], device) for _ in range(depth)]
     hout = [{k: torch.empty_like(sets[0][k], device="cpu").pin_memory() for k in out_keys} for _ in range(depth)]
-    din = [{k: torch.empty_like(sets[0][k]) for k in in_w + in_c} for _ in range(depth)]
-    h2d = sum(t.numel() * t.element_size() for t in h.values())
+    h2d = sum(h[k].numel() * 4 for k in in_keys)
     d2h = sum(t.numel() * t.element_size() for t in hout[0].values())
     s_in, s_cmp, s_out = (torch.cuda.Stream(device) for _ in range(3))
     done, keep = [None] * depth, [None] * depth
-
-    def upload(d, keys):
-        with torch.cuda.stream(s_in):
-            for k in keys:
-                d[k].copy_(h[k], non_blocking=True)
-            ev = torch.cuda.Event(); ev.record(s_in)
-        return ev
 
     def download(out, items):
         ev = torch.cuda.Event(); ev.record(s_cmp)
@@ -533,16 +645,17 @@ def run_gpu(args, w):
         if done[slot] is not None:
             done[slot].synchronize()      # step i-depth is fully on the host: its buffers are free
             keep[slot] = None
-        d, out = din[slot], hout[slot]
-        ev_w, ev_c = upload(d, in_w), upload(d, in_c)
+        (d_buf, d), out = dins[slot], hout[slot]
+        with torch.cuda.stream(s_in):
+            d_buf.copy_(h_buf, non_blocking=True)
+            ev_in = torch.cuda.Event(); ev_in.record(s_in)
         with torch.cuda.stream(s_cmp):
-            s_cmp.wait_event(ev_w)
+            s_cmp.wait_event(ev_in)
             img, disp = d["img"].detach().requires_grad_(True), d["disp"].detach().requires_grad_(True)
-            warped, mask = dssmd_b200.disp_warp(img, disp)     # host waits here for the disp >= 0 flag
+            warped, mask = dssmd_b200.disp_warp(img, disp)
             warped.backward(d["g_img"])
             res_w = (("warped", warped.detach()), ("mask", mask), ("d_img", img.grad), ("d_disp", disp.grad))
             download(out, res_w)
-            s_cmp.wait_event(ev_c)
             L, R = d["L"].detach().requires_grad_(True), d["R"].detach().requires_grad_(True)
             vol = dssmd_b200.build_corr(L, R, w["D"])
             vol.backward(d["g_vol"])
@@ -560,17 +673,48 @@ def run_gpu(args, w):
         e2e_step(i)
     barrier()                             # drains both streams: every step's outputs are on the host
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    dssmd_b200.check_negative_disparity_now()
+    dssmd_b200.set_check_negative_disparity(True)
+
+    # the same bytes with no compute at all: what the host <-> device path of this box gives N ranks at once (the ceiling of
+    # any end-to-end number here); uploads and downloads concurrently, like the step
+    d_out = {k: sets[0][k] for k in out_keys}
+
+    def copy_only(i):
+        slot = i % depth
+        with torch.cuda.stream(s_in):
+            dins[slot][0].copy_(h_buf, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            for k in out_keys:
+                hout[slot][k].copy_(d_out[k], non_blocking=True)
+    for i in range(3):
+        copy_only(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        copy_only(i)
+    s_in.synchronize(); s_out.synchronize()
+    barrier()
+    copy_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+
     if distributed:
-        t = torch.tensor([e2e_ms], device=device, dtype=torch.float64)
+        t = torch.tensor([e2e_ms, copy_ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+        e2e_ms, copy_ms = float(t[0].item()), float(t[1].item())
     e2e_value = B * world / (e2e_ms * 1e-3)
     # the last step's host copy is the result a caller reads: make sure it is the real one
     if rank == 0:
-        last = hout[(e2e_steps - 1) % depth]
+        # the copy-only probe overwrote the host buffers: run one more real step and check ITS host copy
+        dssmd_b200.set_check_negative_disparity("deferred")
+        e2e_step(0)
+        torch.cuda.synchronize(device)
+        dssmd_b200.check_negative_disparity_now()
+        dssmd_b200.set_check_negative_disparity(True)
+        last = hout[0]
         for k in ("vol", "warped"):
             if not torch.equal(last[k], sets[0][k].cpu()):
                 raise SystemExit(f"bench.py: e2e output {k!r} differs from the device-resident result")
+    barrier()
 
     clocks = sampler.stop() if sampler else None
 
@@ -598,14 +742,17 @@ def run_gpu(args, w):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "desc": w["desc"], "per_gpu_batch": B, "global_batch": B * world,
-                       "corr": [B, w["C"], w["Hf"], w["Wf"], w["D"]], "warp": [B, 3, w["H"], w["W"]],
-                       "ops": names, "parallelism": f"batch-sharded x{world}, no data-path collective",
-                       "l2": f"inputs/outputs rotate over {nsets} sets of {set_bytes/1e6:.0f} MB each (> 126 MB L2)"},
+            "config": config_dict(args, w, world),
+            "l2": f"inputs/outputs rotate over {nsets} sets of {set_bytes/1e6:.0f} MB each (> 126 MB L2)",
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "steps": e2e_steps,
-                    "path": "dssmd_b200.build_corr/.backward + disp_warp/.backward on pinned host tensors; "
-                            "upload / compute / download streams, device inputs and host outputs double-buffered"},
+                    "copy_only_ms_per_step": copy_ms, "frac_of_copy_ceiling": round(copy_ms / e2e_ms, 3),
+                    "host_copy_ceiling_gbs": round((h2d + d2h) * world / (copy_ms * 1e-3) / 1e9, 1),
+                    "numa": numa,
+                    "path": "dssmd_b200.build_corr/.backward + disp_warp/.backward on pinned host tensors; one upload per "
+                            "step, upload / compute / download streams, buffers triple-buffered, disp >= 0 check deferred; "
+                            "copy_only = the same bytes with no compute, all ranks at once (max over ranks)"},
+            "api": api,
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "kernels": kern, "aux_kernels": aux, "cpu_baseline": cpu, "clocks": clocks,
         }
@@ -615,20 +762,185 @@ def run_gpu(args, w):
     return 0
 
 
+# ----------------------------------------------------------------------------------
+# BASELINE config 3: a training step under DDP (--workload train_ddp)
+# ----------------------------------------------------------------------------------
+def run_train_ddp(args):
+    """320x640 crops, batch 8 per GPU, disparity-warp reconstruction loss + dehaze (ASM reconstruction) loss, DDP at N GPUs.
+
+    Upstream has no trainer that calls a warp and its only DDP trainer does not import, so the step is a
+    thin driver around THIS repo's ops, shaped like upstream's loop (trainfiles/dssmd_traner_new.py:239-360, DDP wiring as in
+    trainfiles/ffanet_trainer_ddp.py:118,157): a small siamese conv stem of our own -> build_corr_cat (the hot path, D = 24 at
+    1/8 resolution) -> conv head -> a 4-level disparity pyramid, transmission pyramid and airlight -> photometric_loss
+    (disp_warp of the right view) + RecoveredCleanImagesLoss per level -> backward -> Adam(amsgrad).  A parameter pad brings
+    the all-reduced gradient to 164.5 MB, DSSMD_new's 41.12 M parameters.  Reports pairs/s (weak scaling),
+    the NCCL all-reduce time of the same bytes on its own, and how much of it the backward hides."""
+    import torch
+    import torch.distributed as dist
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29533")
+    if world > 1 or "RANK" in os.environ:
+        dist.init_process_group("nccl", device_id=device)
+    else:
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=device)
+    import dssmd_b200
+    torch.backends.cudnn.benchmark = True
+    B, H, W, D = 8, 320, 640, 24
+    TARGET_PARAMS = 41_120_000
+
+    def conv(ci, co, s=1):
+        return nn.Sequential(nn.Conv2d(ci, co, 3, s, 1), nn.ReLU(inplace=True))
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.stem = nn.Sequential(conv(3, 32, 2), conv(32, 64, 2), conv(64, 128, 2))           # siamese, 1/8 resolution
+            self.redir = nn.Conv2d(128, 32, 1)
+            self.fuse = nn.Sequential(conv(32 + D, 128), conv(128, 64))
+            self.disp8, self.trans8 = nn.Conv2d(64, 1, 3, 1, 1), nn.Conv2d(64, 1, 3, 1, 1)
+            self.up = nn.ModuleList([conv(64 + 2, 32), conv(32 + 2, 16), conv(16 + 2, 16)])
+            self.disp_up = nn.ModuleList([nn.Conv2d(c, 1, 3, 1, 1) for c in (32, 16, 16)])
+            self.trans_up = nn.ModuleList([nn.Conv2d(c, 1, 3, 1, 1) for c in (32, 16, 16)])
+            self.air = nn.Linear(128, 1)
+            have = sum(p.numel() for p in self.parameters())
+            self.pad = nn.Parameter(torch.zeros(max(TARGET_PARAMS - have, 1)))                    # gradient bytes of DSSMD_new
+
+        def forward(self, left, right):
+            fl, fr = self.stem(left), self.stem(right)
+            x = self.fuse(dssmd_b200.build_corr_cat(self.redir(fl), fl, fr, D))
+            d, t = F.softplus(self.disp8(x)), torch.sigmoid(self.trans8(x))
+            disps, trans = [d], [t]
+            for up, du, tu in zip(self.up, self.disp_up, self.trans_up):
+                x = F.interpolate(x, scale_factor=2.0, mode="bilinear", align_corners=False)
+                d = F.interpolate(d, scale_factor=2.0, mode="bilinear", align_corners=False) * 2.0
+                t = F.interpolate(t, scale_factor=2.0, mode="bilinear", align_corners=False)
+                x = up(torch.cat((x, d, t), 1))
+                d, t = F.softplus(du(x)) + d, torch.sigmoid(tu(x) + torch.logit(t.clamp(1e-4, 1 - 1e-4)))
+                disps.append(d); trans.append(t)
+            air = torch.sigmoid(self.air(fl.mean((2, 3))))
+            return disps, trans, air, self.pad.sum() * 0.0
+
+    torch.manual_seed(1024)
+    net = Net().to(device)
+    nparams = sum(p.numel() for p in net.parameters())
+    ddp = nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], static_graph=True, gradient_as_bucket_view=True)
+    opt = torch.optim.Adam(ddp.parameters(), 1e-4, betas=(0.9, 0.999), amsgrad=True)
+    rec = dssmd_b200.RecoveredCleanImagesLoss()
+    wts = (0.6, 0.8, 1.0, 1.0)
+    dssmd_b200.set_check_negative_disparity("deferred")
+    g = torch.Generator(device=device).manual_seed(7 + rank)
+    nb = 3   # batches rotated through
+    data = []
+    for _ in range(nb):
+        clear_l = F.avg_pool2d(torch.rand(B, 3, H, W, device=device, generator=g), 9, 1, 4)
+        clear_r = F.avg_pool2d(torch.rand(B, 3, H, W, device=device, generator=g), 9, 1, 4)
+        base = torch.rand(B, 1, H // 32 + 1, W // 32 + 1, device=device, generator=g)
+        disp = 0.5 + 127.5 * F.interpolate(base, size=(H, W), mode="bilinear", align_corners=True)
+        one = torch.ones(B, device=device)
+        haze_l, _, _ = dssmd_b200.synthesize_haze(clear_l, disp, one * 0.1, one * 1050.0, one * 0.1, one * 0.9)
+        haze_r, _, _ = dssmd_b200.synthesize_haze(clear_r, disp, one * 0.1, one * 1050.0, one * 0.1, one * 0.9)
+        data.append((haze_l.float(), haze_r.float(), clear_l))
+
+    def step(i, model):
+        haze_l, haze_r, clear_l = data[i % nb]
+        opt.zero_grad(set_to_none=True)
+        disps, trans, air, pad0 = model(haze_l, haze_r)
+        loss = dssmd_b200.photometric_loss(haze_l, haze_r, disps) + pad0   # sum_s w_s |LRwarp_error(imgL, disp_s, imgR)|
+        for wt, t in zip(wts, trans):
+            loss = loss + wt * rec(t, air, haze_l, clear_l)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def timed(model, steps, warm):
+        for i in range(warm):
+            step(i, model)
+        torch.cuda.synchronize(device); dist.barrier(); torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            loss = step(i, model)
+        e1.record()
+        torch.cuda.synchronize(device); dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), float(loss)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    steps, warm = max(5, min(args.steps, 30)), max(3, min(args.warmup, 5))
+    ms_ddp, loss = timed(ddp, steps, warm)
+    ms_local, _ = timed(net, steps, 2)          # the same step without the gradient all-reduce
+    # the all-reduce of the same gradient bytes on its own
+    buf = torch.empty(nparams, device=device)
+    for _ in range(3):
+        dist.all_reduce(buf)
+    torch.cuda.synchronize(device); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        dist.all_reduce(buf)
+    e1.record()
+    torch.cuda.synchronize(device)
+    t = torch.tensor([e0.elapsed_time(e1) / 10], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_ar = float(t.item())
+    dssmd_b200.check_negative_disparity_now()
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        exposed = max(ms_ddp - ms_local, 0.0)
+        line = {
+            "metric": "stereo_pairs_per_s@320x640_train_step", "value": B * world / (ms_ddp * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": steps, "warmup": warm, "ms_per_step": ms_ddp, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "train_ddp", "desc": "cfg3: training step, 320x640 crops, batch 8/GPU, disparity-warp reconstruction "
+                       "loss + ASM dehaze loss, DDP", "per_gpu_batch": B, "global_batch": B * world,
+                       "parameters": nparams, "allreduce_bytes": nparams * 4,
+                       "model": "siamese conv stem -> build_corr_cat (D=24 @1/8) -> conv head -> 4-level disparity / transmission "
+                                "pyramid + airlight; photometric_loss + RecoveredCleanImagesLoss; Adam(amsgrad)",
+                       "parallelism": f"DDP x{world} (static_graph, gradient_as_bucket_view), NCCL all-reduce"},
+            "ddp": {"ms_per_step": ms_ddp, "ms_per_step_without_allreduce": ms_local, "allreduce_alone_ms": ms_ar,
+                    "allreduce_exposed_ms": exposed, "allreduce_hidden_frac": round(1.0 - min(exposed / ms_ar, 1.0), 3) if world > 1 else None,
+                    "allreduce_bus_gbs": round(nparams * 4 * 2 * (world - 1) / world / (ms_ar * 1e-3) / 1e9, 1) if world > 1 else None},
+            "loss": loss, "clocks": clocks, "gpu_launches": None,
+        }
+        QUIET.emit(json.dumps(line))
+    dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="dssmd_b200", choices=["dssmd_b200", "reference"])
-    ap.add_argument("--workload", default="sceneflow_576x960", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="sceneflow_576x960", choices=sorted(WORKLOADS) + ["train_ddp"])
     ap.add_argument("--sets", type=int, default=4, help="input/output sets rotated through to defeat L2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-aux", action="store_true", help="skip the timings of the kernels either side of the hot path (aux_kernels)")
+    ap.add_argument("--no-api", action="store_true", help="skip the timings of the public API on device tensors (api)")
     args = ap.parse_args()
     global QUIET
     QUIET = QuietStdout()
+    if args.workload == "train_ddp":
+        if args.impl == "reference":
+            if int(os.environ.get("RANK", "0")) == 0:
+                QUIET.emit(json.dumps({"impl": "reference", "unavailable": "train_ddp has no CPU arm (upstream has no trainer on this path)"}))
+            return 0
+        return run_train_ddp(args)
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, w)

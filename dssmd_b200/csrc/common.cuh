@@ -28,6 +28,18 @@ int check_launch(const char *what);  // cudaGetLastError -> DSSMD_ERR_CUDA
 // ---- device properties, cached per device (read-only after first use) ----------
 int sm_count();
 
+// ---- per (kernel, device) launch set-up, asked once and then looked up (abi.cu) ------------------------------------------
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and cudaOccupancyMaxActiveBlocksPerMultiprocessor are properties of a
+// kernel on a device; they used to be re-asked on every launch (a few microseconds each, more than some of the kernels).
+cudaError_t kernel_smem_optin(const void *func, size_t smem);           // no-op once the kernel has been granted >= smem
+int kernel_occupancy(const void *func, int threads, size_t smem);       // resident blocks per SM (>= 1)
+template <typename K> inline cudaError_t kernel_smem_optin(K kern, size_t smem) { return kernel_smem_optin(reinterpret_cast<const void *>(kern), smem); }
+template <typename K> inline int kernel_occupancy(K kern, int threads, size_t smem) { return kernel_occupancy(reinterpret_cast<const void *>(kern), threads, smem); }
+// The DSSMD_* tuning / debug variables are honoured only in processes started with
+// DSSMD_TUNING=1 (read once): a production process pays one cached flag test per knob instead of ~30 getenv() scans of the
+// environment per call.  The test-suite and the sweep scripts set it.
+bool tuning_enabled();
+
 // ---- element conversion --------------------------------------------------------
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
@@ -88,6 +100,7 @@ __device__ __forceinline__ float2 ld_cg(const float2 *p) { return __ldcg(p); }
 __device__ __forceinline__ float4 ld_cg(const float4 *p) { return __ldcg(p); }
 
 static inline bool pdl_enabled() {
+    if (!tuning_enabled()) return true;
     const char *v = std::getenv("DSSMD_PDL");
     return !(v && v[0] == '0');
 }

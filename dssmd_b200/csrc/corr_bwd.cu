@@ -296,6 +296,7 @@ __global__ void corr_bwd_f64_kernel(const double *g, const double *L, const doub
 }
 
 int env_int(const char *name, int dflt) {
+    if (!tuning_enabled()) return dflt;
     const char *v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
 }

@@ -168,6 +168,7 @@ corr_bwd_fused_kernel(const FusedParams p, const __grid_constant__ CUtensorMap m
 }
 
 int env_int_fused(const char *name, int dflt) {
+    if (!tuning_enabled()) return dflt;
     const char *v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
 }
@@ -175,24 +176,11 @@ int env_int_fused(const char *name, int dflt) {
 template <int LOGNH, int CPW, int NW>
 int launch_fused(FusedParams p, const CUtensorMap &mapL, const CUtensorMap &mapR, const CUtensorMap &mapG, size_t smem, cudaStream_t stream) {
     auto kern = corr_bwd_fused_kernel<LOGNH, CPW, NW>;
-    // per (instantiation, device): opt-in shared memory size and occupancy asked once (the smem size of an instantiation can
-    // differ between shapes, so the cache keeps the largest size it has set)
-    static thread_local size_t set_smem[8] = {0};
-    static thread_local int occ_cache[8] = {0};
-    static thread_local size_t occ_smem[8] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 8) dev = 0;
-    if (smem > 48 * 1024 && smem > set_smem[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        cudaError_t e = kernel_smem_optin(kern, smem);   // asked once per (kernel, device), then a table lookup (abi.cu)
         if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_bwd(fused): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
-        set_smem[dev] = smem;
     }
-    int bps = occ_cache[dev];
-    if (bps < 1 || occ_smem[dev] != smem) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, NW * 32, smem) != cudaSuccess || bps < 1) bps = 1;
-        occ_cache[dev] = bps; occ_smem[dev] = smem;
-    }
+    const int bps = kernel_occupancy(kern, NW * 32, smem);
     // persistent grid: the blocks that are resident at once, each with an equal share of rows
     int grid = sm_count() * bps;
     if (grid > p.nrows) grid = p.nrows;

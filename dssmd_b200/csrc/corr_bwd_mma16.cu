@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_bwd_mma16_kernel(const Bw
 }
 
 int env_int_bm16(const char *name, int dflt) {
+    if (!tuning_enabled()) return dflt;
     const char *v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
 }
@@ -201,7 +202,7 @@ template <typename T, int MODE, int NP, bool TMA>
 int launch_bnp2(const BwdMma16Params &p, const CUtensorMap &mapIn, const CUtensorMap &mapG, int grid, int threads, size_t smem, cudaStream_t stream) {
     auto kern = corr_bwd_mma16_kernel<T, MODE, NP, TMA>;
     if (smem > 48 * 1024) {
-        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const cudaError_t e = kernel_smem_optin(kern, smem);
         if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_bwd(mma16): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
     }
     kern<<<grid, threads, smem, stream>>>(p, mapIn, mapG);

@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_bwd_mma32_kernel(const Bw
 }
 
 int env_int_bm32(const char *name, int dflt) {
+    if (!tuning_enabled()) return dflt;
     const char *v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
 }
@@ -153,8 +154,8 @@ int env_int_bm32(const char *name, int dflt) {
 template <int MODE, int NK>
 int launch_bnk(const BwdMma32Params &p, const CUtensorMap &mapIn, const CUtensorMap &mapG, int grid, int threads, size_t smem, cudaStream_t stream) {
     auto kern = corr_bwd_mma32_kernel<MODE, NK>;
-    if (smem > 48 * 1024) {
-        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        const cudaError_t e = kernel_smem_optin(kern, smem);
         if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_bwd(mma32): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
     }
     const cudaError_t le = launch_pdl(kern, dim3((unsigned)grid), dim3((unsigned)threads), smem, stream, p, mapIn, mapG);

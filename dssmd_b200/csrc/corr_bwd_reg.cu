@@ -213,6 +213,7 @@ __global__ void __launch_bounds__(PX == 4 ? 512 : 256) corr_bwd_reg_kernel(const
 }
 
 int env_int_reg(const char *name, int dflt) {
+    if (!tuning_enabled()) return dflt;
     const char *v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
 }
@@ -220,13 +221,12 @@ int env_int_reg(const char *name, int dflt) {
 template <typename T, int MODE, int LOGNH, int PX>
 int launch_reg(RegParams p, const CUtensorMap &mapIn, const CUtensorMap &mapG, int threads, size_t smem, cudaStream_t stream) {
     auto kern = corr_bwd_reg_kernel<T, MODE, LOGNH, PX>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        cudaError_t e = kernel_smem_optin(kern, smem);
         if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_bwd: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
     }
     // persistent grid: exactly the blocks that are resident at once, each with an equal share of items
-    int bps = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, threads, smem) != cudaSuccess || bps < 1) bps = 1;
+    int bps = kernel_occupancy(kern, threads, smem);
     const int o = env_int_reg("DSSMD_CORR_BWD_BPS", 0);
     if (o >= 1 && o < bps) bps = o;
     int grid = sm_count() * bps;

@@ -493,6 +493,7 @@ __global__ void corr_fwd_f64_kernel(const double *L, const double *R, double *ou
 }
 
 int env_int(const char *name, int dflt) {
+    if (!tuning_enabled()) return dflt;
     const char *v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
 }

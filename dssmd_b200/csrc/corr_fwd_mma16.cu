@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_fwd_mma16_kernel(const Mm
 }
 
 int env_int_m16(const char *name, int dflt) {
+    if (!tuning_enabled()) return dflt;
     const char *v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
 }
@@ -187,7 +188,7 @@ template <typename T, int NP, bool TMA>
 int launch_np2(const Mma16Params &p, const CUtensorMap &mapL, const CUtensorMap &mapR, int grid, int threads, size_t smem, cudaStream_t stream) {
     auto kern = corr_fwd_mma16_kernel<T, NP, TMA>;
     if (smem > 48 * 1024) {
-        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const cudaError_t e = kernel_smem_optin(kern, smem);
         if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_fwd(mma16): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
     }
     kern<<<grid, threads, smem, stream>>>(p, mapL, mapR);

@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_fwd_mma32_kernel(const Mm
 }
 
 int env_int_m32(const char *name, int dflt) {
+    if (!tuning_enabled()) return dflt;
     const char *v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
 }
@@ -143,8 +144,8 @@ int env_int_m32(const char *name, int dflt) {
 template <int NT>
 int launch_nt(const Mma32Params &p, const CUtensorMap &mapL, const CUtensorMap &mapR, int grid, int threads, size_t smem, cudaStream_t stream) {
     auto kern = corr_fwd_mma32_kernel<NT>;
-    if (smem > 48 * 1024) {
-        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        const cudaError_t e = kernel_smem_optin(kern, smem);
         if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_fwd(mma32): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
     }
     const cudaError_t le = launch_pdl(kern, dim3((unsigned)grid), dim3((unsigned)threads), smem, stream, p, mapL, mapR);

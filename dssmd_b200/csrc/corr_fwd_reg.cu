@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(512) corr_fwd_reg_kernel(const FwdRegParams p,
 }
 
 int env_int_fwd(const char *name, int dflt) {
+    if (!tuning_enabled()) return dflt;
     const char *v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
 }
@@ -174,13 +175,12 @@ int env_int_fwd(const char *name, int dflt) {
 template <typename T, int LOGNH>
 int launch_fwd_reg(FwdRegParams p, const CUtensorMap &mapL, const CUtensorMap &mapR, int threads, size_t smem, cudaStream_t stream) {
     auto kern = corr_fwd_reg_kernel<T, LOGNH>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        cudaError_t e = kernel_smem_optin(kern, smem);
         if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_fwd: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
     }
     // persistent grid: the blocks that are resident at once, each with an equal share of (row, x tile) groups
-    int bps = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, threads, smem) != cudaSuccess || bps < 1) bps = 1;
+    const int bps = kernel_occupancy(kern, threads, smem);
     int grid = sm_count() * bps;
     if (grid > p.ngroups) grid = p.ngroups;
     p.gpb = ceil_div(p.ngroups, grid);

@@ -370,6 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1) corr_fwd_umma_kernel(const UmmaPa
 }
 
 int env_int(const char *name, int dflt) {
+    if (!tuning_enabled()) return dflt;
     const char *v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
 }

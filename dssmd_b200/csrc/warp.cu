@@ -24,6 +24,7 @@ int warp_fwd_lean_f32(const float *img, const float *disp, float *out, float *ma
 namespace {
 
 int env_int(const char *name, int dflt) {
+    if (!tuning_enabled()) return dflt;
     const char *v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
 }
@@ -486,7 +487,7 @@ int warp_fwd_typed(const void *img, const void *disp, void *warped, void *mask, 
 #undef DSSMD_FWD_PICK
             const size_t smem = (size_t)C * 2 * 4 * ps * sizeof(float);
             if (smem > 48 * 1024) {
-                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaError_t e = kernel_smem_optin(kern, smem);
                 if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "warp_fwd: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
             }
             // W/2 and H/2: IEEE single divisions, the same values the device would compute

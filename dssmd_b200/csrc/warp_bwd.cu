@@ -936,6 +936,7 @@ __global__ void __launch_bounds__(256) warp_bwd_vmix_band_kernel(const float *__
 }
 
 int env_int(const char *name, int dflt) {
+    if (!tuning_enabled()) return dflt;
     const char *v = std::getenv(name);
     return (v && *v) ? std::atoi(v) : dflt;
 }

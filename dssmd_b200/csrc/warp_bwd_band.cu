@@ -409,15 +409,13 @@ int launch_band(const float *g, const float *img, const float *disp, float *g_im
       : C == 3 ? warp_bwd_band_kernel<3, PS, BORDER> : warp_bwd_band_kernel<4, PS, BORDER>;
     const int vw = C == 3 ? 4 : C;
     const size_t smem = 2 * (size_t)C * (4 * (PS + 6) * 4 + 128) + 2 * ((size_t)4 * PS * vw * 4);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = kernel_smem_optin(kern, smem);
     if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "warp_bwd(band): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
     const int threads = round_up(W / 4, 32);
     // rows per band: one wave of co-resident blocks over the whole batch (halo cost 2 / R rows per band)
     int R = env_int_lean("DSSMD_WARP_BWD_BAND_ROWS", 0);
     if (R <= 0) {
-        int occ = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
-        if (e != cudaSuccess || occ < 1) occ = 1;
+        const int occ = kernel_occupancy(kern, threads, smem);
         // A band costs R + 1 row passes (one halo row) and the grid runs in ceil(blocks / slots) waves: take the R that minimises
         // waves * (R + 1).  (The rule "one wave" picked R = 32 at 384x1280 x16 -- 192 blocks on 148 one-block SMs, a second wave 30 %
         // full: 179 us; R = 24 gives 256 blocks in two full-ish waves of 25 passes.)

@@ -515,22 +515,9 @@ int launch_band2(const float *g, const float *img, const float *disp, float *g_i
     const int vw = C == 3 ? 4 : C;
     const size_t smem = 2 * (size_t)C * (4 * (PS + 6) * 4 + 128) + 2 * ((size_t)4 * PS * vw * 4);   // acc[2] | dvr[2]
     const int threads = round_up(W / 4, 32);
-    // per (kernel, device): the opt-in shared-memory size and the occupancy it leaves are properties of the kernel, asked once
-    struct Cfg { int occ; };
-    static thread_local Cfg cache[4][8];   // [C - 1][device] of this instantiation (PS, BORDER, OCC3)
-    static thread_local int cache_threads[4][8];
-    int dev = 0;
-    cudaGetDevice(&dev);
-    int occ = 0;
-    if (dev < 8 && cache[C - 1][dev].occ > 0 && cache_threads[C - 1][dev] == threads) {
-        occ = cache[C - 1][dev].occ;
-    } else {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "warp_bwd(band2): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
-        if (e != cudaSuccess || occ < 1) occ = 1;
-        if (dev < 8) { cache[C - 1][dev].occ = occ; cache_threads[C - 1][dev] = threads; }
-    }
+    cudaError_t e = kernel_smem_optin(kern, smem);   // asked once per (kernel, device), then a table lookup (abi.cu)
+    if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "warp_bwd(band2): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+    const int occ = kernel_occupancy(kern, threads, smem);
     int R = env_int_lean("DSSMD_WARP_BWD_BAND_ROWS", 0);
     if (R <= 0) {
         // a band costs R + 1 row passes (one halo row) and the grid runs in ceil(blocks / slots) waves: the R that minimises
@@ -546,8 +533,8 @@ int launch_band2(const float *g, const float *img, const float *disp, float *g_i
     }
     if (R > kMaxBandRows2) R = kMaxBandRows2;
     if (R > H) R = H;
-    cudaError_t e = launch_pdl(kern, dim3((unsigned)ceil_div(H, R), (unsigned)B), dim3((unsigned)threads), smem, s, g, img, disp, g_img, g_disp, H, W, R,
-                               (float)W / 2.0f, 2.0f / (float)(W - 1), (float)H / 2.0f);
+    e = launch_pdl(kern, dim3((unsigned)ceil_div(H, R), (unsigned)B), dim3((unsigned)threads), smem, s, g, img, disp, g_img, g_disp, H, W, R,
+                   (float)W / 2.0f, 2.0f / (float)(W - 1), (float)H / 2.0f);
     if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "warp_bwd(band2): launch failed: %s", cudaGetErrorString(e));
     return check_launch("warp_bwd(band2)");
 }

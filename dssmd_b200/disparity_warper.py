@@ -12,7 +12,7 @@ import re
 import numpy as np
 import torch
 
-from .functional import DispWarpFn, LRWarpErrorFn
+from .functional import DispWarpFn, lrwarp_error
 
 __all__ = ["read_pfm", "normalize_coords", "meshgrid", "disp_warp", "LRwarp_error"]
 
@@ -78,4 +78,4 @@ def disp_warp(img, disp, padding_mode='border'):
 
 def LRwarp_error(imgL, disp, imgR):
     """imgR - warp(imgL, disp), both images first resized to disp's size when wider (upstream :109-115)."""
-    return LRWarpErrorFn.apply(imgL, disp, imgR)
+    return lrwarp_error(imgL, disp, imgR)

@@ -3,19 +3,28 @@ torch (so the caching allocator and autograd see them), pick the device/stream
 of the input tensors, call the kernel, map errors."""
 from __future__ import annotations
 
+import os
+import threading
+
 import torch
 
 from . import _lib
 
-_CHECK_NEGATIVE = True
+_CHECK_NEGATIVE = True      # True: upstream's behaviour (raise at the call); "deferred": raise at a later call; False: no check
 
 
-def set_check_negative_disparity(flag: bool) -> None:
-    """Upstream's `assert disp.min() >= 0` costs a device->host sync per warp.
-    The check is on by default (same behaviour); callers who guarantee
-    non-negative disparities can turn the read-back off."""
+def set_check_negative_disparity(flag) -> None:
+    """Upstream's `assert disp.min() >= 0` (utils/disparity_warper.py:93) costs a device->host sync per warp.
+
+    True (default)  same behaviour: the call waits for its kernel and raises AssertionError itself.
+    "deferred"      no host wait inside the call: the kernel's verdict is read at a LATER disp_warp / LRwarp_error /
+                    photometric call on the same device and thread (or by check_negative_disparity_now()), and the
+                    AssertionError is raised there, naming how many calls ago the violation happened.
+    False           no check (callers who guarantee non-negative disparities)."""
     global _CHECK_NEGATIVE
-    _CHECK_NEGATIVE = bool(flag)
+    if flag not in (True, False, "deferred"):
+        raise ValueError("set_check_negative_disparity: expected True, False or 'deferred'")
+    _CHECK_NEGATIVE = flag
 
 
 def _check4(name, t):
@@ -39,7 +48,7 @@ class CorrelationFn(torch.autograd.Function):
         L, R = left.contiguous(), right.contiguous()
         out = torch.empty((B, max(D, 0), H, W), dtype=L.dtype, device=L.device)
         if out.numel() > 0 and C > 0:
-            with torch.cuda.device(L.device):
+            with _lib.device_guard(L.device):
                 _lib.check(_lib.lib().dssmd_corr_fwd(_lib.ptr(L), _lib.ptr(R), _lib.ptr(out), B, C, H, W, D,
                                                      _lib.dtype_code(L), _lib.stream_ptr(L.device)))
         elif out.numel() > 0:
@@ -62,7 +71,7 @@ class CorrelationFn(torch.autograd.Function):
                         t.zero_()
             else:
                 g = g.contiguous()
-                with torch.cuda.device(L.device):
+                with _lib.device_guard(L.device):
                     _lib.check(_lib.lib().dssmd_corr_bwd(_lib.ptr(g), _lib.ptr(L), _lib.ptr(R), _lib.ptr(gL), _lib.ptr(gR),
                                                          B, C, H, W, ctx.D, _lib.dtype_code(L), _lib.stream_ptr(L.device)))
         return gL, gR, None
@@ -92,7 +101,7 @@ class CorrelationCatFn(torch.autograd.Function):
         out = torch.empty((B, Ch + D, H, W), dtype=L.dtype, device=L.device)
         out[:, :Ch].copy_(head)
         if D > 0 and out.numel() > 0 and C > 0:
-            with torch.cuda.device(L.device):
+            with _lib.device_guard(L.device):
                 _lib.check(_lib.lib().dssmd_corr_fwd_cat(_lib.ptr(L), _lib.ptr(R), _lib.ptr(out), B, C, H, W, D, Ch + D, Ch,
                                                          _lib.dtype_code(L), _lib.stream_ptr(L.device)))
         elif D > 0 and out.numel() > 0:
@@ -117,7 +126,7 @@ class CorrelationCatFn(torch.autograd.Function):
                     if t is not None:
                         t.zero_()
             else:
-                with torch.cuda.device(L.device):
+                with _lib.device_guard(L.device):
                     _lib.check(_lib.lib().dssmd_corr_bwd_cat(_lib.ptr(g), _lib.ptr(L), _lib.ptr(R), _lib.ptr(gL), _lib.ptr(gR),
                                                              B, C, H, W, D, Ch + D, Ch, _lib.dtype_code(L), _lib.stream_ptr(L.device)))
         return g_head, gL, gR, None
@@ -146,33 +155,112 @@ def _check_warp_args(name, img, disp):
                                   "upstream's own 16-bit path is numerically meaningless at image widths)")
 
 
+def _band_eligible(B, C, H, W, tensors):
+    """Shapes the one-pass band kernel of dssmd_warp_bwd takes (csrc/warp_bwd_band2.cu: image-like channel counts, rows of
+    whole float4s, 16-byte aligned tensors): it needs no workspace, so none is allocated."""
+    if os.environ.get("DSSMD_TUNING") and int(os.environ.get("DSSMD_WARP_BWD_VARIANT") or 7) < 6:
+        return False   # a development override forces one of the paths that want the workspace
+    return (1 <= C <= 4 and W % 4 == 0 and 4 <= W <= 2048 and H >= 2 and B <= 65535 and C * H * W < 2 ** 31
+            and all(t is None or t.data_ptr() % 16 == 0 for t in tensors))
+
+
 def _warp_bwd(g, I, Dp, g_img, g_disp, pad):
-    """dssmd_warp_bwd with the scratch buffer the fast two-kernel path wants."""
+    """dssmd_warp_bwd; the scratch buffer only for the shapes whose fallback (two-kernel) path wants one."""
     B, C, H, W = I.shape
     lib = _lib.lib()
     code = _lib.dtype_code(I)
-    nbytes = int(lib.dssmd_warp_bwd_workspace_bytes(B, C, H, W, code)) if g_img is not None else 0
+    nbytes = 0
+    if g_img is not None and not (I.dtype == torch.float32 and _band_eligible(B, C, H, W, (g, I, Dp, g_img, g_disp))):
+        nbytes = int(lib.dssmd_warp_bwd_workspace_bytes(B, C, H, W, code))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=I.device) if nbytes else None
-    with torch.cuda.device(I.device):
+    with _lib.device_guard(I.device):
         _lib.check(lib.dssmd_warp_bwd(_lib.ptr(g), _lib.ptr(I), _lib.ptr(Dp), _lib.ptr(g_img), _lib.ptr(g_disp),
                                       _lib.ptr(ws), nbytes, B, C, H, W, pad, code, _lib.stream_ptr(I.device)))
 
 
-def _new_flag():
-    """One int32 in pinned host memory, which the GPU can write directly (unified addressing):
-    reading it back needs an event wait on the launch stream, not a device->host copy that
-    would queue behind whatever the copy engine is already moving."""
-    return torch.zeros(1, dtype=torch.int32).pin_memory() if _CHECK_NEGATIVE else None
+# ---- the disp >= 0 check (upstream utils/disparity_warper.py:93) -------------------------------------------------------
+# The kernel sets a flag in PINNED HOST memory with a plain store (unified addressing), so reading it needs an event wait on
+# the launch stream, not a device->host copy that would queue behind whatever the copy engine is moving.  One flag ring and
+# one event per (thread, device): nothing is allocated on the per-call path.
+_RING = 64
+_tls = threading.local()
 
 
-def _raise_if_flag(flag, device):
-    if flag is None:
+class _FlagState:
+    def __init__(self):
+        self.flags = torch.zeros(_RING, dtype=torch.int32).pin_memory()
+        self.base = self.flags.data_ptr()
+        self.event = torch.cuda.Event()
+        self.pending = []       # deferred mode: (slot, event, serial)
+        self.serial = 0
+        self.free_events = []
+
+
+def _flag_state(device):
+    states = getattr(_tls, "states", None)
+    if states is None:
+        states = _tls.states = {}
+    st = states.get(device.index)
+    if st is None:
+        st = states[device.index] = _FlagState()
+    return st
+
+
+def _drain(st, wait):
+    """Deferred mode: read the verdicts of the earlier calls whose kernels have finished (all of them if `wait`)."""
+    bad = None
+    while st.pending:
+        slot, ev, serial = st.pending[0]
+        if wait:
+            ev.synchronize()
+        elif not ev.query():
+            break
+        st.pending.pop(0)
+        st.free_events.append(ev)
+        if int(st.flags[slot]) != 0 and bad is None:
+            bad = serial
+    if bad is not None:
+        ago = st.serial - bad
+        st.pending.clear()
+        raise AssertionError(f"disp.min() >= 0  (deferred check: violated by the warp call {ago} call(s) ago)")
+
+
+def check_negative_disparity_now(device=None) -> None:
+    """Deferred mode: wait for the outstanding warp kernels of this thread and raise if any saw a negative / NaN disparity."""
+    states = getattr(_tls, "states", None) or {}
+    for idx, st in states.items():
+        if device is None or torch.device(device).index == idx:
+            _drain(st, wait=True)
+
+
+def _new_flag(device):
+    """-> (device-visible address of this call's flag or None, token for _raise_if_flag)."""
+    if _CHECK_NEGATIVE is False or torch.cuda.is_current_stream_capturing():
+        return None, None    # a graph replay cannot be interrupted by a host-side read-back: no check while capturing
+    st = _flag_state(device)
+    if _CHECK_NEGATIVE is True:
+        st.flags[0] = 0
+        return st.base, (st, 0)
+    _drain(st, wait=len(st.pending) >= _RING - 1)
+    st.serial += 1
+    slot = 1 + st.serial % (_RING - 1)
+    st.flags[slot] = 0
+    return st.base + 4 * slot, (st, slot)
+
+
+def _raise_if_flag(token, device):
+    if token is None:
         return
-    ev = torch.cuda.Event()
+    st, slot = token
+    if slot == 0:   # upstream's behaviour: wait for the kernel, raise here
+        st.event.record(torch.cuda.current_stream(device))
+        st.event.synchronize()
+        if int(st.flags[0]) != 0:
+            raise AssertionError("disp.min() >= 0")  # upstream utils/disparity_warper.py:93
+        return
+    ev = st.free_events.pop() if st.free_events else torch.cuda.Event()
     ev.record(torch.cuda.current_stream(device))
-    ev.synchronize()
-    if int(flag[0]) != 0:
-        raise AssertionError("disp.min() >= 0")  # upstream utils/disparity_warper.py:93
+    st.pending.append((slot, ev, st.serial))
 
 
 class DispWarpFn(torch.autograd.Function):
@@ -187,11 +275,11 @@ class DispWarpFn(torch.autograd.Function):
         warped = torch.empty_like(I)
         mask = torch.empty_like(I)
         if I.numel() > 0:
-            flag = _new_flag()
-            with torch.cuda.device(I.device):
-                _lib.check(_lib.lib().dssmd_warp_fwd(_lib.ptr(I), _lib.ptr(Dp), _lib.ptr(warped), _lib.ptr(mask), _lib.ptr(flag),
+            flag, token = _new_flag(I.device)
+            with _lib.device_guard(I.device):
+                _lib.check(_lib.lib().dssmd_warp_fwd(_lib.ptr(I), _lib.ptr(Dp), _lib.ptr(warped), _lib.ptr(mask), flag,
                                                      B, C, H, W, pad, _lib.dtype_code(I), _lib.stream_ptr(I.device)))
-            _raise_if_flag(flag, I.device)
+            _raise_if_flag(token, I.device)
         ctx.save_for_backward(I, Dp)
         ctx.pad = pad
         ctx.mark_non_differentiable(mask)
@@ -216,7 +304,7 @@ def resize_bilinear(img, size):
     Ho, Wo = int(size[0]), int(size[1])
     src = img.contiguous()
     out = torch.empty((B, C, Ho, Wo), dtype=img.dtype, device=img.device)
-    with torch.cuda.device(img.device):
+    with _lib.device_guard(img.device):
         _lib.check(_lib.lib().dssmd_resize_bilinear_fwd(_lib.ptr(src), _lib.ptr(out), B, C, Hi, Wi, Ho, Wo,
                                                         _lib.dtype_code(src), _lib.stream_ptr(img.device)))
     return out
@@ -227,10 +315,40 @@ def _resize_bilinear_bwd(g_out, in_size):
     Hi, Wi = in_size
     g = g_out.contiguous()
     g_in = torch.empty((B, C, Hi, Wi), dtype=g.dtype, device=g.device)
-    with torch.cuda.device(g.device):
+    with _lib.device_guard(g.device):
         _lib.check(_lib.lib().dssmd_resize_bilinear_bwd(_lib.ptr(g), _lib.ptr(g_in), B, C, Hi, Wi, Ho, Wo,
                                                         _lib.dtype_code(g), _lib.stream_ptr(g.device)))
     return g_in
+
+
+class ResizeBilinearFn(torch.autograd.Function):
+    """F.interpolate(img, size=size, mode='bilinear', align_corners=False) with its backward (the two kernels of the fused
+    LRwarp_error path, usable on their own)."""
+
+    @staticmethod
+    def forward(ctx, img, size):
+        ctx.in_size = tuple(img.shape[-2:])
+        return resize_bilinear(img, size)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _resize_bilinear_bwd(g, ctx.in_size), None
+
+
+def lrwarp_error(imgL, disp, imgR):
+    """Upstream LRwarp_error (utils/disparity_warper.py:109-115).  Each image that is WIDER than `disp` is resized to
+    disp's size on its own (:110-113), so the two images need not have the same shape; when they do, one fused launch."""
+    if isinstance(imgL, torch.Tensor) and isinstance(imgR, torch.Tensor) and imgL.dim() == 4 and imgR.dim() == 4 \
+            and imgL.shape != imgR.shape and isinstance(disp, torch.Tensor) and disp.dim() == 4:
+        _lib.require_cuda("LRwarp_error", imgL, disp, imgR)
+        size = tuple(disp.shape[-2:])
+        if imgL.size(-1) > disp.size(-1):
+            imgL = ResizeBilinearFn.apply(imgL, size)
+        if imgR.size(-1) > disp.size(-1):
+            imgR = ResizeBilinearFn.apply(imgR, size)
+        warped, _ = DispWarpFn.apply(imgL, disp, 'border')
+        return imgR - warped
+    return LRWarpErrorFn.apply(imgL, disp, imgR)
 
 
 class LRWarpErrorFn(torch.autograd.Function):
@@ -256,11 +374,11 @@ class LRWarpErrorFn(torch.autograd.Function):
         Lc, Rc, Dc = imgL.contiguous(), imgR.contiguous(), disp.contiguous()
         out = torch.empty((B, C, H, W), dtype=Lc.dtype, device=Lc.device)
         if out.numel() > 0:
-            flag = _new_flag()
-            with torch.cuda.device(Lc.device):
-                _lib.check(_lib.lib().dssmd_lrwarp_error_fwd(_lib.ptr(Lc), _lib.ptr(Dc), _lib.ptr(Rc), _lib.ptr(out), _lib.ptr(flag),
+            flag, token = _new_flag(Lc.device)
+            with _lib.device_guard(Lc.device):
+                _lib.check(_lib.lib().dssmd_lrwarp_error_fwd(_lib.ptr(Lc), _lib.ptr(Dc), _lib.ptr(Rc), _lib.ptr(out), flag,
                                                              B, C, H0, W0, H, W, _lib.dtype_code(Lc), _lib.stream_ptr(Lc.device)))
-            _raise_if_flag(flag, Lc.device)
+            _raise_if_flag(token, Lc.device)
         ctx.save_for_backward(Lc, Dc)
         ctx.in_size = (H0, W0)
         return out

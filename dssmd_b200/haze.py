@@ -107,7 +107,7 @@ def _launch(name, clear, src, src_is_disp, baseline, focal, beta, airlight, want
     trans = torch.empty((b, cs, h, w), dtype=cdt, device=dev) if want_trans else None
     depth = torch.empty((b, cs, h, w), dtype=cdt, device=dev) if want_depth else None
     if src.numel() > 0:
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib.check(_lib.lib().dssmd_haze_fwd(
                 _lib.ptr(clearc), _lib.ptr(srcc), 1 if src_is_disp else 0, _lib.ptr(sc["baseline"]), _lib.ptr(sc["focal"]),
                 _lib.ptr(sc["beta"]), _lib.ptr(sc["airlight"]), _lib.ptr(haze), _lib.ptr(trans), _lib.ptr(depth),

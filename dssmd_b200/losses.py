@@ -35,11 +35,11 @@ class _PhotometricL1Fn(torch.autograd.Function):
         rows = torch.empty(B * H, dtype=torch.float32, device=Lc.device)
         need_d = ctx.needs_input_grad[1]
         g_unit = torch.empty_like(Dc) if need_d else None
-        flag = _new_flag()
-        with torch.cuda.device(Lc.device):
+        flag, token = _new_flag(Lc.device)
+        with _lib.device_guard(Lc.device):
             _lib.check(_lib.lib().dssmd_photometric_l1_fwd(_lib.ptr(Lc), _lib.ptr(Rc), _lib.ptr(Dc), _lib.ptr(g_unit), _lib.ptr(rows),
-                                                           _lib.ptr(flag), B, C, H, W, _lib.dtype_code(Lc), _lib.stream_ptr(Lc.device)))
-        _raise_if_flag(flag, Lc.device)
+                                                           flag, B, C, H, W, _lib.dtype_code(Lc), _lib.stream_ptr(Lc.device)))
+        _raise_if_flag(token, Lc.device)
         n = float(B * C * H * W)
         ctx.n = n
         if need_d:
@@ -115,7 +115,7 @@ class _RecoveredCleanL1Fn(torch.autograd.Function):
         lib = _lib.lib()
         need_t = ctx.needs_input_grad[0]
         g_unit = torch.empty_like(T) if need_t else None
-        with torch.cuda.device(T.device):   # the block count depends on the SM count of the tensors' device
+        with _lib.device_guard(T.device):   # the block count depends on the SM count of the tensors' device
             nblk = int(lib.dssmd_asm_recovered_l1_blocks(B, h, w))
             partial = torch.empty((B, nblk, 2), dtype=torch.float32, device=T.device)
             _lib.check(lib.dssmd_asm_recovered_l1_fwd(_lib.ptr(T), _lib.ptr(A), _lib.ptr(Hz), _lib.ptr(Cl), _lib.ptr(g_unit),

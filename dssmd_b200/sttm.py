@@ -58,7 +58,7 @@ class EpipolarAttentionFn(torch.autograd.Function):
         need = any(ctx.needs_input_grad[:3])
         lse = torch.empty((B * H, W), dtype=torch.float32, device=Q.device) if need else None
         if Q.numel() > 0:
-            with torch.cuda.device(Q.device):
+            with _lib.device_guard(Q.device):
                 _lib.check(_lib.lib().dssmd_epipolar_attn_fwd(_lib.ptr(Q), _lib.ptr(K), _lib.ptr(V), _lib.ptr(out), _lib.ptr(lse),
                                                               B, C, H, W, float(scale), _lib.dtype_code(Q), _lib.stream_ptr(Q.device)))
         if need:
@@ -77,7 +77,7 @@ class EpipolarAttentionFn(torch.autograd.Function):
         gv = torch.empty_like(V) if (need_k or need_v) else None
         if Q.numel() > 0 and (need_q or need_k or need_v):
             delta = torch.empty_like(lse)
-            with torch.cuda.device(Q.device):
+            with _lib.device_guard(Q.device):
                 _lib.check(_lib.lib().dssmd_epipolar_attn_bwd(_lib.ptr(Q), _lib.ptr(K), _lib.ptr(V), _lib.ptr(out), _lib.ptr(g), _lib.ptr(lse),
                                                               _lib.ptr(delta), _lib.ptr(gq), _lib.ptr(gk), _lib.ptr(gv), B, C, H, W, ctx.scale,
                                                               _lib.dtype_code(Q), _lib.stream_ptr(Q.device)))

@@ -7,6 +7,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
+os.environ.setdefault("DSSMD_TUNING", "1")   # the sweep / debug variables are honoured only with it
 import torch  # noqa: E402
 
 import bench  # noqa: E402

@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# the DSSMD_* tuning variables the tests switch kernels with are honoured only with DSSMD_TUNING=1 (read once by the library)
+os.environ.setdefault("DSSMD_TUNING", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

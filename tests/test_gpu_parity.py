@@ -395,6 +395,70 @@ def test_warp_error_conventions(ops):
     assert not m.requires_grad and w.shape == img.shape and m.shape == img.shape
 
 
+def test_negative_disparity_check_modes(ops):
+    """True: upstream's behaviour (the call raises).  "deferred": no host wait in the call, a LATER call (or
+    check_negative_disparity_now) raises.  False: no check.  While a CUDA graph is being captured no read-back is
+    attempted (a replay could not be interrupted by it)."""
+    img = torch.rand(1, 3, 16, 64, device="cuda")
+    good = torch.rand(1, 1, 16, 64, device="cuda") * 5
+    bad = good.clone(); bad[0, 0, 3, 7] = -0.5
+    try:
+        ops.set_check_negative_disparity("deferred")
+        ops.disp_warp(img, good)
+        ops.disp_warp(img, bad)                      # does not raise here
+        torch.cuda.synchronize()
+        with pytest.raises(AssertionError, match="deferred"):
+            ops.disp_warp(img, good)                 # ... but at the next call
+        ops.disp_warp(img, bad)
+        with pytest.raises(AssertionError):
+            ops.check_negative_disparity_now()
+        ops.check_negative_disparity_now()           # nothing pending: silent
+        for _ in range(200):                         # the flag ring wraps without losing or inventing verdicts
+            ops.disp_warp(img, good)
+        ops.check_negative_disparity_now()
+        ops.set_check_negative_disparity(False)
+        ops.disp_warp(img, bad)
+        ops.set_check_negative_disparity(True)
+        with pytest.raises(AssertionError):
+            ops.disp_warp(img, bad)
+        # graph capture of the public API: no flag, no host sync inside the captured region
+        w_ref, m_ref = ops.disp_warp(img, good)
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            ops.disp_warp(img, good)
+            with torch.cuda.graph(g):
+                w, m = ops.disp_warp(img, good)
+        torch.cuda.current_stream().wait_stream(s)
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(w, w_ref) and torch.equal(m, m_ref)
+        with pytest.raises(ValueError):
+            ops.set_check_negative_disparity("later")
+    finally:
+        ops.set_check_negative_disparity(True)
+
+
+def test_lrwarp_error_resizes_each_image_on_its_own(ops):
+    """Upstream resizes imgL and imgR independently against disp (utils/disparity_warper.py:110-113): the two images need
+    not have the same size."""
+    _, disp = images(2, 3, 40, 80, 27)
+    imgL, _ = images(2, 3, 80, 160, 25)      # wider than disp: resized
+    imgR, _ = images(2, 3, 40, 80, 26)       # already at disp's size: used as it is
+    L = imgL.clone().requires_grad_(True); R = imgR.clone().requires_grad_(True); d = disp.clone().requires_grad_(True)
+    err = ops.LRwarp_error(L, d, R)
+    Lr = imgL.clone().requires_grad_(True); Rr = imgR.clone().requires_grad_(True); dr = disp.clone().requires_grad_(True)
+    ref = ref_torch.lrwarp_ref(Lr, dr, Rr)
+    assert err.shape == ref.shape == (2, 3, 40, 80)
+    assert rel_err(err.detach().cpu().numpy(), ref.detach().cpu().numpy()) <= TOL_F32
+    g = feat((2, 3, 40, 80), 28, False)
+    err.backward(g); ref.backward(g)
+    assert rel_err(L.grad.cpu().numpy(), Lr.grad.cpu().numpy()) <= TOL_F32
+    assert rel_err(R.grad.cpu().numpy(), Rr.grad.cpu().numpy()) <= TOL_F32
+    assert rel_err(d.grad.cpu().numpy(), dr.grad.cpu().numpy()) <= TOL_F32
+
+
 # ---------------------------------------------------------------- LRwarp_error
 @pytest.mark.parametrize("name", sorted(LRW))
 def test_lrwarp_golden(ops, name):
@@ -551,7 +615,9 @@ def test_warp_bwd_band_matches_two_kernel_path(ops, monkeypatch):
     i3 = img.clone().requires_grad_(True); d3 = disp.clone().requires_grad_(True)
     w, _ = ops.disp_warp(i3, d3)
     w.backward(g)
-    assert torch.equal(i3.grad, outs[0][0]) and torch.equal(d3.grad, outs[0][1])
+    for name, a, b in (("g_img", i3.grad, outs[0][0]), ("g_disp", d3.grad, outs[0][1])):
+        bad = (a != b)
+        assert not bool(bad.any()), (name, int(bad.sum()), float((a - b).abs().max()), bad.nonzero()[:8].tolist())
 
 
 @pytest.mark.parametrize("pad", ["border", "zeros"])
@@ -911,6 +977,38 @@ def test_recovered_clean_loss_errors(ops):
         ops.recovered_clean_l1(t.double(), A.double(), img.double(), img.double())
     with pytest.raises(UnboundLocalError):
         ops.RecoveredCleanImagesLoss(type="other")(t, A, img, img)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (run with gpurun --gpus 2)")
+def test_data_parallel_two_gpus_matches_one(ops):
+    """Upstream's live parallel mode is nn.DataParallel (trainfiles/dssmd_traner_new.py:131-135): one Python thread per GPU
+    calls the ops concurrently, each on its own device and stream.  Forward and backward of a module built on build_corr +
+    disp_warp must give the same numbers split over two GPUs as on one."""
+    import torch.nn as nn
+
+    class Path(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.scale = nn.Parameter(torch.tensor(1.5))
+
+        def forward(self, L, R, img, disp):
+            vol = ops.build_corr(L * self.scale, R, 24)
+            warped, mask = ops.disp_warp(img, disp)
+            return vol.mean((1, 2, 3)) + (warped * mask).mean((1, 2, 3))
+
+    B = 4
+    L, R = feat((B, 128, 16, 120), 101), feat((B, 128, 16, 120), 102)
+    img, disp = images(B, 3, 64, 256, 103)
+    outs = []
+    for ids in ([0], [0, 1]):
+        m = nn.DataParallel(Path().cuda(0), device_ids=ids)
+        Lg, Rg = L.clone().requires_grad_(True), R.clone().requires_grad_(True)
+        ig, dg = img.clone().requires_grad_(True), disp.clone().requires_grad_(True)
+        y = m(Lg, Rg, ig, dg)
+        y.sum().backward()
+        outs.append([t.detach().cpu().numpy() for t in (y, Lg.grad, Rg.grad, ig.grad, dg.grad, m.module.scale.grad)])
+    for a, b in zip(*outs):
+        assert rel_err(a, b) <= TOL_F32
 
 
 def test_fast_paths_are_taken_from_fresh_threads():
