@@ -533,6 +533,9 @@ int launch_band2(const float *g, const float *img, const float *disp, float *g_i
     }
     if (R > kMaxBandRows2) R = kMaxBandRows2;
     if (R > H) R = H;
+    if (env_int_lean("DSSMD_CORR_DEBUG", 0))
+        fprintf(stderr, "warp_bwd band2 cfg: PS=%d border=%d occ3=%d R=%d grid=(%d,%d) (x%d/SM) threads=%d smem=%zu\n", PS, (int)BORDER, (int)OCC3, R,
+                ceil_div(H, R), B, occ, threads, smem);
     e = launch_pdl(kern, dim3((unsigned)ceil_div(H, R), (unsigned)B), dim3((unsigned)threads), smem, s, g, img, disp, g_img, g_disp, H, W, R,
                    (float)W / 2.0f, 2.0f / (float)(W - 1), (float)H / 2.0f);
     if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "warp_bwd(band2): launch failed: %s", cudaGetErrorString(e));

@@ -541,6 +541,7 @@ int warp_fwd_lean_f32(const float *img, const float *disp, float *out, float *ma
     if (!eligible(B, C, H, W) || env_int_lean("DSSMD_WARP_LEAN", 1) == 0) return -1;
     if (((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(disp) | reinterpret_cast<uintptr_t>(out) |
           reinterpret_cast<uintptr_t>(mask)) & 15) != 0) return -1;
+    if (env_int_lean("DSSMD_CORR_DEBUG", 0)) fprintf(stderr, "warp_fwd lean cfg: C=%d H=%d W=%d border=%d\n", C, H, W, border);
     DSSMD_LEAN_PICK(launch_fwd, img, disp, out, mask, neg_flag, B, C, H, W, s);
 }
 

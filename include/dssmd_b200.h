@@ -106,9 +106,15 @@ DSSMD_API int dssmd_warp_fwd(const void *img, const void *disp, void *warped, vo
  * coordinate arithmetic of :95-99); the mask carries no gradient.
  * g: [B,C,H,W] gradient of `warped`; g_img: [B,C,H,W]; g_disp: [B,1,H,W]; both
  * fully overwritten, either may be NULL to skip it.
+ * Image-like fp32 shapes (C <= 4, W % 4 == 0, 4 <= W <= 2048, H >= 2, every pointer
+ * 16-byte aligned) take a one-pass kernel that needs NO workspace: pass NULL / 0.
  * `workspace` is an optional caller-owned device scratch buffer of at least
- * dssmd_warp_bwd_workspace_bytes(...) bytes (contents undefined afterwards); with
- * it the fast two-kernel path runs, with NULL a slower single-kernel path. */
+ * dssmd_warp_bwd_workspace_bytes(...) bytes (contents undefined afterwards) for the
+ * other fp32 shapes (wider rows): with it a two-kernel path runs (horizontal scatter
+ * into the workspace, vertical mix), without it a slower generic kernel.
+ * Accuracy of g_img: per row a 2^-30 fixed-point quantum of the row's sum of |g|
+ * (deterministic); rows with an outlier, unbalanced channels or non-finite values
+ * take exact / fp32 paths. */
 #include <stddef.h>
 DSSMD_API size_t dssmd_warp_bwd_workspace_bytes(int B, int C, int H, int W, int dtype);
 DSSMD_API int dssmd_warp_bwd(const void *g, const void *img, const void *disp, void *g_img, void *g_disp,

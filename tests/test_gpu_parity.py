@@ -1011,6 +1011,57 @@ def test_data_parallel_two_gpus_matches_one(ops):
         assert rel_err(a, b) <= TOL_F32
 
 
+def test_default_dispatch_of_the_baseline_configs():
+    """Which kernel each BASELINE.json config takes BY DEFAULT is part of the measured result (the dispatcher's rules were set
+    by measurement): a heuristic regression must fail here, not only show up as a slower bench.  DSSMD_CORR_DEBUG prints the
+    configuration of every launch; run in a subprocess with no variant override."""
+    import os
+    import subprocess
+    import sys
+    from helpers import ROOT
+    code = r'''
+import sys
+sys.path.insert(0, %r)
+import torch, dssmd_b200
+def corr(tag, B, C, H, W, D):
+    print("##", tag, file=sys.stderr, flush=True)
+    L = torch.randn(B, C, H, W, device="cuda").relu().requires_grad_(True)
+    R = torch.randn(B, C, H, W, device="cuda").relu().requires_grad_(True)
+    dssmd_b200.build_corr(L, R, D).sum().backward()
+    torch.cuda.synchronize()
+def warp(tag, B, H, W):
+    print("##", tag, file=sys.stderr, flush=True)
+    img = torch.rand(B, 3, H, W, device="cuda", requires_grad=True)
+    disp = (torch.rand(B, 1, H, W, device="cuda") * 20).requires_grad_(True)
+    dssmd_b200.disp_warp(img, disp)[0].sum().backward()
+    torch.cuda.synchronize()
+corr("cfg5", 4, 128, 72, 120, 24); warp("cfg5w", 4, 576, 960)
+corr("cfg2", 8, 256, 80, 160, 41)
+corr("cfg3", 8, 128, 40, 80, 24); warp("cfg3w", 8, 320, 640)
+corr("cfg4", 16, 128, 48, 160, 24); warp("cfg4w", 2, 384, 1280)
+print("done")
+''' % ROOT
+    env = {k: v for k, v in os.environ.items() if not k.startswith("DSSMD_")}
+    env.update(DSSMD_TUNING="1", DSSMD_CORR_DEBUG="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "done" in r.stdout, r.stderr[-3000:]
+    sec, cur = {}, None
+    for line in r.stderr.splitlines():
+        if line.startswith("## "):
+            cur = line[3:].strip(); sec[cur] = []
+        elif cur and " cfg:" in line:
+            sec[cur].append(line.split(" cfg:")[0].strip())
+    assert "not eligible" not in r.stderr, r.stderr[-3000:]
+    # the model shape of the headline config: register-blocked TMA forward, ONE fused backward launch
+    assert sec["cfg5"] == ["corr_fwd reg", "corr_bwd fused"], sec
+    # C256 80x160 D41, 320x640 and KITTI feature maps: the fp32 mma.sync (3xTF32) kernels, one launch per gradient
+    for k in ("cfg2", "cfg3", "cfg4"):
+        assert sec[k] == ["corr_fwd mma32", "corr_bwd mma32", "corr_bwd mma32"], (k, sec)
+    # image-sized warps: lean forward, one-pass band backward (rewritten kernel)
+    for k in ("cfg5w", "cfg3w", "cfg4w"):
+        assert sec[k] == ["warp_fwd lean", "warp_bwd band2"], (k, sec)
+
+
 def test_fast_paths_are_taken_from_fresh_threads():
     """The TMA-staged kernels need tensor maps, and the driver's encoder needs a current context in the calling thread.
     An autograd worker on its first backward and every nn.DataParallel replica thread (trainfiles/dssmd_traner_new.py:131-135)
