@@ -29,6 +29,8 @@ namespace dssmd {
 int corr_fwd_umma_f32(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, long long obs, cudaStream_t stream);
 // register-blocked, TMA-staged FFMA path (corr_fwd_reg.cu), fp32 / bf16 / fp16; -1 when the shape is not eligible
 int corr_fwd_reg(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, long long obs, int dtype, cudaStream_t stream);
+// second tcgen05 design (corr_fwd_umma2.cu): row-aligned tiles, deep raw ring; -1 when the shape is outside its limits
+int corr_fwd_umma2_f32(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, long long obs, cudaStream_t stream);
 // fp32 on mma.sync with 3xTF32 splitting (corr_fwd_mma32.cu); -1 when the shape is outside its limits
 int corr_fwd_mma32(const void *L, const void *R, void *out, int B, int C, int H, int W, int D, long long obs, cudaStream_t stream);
 // tensor-core path for 16-bit tensors (corr_fwd_mma16.cu); -1 when the shape is outside its limits
@@ -604,6 +606,12 @@ int launch_typed(const void *L, const void *R, void *out, int B, int C, int H, i
         // 16-bit tensors: mma.sync on the banded row GEMM unless a variant is forced
         if (variant < 0) {
             const int rc = corr_fwd_mma16(L, R, out, B, C, H, W, D, obs, std::is_same<T, __nv_bfloat16>::value ? DSSMD_BF16 : DSSMD_F16, stream);
+            if (rc >= 0) return rc;
+        }
+    }
+    if constexpr (sizeof(T) == 4) {
+        if (variant == 4) {   // second tcgen05 design, forced
+            const int rc = corr_fwd_umma2_f32(L, R, out, B, C, H, W, D, obs, stream);
             if (rc >= 0) return rc;
         }
     }

@@ -1,6 +1,7 @@
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("DSSMD_TUNING", "1")
 import torch, dssmd_b200
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 def timeit(fn, reps=20):

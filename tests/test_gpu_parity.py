@@ -181,6 +181,36 @@ def test_corr_fwd_tensor_core_variant(ops, oracle, shape, monkeypatch, capfd):
         assert torch.count_nonzero(tc[:, d, :, :d]) == 0
 
 
+UMMA2_SHAPES = [
+    # B, C, H, W, D, relu
+    (2, 64, 6, 120, 24, True),      # model row (cfg5): one tile, 120 valid pixels, N = 144
+    (2, 64, 5, 160, 41, True),      # cfg2 row: a full tile (N = 176) and a 32-pixel tail tile (N = 80)
+    (1, 64, 3, 160, 24, False),     # KITTI row, zero-mean features (cancellation)
+    (1, 32, 4, 320, 58, True),      # three tiles per row, the largest D the epilogue window takes
+    (1, 48, 7, 36, 2, True),        # a single short tile, D = 2
+    (3, 128, 9, 132, 33, False),    # a 4-pixel tail tile; more tiles than one wave of stages
+]
+
+
+@pytest.mark.parametrize("n32", ["0", "1"])
+@pytest.mark.parametrize("shape", UMMA2_SHAPES, ids=lambda s: "x".join(map(str, s[:5])))
+def test_corr_fwd_tcgen05_row_tiles(ops, oracle, shape, n32, monkeypatch, capfd):
+    """DSSMD_CORR_FWD_VARIANT=4: the second tcgen05 design (row-aligned tiles, raw ring + lo ring, truncation split)."""
+    B, C, H, W, D, relu = shape
+    L = feat((B, C, H, W), 23, relu)
+    R = feat((B, C, H, W), 24, relu)
+    monkeypatch.setenv("DSSMD_CORR_FWD_VARIANT", "4")
+    monkeypatch.setenv("DSSMD_UMMA2_N32", n32)
+    monkeypatch.setenv("DSSMD_CORR_DEBUG", "1")
+    tc = ops.build_corr(L, R, D)
+    torch.cuda.synchronize()
+    assert "corr_fwd umma2 cfg" in capfd.readouterr().err, "shape fell back"
+    ref64 = oracle.corr_fwd(L.cpu().numpy().astype(np.float64), R.cpu().numpy().astype(np.float64), D)
+    assert rel_err(tc.cpu().numpy(), ref64) <= TOL_F32
+    for d in range(min(D, W)):                       # exact structural zeros
+        assert torch.count_nonzero(tc[:, d, :, :d]) == 0
+
+
 def test_corr_f64_and_gradcheck(ops):
     L = feat((1, 5, 3, 9), 1, False, torch.float64).requires_grad_(True)
     R = feat((1, 5, 3, 9), 2, False, torch.float64).requires_grad_(True)
