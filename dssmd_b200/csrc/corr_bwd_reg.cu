@@ -306,7 +306,11 @@ int corr_bwd_reg_typed(const void *g, const void *in, void *out, int mode, int B
     // two stages of (operand tile + g tile) must leave room for two resident blocks
     {
         const size_t gbytes = (size_t)D * p.GW * ES + 128, rowb = (size_t)p.WP * ES;
-        const size_t budget = (size_t)env_int_reg("DSSMD_CORR_BWD_SMEM_KB2", 100) * 1024 / 2;
+        size_t budget = (size_t)env_int_reg("DSSMD_CORR_BWD_SMEM_KB2", 100) * 1024 / 2;
+        // large D (the max_disp stress sweep: D = 96 on the 1/8 feature map): the g tile alone outgrows half an SM -- one
+        // resident block with the whole budget is still far ahead of the generic kernel (D-sweep, profiles/r02j_measure.json:
+        // 131 / 156 us per gradient at D = 96 there)
+        if (gbytes + rowb * cgw > budget) budget = (size_t)99 * 1024;
         if (gbytes + rowb * cgw > budget) return reg_reject(6);
         while (cb > cgw && gbytes + rowb * cb + 128 > budget) cb -= cgw;
     }
