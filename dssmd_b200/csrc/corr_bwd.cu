@@ -30,6 +30,9 @@ int corr_bwd_mma32(const void *g, const void *in, void *out, int mode, int B, in
 // corr_bwd_fused.cu: both gradients of an fp32 correlation in one launch; -1 = not eligible
 int corr_bwd_fused_f32(const void *g, const void *L, const void *R, void *gL, void *gR, int B, int C, int H, int W, int D, long long gbs,
                        cudaStream_t stream);
+// corr_bwd_wide.cu: the same for D <= 24 with a lane owning all disparities of its pixels; -1 = not eligible
+int corr_bwd_wide_f32(const void *g, const void *L, const void *R, void *gL, void *gR, int B, int C, int H, int W, int D, long long gbs,
+                       cudaStream_t stream);
 // corr_bwd_mma16.cu: 16-bit tensors on the tensor cores; -1 = shape not eligible
 int corr_bwd_mma16(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, long long gbs, int dtype, cudaStream_t stream);
 
@@ -418,7 +421,9 @@ int launch_typed(const void *g, const void *L, const void *R, void *gL, void *gR
         // both gradients wanted (the autograd case): one fused launch where the shape is eligible (corr_bwd_fused.cu).  A forced
         // per-gradient variant (DSSMD_CORR_BWD_VARIANT) keeps the two-launch path; DSSMD_CORR_BWD_FUSED=0 disables the fusion.
         if (gL && gR && env_int("DSSMD_CORR_BWD_VARIANT", -1) < 0) {
-            const int rc = corr_bwd_fused_f32(g, L, R, gL, gR, B, C, H, W, D, gbs, stream);
+            int rc = corr_bwd_wide_f32(g, L, R, gL, gR, B, C, H, W, D, gbs, stream);
+            if (rc >= 0) return rc;
+            rc = corr_bwd_fused_f32(g, L, R, gL, gR, B, C, H, W, D, gbs, stream);
             if (rc >= 0) return rc;
         }
     }

@@ -1082,10 +1082,12 @@ print("done")
         elif cur and " cfg:" in line:
             sec[cur].append(line.split(" cfg:")[0].strip())
     assert "not eligible" not in r.stderr, r.stderr[-3000:]
-    # the model shape of the headline config: register-blocked TMA forward, ONE fused backward launch
-    assert sec["cfg5"] == ["corr_fwd reg", "corr_bwd fused"], sec
-    # C256 80x160 D41, 320x640 and KITTI feature maps: the fp32 mma.sync (3xTF32) kernels, one launch per gradient
-    for k in ("cfg2", "cfg3", "cfg4"):
+    # the model shape of the headline config: register-blocked TMA forward, ONE backward launch for both gradients (the
+    # D <= 24 kernel with a lane owning all disparities of its pixels); 320x640 feature maps (W = 80): the same backward
+    assert sec["cfg5"] == ["corr_fwd reg", "corr_bwd wide"], sec
+    assert sec["cfg3"] == ["corr_fwd mma32", "corr_bwd wide"], sec
+    # C256 80x160 D41 and KITTI feature maps: the fp32 mma.sync (3xTF32) kernels, one launch per gradient
+    for k in ("cfg2", "cfg4"):
         assert sec[k] == ["corr_fwd mma32", "corr_bwd mma32", "corr_bwd mma32"], (k, sec)
     # image-sized warps: lean forward, one-pass band backward (rewritten kernel)
     for k in ("cfg5w", "cfg3w", "cfg4w"):
@@ -1123,7 +1125,7 @@ print("done")
     assert r.returncode == 0 and "done" in r.stdout, r.stderr[-2000:]
     assert "corr_fwd reg cfg" in r.stderr, r.stderr[-2000:]
     # one fused TMA-staged launch for both gradients, or a TMA-staged kernel each
-    assert (r.stderr.count("corr_bwd fused cfg") == 1
+    assert (r.stderr.count("corr_bwd fused cfg") + r.stderr.count("corr_bwd wide cfg") == 1
             or r.stderr.count("corr_bwd reg cfg") + r.stderr.count("corr_bwd mma32 cfg") == 2), r.stderr[-2000:]
     assert "not eligible" not in r.stderr, r.stderr[-2000:]
 
@@ -1343,6 +1345,44 @@ def test_corr_fwd_mma32(ops, oracle, shape, relu, monkeypatch, capfd):
     assert bool((out[:, W:] == 0).all())
     head = feat((B, 3, H, W), 33, False)
     assert torch.equal(ops.build_corr_cat(head, L, R, D), torch.cat((head, out), dim=1))
+
+
+WIDE_SHAPES = [
+    (4, 128, 3, 120, 24),    # cfg5 rows: one tile of 120 pixels, two rows per block
+    (1, 128, 40, 80, 24),    # cfg1 / cfg3 model shape (20 of 32 lanes)
+    (2, 128, 5, 160, 24),    # KITTI rows: two x tiles of 80 pixels
+    (1, 72, 7, 132, 17),     # ragged channel blocks (72 = 2 x 32 + 8), D < 24, tiles of 68 pixels
+    (3, 32, 2, 128, 13),     # one channel block per row (ring depth limited to 2), full 128-pixel tile, smallest D
+    (1, 20, 3, 8, 24),       # D > W, 16 channels per item
+    (2, 40, 9, 300, 20),     # three x tiles, ragged channels
+]
+
+
+@pytest.mark.parametrize("cpw", [8, 4])
+@pytest.mark.parametrize("relu", [True, False])
+@pytest.mark.parametrize("shape", WIDE_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_corr_bwd_wide(ops, oracle, shape, relu, cpw, monkeypatch, capfd):
+    """corr_bwd_wide.cu (a lane owns 4 pixels x all D <= 24 disparities; decoupled warps on a ring of TMA stages) forced on every
+    shape it accepts, at the fp32 bar against the oracle, bit-identical through the concat gradient and from run to run."""
+    B, C, H, W, D = shape
+    L0, R0 = feat((B, C, H, W), 51, relu), feat((B, C, H, W), 52, relu)
+    g = feat((B, D, H, W), 53, False)
+    monkeypatch.setenv("DSSMD_CORR_BWD_WIDE", "2")
+    monkeypatch.setenv("DSSMD_CORR_BWD_WIDE_CPW", str(cpw))
+    monkeypatch.setenv("DSSMD_CORR_DEBUG", "1")
+    L, R = L0.clone().requires_grad_(True), R0.clone().requires_grad_(True)
+    ops.build_corr(L, R, D).backward(g)
+    torch.cuda.synchronize()
+    err = capfd.readouterr().err
+    assert err.count("corr_bwd wide cfg") == 1, err
+    gL, gR = oracle.corr_bwd(g.cpu().numpy(), L0.cpu().numpy(), R0.cpu().numpy())
+    assert rel_err(L.grad.cpu().numpy(), gL) <= TOL_F32
+    assert rel_err(R.grad.cpu().numpy(), gR) <= TOL_F32
+    head = feat((B, 3, H, W), 54, False).requires_grad_(True)
+    L2, R2 = L0.clone().requires_grad_(True), R0.clone().requires_grad_(True)
+    gcat = torch.cat((feat((B, 3, H, W), 55, False), g), dim=1)
+    ops.build_corr_cat(head, L2, R2, D).backward(gcat)
+    assert torch.equal(L2.grad, L.grad) and torch.equal(R2.grad, R.grad)
 
 
 @pytest.mark.parametrize("relu", [True, False])
