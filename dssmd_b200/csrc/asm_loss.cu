@@ -215,6 +215,33 @@ __global__ void __launch_bounds__(kThreads) asm_recovered_l1_even_kernel(const f
     }
 }
 
+// out[0] = sum(partial[:, :, 0]) * inv_n (the loss), out[1 + b] = sum(partial[b, :, 1]): one block, fixed order (deterministic)
+__global__ void __launch_bounds__(256) asm_reduce_partials_kernel(const float *partial, float *__restrict__ out, int B, int nblk, float inv_n) {
+    __shared__ float s_a[8], s_g[8];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float total = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const float *p = partial + (size_t)b * nblk * 2;
+        float a = 0.f, g = 0.f;
+        for (int i = tid; i < nblk; i += 256) { a += ld_cg(p + 2 * i); g += ld_cg(p + 2 * i + 1); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); g += __shfl_xor_sync(0xffffffffu, g, o); }
+        if (lane == 0) { s_a[wid] = a; s_g[wid] = g; }
+        __syncthreads();
+        if (tid == 0) {
+            float sa = 0.f, sg = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { sa += s_a[k]; sg += s_g[k]; }
+            total += sa;
+            out[1 + b] = sg;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) out[0] = total * inv_n;
+}
+
 int asm_blocks(int h, int w, int B) {
     const long long hw = (long long)h * w;
     long long nb = (hw + kThreads - 1) / kThreads;               // at most one pixel per thread; the cap makes the big levels loop
@@ -235,7 +262,26 @@ extern "C" int dssmd_asm_recovered_l1_blocks(int B, int h, int w) {
     return asm_blocks(h, w, B);
 }
 
+static int asm_fwd_impl(const void *trans, const void *airlight, const void *haze, const void *clean, void *g_trans_unit,
+                        void *partial, int B, int C, int H0, int W0, int h, int w, int dtype, void *stream);
+
 extern "C" int dssmd_asm_recovered_l1_fwd(const void *trans, const void *airlight, const void *haze, const void *clean, void *g_trans_unit,
+                                          void *partial, int B, int C, int H0, int W0, int h, int w, int dtype, void *stream) {
+    return asm_fwd_impl(trans, airlight, haze, clean, g_trans_unit, partial, B, C, H0, W0, h, w, dtype, stream);
+}
+
+extern "C" int dssmd_asm_recovered_l1_loss(const void *trans, const void *airlight, const void *haze, const void *clean, void *g_trans_unit,
+                                           void *partial, void *out, int B, int C, int H0, int W0, int h, int w, int dtype, void *stream) {
+    DSSMD_REQUIRE(out, "asm_recovered_l1_loss: null output pointer");
+    if (const int rc = asm_fwd_impl(trans, airlight, haze, clean, g_trans_unit, partial, B, C, H0, W0, h, w, dtype, stream)) return rc;
+    const float inv_n = (float)(1.0 / ((double)B * C * h * w));
+    const cudaError_t e = launch_pdl(asm_reduce_partials_kernel, dim3(1), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                                     (const float *)partial, (float *)out, B, asm_blocks(h, w, B), inv_n);
+    if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "asm_recovered_l1_loss: launch failed: %s", cudaGetErrorString(e));
+    return check_launch("asm_recovered_l1_loss");
+}
+
+static int asm_fwd_impl(const void *trans, const void *airlight, const void *haze, const void *clean, void *g_trans_unit,
                                           void *partial, int B, int C, int H0, int W0, int h, int w, int dtype, void *stream) {
     DSSMD_REQUIRE(trans && airlight && haze && clean && partial, "asm_recovered_l1: null pointer");
     DSSMD_REQUIRE(B > 0 && C > 0 && H0 > 0 && W0 > 0 && h > 0 && w > 0, "asm_recovered_l1: sizes must be positive");

@@ -103,6 +103,9 @@ def photometric_loss(imgL, imgR, disp_pyramid, weights=None):
 
 
 # ---- ASM reconstruction loss -------------------------------------------------------------------
+_ASM_BLOCKS = {}   # (B, h, w, device index) -> blocks of the launch (a property of the shape and the device's SM count)
+
+
 class _RecoveredCleanL1Fn(torch.autograd.Function):
     """mean |clamp((haze_s - A (1 - t)) / t, 0, 1) - clean_s| with d/dt and d/dA computed in the forward launch."""
 
@@ -116,15 +119,20 @@ class _RecoveredCleanL1Fn(torch.autograd.Function):
         need_t = ctx.needs_input_grad[0]
         g_unit = torch.empty_like(T) if need_t else None
         with _lib.device_guard(T.device):   # the block count depends on the SM count of the tensors' device
-            nblk = int(lib.dssmd_asm_recovered_l1_blocks(B, h, w))
-            partial = torch.empty((B, nblk, 2), dtype=torch.float32, device=T.device)
-            _lib.check(lib.dssmd_asm_recovered_l1_fwd(_lib.ptr(T), _lib.ptr(A), _lib.ptr(Hz), _lib.ptr(Cl), _lib.ptr(g_unit),
-                                                      _lib.ptr(partial), B, C, H0, W0, h, w, _lib.dtype_code(T), _lib.stream_ptr(T.device)))
-        sums = partial.sum(dim=1)                      # [B, 2], fixed order
+            key = (B, h, w, T.device.index)
+            nblk = _ASM_BLOCKS.get(key)
+            if nblk is None:
+                nblk = _ASM_BLOCKS[key] = int(lib.dssmd_asm_recovered_l1_blocks(B, h, w))
+            # one buffer: [B, nblk, 2] block partials, then 1 + B results (loss, d sum|diff| / d airlight[b]) reduced on the device
+            buf = torch.empty(B * nblk * 2 + 1 + B, dtype=torch.float32, device=T.device)
+            out = buf[B * nblk * 2:]
+            _lib.check(lib.dssmd_asm_recovered_l1_loss(_lib.ptr(T), _lib.ptr(A), _lib.ptr(Hz), _lib.ptr(Cl), _lib.ptr(g_unit),
+                                                       _lib.ptr(buf), _lib.ptr(out), B, C, H0, W0, h, w, _lib.dtype_code(T),
+                                                       _lib.stream_ptr(T.device)))
         ctx.n = float(B * C * h * w)
         ctx.a_shape = tuple(airlight.shape)
-        ctx.save_for_backward(g_unit, sums[:, 1])
-        return sums[:, 0].sum() / ctx.n
+        ctx.save_for_backward(g_unit, out[1:])
+        return out[0]
 
     @staticmethod
     def backward(ctx, g):

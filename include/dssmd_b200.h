@@ -185,6 +185,12 @@ DSSMD_API int dssmd_asm_recovered_l1_blocks(int B, int h, int w);
 DSSMD_API int dssmd_asm_recovered_l1_fwd(const void *trans, const void *airlight, const void *haze, const void *clean,
                                void *g_trans_unit, void *partial, int B, int C, int H0, int W0, int h, int w,
                                int dtype, void *stream);
+/* The same launch followed by the reduction of the partials on the device (one small block, fixed order), so that the
+ * caller needs no further arithmetic: out: 1 + B floats, out[0] = the loss (mean |diff| over B*C*h*w elements, what
+ * upstream's forward returns), out[1 + b] = sum(partial[b, :, 1]) (d(sum |diff|)/d airlight[b]; scale by 1/(B*C*h*w)). */
+DSSMD_API int dssmd_asm_recovered_l1_loss(const void *trans, const void *airlight, const void *haze, const void *clean,
+                               void *g_trans_unit, void *partial, void *out, int B, int C, int H0, int W0, int h, int w,
+                               int dtype, void *stream);
 
 /* ---- attention along the epipolar line ---------------------------------------------
  * Replaces the core of STTM_Single.forward, models/BidNet/STTM_Simple.py:43-57 (q, k, v are the outputs of its three
