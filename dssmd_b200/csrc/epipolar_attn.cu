@@ -312,6 +312,12 @@ int check_shape(const char *what, int B, int C, int H, int W, int dtype) {
 
 using namespace dssmd;
 
+namespace dssmd {
+// epipolar_attn_mma.cu: the forward on mma.sync (fp16 hi / lo operand splitting); -1 = not eligible
+int epipolar_attn_fwd_mma(const float *q, const float *k, const float *v, float *out, float *lse, int B, int C, int H, int W, float scale,
+                          cudaStream_t s);
+}  // namespace dssmd
+
 extern "C" int dssmd_epipolar_attn_fwd(const void *q, const void *k, const void *v, void *out, void *lse, int B, int C, int H, int W,
                                        float scale, int dtype, void *stream) {
     DSSMD_REQUIRE(q && k && v && out, "epipolar_attn_fwd: null pointer");
@@ -320,6 +326,10 @@ extern "C" int dssmd_epipolar_attn_fwd(const void *q, const void *k, const void 
                     reinterpret_cast<uintptr_t>(lse)) & 15) == 0, "epipolar_attn_fwd: tensors must be 16-byte aligned");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const float *Q = (const float *)q, *K = (const float *)k, *V = (const float *)v;
+    {
+        const int rc = epipolar_attn_fwd_mma(Q, K, V, (float *)out, (float *)lse, B, C, H, W, scale, s);
+        if (rc >= 0) return rc;
+    }
     switch (C) {
         case 16: return fwd_ch<1>(Q, K, V, (float *)out, (float *)lse, B, H, W, scale, s);
         case 32: return fwd_ch<2>(Q, K, V, (float *)out, (float *)lse, B, H, W, scale, s);

@@ -1206,6 +1206,46 @@ def test_epipolar_attention_vs_torch_and_oracle(ops, oracle, B, C, H, W):
     assert torch.equal(out3[:, :, 1:], out2[:, :, 1:]) and not torch.equal(out3[:, :, 0], out2[:, :, 0])
 
 
+@pytest.mark.parametrize("case", ["large", "small", "mixed_rows", "outlier", "zero_v", "c16"])
+def test_epipolar_attention_mma_forward_scaling(ops, case, monkeypatch, capfd):
+    """The tensor-core forward splits every staged tile into fp16 hi / lo after dividing it by a power of two >= its largest
+    magnitude (epipolar_attn_mma.cu): inputs far outside fp16's range, rows of very different magnitude inside one image, a
+    single outlier key and an all-zero value tensor must stay at the fp32 bar against upstream's expression in float64."""
+    B, C, H, W = (2, 16, 3, 200) if case == "c16" else (2, 32, 3, 328)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    q, k, v = (torch.randn(B, C, H, W, generator=g, device="cuda") for _ in range(3))
+    scale = C ** -0.5
+    if case == "large":
+        q, k, v, scale = q * 3.0e4, k * 2.0e3, v * 1.0e6, scale / 6.0e7
+    elif case == "small":
+        q, k, v, scale = q * 1.0e-5, k * 3.0e-6, v * 1.0e-7, scale * 3.3e10
+    elif case == "mixed_rows":
+        k = k * torch.logspace(-6, 6, W, device="cuda").roll(37)       # key tiles of very different scale
+        v = v * torch.logspace(5, -5, W, device="cuda")
+        scale = scale * 1e-6
+    elif case == "outlier":
+        k[0, :, 1, 77] *= 1.0e4
+        v[1, 3, 2, 5] = 3.0e5
+    elif case == "zero_v":
+        v = torch.zeros_like(v)
+    monkeypatch.setenv("DSSMD_CORR_DEBUG", "1")
+    out = ops.epipolar_attention(q, k, v, scale)
+    torch.cuda.synchronize()
+    assert "epipolar_attn_fwd mma cfg" in capfd.readouterr().err
+    q2, k2, v2 = (t.double().permute(0, 2, 3, 1).reshape(B * H, W, C) for t in (q, k, v))
+    ref = torch.matmul(torch.softmax(torch.matmul(q2, k2.transpose(-1, -2)) * scale, dim=-1), v2).view(B, H, W, C).permute(0, 3, 1, 2)
+    if case == "zero_v":
+        assert torch.count_nonzero(out) == 0
+    else:
+        assert rel_err(out.cpu().numpy(), ref.float().cpu().numpy()) <= TOL_F32
+        if case == "mixed_rows":   # element-wise where the reference is not tiny: small-magnitude outputs keep their own precision
+            big = ref.abs() > 1e-3 * ref.abs().amax(dim=(1, 3), keepdim=True)
+            assert ((out.double() - ref).abs()[big] <= 1e-4 * ref.abs()[big] + 1e-6 * ref.abs().amax()).all()
+    monkeypatch.setenv("DSSMD_ATTN_FWD_MMA", "0")       # the FFMA kernel it replaces agrees
+    out2 = ops.epipolar_attention(q, k, v, scale)
+    assert rel_err(out.cpu().numpy(), out2.cpu().numpy()) <= TOL_F32
+
+
 def test_epipolar_attention_errors(ops):
     x = torch.randn(1, 32, 2, 8, device="cuda")
     with pytest.raises(NotImplementedError, match="needs C in"):
