@@ -297,7 +297,7 @@ def aux_kernels(torch, lib, _lib, w, device, peak, nsets=4, rounds=10):
     # ---- attention along the epipolar line at BidNet's shape (models/BidNet/BidNet.py:115: B8, 32 channels, 320 x 640)
     Ba, Ca, Ha, Wa = 8, 32, 320, 640
     q, k, v, go = (torch.randn(Ba, Ca, Ha, Wa, generator=g, device=device) for _ in range(4))
-    o, lse, dl = torch.empty_like(q), torch.empty(Ba * Ha, Wa, device=device), torch.empty(Ba * Ha, Wa, device=device)
+    o, lse, dl = torch.empty_like(q), torch.empty(Ba * Ha, Wa, device=device), torch.empty(Ba * Ha * (Wa + 4), device=device)   # delta + per-row scales
     gq, gk, gv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
     scale = Ca ** -0.5
     unit = 2.0 * Ba * Ha * Wa * Wa * Ca      # one W x W x C product per row

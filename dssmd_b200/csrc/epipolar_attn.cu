@@ -316,6 +316,8 @@ namespace dssmd {
 // epipolar_attn_mma.cu: the forward on mma.sync (fp16 hi / lo operand splitting); -1 = not eligible
 int epipolar_attn_fwd_mma(const float *q, const float *k, const float *v, float *out, float *lse, int B, int C, int H, int W, float scale,
                           cudaStream_t s);
+int epipolar_attn_bwd_mma(const float *q, const float *k, const float *v, const float *out, const float *g_out, const float *lse, float *delta,
+                          float *gq, float *gk, float *gv, int B, int C, int H, int W, float scale, cudaStream_t s);
 }  // namespace dssmd
 
 extern "C" int dssmd_epipolar_attn_fwd(const void *q, const void *k, const void *v, void *out, void *lse, int B, int C, int H, int W,
@@ -345,10 +347,16 @@ extern "C" int dssmd_epipolar_attn_bwd(const void *q, const void *k, const void 
     DSSMD_REQUIRE((g_k == nullptr) == (g_v == nullptr), "epipolar_attn_bwd: g_k and g_v come from one kernel: pass both or neither");
     if (const int rc = check_shape("epipolar_attn_bwd", B, C, H, W, dtype)) return rc;
     DSSMD_REQUIRE(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(g_out) |
+                    reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(delta) |
                     reinterpret_cast<uintptr_t>(g_q) | reinterpret_cast<uintptr_t>(g_k) | reinterpret_cast<uintptr_t>(g_v)) & 15) == 0,
                   "epipolar_attn_bwd: tensors must be 16-byte aligned");
     if (!g_q && !g_k) return DSSMD_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    {
+        const int rc = epipolar_attn_bwd_mma((const float *)q, (const float *)k, (const float *)v, (const float *)out, (const float *)g_out,
+                                             (const float *)lse, (float *)delta, (float *)g_q, (float *)g_k, (float *)g_v, B, C, H, W, scale, s);
+        if (rc >= 0) return rc;
+    }
     {
         const long long n = (long long)B * H * W;
         long long nb = (n + 255) / 256;

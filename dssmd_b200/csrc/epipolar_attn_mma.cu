@@ -6,7 +6,7 @@
 // mma.sync path tops out at 476 MAC/clk/SM / 3 products = 92 TFLOP/s at a full pipe.  The fp16 instruction runs at twice that rate
 // (949 MAC/clk/SM, scripts/micro/mma_rate.cu) and a pair of halves carries the same 22 significand bits as a tf32 pair, PROVIDED the
 // values sit in fp16's range -- so every staged tile is divided by a power of two >= its largest magnitude first (exact), and
-//     x / s = hi + lo,   hi = fp16(x / s),   lo = fp16(x / s - hi)        |x / s - hi - lo| <= 2^-25
+//     x / s = hi + lo,   hi = fp16(x / s),   lo = fp16(x / s - hi)        (stored times 2^10, see kUp: 22 significant bits)
 //     a . b ~= hi_a hi_b + lo_a hi_b + hi_a lo_b                          (fp32 accumulation; the dropped lo lo term is 2^-22)
 // with the scales folded back in fp32: S = (sq sk scale) (Q~^T K~); the V scale rides on the online-softmax correction (the
 // accumulator is kept in units of the largest V scale seen so far, a change of units is an exact power-of-two multiply).
@@ -32,6 +32,13 @@ constexpr int kKT = 64;           // keys per tile
 constexpr int kQS = kQT + 8;      // row strides in halves: 272 B = 17 chunks, 144 B = 9 chunks of 16 bytes
 constexpr int kKS = kKT + 8;
 constexpr int kAThreads = 256;
+// Every split operand is stored multiplied by a power of two on top of its normalisation to [-1, 1]: the `lo` halves of values
+// down to 2^-13 of the tile's scale then stay in fp16's NORMAL range (>= 2^-14) and keep their 11 bits -- without it the lo of a
+// typical element (|x / s| ~ 0.1, lo ~ 2^-15) is subnormal, the pair carries an absolute 2^-25 instead of a relative 2^-22, and
+// the backward's recomputed probabilities land at 1.0e-5 of the reference instead of ~1e-6.  All factors are folded back in fp32.
+constexpr float kUp = 1024.0f;     // q, k, v, dO tiles: |stored| <= 1024
+constexpr float kUpP = 1024.0f;    // probabilities (<= 1)
+constexpr float kUpD = 256.0f;     // D~ = P (dP~ - delta~), |D~| <= 2 C = 64
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -144,9 +151,9 @@ epipolar_attn_fwd_mma_kernel(const float *q, const float *k, const float *v, flo
     const float sq = pow2_ceil(__uint_as_float(s_qmax));
     float sk = pow2_ceil(__uint_as_float(s_kmax[0]));
     float sv = pow2_ceil(__uint_as_float(s_vmax[0]));   // units of the O accumulator: the largest V scale so far
-    qr.template store<kQS>(Qh, Ql, 1.0f / sq, tid);
-    kr.template store<kKS>(Kh, Kl, 1.0f / sk, tid);
-    vr.template store<kKS>(Vh, Vl, 1.0f / sv, tid);
+    qr.template store<kQS>(Qh, Ql, kUp / sq, tid);
+    kr.template store<kKS>(Kh, Kl, kUp / sk, tid);
+    vr.template store<kKS>(Vh, Vl, kUp / sv, tid);
     __syncthreads();
 
     // this warp's Q^T fragments (16 queries x C channels), hi and lo, for the whole kernel
@@ -167,7 +174,7 @@ epipolar_attn_fwd_mma_kernel(const float *q, const float *k, const float *v, flo
 #pragma unroll
         for (int i = 0; i < 4; ++i) o[n][i] = 0.f;
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // rows g and g + 8 of this warp's 16 queries (exp2 domain)
-    const float qscale = scale * 1.4426950408889634f * sq;
+    const float qscale = scale * 1.4426950408889634f * sq * (1.0f / (kUp * kUp));
 
     const int ntiles = (W + kKT - 1) / kKT;
     for (int t = 0; t < ntiles; ++t) {
@@ -226,7 +233,7 @@ epipolar_attn_fwd_mma_kernel(const float *q, const float *k, const float *v, flo
         const float sv_t = pow2_ceil(__uint_as_float(s_vmax[buf]));
         const float sv_new = fmaxf(sv, sv_t);
         const float unit = sv / sv_new;            // <= 1, exact
-        const float pv_unit = sv_t / sv_new;       // this tile's V~ values are in units of sv_t: fold the change into P
+        const float pv_unit = sv_t / sv_new * kUpP;   // this tile's V~ values are in units of sv_t: fold the change (and P's up-shift) into P
         const float c0 = fast_exp2(m0 - mn0), c1 = fast_exp2(m1 - mn1);   // exp2(-inf) = 0 on the first tile
         m0 = mn0; m1 = mn1; sv = sv_new;
         float ps0 = 0.f, ps1 = 0.f;
@@ -276,8 +283,8 @@ epipolar_attn_fwd_mma_kernel(const float *q, const float *k, const float *v, flo
             if (tid == 0) { s_kmax[buf] = 0u; s_vmax[buf] = 0u; }
             sk = pow2_ceil(__uint_as_float(s_kmax[buf ^ 1]));
             const float svn = pow2_ceil(__uint_as_float(s_vmax[buf ^ 1]));
-            kr.template store<kKS>(Kh + (buf ^ 1) * C * kKS, Kl + (buf ^ 1) * C * kKS, 1.0f / sk, tid);
-            vr.template store<kKS>(Vh + (buf ^ 1) * C * kKS, Vl + (buf ^ 1) * C * kKS, 1.0f / svn, tid);
+            kr.template store<kKS>(Kh + (buf ^ 1) * C * kKS, Kl + (buf ^ 1) * C * kKS, kUp / sk, tid);
+            vr.template store<kKS>(Vh + (buf ^ 1) * C * kKS, Vl + (buf ^ 1) * C * kKS, kUp / svn, tid);
             __syncthreads();   // tile t + 1 staged
         }
     }
@@ -285,7 +292,7 @@ epipolar_attn_fwd_mma_kernel(const float *q, const float *k, const float *v, flo
     // ---- epilogue: O * sv / l -> out[b, c, y, x]; lse in natural units --------------------------------------------------------------
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float i0 = sv / l0, i1 = sv / l1;
+    const float i0 = sv * (1.0f / (kUp * kUpP)) / l0, i1 = sv * (1.0f / (kUp * kUpP)) / l1;
     const int xa = x0 + warp * 16 + g, xb = xa + 8;
     float *orow = out + rowoff;
 #pragma unroll
@@ -298,6 +305,247 @@ epipolar_attn_fwd_mma_kernel(const float *q, const float *k, const float *v, flo
         const float ln2 = 0.6931471805599453f;
         if (xa < W) lse[(size_t)r * W + xa] = (m0 + log2f(l0)) * ln2;
         if (xb < W) lse[(size_t)r * W + xb] = (m1 + log2f(l1)) * ln2;
+    }
+}
+
+// ================================================================================================================================
+// Backward on the same machinery.  With lse and delta[x] = sum_c dO[c,x] O[c,x] (FlashAttention's recomputation):
+//     P = exp(scale Q^T K - lse[x]);  dP = dO^T V;  dS = P o (dP - delta[x])
+//     dQ[c,x] = scale sum_j dS[x,j] K[c,j];   dK[c,j] = scale sum_x dS[x,j] Q[c,x];   dV[c,j] = sum_x P[x,j] dO[c,x]
+// Seven GEMMs (S and dP are recomputed by both kernels), all with fp16 hi / lo split operands.  Here the scales are one power
+// of two per IMAGE ROW and tensor (the largest |q|, |k|, |v|, |dO| of the row, found by the launch that also writes delta):
+// a per-tile scale of V would leave delta / (s_dO s_V) unbounded for fp16, with per-row scales
+//     D~ = P (dP~ - delta~),  dP~ = dO~^T V~,  delta~ = delta / (s_dO s_V),  |D~| <= 2 C
+// and the three results are D~ K~, D~^T Q~, P^T dO~ times constants of the row.  Both kernels walk 16 columns at a time: the S and dP
+// accumulators of a 16-column step become the A fragments of the gradient GEMMs of that step at once (few live registers).
+
+// one block per image row: delta[r, x] and stats[r] = (s_q, s_k, s_v, s_dO)
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const float *q, const float *k, const float *v, const float *g_out, const float *out,
+                                                            float *__restrict__ delta, float *__restrict__ stats, int C, int H, int W) {
+    __shared__ unsigned s_m[4];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int r = blockIdx.x, b = r / H, y = r - b * H;
+    const size_t HW = (size_t)H * W;
+    const size_t rowoff = (size_t)b * C * HW + (size_t)y * W;
+    if (tid < 4) s_m[tid] = 0u;
+    pdl_launch_dependents();
+    pdl_wait();
+    __syncthreads();
+    float mq = 0.f, mk = 0.f, mv = 0.f, mg = 0.f;
+    auto amax4 = [](float m, const float4 &a) { return fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)))); };
+    for (int x = 4 * tid; x < W; x += 4 * 256) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < C; ++c) {
+            const size_t o = rowoff + (size_t)c * HW + x;
+            const float4 a = ld_cg(reinterpret_cast<const float4 *>(g_out + o)), p = ld_cg(reinterpret_cast<const float4 *>(out + o));
+            const float4 fq = ld_cg(reinterpret_cast<const float4 *>(q + o)), fk = ld_cg(reinterpret_cast<const float4 *>(k + o));
+            const float4 fv = ld_cg(reinterpret_cast<const float4 *>(v + o));
+            acc.x = fmaf(a.x, p.x, acc.x); acc.y = fmaf(a.y, p.y, acc.y); acc.z = fmaf(a.z, p.z, acc.z); acc.w = fmaf(a.w, p.w, acc.w);
+            mq = amax4(mq, fq); mk = amax4(mk, fk); mv = amax4(mv, fv); mg = amax4(mg, a);
+        }
+        *reinterpret_cast<float4 *>(delta + (size_t)r * W + x) = acc;
+    }
+    block_max_into(&s_m[0], mq, lane); block_max_into(&s_m[1], mk, lane);
+    block_max_into(&s_m[2], mv, lane); block_max_into(&s_m[3], mg, lane);
+    __syncthreads();
+    if (tid < 4) stats[(size_t)r * 4 + tid] = pow2_ceil(__uint_as_float(s_m[tid]));
+}
+
+// A fragments of a 16-column step from the values of its two 8-column accumulator tiles (rows g / g + 8)
+__device__ __forceinline__ void frag_from_acc(const float (&t0)[4], const float (&t1)[4], uint32_t (&hi)[4], uint32_t (&lo)[4]) {
+    split_h2(t0[0], t0[1], hi[0], lo[0]);
+    split_h2(t0[2], t0[3], hi[1], lo[1]);
+    split_h2(t1[0], t1[1], hi[2], lo[2]);
+    split_h2(t1[2], t1[3], hi[3], lo[3]);
+}
+// c += A B with split operands, small terms first
+__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+    mma16816(c, al, bh0, bh1);
+    mma16816(c, ah, bl0, bl1);
+    mma16816(c, ah, bh0, bh1);
+}
+
+// KEYMAJOR = false: block rows = 128 queries, columns = keys, writes dQ.  true: rows = 128 keys, columns = queries, writes dK and dV.
+// Row side (X1, X2) = (Q, dO) | (K, V); column side (Y1, Y2) = (K, V) | (Q, dO).  S (or S^T) = X1^T Y1, dP (or dP^T) = X2^T Y2.
+template <int CH, bool KEYMAJOR>
+__global__ void __launch_bounds__(kAThreads, 2)
+epipolar_attn_bwd_mma_kernel(const float *q, const float *k, const float *v, const float *g_out, const float *lse, const float *delta,
+                             const float *stats, float *__restrict__ g1, float *__restrict__ g2, int H, int W, float scale) {
+    constexpr int C = 16 * CH;
+    constexpr int NO = C / 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float s_l2[2][kKT], s_dl[2][kKT];   // KEYMAJOR: lse (exp2 domain) and delta~ of the column tile's queries
+    __half *X1h = reinterpret_cast<__half *>(smem_raw), *X1l = X1h + C * kQS, *X2h = X1l + C * kQS, *X2l = X2h + C * kQS;
+    __half *Y1h = X2l + C * kQS;          // [2][C][kKS] each
+    __half *Y1l = Y1h + 2 * C * kKS, *Y2h = Y1l + 2 * C * kKS, *Y2l = Y2h + 2 * C * kKS;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, tq = lane & 3;
+    const int r = blockIdx.y, b = r / H, y = r - b * H;
+    const int x0 = blockIdx.x * kQT;
+    const size_t HW = (size_t)H * W;
+    const size_t rowoff = (size_t)b * C * HW + (size_t)y * W;
+    const float *x1 = (KEYMAJOR ? k : q) + rowoff, *x2 = (KEYMAJOR ? v : g_out) + rowoff;
+    const float *y1 = (KEYMAJOR ? q : k) + rowoff, *y2 = (KEYMAJOR ? g_out : v) + rowoff;
+    const float *lrow = lse + (size_t)r * W, *drow = delta + (size_t)r * W;
+    pdl_launch_dependents();
+    pdl_wait();
+    const float sq = ld_cg(stats + (size_t)r * 4 + 0), sk = ld_cg(stats + (size_t)r * 4 + 1);
+    const float sv = ld_cg(stats + (size_t)r * 4 + 2), sg = ld_cg(stats + (size_t)r * 4 + 3);
+    const float ix1 = kUp / (KEYMAJOR ? sk : sq), ix2 = kUp / (KEYMAJOR ? sv : sg);
+    const float iy1 = kUp / (KEYMAJOR ? sq : sk), iy2 = kUp / (KEYMAJOR ? sg : sv);
+    const float kLog2e = 1.4426950408889634f;
+    const float fs = scale * kLog2e * sq * sk * (1.0f / (kUp * kUp));
+    const float dn = 1.0f / (kUp * kUp);   // dP~ back to products of [-1, 1] operands
+    const float idl = 1.0f / (sg * sv);
+
+    TileRegs<C, kQT> xr;
+    TileRegs<C, kKT> yr1, yr2;
+    float cl = 0.f, cd = 0.f;   // KEYMAJOR: thread tid < 64 carries one column's lse / delta towards shared memory
+    xr.load(x1, HW, x0, W, tid);
+    xr.template store<kQS>(X1h, X1l, ix1, tid);
+    xr.load(x2, HW, x0, W, tid);
+    xr.template store<kQS>(X2h, X2l, ix2, tid);
+    yr1.load(y1, HW, 0, W, tid);
+    yr2.load(y2, HW, 0, W, tid);
+    yr1.template store<kKS>(Y1h, Y1l, iy1, tid);
+    yr2.template store<kKS>(Y2h, Y2l, iy2, tid);
+    if (KEYMAJOR && tid < kKT) {
+        s_l2[0][tid] = tid < W ? ld_cg(lrow + tid) * kLog2e : 0.f;
+        s_dl[0][tid] = tid < W ? ld_cg(drow + tid) * idl : 0.f;
+    }
+    __syncthreads();
+
+    uint32_t a1h[CH][4], a1l[CH][4], a2h[CH][4], a2l[CH][4];   // this warp's 16 rows of X1^T and X2^T
+    {
+        const int xq = warp * 16 + ((lane >> 3) & 1) * 8;
+        const int cq = (lane & 7) + ((lane >> 4) & 1) * 8;
+#pragma unroll
+        for (int ks = 0; ks < CH; ++ks) {
+            ldsm_x4_t(smem_u32(X1h + (ks * 16 + cq) * kQS + xq), a1h[ks]);
+            ldsm_x4_t(smem_u32(X1l + (ks * 16 + cq) * kQS + xq), a1l[ks]);
+            ldsm_x4_t(smem_u32(X2h + (ks * 16 + cq) * kQS + xq), a2h[ks]);
+            ldsm_x4_t(smem_u32(X2l + (ks * 16 + cq) * kQS + xq), a2l[ks]);
+        }
+    }
+    // softmax statistics belong to the QUERY: the row here (queries as rows) or the column (keys as rows)
+    const int xa = x0 + warp * 16 + g, xb = xa + 8;
+    float rl0 = 0.f, rl1 = 0.f, rd0 = 0.f, rd1 = 0.f;
+    if (!KEYMAJOR) {
+        rl0 = xa < W ? ld_cg(lrow + xa) * kLog2e : 0.f; rl1 = xb < W ? ld_cg(lrow + xb) * kLog2e : 0.f;
+        rd0 = xa < W ? ld_cg(drow + xa) * idl : 0.f;    rd1 = xb < W ? ld_cg(drow + xb) * idl : 0.f;
+    }
+
+    float acc1[NO][4], acc2[KEYMAJOR ? NO : 1][4];
+#pragma unroll
+    for (int n = 0; n < NO; ++n)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { acc1[n][i] = 0.f; if (KEYMAJOR) acc2[n][i] = 0.f; }
+
+    const int ntiles = (W + kKT - 1) / kKT;
+    for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        const bool more = t + 1 < ntiles;
+        if (more) {
+            yr1.load(y1, HW, (t + 1) * kKT, W, tid);
+            yr2.load(y2, HW, (t + 1) * kKT, W, tid);
+            if (KEYMAJOR && tid < kKT) {
+                const int xc = (t + 1) * kKT + tid;
+                cl = xc < W ? ld_cg(lrow + xc) * kLog2e : 0.f;
+                cd = xc < W ? ld_cg(drow + xc) * idl : 0.f;
+            }
+        }
+        const __half *y1h = Y1h + buf * C * kKS, *y1l = Y1l + buf * C * kKS, *y2h = Y2h + buf * C * kKS, *y2l = Y2l + buf * C * kKS;
+        const int cb = (lane & 7) + ((lane >> 3) & 1) * 8, nb = ((lane >> 4) & 1) * 8;   // .trans B fragments (k = channel, n = column)
+        const int cv = (lane & 7) + ((lane >> 4) & 1) * 8, jv = ((lane >> 3) & 1) * 8;   // plain B fragments (k = column, n = channel)
+#pragma unroll
+        for (int ks = 0; ks < kKT / 16; ++ks) {
+            float s2[2][4], dp2[2][4];
+#pragma unroll
+            for (int n = 0; n < 2; ++n)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { s2[n][i] = 0.f; dp2[n][i] = 0.f; }
+#pragma unroll
+            for (int kc = 0; kc < CH; ++kc) {
+                uint32_t bh[4], bl[4];
+                const int off = (kc * 16 + cb) * kKS + ks * 16 + nb;
+                ldsm_x4_t(smem_u32(y1h + off), bh);
+                ldsm_x4_t(smem_u32(y1l + off), bl);
+                mma3(s2[0], a1h[kc], a1l[kc], bh[0], bh[1], bl[0], bl[1]);
+                mma3(s2[1], a1h[kc], a1l[kc], bh[2], bh[3], bl[2], bl[3]);
+                ldsm_x4_t(smem_u32(y2h + off), bh);
+                ldsm_x4_t(smem_u32(y2l + off), bl);
+                mma3(dp2[0], a2h[kc], a2l[kc], bh[0], bh[1], bl[0], bl[1]);
+                mma3(dp2[1], a2h[kc], a2l[kc], bh[2], bh[3], bl[2], bl[3]);
+            }
+            // P = exp2(S fs - lse2), D~ = P (dP~ - delta~); columns past the row end carry nothing
+            float pr[2][4], ds[2][4];
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+                const int jl = ks * 16 + n * 8 + 2 * tq;        // column inside the tile
+                const int jg = t * kKT + jl;
+                const bool in0 = jg < W, in1 = jg + 1 < W;
+                float l0c, l1c, d0c, d1c;
+                if (KEYMAJOR) { l0c = s_l2[buf][jl]; l1c = s_l2[buf][jl + 1]; d0c = s_dl[buf][jl]; d1c = s_dl[buf][jl + 1]; }
+                pr[n][0] = in0 ? fast_exp2(fmaf(s2[n][0], fs, -(KEYMAJOR ? l0c : rl0))) : 0.f;
+                pr[n][1] = in1 ? fast_exp2(fmaf(s2[n][1], fs, -(KEYMAJOR ? l1c : rl0))) : 0.f;
+                pr[n][2] = in0 ? fast_exp2(fmaf(s2[n][2], fs, -(KEYMAJOR ? l0c : rl1))) : 0.f;
+                pr[n][3] = in1 ? fast_exp2(fmaf(s2[n][3], fs, -(KEYMAJOR ? l1c : rl1))) : 0.f;
+                ds[n][0] = pr[n][0] * kUpD * fmaf(dp2[n][0], dn, -(KEYMAJOR ? d0c : rd0));
+                ds[n][1] = pr[n][1] * kUpD * fmaf(dp2[n][1], dn, -(KEYMAJOR ? d1c : rd0));
+                ds[n][2] = pr[n][2] * kUpD * fmaf(dp2[n][2], dn, -(KEYMAJOR ? d0c : rd1));
+                ds[n][3] = pr[n][3] * kUpD * fmaf(dp2[n][3], dn, -(KEYMAJOR ? d1c : rd1));
+            }
+            uint32_t dh[4], dl[4];
+            frag_from_acc(ds[0], ds[1], dh, dl);
+            // acc1 += D~ Y1~^T (dQ += dS K | dK += dS^T Q); KEYMAJOR: acc2 += P^T dO~ (dV)
+#pragma unroll
+            for (int np = 0; np < NO / 2; ++np) {
+                uint32_t bh[4], bl[4];
+                const int off = (np * 16 + cv) * kKS + ks * 16 + jv;
+                ldsm_x4(smem_u32(y1h + off), bh);
+                ldsm_x4(smem_u32(y1l + off), bl);
+                mma3(acc1[2 * np], dh, dl, bh[0], bh[1], bl[0], bl[1]);
+                mma3(acc1[2 * np + 1], dh, dl, bh[2], bh[3], bl[2], bl[3]);
+            }
+            if constexpr (KEYMAJOR) {
+                uint32_t ph[4], pl[4];
+#pragma unroll
+                for (int n = 0; n < 2; ++n)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) pr[n][i] *= kUpP;
+                frag_from_acc(pr[0], pr[1], ph, pl);
+#pragma unroll
+                for (int np = 0; np < NO / 2; ++np) {
+                    uint32_t bh[4], bl[4];
+                    const int off = (np * 16 + cv) * kKS + ks * 16 + jv;
+                    ldsm_x4(smem_u32(y2h + off), bh);
+                    ldsm_x4(smem_u32(y2l + off), bl);
+                    mma3(acc2[2 * np], ph, pl, bh[0], bh[1], bl[0], bl[1]);
+                    mma3(acc2[2 * np + 1], ph, pl, bh[2], bh[3], bl[2], bl[3]);
+                }
+            }
+        }
+        if (more) {   // buffer buf ^ 1 was last read two tiles ago, before the barrier that ended the previous iteration
+            yr1.template store<kKS>(Y1h + (buf ^ 1) * C * kKS, Y1l + (buf ^ 1) * C * kKS, iy1, tid);
+            yr2.template store<kKS>(Y2h + (buf ^ 1) * C * kKS, Y2l + (buf ^ 1) * C * kKS, iy2, tid);
+            if (KEYMAJOR && tid < kKT) { s_l2[buf ^ 1][tid] = cl; s_dl[buf ^ 1][tid] = cd; }
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue: constants of the row ----------------------------------------------------------------------------------------
+    const float f1 = scale * sg * sv * (KEYMAJOR ? sq : sk) * (1.0f / (kUpD * kUp)), f2 = sg * (1.0f / (kUpP * kUp));
+    float *o1 = g1 + rowoff, *o2 = KEYMAJOR ? g2 + rowoff : nullptr;
+#pragma unroll
+    for (int n = 0; n < NO; ++n) {
+        const int c = 8 * n + 2 * tq;
+        if (xa < W) { o1[(size_t)c * HW + xa] = acc1[n][0] * f1; o1[(size_t)(c + 1) * HW + xa] = acc1[n][1] * f1; }
+        if (xb < W) { o1[(size_t)c * HW + xb] = acc1[n][2] * f1; o1[(size_t)(c + 1) * HW + xb] = acc1[n][3] * f1; }
+        if constexpr (KEYMAJOR) {
+            if (xa < W) { o2[(size_t)c * HW + xa] = acc2[n][0] * f2; o2[(size_t)(c + 1) * HW + xa] = acc2[n][1] * f2; }
+            if (xb < W) { o2[(size_t)c * HW + xb] = acc2[n][2] * f2; o2[(size_t)(c + 1) * HW + xb] = acc2[n][3] * f2; }
+        }
     }
 }
 
@@ -321,6 +569,35 @@ int launch_attn_mma(const float *q, const float *k, const float *v, float *out, 
     return check_launch("epipolar_attn_fwd(mma)");
 }
 
+template <int CH>
+int launch_attn_bwd_mma(const float *q, const float *k, const float *v, const float *out, const float *g_out, const float *lse, float *delta,
+                        float *stats, float *gq, float *gk, float *gv, int B, int H, int W, float scale, cudaStream_t s) {
+    constexpr int C = 16 * CH;
+    {
+        const cudaError_t e = launch_pdl(attn_bwd_prep_kernel, dim3((unsigned)(B * H)), dim3(256), 0, s, q, k, v, g_out, out, delta, stats, C, H, W);
+        if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "epipolar_attn_bwd(mma, prep): launch failed: %s", cudaGetErrorString(e));
+    }
+    const size_t smem = (size_t)(4 * C * kQS + 8 * C * kKS) * sizeof(__half);
+    const dim3 grid((unsigned)ceil_div(W, kQT), (unsigned)(B * H));
+    if (env_int_attn("DSSMD_CORR_DEBUG", 0))
+        fprintf(stderr, "epipolar_attn_bwd mma cfg: C=%d grid=(%u,%u) threads=%d smem=%zu dq=%d dkv=%d\n", C, grid.x, grid.y, kAThreads, smem, gq != nullptr, gk != nullptr);
+    if (gq) {
+        auto kern = epipolar_attn_bwd_mma_kernel<CH, false>;
+        const cudaError_t ea = kernel_smem_optin(kern, smem);
+        if (ea != cudaSuccess) return fail(DSSMD_ERR_CUDA, "epipolar_attn_bwd(mma, dQ): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(ea));
+        const cudaError_t e = launch_pdl(kern, grid, dim3(kAThreads), smem, s, q, k, v, g_out, lse, (const float *)delta, (const float *)stats, gq, (float *)nullptr, H, W, scale);
+        if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "epipolar_attn_bwd(mma, dQ): launch failed: %s", cudaGetErrorString(e));
+    }
+    if (gk && gv) {
+        auto kern = epipolar_attn_bwd_mma_kernel<CH, true>;
+        const cudaError_t ea = kernel_smem_optin(kern, smem);
+        if (ea != cudaSuccess) return fail(DSSMD_ERR_CUDA, "epipolar_attn_bwd(mma, dK dV): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(ea));
+        const cudaError_t e = launch_pdl(kern, grid, dim3(kAThreads), smem, s, q, k, v, g_out, lse, (const float *)delta, (const float *)stats, gk, gv, H, W, scale);
+        if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "epipolar_attn_bwd(mma, dK dV): launch failed: %s", cudaGetErrorString(e));
+    }
+    return check_launch("epipolar_attn_bwd(mma)");
+}
+
 }  // namespace
 
 // fp32 tensors, C in {16, 32}: -1 = not eligible (the caller takes the FFMA kernel), else a DSSMD_* code.  DSSMD_ATTN_FWD_MMA=0 disables it.
@@ -329,6 +606,17 @@ int epipolar_attn_fwd_mma(const float *q, const float *k, const float *v, float 
     if (env_int_attn("DSSMD_ATTN_FWD_MMA", 1) == 0) return -1;
     if (C == 16) return launch_attn_mma<1>(q, k, v, out, lse, B, H, W, scale, s);
     if (C == 32) return launch_attn_mma<2>(q, k, v, out, lse, B, H, W, scale, s);
+    return -1;
+}
+
+// The backward for the same shapes; delta: B*H*W floats followed by 4*B*H floats of per-row scales (both written here).
+// DSSMD_ATTN_BWD_MMA=0 disables it.
+int epipolar_attn_bwd_mma(const float *q, const float *k, const float *v, const float *out, const float *g_out, const float *lse, float *delta,
+                          float *gq, float *gk, float *gv, int B, int C, int H, int W, float scale, cudaStream_t s) {
+    if (env_int_attn("DSSMD_ATTN_BWD_MMA", 1) == 0) return -1;
+    float *stats = delta + (size_t)B * H * W;
+    if (C == 16) return launch_attn_bwd_mma<1>(q, k, v, out, g_out, lse, delta, stats, gq, gk, gv, B, H, W, scale, s);
+    if (C == 32) return launch_attn_bwd_mma<2>(q, k, v, out, g_out, lse, delta, stats, gq, gk, gv, B, H, W, scale, s);
     return -1;
 }
 

@@ -5,7 +5,8 @@
 and returns `softmax(q k^T * scale) v` per image row in NCHW: no permute / reshape / contiguous copies and no
 [B*H, W, W] attention matrix (two 4.2 GB fp32 intermediates at BidNet's B8 x 32 x 320 x 640).  `STTM_Single` is
 upstream's module with the same constructor, parameter names (state_dicts load unchanged) and forward signature, its
-attention core swapped for the kernel.  fp32, C in {16, 32, 64, 128}, W % 4 == 0; anything else raises
+attention core swapped for the kernel (C <= 32: tensor cores with fp16 hi / lo split operands at the fp32 parity bar,
+csrc/epipolar_attn_mma.cu; C = 64 / 128: fp32 FFMA).  fp32, C in {16, 32, 64, 128}, W % 4 == 0; anything else raises
 NotImplementedError -- there is no fallback in this package.  `install()` does not replace upstream's class: it patches
 the class's `forward` with `guarded_forward`, which takes the kernel for inputs inside those limits and hands everything
 else to upstream's own, saved `forward`.
@@ -76,7 +77,7 @@ class EpipolarAttentionFn(torch.autograd.Function):
         gk = torch.empty_like(K) if (need_k or need_v) else None     # dK and dV come out of one kernel
         gv = torch.empty_like(V) if (need_k or need_v) else None
         if Q.numel() > 0 and (need_q or need_k or need_v):
-            delta = torch.empty_like(lse)
+            delta = torch.empty(B * H * W + 4 * B * H, dtype=torch.float32, device=Q.device)   # [B*H, W] sums + per-row scales
             with _lib.device_guard(Q.device):
                 _lib.check(_lib.lib().dssmd_epipolar_attn_bwd(_lib.ptr(Q), _lib.ptr(K), _lib.ptr(V), _lib.ptr(out), _lib.ptr(g), _lib.ptr(lse),
                                                               _lib.ptr(delta), _lib.ptr(gq), _lib.ptr(gk), _lib.ptr(gv), B, C, H, W, ctx.scale,

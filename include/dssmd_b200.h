@@ -201,8 +201,9 @@ DSSMD_API int dssmd_asm_recovered_l1_loss(const void *trans, const void *airligh
  * C in {16, 32, 64, 128}, W % 4 == 0, B*H <= 65535, 16-byte aligned tensors; anything else: DSSMD_ERR_UNSUPPORTED. */
 DSSMD_API int dssmd_epipolar_attn_fwd(const void *q, const void *k, const void *v, void *out, void *lse,
                             int B, int C, int H, int W, float scale, int dtype, void *stream);
-/* Backward of the above: g_q, g_k, g_v: [B,C,H,W] (g_q may be NULL, g_k / g_v only together); delta: [B*H, W] scratch
- * (sum_c g_out * out, written by the first of the three launches).  Deterministic, no atomics. */
+/* Backward of the above: g_q, g_k, g_v: [B,C,H,W] (g_q may be NULL, g_k / g_v only together); delta: scratch of
+ * B*H*W + 4*B*H floats ([B*H, W] sums sum_c g_out * out, then one power-of-two scale per image row for q, k, v and
+ * g_out; written by the first of the three launches).  Deterministic, no atomics. */
 DSSMD_API int dssmd_epipolar_attn_bwd(const void *q, const void *k, const void *v, const void *out, const void *g_out,
                             const void *lse, void *delta, void *g_q, void *g_k, void *g_v,
                             int B, int C, int H, int W, float scale, int dtype, void *stream);

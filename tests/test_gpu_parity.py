@@ -1246,6 +1246,58 @@ def test_epipolar_attention_mma_forward_scaling(ops, case, monkeypatch, capfd):
     assert rel_err(out.cpu().numpy(), out2.cpu().numpy()) <= TOL_F32
 
 
+@pytest.mark.parametrize("case", ["plain", "large", "small", "mixed_rows", "outlier", "c16"])
+def test_epipolar_attention_mma_backward_scaling(ops, case, monkeypatch, capfd):
+    """The tensor-core backward (one power-of-two scale per image row and tensor, fp16 hi / lo split operands, seven GEMMs) against
+    float64 autograd of upstream's expression: gradients at the fp32 bar for inputs far outside fp16's range, image rows of very
+    different magnitude, single outliers; bit-identical from run to run; the FFMA kernels it replaces agree."""
+    B, C, H, W = (2, 16, 3, 200) if case == "c16" else (2, 32, 3, 328)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    q, k, v, go = (torch.randn(B, C, H, W, generator=g, device="cuda") for _ in range(4))
+    scale = C ** -0.5
+    if case == "large":
+        q, k, v, go, scale = q * 3.0e4, k * 2.0e3, v * 1.0e6, go * 5.0e3, scale / 6.0e7
+    elif case == "small":
+        q, k, v, go, scale = q * 1.0e-5, k * 3.0e-6, v * 1.0e-7, go * 1.0e-4, scale * 3.3e10
+    elif case == "mixed_rows":     # every image row (b, y) at its own magnitude
+        m = torch.logspace(-4, 4, B * H, device="cuda").view(B, 1, H, 1)
+        q, v, go = q * m, v * m.flip(2), go / m
+        scale_rows = None
+        k = k / m
+    elif case == "outlier":
+        k[0, :, 1, 77] *= 50.0
+        v[1, 3, 2, 5] = 3.0e3
+        go[0, 7, 0, 100] = -2.0e3
+    monkeypatch.setenv("DSSMD_CORR_DEBUG", "1")
+
+    def run():
+        qq, kk, vv = (t.clone().requires_grad_(True) for t in (q, k, v))
+        ops.epipolar_attention(qq, kk, vv, scale).backward(go)
+        return qq.grad, kk.grad, vv.grad
+    got = run()
+    torch.cuda.synchronize()
+    assert "epipolar_attn_bwd mma cfg" in capfd.readouterr().err
+    q2, k2, v2 = (t.double().requires_grad_(True) for t in (q, k, v))
+    qr_, kr_, vr_ = (t.permute(0, 2, 3, 1).reshape(B * H, W, C) for t in (q2, k2, v2))
+    ref = torch.matmul(torch.softmax(torch.matmul(qr_, kr_.transpose(-1, -2)) * scale, dim=-1), vr_).view(B, H, W, C).permute(0, 3, 1, 2)
+    ref.backward(go.double())
+    for a, b_, name in zip(got, (q2.grad, k2.grad, v2.grad), "qkv"):
+        if case == "mixed_rows":   # rows differ by 8 decades: compare every image row with its own maximum
+            for bb in range(B):
+                for yy in range(H):
+                    assert rel_err(a[bb, :, yy].cpu().numpy(), b_[bb, :, yy].float().cpu().numpy()) <= TOL_F32, (name, bb, yy)
+        else:
+            assert rel_err(a.cpu().numpy(), b_.float().cpu().numpy()) <= TOL_F32, name
+    again = run()
+    assert all(torch.equal(x, y) for x, y in zip(got, again))
+    monkeypatch.setenv("DSSMD_ATTN_BWD_MMA", "0")
+    monkeypatch.setenv("DSSMD_ATTN_FWD_MMA", "0")
+    old = run()
+    for a, b_ in zip(got, old):
+        if case != "mixed_rows":
+            assert rel_err(a.cpu().numpy(), b_.cpu().numpy()) <= 2 * TOL_F32
+
+
 def test_epipolar_attention_errors(ops):
     x = torch.randn(1, 32, 2, 8, device="cuda")
     with pytest.raises(NotImplementedError, match="needs C in"):
