@@ -59,6 +59,22 @@ def algorithmic_bytes(w, esize=4, cimg=3):
     }
 
 
+def algorithmic_rw_bytes(w, esize=4, cimg=3):
+    """The same split into bytes read and bytes written (roofline.traffic compares them with DRAM reads / writes separately)."""
+    B, C, Hf, Wf, D, H, W = (w[k] for k in ("B", "C", "Hf", "Wf", "D", "H", "W"))
+    feat = B * C * Hf * Wf * esize
+    vol = B * D * Hf * Wf * esize
+    px = B * H * W * 4
+    return {
+        "corr_fwd": (2 * feat, vol),
+        "corr_bwd": (vol + 2 * feat, 2 * feat),
+        "corr_bwd_gL": (vol + feat, feat),
+        "corr_bwd_gR": (vol + feat, feat),
+        "warp_fwd": (px * (cimg + 1), px * 2 * cimg),
+        "warp_bwd": (px * (2 * cimg + 1), px * (cimg + 1)),
+    }
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -133,12 +149,12 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------
 # synthetic data, seeded like upstream scripts/train.sh:33
 # ----------------------------------------------------------------------------------
-def measured_traffic(workload, kernel):
-    """DRAM bytes (read + write) per call of `kernel`, from the committed ncu --set full capture
-    of this workload (profiles/traffic.json, written by scripts/profile_summary.py); None if absent."""
+def measured_traffic(workload, kernel, key="dram_bytes"):
+    """DRAM bytes (read + write, or `key` = dram_read_bytes / dram_write_bytes) per call of `kernel`, from the committed
+    ncu --set full capture of this workload (profiles/traffic.json, written by scripts/profile_summary.py); None if absent."""
     try:
         with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as f:
-            return json.load(f)[workload][kernel]["dram_bytes"]
+            return json.load(f)[workload][kernel][key]
     except (OSError, KeyError, ValueError):
         return None
 
@@ -586,8 +602,9 @@ def run_gpu(args, w):
             torch.cuda.synchronize(device)
             us = k0.elapsed_time(k1) * 1e3 / reps
             gbs = abytes[n] / (us * 1e-6) / 1e9
-            kern[n] = {"us": round(us, 3), "algorithmic_bytes": abytes[n], "GBps": round(gbs, 1),
-                       "frac_of_peak": round(gbs / peak, 4)}
+            rb, wb = algorithmic_rw_bytes(w)[n]
+            kern[n] = {"us": round(us, 3), "algorithmic_bytes": abytes[n], "algorithmic_read_bytes": rb, "algorithmic_write_bytes": wb,
+                       "GBps": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4)}
     barrier()
 
     # ---- the public API on device-resident tensors: what the Python / autograd layer costs --------------------------------
@@ -722,6 +739,11 @@ def run_gpu(args, w):
         dom = max(kern, key=lambda n: kern[n]["us"])
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["GBps"], "peak": peak, "unit": "GB/s",
                     "frac": kern[dom]["frac_of_peak"], "traffic": measured_traffic(args.workload, dom), "peak_source": peak_src,
+                    # a 20-100 MB kernel's writes are still dirty in the 126 MB L2 when it ends: only the READ side can show re-reads
+                    "traffic_read": measured_traffic(args.workload, dom, "dram_read_bytes"),
+                    "traffic_write": measured_traffic(args.workload, dom, "dram_write_bytes"),
+                    "algorithmic_read_bytes": kern[dom].get("algorithmic_read_bytes"),
+                    "algorithmic_write_bytes": kern[dom].get("algorithmic_write_bytes"),
                     "share_of_step": round(kern[dom]["us"] / sum(k["us"] for k in kern.values()), 3)}
         # CPU baseline: oracle port, bounded sample (one per-GPU batch, best of 2)
         cpu = None
