@@ -199,17 +199,20 @@ epipolar_attn_fwd_mma_kernel(const float *q, const float *k, const float *v, flo
 #pragma unroll
             for (int ks = 0; ks < CH; ++ks) {
 #pragma unroll
-                for (int np = 0; np < 4; ++np) {
-                    uint32_t bh[4], bl[4];
-                    const int off = (ks * 16 + cb) * kKS + np * 16 + nb;
-                    ldsm_x4_t(smem_u32(kh + off), bh);
-                    ldsm_x4_t(smem_u32(kl + off), bl);
-                    mma16816(s[2 * np], ql[ks], bh[0], bh[1]);
-                    mma16816(s[2 * np], qh[ks], bl[0], bl[1]);
-                    mma16816(s[2 * np], qh[ks], bh[0], bh[1]);
-                    mma16816(s[2 * np + 1], ql[ks], bh[2], bh[3]);
-                    mma16816(s[2 * np + 1], qh[ks], bl[2], bl[3]);
-                    mma16816(s[2 * np + 1], qh[ks], bh[2], bh[3]);
+                for (int npp = 0; npp < 2; ++npp) {   // four accumulators at a time: the three products of one accumulator are 4 MMAs apart
+                    uint32_t bh[2][4], bl[2][4];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int off = (ks * 16 + cb) * kKS + (2 * npp + u) * 16 + nb;
+                        ldsm_x4_t(smem_u32(kh + off), bh[u]);
+                        ldsm_x4_t(smem_u32(kl + off), bl[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) { mma16816(s[4 * npp + 2 * u], ql[ks], bh[u][0], bh[u][1]); mma16816(s[4 * npp + 2 * u + 1], ql[ks], bh[u][2], bh[u][3]); }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) { mma16816(s[4 * npp + 2 * u], qh[ks], bl[u][0], bl[u][1]); mma16816(s[4 * npp + 2 * u + 1], qh[ks], bl[u][2], bl[u][3]); }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) { mma16816(s[4 * npp + 2 * u], qh[ks], bh[u][0], bh[u][1]); mma16816(s[4 * npp + 2 * u + 1], qh[ks], bh[u][2], bh[u][3]); }
                 }
             }
         }
@@ -258,19 +261,19 @@ epipolar_attn_fwd_mma_kernel(const float *q, const float *k, const float *v, flo
             const int jv = ((lane >> 3) & 1) * 8;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
+                uint32_t bh[NO / 2][4], bl[NO / 2][4];
 #pragma unroll
                 for (int np = 0; np < NO / 2; ++np) {
-                    uint32_t bh[4], bl[4];
                     const int off = (np * 16 + cv) * kKS + ks * 16 + jv;
-                    ldsm_x4(smem_u32(vh + off), bh);
-                    ldsm_x4(smem_u32(vl + off), bl);
-                    mma16816(o[2 * np], pl[ks], bh[0], bh[1]);
-                    mma16816(o[2 * np], ph[ks], bl[0], bl[1]);
-                    mma16816(o[2 * np], ph[ks], bh[0], bh[1]);
-                    mma16816(o[2 * np + 1], pl[ks], bh[2], bh[3]);
-                    mma16816(o[2 * np + 1], ph[ks], bl[2], bl[3]);
-                    mma16816(o[2 * np + 1], ph[ks], bh[2], bh[3]);
+                    ldsm_x4(smem_u32(vh + off), bh[np]);
+                    ldsm_x4(smem_u32(vl + off), bl[np]);
                 }
+#pragma unroll
+                for (int np = 0; np < NO / 2; ++np) { mma16816(o[2 * np], pl[ks], bh[np][0], bh[np][1]); mma16816(o[2 * np + 1], pl[ks], bh[np][2], bh[np][3]); }
+#pragma unroll
+                for (int np = 0; np < NO / 2; ++np) { mma16816(o[2 * np], ph[ks], bl[np][0], bl[np][1]); mma16816(o[2 * np + 1], ph[ks], bl[np][2], bl[np][3]); }
+#pragma unroll
+                for (int np = 0; np < NO / 2; ++np) { mma16816(o[2 * np], ph[ks], bh[np][0], bh[np][1]); mma16816(o[2 * np + 1], ph[ks], bh[np][2], bh[np][3]); }
             }
         }
 
@@ -358,13 +361,6 @@ __device__ __forceinline__ void frag_from_acc(const float (&t0)[4], const float 
     split_h2(t1[0], t1[1], hi[2], lo[2]);
     split_h2(t1[2], t1[3], hi[3], lo[3]);
 }
-// c += A B with split operands, small terms first
-__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
-    mma16816(c, al, bh0, bh1);
-    mma16816(c, ah, bl0, bl1);
-    mma16816(c, ah, bh0, bh1);
-}
-
 // KEYMAJOR = false: block rows = 128 queries, columns = keys, writes dQ.  true: rows = 128 keys, columns = queries, writes dK and dV.
 // Row side (X1, X2) = (Q, dO) | (K, V); column side (Y1, Y2) = (K, V) | (Q, dO).  S (or S^T) = X1^T Y1, dP (or dP^T) = X2^T Y2.
 template <int CH, bool KEYMAJOR>
@@ -467,16 +463,18 @@ epipolar_attn_bwd_mma_kernel(const float *q, const float *k, const float *v, con
                 for (int i = 0; i < 4; ++i) { s2[n][i] = 0.f; dp2[n][i] = 0.f; }
 #pragma unroll
             for (int kc = 0; kc < CH; ++kc) {
-                uint32_t bh[4], bl[4];
+                uint32_t bh[4], bl[4], ch[4], cl2[4];   // S and dP together: four independent accumulators per product
                 const int off = (kc * 16 + cb) * kKS + ks * 16 + nb;
                 ldsm_x4_t(smem_u32(y1h + off), bh);
                 ldsm_x4_t(smem_u32(y1l + off), bl);
-                mma3(s2[0], a1h[kc], a1l[kc], bh[0], bh[1], bl[0], bl[1]);
-                mma3(s2[1], a1h[kc], a1l[kc], bh[2], bh[3], bl[2], bl[3]);
-                ldsm_x4_t(smem_u32(y2h + off), bh);
-                ldsm_x4_t(smem_u32(y2l + off), bl);
-                mma3(dp2[0], a2h[kc], a2l[kc], bh[0], bh[1], bl[0], bl[1]);
-                mma3(dp2[1], a2h[kc], a2l[kc], bh[2], bh[3], bl[2], bl[3]);
+                ldsm_x4_t(smem_u32(y2h + off), ch);
+                ldsm_x4_t(smem_u32(y2l + off), cl2);
+                mma16816(s2[0], a1l[kc], bh[0], bh[1]); mma16816(s2[1], a1l[kc], bh[2], bh[3]);
+                mma16816(dp2[0], a2l[kc], ch[0], ch[1]); mma16816(dp2[1], a2l[kc], ch[2], ch[3]);
+                mma16816(s2[0], a1h[kc], bl[0], bl[1]); mma16816(s2[1], a1h[kc], bl[2], bl[3]);
+                mma16816(dp2[0], a2h[kc], cl2[0], cl2[1]); mma16816(dp2[1], a2h[kc], cl2[2], cl2[3]);
+                mma16816(s2[0], a1h[kc], bh[0], bh[1]); mma16816(s2[1], a1h[kc], bh[2], bh[3]);
+                mma16816(dp2[0], a2h[kc], ch[0], ch[1]); mma16816(dp2[1], a2h[kc], ch[2], ch[3]);
             }
             // P = exp2(S fs - lse2), D~ = P (dP~ - delta~); columns past the row end carry nothing
             float pr[2][4], ds[2][4];
@@ -499,14 +497,20 @@ epipolar_attn_bwd_mma_kernel(const float *q, const float *k, const float *v, con
             uint32_t dh[4], dl[4];
             frag_from_acc(ds[0], ds[1], dh, dl);
             // acc1 += D~ Y1~^T (dQ += dS K | dK += dS^T Q); KEYMAJOR: acc2 += P^T dO~ (dV)
+            {
+                uint32_t bh[NO / 2][4], bl[NO / 2][4];
 #pragma unroll
-            for (int np = 0; np < NO / 2; ++np) {
-                uint32_t bh[4], bl[4];
-                const int off = (np * 16 + cv) * kKS + ks * 16 + jv;
-                ldsm_x4(smem_u32(y1h + off), bh);
-                ldsm_x4(smem_u32(y1l + off), bl);
-                mma3(acc1[2 * np], dh, dl, bh[0], bh[1], bl[0], bl[1]);
-                mma3(acc1[2 * np + 1], dh, dl, bh[2], bh[3], bl[2], bl[3]);
+                for (int np = 0; np < NO / 2; ++np) {
+                    const int off = (np * 16 + cv) * kKS + ks * 16 + jv;
+                    ldsm_x4(smem_u32(y1h + off), bh[np]);
+                    ldsm_x4(smem_u32(y1l + off), bl[np]);
+                }
+#pragma unroll
+                for (int np = 0; np < NO / 2; ++np) { mma16816(acc1[2 * np], dl, bh[np][0], bh[np][1]); mma16816(acc1[2 * np + 1], dl, bh[np][2], bh[np][3]); }
+#pragma unroll
+                for (int np = 0; np < NO / 2; ++np) { mma16816(acc1[2 * np], dh, bl[np][0], bl[np][1]); mma16816(acc1[2 * np + 1], dh, bl[np][2], bl[np][3]); }
+#pragma unroll
+                for (int np = 0; np < NO / 2; ++np) { mma16816(acc1[2 * np], dh, bh[np][0], bh[np][1]); mma16816(acc1[2 * np + 1], dh, bh[np][2], bh[np][3]); }
             }
             if constexpr (KEYMAJOR) {
                 uint32_t ph[4], pl[4];
@@ -515,15 +519,19 @@ epipolar_attn_bwd_mma_kernel(const float *q, const float *k, const float *v, con
 #pragma unroll
                     for (int i = 0; i < 4; ++i) pr[n][i] *= kUpP;
                 frag_from_acc(pr[0], pr[1], ph, pl);
+                uint32_t bh[NO / 2][4], bl[NO / 2][4];
 #pragma unroll
                 for (int np = 0; np < NO / 2; ++np) {
-                    uint32_t bh[4], bl[4];
                     const int off = (np * 16 + cv) * kKS + ks * 16 + jv;
-                    ldsm_x4(smem_u32(y2h + off), bh);
-                    ldsm_x4(smem_u32(y2l + off), bl);
-                    mma3(acc2[2 * np], ph, pl, bh[0], bh[1], bl[0], bl[1]);
-                    mma3(acc2[2 * np + 1], ph, pl, bh[2], bh[3], bl[2], bl[3]);
+                    ldsm_x4(smem_u32(y2h + off), bh[np]);
+                    ldsm_x4(smem_u32(y2l + off), bl[np]);
                 }
+#pragma unroll
+                for (int np = 0; np < NO / 2; ++np) { mma16816(acc2[2 * np], pl, bh[np][0], bh[np][1]); mma16816(acc2[2 * np + 1], pl, bh[np][2], bh[np][3]); }
+#pragma unroll
+                for (int np = 0; np < NO / 2; ++np) { mma16816(acc2[2 * np], ph, bl[np][0], bl[np][1]); mma16816(acc2[2 * np + 1], ph, bl[np][2], bl[np][3]); }
+#pragma unroll
+                for (int np = 0; np < NO / 2; ++np) { mma16816(acc2[2 * np], ph, bh[np][0], bh[np][1]); mma16816(acc2[2 * np + 1], ph, bh[np][2], bh[np][3]); }
             }
         }
         if (more) {   // buffer buf ^ 1 was last read two tiles ago, before the barrier that ended the previous iteration
