@@ -254,7 +254,8 @@ int launch_wide(WideParams p, const CUtensorMap &mapL, const CUtensorMap &mapR, 
 // to the other kernels), else a DSSMD_* code.  gbs = elements between two images of g (the concat buffer's stride for
 // corr_bwd_cat).  Taken by default for rows of 80 .. 128 pixels (one x tile with at least 20 of a warp's 32 lanes busy):
 // measured against the kernels it replaces -- 576x960 model shape (W = 120) 23.1 -> 20.1 us, 320x640 (W = 80) 30.0 -> 26.7 us;
-// KITTI (W = 160, two tiles of 80 pixels) 74.7 -> 90.3 us stays on the mma.sync kernels.  DSSMD_CORR_BWD_WIDE=2 takes it
+// KITTI (W = 160, two tiles of 80 pixels) at batch 16 74.7 -> 90.3 us stays on the mma.sync kernels, at batch 1 .. 4 it is taken
+// (batch 1: 16.9 -> 9.9 us).  DSSMD_CORR_BWD_WIDE=2 takes it
 // wherever it is eligible, =0 never.
 int corr_bwd_wide_f32(const void *g, const void *L, const void *R, void *gL, void *gR, int B, int C, int H, int W, int D, long long gbs,
                       cudaStream_t stream) {
@@ -270,7 +271,10 @@ int corr_bwd_wide_f32(const void *g, const void *L, const void *R, void *gL, voi
     p.invC = 1.0f / (float)C;
     p.XT = ceil_div(W, 128);
     p.TX = round_up(ceil_div(W, p.XT), 4);
-    if (want < 2 && (p.XT > 1 || p.TX < 80)) return -1;
+    // several x tiles per row (KITTI, W = 160: two tiles of 80 pixels): only while the problem is small -- measured at C128 48x160 D24
+    // over the batch size (scripts/kitti_b_sweep.py), wide vs the two mma.sync launches: B = 1 10.4 / 20.2 us, B = 4 26.1 / 30.6,
+    // B = 6 33.5 / 32.8, B = 16 82.9 / 74.5
+    if (want < 2 && (p.TX < 80 || (p.XT > 1 && (long)B * H * p.XT > 3L * sm_count()))) return -1;
     p.WP = p.TX + kWD;
     constexpr int NWG = 4;
     int cpw = env_int_wide("DSSMD_CORR_BWD_WIDE_CPW", 8);

@@ -41,7 +41,7 @@ struct FwdRegParams {
     float invC;
 };
 
-template <typename T, int LOGNH>
+template <typename T, int LOGNH, int CPW>
 __global__ void __launch_bounds__(512) corr_fwd_reg_kernel(const FwdRegParams p, const __grid_constant__ CUtensorMap mapL,
                                                            const __grid_constant__ CUtensorMap mapR) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -108,16 +108,24 @@ __global__ void __launch_bounds__(512) corr_fwd_reg_kernel(const FwdRegParams p,
         const T *lrow = lt + cgw * p.TX + xl;
         const T *wrow = rt + cgw * p.WP + woff;
         const int lstep = p.CGW * p.TX, wstep = p.CGW * p.WP;
-#pragma unroll 2
-        for (int c = cgw; c < cn; c += p.CGW, lrow += lstep, wrow += wstep) {
+        auto channel = [&](const T *lr, const T *wr) {
             float l[PX], w[PX + kDP];
-            load4<T>(lrow, l[0], l[1], l[2], l[3]);
+            load4<T>(lr, l[0], l[1], l[2], l[3]);
 #pragma unroll
-            for (int q = 0; q < (PX + kDP) / 4; ++q) load4<T>(wrow + 4 * q, w[4 * q + 0], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+            for (int q = 0; q < (PX + kDP) / 4; ++q) load4<T>(wr + 4 * q, w[4 * q + 0], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
 #pragma unroll
             for (int dd = 0; dd < kDP; ++dd)
 #pragma unroll
                 for (int i = 0; i < PX; ++i) acc[dd][i] = fmaf(l[i], w[i - dd + kDP], acc[dd][i]);
+        };
+        if (CPW > 0 && cn == p.CB) {
+            // full item with a compile-time channel count per warp: straight-line code, the window loads of channel k + 1 start under
+            // the FFMAs of channel k (with a run-time trip count the loads of every iteration wait at the top of the loop body)
+#pragma unroll
+            for (int k = 0; k < CPW; ++k) channel(lrow + k * lstep, wrow + k * wstep);
+        } else {
+#pragma unroll 2
+            for (int c = cgw; c < cn; c += p.CGW, lrow += lstep, wrow += wstep) channel(lrow, wrow);
         }
 
         if (cb == p.NCB - 1) {
@@ -172,9 +180,9 @@ int env_int_fwd(const char *name, int dflt) {
     return (v && *v) ? std::atoi(v) : dflt;
 }
 
-template <typename T, int LOGNH>
-int launch_fwd_reg(FwdRegParams p, const CUtensorMap &mapL, const CUtensorMap &mapR, int threads, size_t smem, cudaStream_t stream) {
-    auto kern = corr_fwd_reg_kernel<T, LOGNH>;
+template <typename T, int LOGNH, int CPW>
+int launch_fwd_reg_cpw(FwdRegParams p, const CUtensorMap &mapL, const CUtensorMap &mapR, int threads, size_t smem, cudaStream_t stream) {
+    auto kern = corr_fwd_reg_kernel<T, LOGNH, CPW>;
     {
         cudaError_t e = kernel_smem_optin(kern, smem);
         if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_fwd: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
@@ -191,6 +199,15 @@ int launch_fwd_reg(FwdRegParams p, const CUtensorMap &mapL, const CUtensorMap &m
     const cudaError_t le = launch_pdl(kern, dim3((unsigned)grid), dim3((unsigned)threads), smem, stream, p, mapL, mapR);
     if (le != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_fwd(reg): launch failed: %s", cudaGetErrorString(le));
     return check_launch("corr_fwd(reg)");
+}
+
+// channels per warp and item as a compile-time constant where it is the common 8 (fp32 model shapes: 32 channels per item over 4
+// channel groups); 0 = run-time loop
+template <typename T, int LOGNH>
+int launch_fwd_reg(FwdRegParams p, const CUtensorMap &mapL, const CUtensorMap &mapR, int threads, size_t smem, cudaStream_t stream) {
+    if (sizeof(T) == 4 && p.CB == 8 * p.CGW && env_int_fwd("DSSMD_CORR_FWD_UNROLLED", 1) != 0)
+        return launch_fwd_reg_cpw<T, LOGNH, 8>(p, mapL, mapR, threads, smem, stream);
+    return launch_fwd_reg_cpw<T, LOGNH, 0>(p, mapL, mapR, threads, smem, stream);
 }
 
 template <typename T>
