@@ -449,11 +449,11 @@ def api_timings(torch, dssmd_b200, w, sets, nsets, device, graph_ms):
         s, lv = sets[i % nsets], leaves[i % nsets]
         for t in lv.values():
             t.grad = None
-        dssmd_b200.build_corr(lv["L"], lv["R"], w["D"]).backward(s["g_vol"])
+        vol = dssmd_b200.build_corr(lv["L"], lv["R"], w["D"])
         warped, _ = dssmd_b200.disp_warp(lv["img"], lv["disp"])
-        warped.backward(s["g_img"])
+        torch.autograd.backward([vol, warped], [s["g_vol"], s["g_img"]])   # one engine run for the step, as a training step has
 
-    out = {"what": "build_corr(L, R, D).backward(g) + disp_warp(img, disp)[0].backward(g) on device tensors, us per step"}
+    out = {"what": "build_corr(L, R, D), disp_warp(img, disp), one autograd.backward over both outputs, on device tensors, us per step"}
     for mode, key in ((True, "eager_us"), ("deferred", "eager_deferred_check_us"), (False, "eager_no_check_us")):
         dssmd_b200.set_check_negative_disparity(mode)
         for i in range(10):

@@ -622,12 +622,14 @@ int launch_typed(const void *L, const void *R, void *out, int B, int C, int H, i
         // well-fitting shapes (cfg5, W = 120: 12.9 vs 14.4 us)
         const long warp_tiles = (long)B * H * ceil_div(W, 16);
         const bool fills_reg_tiles = (double)W >= 0.75 * (double)(ceil_div(W, 128) * 128);
-        if (variant == 3 || (variant < 0 && (!fills_reg_tiles || warp_tiles >= 4000))) {
+        if (variant == 3 || (variant < 0 && (!fills_reg_tiles || warp_tiles >= 3500))) {
             const int rc = corr_fwd_mma32(L, R, out, B, C, H, W, D, obs, stream);
             if (rc >= 0) return rc;
         }
     }
-    if (variant < 0) variant = (sizeof(T) == 4 && C >= 64 && D >= 32 && (long)B * H * W / 128 >= 3L * sm_count()) ? 2 : 1;
+    // the tcgen05 kernels (2, 4) are opt-in: the mma.sync 3xTF32 kernel is faster on every shape measured (profiles/r02s_tcgen05_vs_mma32.md);
+    // until round 2 a narrow window of problem sizes still selected variant 2 by itself
+    if (variant < 0) variant = 1;
     if constexpr (sizeof(T) == 4) {
         if (variant == 2) {
             const int rc = corr_fwd_umma_f32(L, R, out, B, C, H, W, D, obs, stream);
