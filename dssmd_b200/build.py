@@ -20,7 +20,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 OBJ_DIR = os.path.join(HERE, "_obj")
 LIB_PATH = os.path.join(HERE, "libdssmd_b200.so")
 
-SOURCES = ["abi.cu", "corr_fwd.cu", "corr_fwd_umma.cu", "corr_fwd_umma2.cu", "corr_bwd.cu", "corr_bwd_reg.cu", "corr_bwd_fused.cu", "corr_bwd_wide.cu", "corr_fwd_reg.cu", "corr_fwd_mma16.cu", "corr_bwd_mma16.cu", "corr_fwd_mma32.cu", "corr_bwd_mma32.cu", "warp.cu", "warp_bwd.cu", "warp_lean.cu", "warp_bwd_band.cu", "warp_bwd_band2.cu", "photometric.cu", "haze.cu", "asm_loss.cu", "epipolar_attn.cu", "epipolar_attn_mma.cu"]
+SOURCES = ["abi.cu", "corr_fwd.cu", "corr_fwd_umma.cu", "corr_fwd_umma2.cu", "corr_bwd.cu", "corr_bwd_reg.cu", "corr_bwd_fused.cu", "corr_bwd_wide.cu", "corr_fwd_reg.cu", "corr_fwd_mma16.cu", "corr_bwd_mma16.cu", "corr_fwd_mma32.cu", "corr_bwd_mma32.cu", "warp.cu", "warp_bwd.cu", "warp_lean.cu", "warp_bwd_band.cu", "warp_bwd_band2.cu", "photometric.cu", "haze.cu", "asm_loss.cu", "epipolar_attn.cu", "epipolar_attn_mma.cu", "epipolar_attn_umma.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "warp_common.cuh"), os.path.join(CSRC, "warp_lean.cuh"), os.path.join(CSRC, "tma.cuh"), os.path.join(CSRC, "corr_reg.cuh"), os.path.join(INCLUDE, "dssmd_b200.h")]
 
 NVCC_FLAGS = [

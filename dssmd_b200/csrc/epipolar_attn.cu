@@ -316,6 +316,9 @@ namespace dssmd {
 // epipolar_attn_mma.cu: the forward on mma.sync (fp16 hi / lo operand splitting); -1 = not eligible
 int epipolar_attn_fwd_mma(const float *q, const float *k, const float *v, float *out, float *lse, int B, int C, int H, int W, float scale,
                           cudaStream_t s);
+// epipolar_attn_umma.cu: the forward on tcgen05 + TMEM (C = 32); -1 = not eligible
+int epipolar_attn_fwd_umma(const float *q, const float *k, const float *v, float *out, float *lse, int B, int C, int H, int W, float scale,
+                           cudaStream_t s);
 int epipolar_attn_bwd_mma(const float *q, const float *k, const float *v, const float *out, const float *g_out, const float *lse, float *delta,
                           float *gq, float *gk, float *gv, int B, int C, int H, int W, float scale, cudaStream_t s);
 }  // namespace dssmd
@@ -329,7 +332,9 @@ extern "C" int dssmd_epipolar_attn_fwd(const void *q, const void *k, const void 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const float *Q = (const float *)q, *K = (const float *)k, *V = (const float *)v;
     {
-        const int rc = epipolar_attn_fwd_mma(Q, K, V, (float *)out, (float *)lse, B, C, H, W, scale, s);
+        int rc = epipolar_attn_fwd_umma(Q, K, V, (float *)out, (float *)lse, B, C, H, W, scale, s);
+        if (rc >= 0) return rc;
+        rc = epipolar_attn_fwd_mma(Q, K, V, (float *)out, (float *)lse, B, C, H, W, scale, s);
         if (rc >= 0) return rc;
     }
     switch (C) {
