@@ -8,11 +8,12 @@
 // One CTA per SM owns 128 queries of one image row at a time (M = 128 = the TMEM lanes) and walks over key tiles of 128:
 //   S  = Q~^T K~   tcgen05.mma M128 N128 K16 x 2 channel steps x 3 products  -> TMEM [128 lanes x 128 columns], two buffers
 //   P  = exp2(S fs - m)  one softmax THREAD per query row (tcgen05.ld 32x32b: no shuffles), split into fp16 hi / lo in registers
-//   O += P V~^T    tcgen05.mma M128 N32 K16 x 8 key steps x 3 products        -> TMEM [128 x 32]
+//   O += P V~^T    tcgen05.mma M128 N32 K16 x 8 key steps x 3 products, A = P from TMEM  -> TMEM [128 x 32] per query tile
 // Operand tiles are fp16 planes in the no-swizzle canonical layouts (8 x 16-byte core matrices): the staging threads read 8
 // consecutive pixels of one channel from the NCHW tensor and write ONE 16-byte unit -- for Q and K that is the MN-major
 // layout of a [pixels x channels] operand, for V the K-major layout of a [channels x keys] operand: the same address
-// arithmetic; P is written K-major by its row's thread (32 lanes = 512 contiguous bytes per store).
+// arithmetic.  P never touches shared memory: its threads write the packed halves over the S buffer they came from (tcgen05.st)
+// and the second GEMM takes its A operand from tensor memory.
 // Warps: 0-7 softmax -- TMEM lane quarter = warp % 4, and the two warps of a quarter split a row's 128 score columns (and its 32
 // output channels) in halves: TWO threads per query row, their row maxima exchanged through shared memory once per tile --,
 // 8-10 staging (global fp32 -> scale -> hi / lo planes), 11 MMA issue (one lane).  A thread pulls its 64 scores into registers
@@ -36,9 +37,9 @@ constexpr int kUThreads = 384;     // 8 softmax + 3 staging + 1 MMA warp (13 war
 constexpr float kUUp = 1024.0f;    // up-shift of stored operands (see epipolar_attn_mma.cu)
 constexpr float kUUpP = 1024.0f;   // probabilities
 
-// shared memory (bytes): Q hi/lo 2 x 8192 per query tile of the group | K hi/lo, V hi/lo per buffer 4 x 8192, two buffers | P hi/lo 2 x 32768
+// shared memory (bytes): Q hi/lo 2 x 8192 per query tile of the group | K hi/lo, V hi/lo per buffer 4 x 8192, two buffers (P lives in TMEM)
 constexpr int kPlane = kUM * kUC * 2;                 // 8192
-constexpr int kOffQ = 0, kOffKV = kUG * 2 * kPlane, kOffP = kOffKV + 2 * 4 * kPlane, kUSmem = kOffP + 2 * kUM * kUN * 2;   // 212992
+constexpr int kOffQ = 0, kOffKV = kUG * 2 * kPlane, kUSmem = kOffKV + 2 * 4 * kPlane;   // 147456
 
 enum { kKvFull = 0, kKvEmpty = 2, kSFull = 4, kSEmpty = 6, kPFull = 8, kODone = 9, kUBars = 10 };
 
@@ -109,6 +110,25 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
           "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
         : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32u_nowait(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+          "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]),
+          "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// A operand from tensor memory (K-major: lane = row, two 16-bit K elements per 32-bit column), B from shared memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
 }
 __device__ __forceinline__ void u_wait(uint32_t bar, uint32_t parity) {   // bounded: a protocol bug traps instead of hanging the GPU
     for (int spin = 0; spin < (1 << 27); ++spin) {
@@ -182,7 +202,7 @@ epipolar_attn_fwd_umma_kernel(const float *q, const float *k, const float *v, fl
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(UBAR(kKvFull + i), 3); mbar_init(UBAR(kKvEmpty + i), 1);
-            mbar_init(UBAR(kSFull + i), 1); mbar_init(UBAR(kSEmpty + i), 8);
+            mbar_init(UBAR(kSFull + i), 1); mbar_init(UBAR(kSEmpty + i), 1);
         }
         mbar_init(UBAR(kPFull), 8);
         mbar_init(UBAR(kODone), 1);
@@ -246,7 +266,6 @@ epipolar_attn_fwd_umma_kernel(const float *q, const float *k, const float *v, fl
             if (lane == 0) {
                 const uint32_t idesc1 = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(kUN >> 3) << 17) | ((uint32_t)(kUM >> 4) << 24);   // F16 x F16 -> F32, A, B MN-major
                 const uint32_t idesc2 = (1u << 4) | ((uint32_t)(kUC >> 3) << 17) | ((uint32_t)(kUM >> 4) << 24);                            // A, B K-major, N = 32
-                const uint32_t ph_ = sb + kOffP, pl_ = ph_ + kUM * kUN * 2;
                 const int npairs = nkt * G;
                 auto gemm1 = [&](int pi) {   // pair pi = (kt, g): S[c & 1] = Q_g~^T K_kt~
                     const int kt = pi / G, g = pi - kt * G;
@@ -276,14 +295,16 @@ epipolar_attn_fwd_umma_kernel(const float *q, const float *k, const float *v, fl
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t vh = sb + kOffKV + kbuf * 4 * kPlane + 2 * kPlane, vl = vh + kPlane;
                     const uint32_t od = tmem + 2 * kUN + (uint32_t)g * kUC;
+                    const uint32_t pth = tmem + (c & 1u) * kUN, ptl = pth + 64;   // P hi / lo over the S buffer they were computed from
 #pragma unroll
                     for (int ks = 0; ks < kUN / 16; ++ks) {
-                        const uint32_t oa = ks * 2 * 2048, ob = ks * 2 * 512;   // two key chunks per step
-                        umma_f16(od, u_desc(pl_ + oa, 2048, 128), u_desc(vh + ob, 512, 128), idesc2, (kt > 0 || ks > 0) ? 1u : 0u);
-                        umma_f16(od, u_desc(ph_ + oa, 2048, 128), u_desc(vl + ob, 512, 128), idesc2, 1u);
-                        umma_f16(od, u_desc(ph_ + oa, 2048, 128), u_desc(vh + ob, 512, 128), idesc2, 1u);
+                        const uint32_t oa = ks * 8, ob = ks * 2 * 512;   // 16 keys = 8 columns of packed halves | two key chunks of V
+                        umma_f16_ts(od, ptl + oa, u_desc(vh + ob, 512, 128), idesc2, (kt > 0 || ks > 0) ? 1u : 0u);
+                        umma_f16_ts(od, pth + oa, u_desc(vl + ob, 512, 128), idesc2, 1u);
+                        umma_f16_ts(od, pth + oa, u_desc(vh + ob, 512, 128), idesc2, 1u);
                     }
-                    u_commit(UBAR(kODone));                              // O_g updated, P read
+                    u_commit(UBAR(kODone));                              // O_g updated
+                    u_commit(UBAR(kSEmpty + (c & 1u)));                  // P read: the S buffer may take the pair after next
                     if (g == G - 1) u_commit(UBAR(kKvEmpty + kbuf));     // K / V buffer free
                 }
             }
@@ -297,7 +318,6 @@ epipolar_attn_fwd_umma_kernel(const float *q, const float *k, const float *v, fl
 #pragma unroll
             for (int g = 0; g < kUG; ++g) { mrun[g] = -INFINITY; lrun[g] = 0.f; svu[g] = 0.f; }
             auto rowsync = [] { asm volatile("bar.sync 3, 256;" ::: "memory"); };
-            unsigned char *prow_h = smem + kOffP + m * 16 + half * 8 * 2048, *prow_l = prow_h + kUM * kUN * 2;
             uint32_t c = pair_count;
             for (int kt = 0; kt < nkt; ++kt) {
                 const uint32_t kbuf = (kv_count + (uint32_t)kt) & 1u;
@@ -313,9 +333,6 @@ epipolar_attn_fwd_umma_kernel(const float *q, const float *k, const float *v, fl
                     tmem_ld32_nowait(tmem + lane_addr + sbuf * kUN + half * 64, sc);
                     tmem_ld32_nowait(tmem + lane_addr + sbuf * kUN + half * 64 + 32, sc + 32);
                     tmem_wait_ld();
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(UBAR(kSEmpty + sbuf)); // the scores are in registers: the buffer may take the pair after next
                     const int j0 = kt * kUN + half * 64;              // first key of this thread's columns
                     float mx = -INFINITY;
                     if (j0 + 64 <= W) {                               // uniform over the warp
@@ -334,13 +351,21 @@ epipolar_attn_fwd_umma_kernel(const float *q, const float *k, const float *v, fl
                     const float unit = svu[g] / sv_new, pvu = sv_t / sv_new * kUUpP;           // exact powers of two
                     const float off = mn - (float)((int)(__float_as_uint(pvu) >> 23) - 127);   // exp2(s fs - off) = p * pvu
                     mrun[g] = mn; svu[g] = sv_new;
-                    // exponentials in place (under the P V of the previous pair), then wait for it: it reads the P planes and may
-                    // update this O tile
+                    // probabilities -> packed fp16 hi / lo pairs, written over this thread's half of the S buffer (every thread of the
+                    // row pair has its scores in registers: the row barrier above); all of it runs under the P V of the previous pair
                     float psum = 0.f;
+                    uint32_t phi[32], plo[32];
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) { sc[i] = u_exp2(fmaf(sc[i], fs, -off)); psum += sc[i]; }   // exp2(-inf) = 0 for masked keys
+                    for (int i = 0; i < 32; ++i) {
+                        const float p0 = u_exp2(fmaf(sc[2 * i], fs, -off)), p1 = u_exp2(fmaf(sc[2 * i + 1], fs, -off));   // exp2(-inf) = 0 for masked keys
+                        psum += p0 + p1;
+                        u_split(p0, p1, phi[i], plo[i]);
+                    }
                     lrun[g] = fmaf(lrun[g], corr, psum * (1.0f / pvu));   // exact rescale back to probabilities
-                    if (c != pair_count) {
+                    tmem_st32u_nowait(tmem + lane_addr + sbuf * kUN + half * 32, phi);
+                    tmem_st32u_nowait(tmem + lane_addr + sbuf * kUN + 64 + half * 32, plo);
+                    tmem_wait_st();
+                    if (c != pair_count) {   // the previous P V may still be updating an O tile
                         u_wait(UBAR(kODone), (c - 1u) & 1u);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
@@ -354,17 +379,7 @@ epipolar_attn_fwd_umma_kernel(const float *q, const float *k, const float *v, fl
                             tmem_st16(tmem + lane_addr + 2 * kUN + g * kUC + half * 16, o16);
                         }
                     }
-                    // fp16 hi / lo units (8 keys = 16 bytes) of this row
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        uint32_t h[4], l[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) u_split(sc[u * 8 + 2 * e], sc[u * 8 + 2 * e + 1], h[e], l[e]);
-                        *reinterpret_cast<uint4 *>(prow_h + u * 2048) = make_uint4(h[0], h[1], h[2], h[3]);
-                        *reinterpret_cast<uint4 *>(prow_l + u * 2048) = make_uint4(l[0], l[1], l[2], l[3]);
-                    }
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(UBAR(kPFull));
                     ++c;
