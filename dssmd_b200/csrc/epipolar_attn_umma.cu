@@ -263,49 +263,59 @@ epipolar_attn_fwd_umma_kernel(const float *q, const float *k, const float *v, fl
             }
         } else if (warp == 11) {
             // =============================== MMA issue ============================================
+            // ONE thread issues ~30 MMAs per (key tile, query tile) pair: its instruction stream is on the critical path, so the
+            // descriptors are built once per group / key tile and advanced by adding to their address field
             if (lane == 0) {
                 const uint32_t idesc1 = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(kUN >> 3) << 17) | ((uint32_t)(kUM >> 4) << 24);   // F16 x F16 -> F32, A, B MN-major
                 const uint32_t idesc2 = (1u << 4) | ((uint32_t)(kUC >> 3) << 17) | ((uint32_t)(kUM >> 4) << 24);                            // A, B K-major, N = 32
+                const uint64_t dq0 = u_desc(sb + kOffQ, 128, 512);            // Q hi of query tile 0; lo: + kPlane; tile g: + g * 2 * kPlane
+                const uint64_t dk0 = u_desc(sb + kOffKV, 128, 512);           // K hi of buffer 0; lo: + kPlane; buffer 1: + 4 * kPlane
+                const uint64_t dv0 = u_desc(sb + kOffKV + 2 * kPlane, 512, 128);   // V hi of buffer 0
+                constexpr uint64_t PL = kPlane >> 4;                          // descriptor address units are 16 bytes
                 const int npairs = nkt * G;
-                auto gemm1 = [&](int pi) {   // pair pi = (kt, g): S[c & 1] = Q_g~^T K_kt~
-                    const int kt = pi / G, g = pi - kt * G;
-                    const uint32_t c = pair_count + (uint32_t)pi, sbuf = c & 1u, sph = (c >> 1) & 1u;
-                    const uint32_t ck = kv_count + (uint32_t)kt, kbuf = ck & 1u;
-                    if (g == 0) u_wait(UBAR(kKvFull + kbuf), (ck >> 1) & 1u);
+                int kt1 = 0, g1 = 0;          // the pair gemm1 takes next
+                auto gemm1 = [&]() {          // S[c & 1] = Q_g~^T K_kt~ for pair (kt1, g1), then advance
+                    const uint32_t c = pair_count + (uint32_t)(kt1 * G + g1), sbuf = c & 1u, sph = (c >> 1) & 1u;
+                    const uint32_t ck = kv_count + (uint32_t)kt1, kbuf = ck & 1u;
+                    if (g1 == 0) u_wait(UBAR(kKvFull + kbuf), (ck >> 1) & 1u);
                     u_wait(UBAR(kSEmpty + sbuf), sph ^ 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t qh = sb + kOffQ + g * 2 * kPlane, ql = qh + kPlane;
-                    const uint32_t kh = sb + kOffKV + kbuf * 4 * kPlane, kl = kh + kPlane;
-#pragma unroll
-                    for (int ks = 0; ks < kUC / 16; ++ks) {
-                        const uint32_t o = ks * 256;   // two channel groups of 128 B
-                        umma_f16(tmem + sbuf * kUN, u_desc(ql + o, 128, 512), u_desc(kh + o, 128, 512), idesc1, ks > 0 ? 1u : 0u);
-                        umma_f16(tmem + sbuf * kUN, u_desc(qh + o, 128, 512), u_desc(kl + o, 128, 512), idesc1, 1u);
-                        umma_f16(tmem + sbuf * kUN, u_desc(qh + o, 128, 512), u_desc(kh + o, 128, 512), idesc1, 1u);
-                    }
+                    const uint64_t qh = dq0 + (uint64_t)g1 * 2 * PL, ql = qh + PL;
+                    const uint64_t kh = dk0 + (uint64_t)kbuf * 4 * PL, kl = kh + PL;
+                    const uint32_t sd = tmem + sbuf * kUN;
+                    umma_f16(sd, ql, kh, idesc1, 0u);
+                    umma_f16(sd, qh, kl, idesc1, 1u);
+                    umma_f16(sd, qh, kh, idesc1, 1u);
+                    umma_f16(sd, ql + 16, kh + 16, idesc1, 1u);   // second 16 channels: two channel groups of 128 B further
+                    umma_f16(sd, qh + 16, kl + 16, idesc1, 1u);
+                    umma_f16(sd, qh + 16, kh + 16, idesc1, 1u);
                     u_commit(UBAR(kSFull + sbuf));
+                    if (++g1 == G) { g1 = 0; ++kt1; }
                 };
-                gemm1(0);
+                gemm1();
+                int kt = 0, g = 0;
                 for (int pi = 0; pi < npairs; ++pi) {
-                    const int kt = pi / G, g = pi - kt * G;
                     const uint32_t c = pair_count + (uint32_t)pi;
                     const uint32_t kbuf = (kv_count + (uint32_t)kt) & 1u;
-                    if (pi + 1 < npairs) gemm1(pi + 1);   // the next S while the softmax threads work on this one
-                    u_wait(UBAR(kPFull), c & 1u);         // P planes written, O rows rescaled
+                    if (pi + 1 < npairs) gemm1();         // the next S while the softmax threads work on this one
+                    u_wait(UBAR(kPFull), c & 1u);         // P written, O rows rescaled
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t vh = sb + kOffKV + kbuf * 4 * kPlane + 2 * kPlane, vl = vh + kPlane;
+                    const uint64_t vh = dv0 + (uint64_t)kbuf * 4 * PL, vl = vh + PL;
                     const uint32_t od = tmem + 2 * kUN + (uint32_t)g * kUC;
                     const uint32_t pth = tmem + (c & 1u) * kUN, ptl = pth + 64;   // P hi / lo over the S buffer they were computed from
+                    umma_f16_ts(od, ptl, vh, idesc2, kt > 0 ? 1u : 0u);
+                    umma_f16_ts(od, pth, vl, idesc2, 1u);
+                    umma_f16_ts(od, pth, vh, idesc2, 1u);
 #pragma unroll
-                    for (int ks = 0; ks < kUN / 16; ++ks) {
-                        const uint32_t oa = ks * 8, ob = ks * 2 * 512;   // 16 keys = 8 columns of packed halves | two key chunks of V
-                        umma_f16_ts(od, ptl + oa, u_desc(vh + ob, 512, 128), idesc2, (kt > 0 || ks > 0) ? 1u : 0u);
-                        umma_f16_ts(od, pth + oa, u_desc(vl + ob, 512, 128), idesc2, 1u);
-                        umma_f16_ts(od, pth + oa, u_desc(vh + ob, 512, 128), idesc2, 1u);
+                    for (int ks = 1; ks < kUN / 16; ++ks) {   // 16 keys = 8 columns of packed halves | two key chunks of V (1024 B)
+                        umma_f16_ts(od, ptl + ks * 8, vh + ks * 64, idesc2, 1u);
+                        umma_f16_ts(od, pth + ks * 8, vl + ks * 64, idesc2, 1u);
+                        umma_f16_ts(od, pth + ks * 8, vh + ks * 64, idesc2, 1u);
                     }
                     u_commit(UBAR(kODone));                              // O_g updated
                     u_commit(UBAR(kSEmpty + (c & 1u)));                  // P read: the S buffer may take the pair after next
                     if (g == G - 1) u_commit(UBAR(kKvEmpty + kbuf));     // K / V buffer free
+                    if (++g == G) { g = 0; ++kt; }
                 }
             }
         } else if (warp < 8) {
