@@ -99,6 +99,23 @@ __device__ __forceinline__ double ld_cg(const double *p) { return __ldcg(p); }
 __device__ __forceinline__ float2 ld_cg(const float2 *p) { return __ldcg(p); }
 __device__ __forceinline__ float4 ld_cg(const float4 *p) { return __ldcg(p); }
 
+// L2 prefetch of the lines a block reads FIRST, issued BEFORE griddepcontrol.wait: while the predecessor on the stream is
+// still draining, the blocks that are already resident pull their first tiles from HBM into the L2, so the loads after the
+// wait start from an L2 hit instead of a cold DRAM access.  A prefetch returns nothing to the thread and the L2 is the
+// point of coherence of the device: if the predecessor still writes one of those lines the line is simply updated in
+// place, so unlike a load this is legal before the wait.  DSSMD_PDL_PREFETCH=0 (tuning) disables it, =n sets the amount.
+// Measured at the 576x960 model shapes (profiles/r04c_pdl_prefetch.log): ONE item per block is the optimum -- corr_fwd 12.35 ->
+// 11.7 us, corr_bwd 20.3 -> 18.5 us, warp_fwd 18.6 -> 18.0 us, warp_bwd 29.25 -> 28.9 us; two items give half of that and
+// four or more are slower than none (the extra traffic slows the predecessor's last blocks, which everybody waits for).
+// Touching one line per later item (address translation only) changed nothing.
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+static inline int pdl_prefetch(int dflt) {   // how much a kernel prefetches (its own unit: groups, items, rows); 0 = nothing
+    if (!tuning_enabled()) return dflt;
+    const char *v = std::getenv("DSSMD_PDL_PREFETCH");
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
 static inline bool pdl_enabled() {
     if (!tuning_enabled()) return true;
     const char *v = std::getenv("DSSMD_PDL");

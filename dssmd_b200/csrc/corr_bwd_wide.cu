@@ -39,6 +39,9 @@ constexpr int kWideMaxStages = 8;
 
 struct WideParams {
     float *gL, *gR;
+    const float *L, *R, *g;   // the tensors behind the tensor maps (L2 prefetch before griddepcontrol.wait)
+    long long gbs;            // elements between two images of g
+    int pf;                   // items of a block prefetched that way (> 0: by lines, < 0: by TMA prefetch); 0 = none
     int C, H, W, D;
     int TX, XT;     // x tile in pixels (multiple of 4, <= 128), tiles per row
     int CB;         // channels per item = NWG * CPW
@@ -106,7 +109,43 @@ corr_bwd_wide_kernel(const WideParams p, const __grid_constant__ CUtensorMap map
     }
     __syncthreads();
     pdl_launch_dependents();  // the next kernel on the stream may start its ramp
-    pdl_wait();               // nothing above touches global memory
+    if (p.pf != 0) {
+        // the boxes of this block's first items towards the L2 while the previous kernel drains (common.cuh: prefetch_l2);
+        // pf > 0: as 128-byte lines by all threads, pf < 0: as TMA prefetches of the same boxes by one thread
+        const int np = nitems < abs(p.pf) ? nitems : abs(p.pf);
+        if (p.pf < 0 && tid == 32) { tma_prefetch_desc(&mapL); tma_prefetch_desc(&mapR); tma_prefetch_desc(&mapG); }
+        const int nl = ((p.WP * 4) >> 7) + 2;   // 128-byte lines one operand row of an item can touch
+        const size_t HWp = (size_t)p.H * p.W;
+        for (int k = 0; k < np; ++k) {
+            const int it = i0 + k, cb = it % p.NCB, grp = it / p.NCB, xt = grp % p.XT, row = grp / p.XT;
+            const int b = row / p.H, y = row - b * p.H;
+            if (p.pf < 0) {
+                if (tid == 32) {
+                    tma_prefetch_4d(&mapR, xt * p.TX - kWD, y, cb * p.CB, b);
+                    tma_prefetch_4d(&mapL, xt * p.TX, y, cb * p.CB, b);
+                    if (k == 0 || cb == 0) tma_prefetch_4d(&mapG, xt * p.TX, y, 0, b);
+                }
+                continue;
+            }
+            const int xlo = (xt * p.TX - kWD > 0) ? xt * p.TX - kWD : 0;
+            const int xhi = (xt * p.TX + p.TX + kWD < p.W) ? xt * p.TX + p.TX + kWD : p.W;
+            const int nrow = 2 * p.CB + ((k == 0 || cb == 0) ? p.D : 0);   // L and R channel rows, and the g rows of a new group
+            for (int idx = tid; idx < nrow * nl; idx += (int)blockDim.x) {
+                const int j = idx % nl, r = idx / nl;
+                const float *rowp;
+                if (r < 2 * p.CB) {
+                    const int c = cb * p.CB + (r >> 1);
+                    if (c >= p.C) continue;
+                    rowp = ((r & 1) ? p.R : p.L) + ((size_t)b * p.C + c) * HWp + (size_t)y * p.W;
+                } else {
+                    rowp = p.g + (size_t)b * p.gbs + (size_t)(r - 2 * p.CB) * HWp + (size_t)y * p.W;
+                }
+                const uintptr_t a = (reinterpret_cast<uintptr_t>(rowp + xlo) & ~(uintptr_t)127) + (uintptr_t)j * 128;
+                if (a < reinterpret_cast<uintptr_t>(rowp + xhi)) prefetch_l2(reinterpret_cast<const void *>(a));
+            }
+        }
+    }
+    pdl_wait();               // no load or store above
 
     // first item of this block: channel block, x tile, row
     const int cb0 = i0 % p.NCB, grp0 = i0 / p.NCB;
@@ -267,6 +306,7 @@ int corr_bwd_wide_f32(const void *g, const void *L, const void *R, void *gL, voi
     if ((gbs * 4) % 16 != 0 || (long long)B * H * 64 >= (1LL << 30)) return -1;
     WideParams p{};
     p.gL = (float *)gL; p.gR = (float *)gR;
+    p.L = (const float *)L; p.R = (const float *)R; p.g = (const float *)g; p.gbs = gbs; p.pf = pdl_prefetch(-1);
     p.C = C; p.H = H; p.W = W; p.D = D;
     p.invC = 1.0f / (float)C;
     p.XT = ceil_div(W, 128);

@@ -25,6 +25,8 @@ namespace {
 
 struct FwdRegParams {
     void *out;
+    const void *L, *R;  // the tensors behind the two tensor maps (L2 prefetch before griddepcontrol.wait)
+    int pf;             // items of a block prefetched that way (> 0: by lines, < 0: by TMA prefetch); 0 = none
     long long OBS;  // elements between two images of `out`
     int C, H, W, D;
     int NH;         // lanes per pixel group (power of two), D <= 12*NH
@@ -63,7 +65,34 @@ __global__ void __launch_bounds__(512) corr_fwd_reg_kernel(const FwdRegParams p,
     }
     __syncthreads();
     pdl_launch_dependents();  // the next kernel on the stream may start its ramp
-    pdl_wait();               // nothing above touches global memory
+    if (p.pf != 0) {
+        // the boxes of this block's first items towards the L2 while the previous kernel drains (common.cuh: prefetch_l2);
+        // pf > 0: as 128-byte lines by all threads, pf < 0: as TMA prefetches of the same boxes by one thread
+        const int np = (i1 - i0 < abs(p.pf)) ? i1 - i0 : abs(p.pf);
+        const int nl = ((p.WP * (int)sizeof(T)) >> 7) + 2;   // 128-byte lines a staged row can touch
+        if (p.pf < 0 && tid == 32) { tma_prefetch_desc(&mapL); tma_prefetch_desc(&mapR); }
+        for (int k = 0; k < np; ++k) {
+            const int it = i0 + k, cb = it % p.NCB, gx = it / p.NCB, xt = gx % p.XT, row = gx / p.XT;
+            const int b = row / p.H, y = row - b * p.H;
+            if (p.pf < 0) {
+                if (tid == 32) {
+                    tma_prefetch_4d(&mapL, xt * p.TX, y, cb * p.CB, b);
+                    tma_prefetch_4d(&mapR, xt * p.TX - p.HALO, y, cb * p.CB, b);
+                }
+                continue;
+            }
+            const int xlo = (xt * p.TX - p.HALO > 0) ? xt * p.TX - p.HALO : 0;
+            const int xhi = (xt * p.TX + p.TX < p.W) ? xt * p.TX + p.TX : p.W;
+            for (int idx = tid; idx < 2 * p.CB * nl; idx += (int)blockDim.x) {
+                const int j = idx % nl, r = idx / nl, c = cb * p.CB + (r >> 1);
+                if (c >= p.C) continue;
+                const char *rowp = reinterpret_cast<const char *>((r & 1) ? p.R : p.L) + (((size_t)b * p.C + c) * p.H + y) * p.W * sizeof(T);
+                const uintptr_t a = (reinterpret_cast<uintptr_t>(rowp + (size_t)xlo * sizeof(T)) & ~(uintptr_t)127) + (uintptr_t)j * 128;
+                if (a < reinterpret_cast<uintptr_t>(rowp + (size_t)xhi * sizeof(T))) prefetch_l2(reinterpret_cast<const void *>(a));
+            }
+        }
+    }
+    pdl_wait();               // no load or store above
 
     auto issue = [&](int it, int s) {  // one thread
         const int cb = it % p.NCB, gx = it / p.NCB;
@@ -219,6 +248,7 @@ int corr_fwd_reg_typed(const void *L, const void *R, void *out, int B, int C, in
     if ((long long)B * H * 64 >= (1LL << 31)) return -1;
     FwdRegParams p{};
     p.out = out; p.OBS = obs;
+    p.L = L; p.R = R; p.pf = pdl_prefetch(1);
     p.C = C; p.H = H; p.W = W; p.D = D;
     p.invC = 1.0f / (float)C;
     int nh = 1, lognh = 0;

@@ -56,7 +56,7 @@ template <int NCT, int PS, bool BORDER, bool OCC3>
 __global__ void __launch_bounds__(PS - 2, ((OCC3 ? 768 : 512) / (PS - 2)) > 0 ? ((OCC3 ? 768 : 512) / (PS - 2)) : 1)
 warp_bwd_band2_kernel(const float *g, const float *img, const float *disp,
                       float *__restrict__ g_img, float *__restrict__ g_disp, int H, int W, int R,
-                      float halfW, float tscale, float halfH) {
+                      float halfW, float tscale, float halfH, int pf) {
     constexpr int P = PS + 6;                 // accumulator slots per plane; cell of tap position k: p = k + 4
     constexpr int ACH = 4 * P * 4 + 128;      // bytes of one accumulator channel: int acc[4][P]; int sink[32]
     constexpr int ABUF = NCT * ACH;           // one accumulator buffer
@@ -294,7 +294,26 @@ warp_bwd_band2_kernel(const float *g, const float *img, const float *disp,
     // ---- first row ------------------------------------------------------------------------------------------------
     __syncthreads();   // table, zeroed accumulators and statistics visible
     pdl_launch_dependents();
-    pdl_wait();        // nothing above touches global memory
+    if (pf > 0 && active && (tid & 7) == 0) {
+        // the first rows of the band towards the L2 while the previous kernel drains (common.cuh: prefetch_l2); one thread per
+        // 128 bytes of a row
+        const int yp1 = min(ys + pf, y_real);
+        for (int y = ys; y < yp1; ++y) {
+            const unsigned o = (unsigned)(y * W + xl);
+            prefetch_l2(dB + o);
+#pragma unroll
+            for (int c = 0; c < NCT; ++c) prefetch_l2(gB + (o + (unsigned)c * HW));
+        }
+        if (g_disp) {
+            const int ya = max(ys - 1, 0), yb = min(yp1, H - 1);   // the source rows those output rows blend
+            for (int y = ya; y <= yb; ++y) {
+                const unsigned o = (unsigned)(y * W + xl);
+#pragma unroll
+                for (int c = 0; c < NCT; ++c) prefetch_l2(iB + (o + (unsigned)c * HW));
+            }
+        }
+    }
+    pdl_wait();        // no load or store above
     {
         const unsigned orow = (unsigned)(ys * W + xl);
         const float4 d4 = ld_cg(reinterpret_cast<const float4 *>(dB + orow));
@@ -509,7 +528,7 @@ warp_bwd_band2_kernel(const float *g, const float *img, const float *disp,
 
 template <int PS, bool BORDER, bool OCC3>
 int launch_band2(const float *g, const float *img, const float *disp, float *g_img, float *g_disp, int B, int C, int H, int W, cudaStream_t s) {
-    void (*kern)(const float *, const float *, const float *, float *, float *, int, int, int, float, float, float) =
+    void (*kern)(const float *, const float *, const float *, float *, float *, int, int, int, float, float, float, int) =
         C == 1 ? warp_bwd_band2_kernel<1, PS, BORDER, OCC3> : C == 2 ? warp_bwd_band2_kernel<2, PS, BORDER, OCC3>
       : C == 3 ? warp_bwd_band2_kernel<3, PS, BORDER, OCC3> : warp_bwd_band2_kernel<4, PS, BORDER, OCC3>;
     const int vw = C == 3 ? 4 : C;
@@ -537,7 +556,7 @@ int launch_band2(const float *g, const float *img, const float *disp, float *g_i
         fprintf(stderr, "warp_bwd band2 cfg: PS=%d border=%d occ3=%d R=%d grid=(%d,%d) (x%d/SM) threads=%d smem=%zu\n", PS, (int)BORDER, (int)OCC3, R,
                 ceil_div(H, R), B, occ, threads, smem);
     e = launch_pdl(kern, dim3((unsigned)ceil_div(H, R), (unsigned)B), dim3((unsigned)threads), smem, s, g, img, disp, g_img, g_disp, H, W, R,
-                   (float)W / 2.0f, 2.0f / (float)(W - 1), (float)H / 2.0f);
+                   (float)W / 2.0f, 2.0f / (float)(W - 1), (float)H / 2.0f, pdl_prefetch(1));
     if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "warp_bwd(band2): launch failed: %s", cudaGetErrorString(e));
     return check_launch("warp_bwd(band2)");
 }

@@ -36,7 +36,7 @@ namespace {
 template <int NCT, int PS, bool BORDER>
 __global__ void __launch_bounds__(PS - 2, 1024 / (PS - 2)) warp_fwd_lean_kernel(const float *img, const float *disp,
                                                                                 float *__restrict__ out, float *__restrict__ mask,
-                                                                                int *neg_flag, int H, int W, float halfW, float halfH) {
+                                                                                int *neg_flag, int H, int W, float halfW, float halfH, int pf) {
     constexpr int VW = NCT == 3 ? 4 : NCT;
     extern __shared__ __align__(16) float s_row[];  // [4][PS] cells of VW floats
     const int W4 = W >> 2;
@@ -58,13 +58,23 @@ __global__ void __launch_bounds__(PS - 2, 1024 / (PS - 2)) warp_fwd_lean_kernel(
     else { yi0 = ymi0; yw0 = ymw0; yw1 = ymw1; }
 
     pdl_launch_dependents();
-    pdl_wait();   // first global access below
+    const int xl = active ? x0 : W - 4;
+    const int ya = min(max(yi0, 0), H - 1), yb = min(max(yi0 + 1, 0), H - 1);
+    if (pf > 0 && active && (tid & 7) == 0) {
+        // this row's lines towards the L2 while the previous kernel drains (common.cuh: prefetch_l2); one thread per 128 bytes
+        const float *ib = img + (size_t)b * NCT * HW + xl;
+        prefetch_l2(disp + (size_t)b * HW + (unsigned)(y * W + xl));
+#pragma unroll
+        for (int c = 0; c < NCT; ++c) {
+            prefetch_l2(ib + c * HW + (unsigned)(ya * W));
+            prefetch_l2(ib + c * HW + (unsigned)(yb * W));
+        }
+    }
+    pdl_wait();   // first load below
 
     // source rows -> registers (in flight while the coordinates are computed).  Loads are unconditional (a
     // predicated load costs a branch): a tap row outside the image is read from the nearest row and has
     // weight 0, idle threads of the last warp re-read the last pixels.
-    const int xl = active ? x0 : W - 4;
-    const int ya = min(max(yi0, 0), H - 1), yb = min(max(yi0 + 1, 0), H - 1);
     float4 st[NCT][2];
     {
         const float *ib = img + (size_t)b * NCT * HW + xl;
@@ -491,7 +501,7 @@ int launch_photo(const float *imgL, const float *imgR, const float *disp, float 
 
 template <int PS, bool BORDER>
 int launch_fwd(const float *img, const float *disp, float *out, float *mask, int *neg_flag, int B, int C, int H, int W, cudaStream_t s) {
-    void (*kern)(const float *, const float *, float *, float *, int *, int, int, float, float) =
+    void (*kern)(const float *, const float *, float *, float *, int *, int, int, float, float, int) =
         C == 1 ? warp_fwd_lean_kernel<1, PS, BORDER> : C == 2 ? warp_fwd_lean_kernel<2, PS, BORDER>
       : C == 3 ? warp_fwd_lean_kernel<3, PS, BORDER> : warp_fwd_lean_kernel<4, PS, BORDER>;
     const size_t smem = (size_t)(C == 3 ? 4 : C) * 4 * PS * sizeof(float);
@@ -501,7 +511,7 @@ int launch_fwd(const float *img, const float *disp, float *out, float *mask, int
     }
     // W/2 and H/2: IEEE single divisions, the same values the device would compute
     const cudaError_t le = launch_pdl(kern, dim3((unsigned)H, (unsigned)B), dim3((unsigned)round_up(W / 4, 32)), smem, s, img, disp, out, mask, neg_flag, H, W,
-                                      (float)W / 2.0f, (float)H / 2.0f);
+                                      (float)W / 2.0f, (float)H / 2.0f, pdl_prefetch(1));
     if (le != cudaSuccess) return fail(DSSMD_ERR_CUDA, "warp_fwd(lean): launch failed: %s", cudaGetErrorString(le));
     return check_launch("warp_fwd(lean)");
 }

@@ -36,7 +36,7 @@ def timed(fn, rounds):
 
 def main():
     torch.backends.cuda.matmul.allow_tf32 = False
-    for (B, C, H, W) in ((8, 32, 320, 640), (4, 32, 384, 1280), (8, 128, 40, 80)):
+    for (B, C, H, W) in ((8, 32, 320, 640), (4, 32, 384, 1280), (8, 128, 40, 80))[:int(os.environ.get("ATTN_BENCH_SHAPES", "3"))]:
         q, k, v, go = (torch.randn(B, C, H, W, device="cuda") for _ in range(4))
         scale = 32 ** -0.5
         flop = 2 * 2.0 * B * H * W * W * C
