@@ -31,6 +31,7 @@ struct BwdMma32Params {
     int RW;          // staged operand row width in floats (= box width, 4 mod 32)
     int GW;          // staged g row width in floats (= box width, multiple of 4)
     float invC;
+    int pf;          // first stage's boxes prefetched towards the L2 before griddepcontrol.wait (common.cuh: prefetch_l2)
 };
 
 __device__ __forceinline__ void split_tf32b(float v, uint32_t &hi, uint32_t &lo) {
@@ -77,7 +78,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_bwd_mma32_kernel(const Bw
     }
     __syncthreads();
     pdl_launch_dependents();
-    pdl_wait();            // nothing above touches global memory
+    if (p.pf && tid == (int)blockDim.x - 1) {   // the first stage towards the L2 while the previous kernel drains
+        tma_prefetch_desc(&mapIn); tma_prefetch_desc(&mapG);
+        tma_prefetch_4d(&mapIn, xin0, y, 0, b);
+        tma_prefetch_4d(&mapG, X0, y, 0, b);
+    }
+    pdl_wait();            // no load or store above
     if (tid == 0) issue(0, 0, true);
 
     const int g8 = lane >> 2, tq = lane & 3;
@@ -170,6 +176,7 @@ int corr_bwd_mma32_mode(const void *g, const void *in, void *out, int B, int C, 
     if ((reinterpret_cast<uintptr_t>(out) & 7) != 0) return -1;   // 8-byte stores
     BwdMma32Params p{};
     p.out = static_cast<float *>(out);
+    p.pf = pdl_prefetch(1);
     p.C = C; p.H = H; p.W = W; p.D = D;
     p.invC = 1.0f / (float)C;
     p.HALO = round_up(D - 1, 4);

@@ -113,14 +113,14 @@ corr_bwd_wide_kernel(const WideParams p, const __grid_constant__ CUtensorMap map
         // the boxes of this block's first items towards the L2 while the previous kernel drains (common.cuh: prefetch_l2);
         // pf > 0: as 128-byte lines by all threads, pf < 0: as TMA prefetches of the same boxes by one thread
         const int np = nitems < abs(p.pf) ? nitems : abs(p.pf);
-        if (p.pf < 0 && tid == 32) { tma_prefetch_desc(&mapL); tma_prefetch_desc(&mapR); tma_prefetch_desc(&mapG); }
+        if (p.pf < 0 && tid == (int)blockDim.x - 1) { tma_prefetch_desc(&mapL); tma_prefetch_desc(&mapR); tma_prefetch_desc(&mapG); }
         const int nl = ((p.WP * 4) >> 7) + 2;   // 128-byte lines one operand row of an item can touch
         const size_t HWp = (size_t)p.H * p.W;
         for (int k = 0; k < np; ++k) {
             const int it = i0 + k, cb = it % p.NCB, grp = it / p.NCB, xt = grp % p.XT, row = grp / p.XT;
             const int b = row / p.H, y = row - b * p.H;
             if (p.pf < 0) {
-                if (tid == 32) {
+                if (tid == (int)blockDim.x - 1) {
                     tma_prefetch_4d(&mapR, xt * p.TX - kWD, y, cb * p.CB, b);
                     tma_prefetch_4d(&mapL, xt * p.TX, y, cb * p.CB, b);
                     if (k == 0 || cb == 0) tma_prefetch_4d(&mapG, xt * p.TX, y, 0, b);

@@ -30,6 +30,7 @@ struct Mma32Params {
     int TX, XT;      // pixels per block tile (multiple of 16), tiles per row
     int LW, RW;      // staged row widths in floats (= box widths, 8 mod 32)
     float invC;
+    int pf;          // first stage's boxes prefetched towards the L2 before griddepcontrol.wait (common.cuh: prefetch_l2)
 };
 
 __device__ __forceinline__ void split_tf32(float v, uint32_t &hi, uint32_t &lo) {
@@ -74,7 +75,12 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_fwd_mma32_kernel(const Mm
     }
     __syncthreads();
     pdl_launch_dependents();
-    pdl_wait();            // nothing above touches global memory
+    if (p.pf && tid == (int)blockDim.x - 1) {   // the first stage towards the L2 while the previous kernel drains
+        tma_prefetch_desc(&mapL); tma_prefetch_desc(&mapR);
+        tma_prefetch_4d(&mapL, X0, y, 0, b);
+        tma_prefetch_4d(&mapR, X0 - p.HALO, y, 0, b);
+    }
+    pdl_wait();            // no load or store above
     if (tid == 0) issue(0, 0);
 
     float acc[NT][4];
@@ -161,6 +167,7 @@ int corr_fwd_mma32(const void *L, const void *R, void *out, int B, int C, int H,
     if (((reinterpret_cast<uintptr_t>(L) | reinterpret_cast<uintptr_t>(R)) & 15) != 0) return -1;
     Mma32Params p{};
     p.out = static_cast<float *>(out); p.OBS = obs;
+    p.pf = pdl_prefetch(1);
     p.C = C; p.H = H; p.W = W; p.D = D;
     p.invC = 1.0f / (float)C;
     p.HALO = round_up(D - 1, 4);

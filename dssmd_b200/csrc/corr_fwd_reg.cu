@@ -70,12 +70,12 @@ __global__ void __launch_bounds__(512) corr_fwd_reg_kernel(const FwdRegParams p,
         // pf > 0: as 128-byte lines by all threads, pf < 0: as TMA prefetches of the same boxes by one thread
         const int np = (i1 - i0 < abs(p.pf)) ? i1 - i0 : abs(p.pf);
         const int nl = ((p.WP * (int)sizeof(T)) >> 7) + 2;   // 128-byte lines a staged row can touch
-        if (p.pf < 0 && tid == 32) { tma_prefetch_desc(&mapL); tma_prefetch_desc(&mapR); }
+        if (p.pf < 0 && tid == (int)blockDim.x - 1) { tma_prefetch_desc(&mapL); tma_prefetch_desc(&mapR); }
         for (int k = 0; k < np; ++k) {
             const int it = i0 + k, cb = it % p.NCB, gx = it / p.NCB, xt = gx % p.XT, row = gx / p.XT;
             const int b = row / p.H, y = row - b * p.H;
             if (p.pf < 0) {
-                if (tid == 32) {
+                if (tid == (int)blockDim.x - 1) {
                     tma_prefetch_4d(&mapL, xt * p.TX, y, cb * p.CB, b);
                     tma_prefetch_4d(&mapR, xt * p.TX - p.HALO, y, cb * p.CB, b);
                 }
@@ -230,12 +230,15 @@ int launch_fwd_reg_cpw(FwdRegParams p, const CUtensorMap &mapL, const CUtensorMa
     return check_launch("corr_fwd(reg)");
 }
 
-// channels per warp and item as a compile-time constant where it is the common 8 (fp32 model shapes: 32 channels per item over 4
+// channels per warp and item as a compile-time constant where it is 8, 4 or 2 (fp32 model shapes: 32 channels per item over 4
 // channel groups); 0 = run-time loop
 template <typename T, int LOGNH>
 int launch_fwd_reg(FwdRegParams p, const CUtensorMap &mapL, const CUtensorMap &mapR, int threads, size_t smem, cudaStream_t stream) {
-    if (sizeof(T) == 4 && p.CB == 8 * p.CGW && env_int_fwd("DSSMD_CORR_FWD_UNROLLED", 1) != 0)
-        return launch_fwd_reg_cpw<T, LOGNH, 8>(p, mapL, mapR, threads, smem, stream);
+    if (sizeof(T) == 4 && env_int_fwd("DSSMD_CORR_FWD_UNROLLED", 1) != 0) {
+        if (p.CB == 8 * p.CGW) return launch_fwd_reg_cpw<T, LOGNH, 8>(p, mapL, mapR, threads, smem, stream);
+        if (p.CB == 4 * p.CGW) return launch_fwd_reg_cpw<T, LOGNH, 4>(p, mapL, mapR, threads, smem, stream);
+        if (p.CB == 2 * p.CGW) return launch_fwd_reg_cpw<T, LOGNH, 2>(p, mapL, mapR, threads, smem, stream);
+    }
     return launch_fwd_reg_cpw<T, LOGNH, 0>(p, mapL, mapR, threads, smem, stream);
 }
 
