@@ -52,8 +52,18 @@ __device__ __forceinline__ void red_add_nc(uint32_t addr, int q) {
     asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(q));
 }
 
+// resident blocks asked for: 512 threads per SM (768 with OCC3).  PS = 322 (rows of 1028 .. 1280 pixels: KITTI) asks for two blocks
+// of 320 threads (96 registers, 32 - 48 bytes of spill in the 3-channel build): as a 512-thread instance it ran ONE block of 10 warps
+// per SM (111.9 -> 97.5 us at 384x1280 x16).  The same for rows of 640 pixels (PS = 162, four blocks of 5 warps instead of three)
+// was slower: 22.5 -> 26.5 us at 320x640 x8 (shorter bands, so more halo rows); three blocks of 256 threads at 960 pixels (OCC3,
+// 80 registers): 29.0 -> 39.6 us
+template <int PS, bool OCC3>
+constexpr int band2_min_blocks() {
+    return PS == 322 ? 2 : ((OCC3 ? 768 : 512) / (PS - 2)) > 0 ? ((OCC3 ? 768 : 512) / (PS - 2)) : 1;
+}
+
 template <int NCT, int PS, bool BORDER, bool OCC3>
-__global__ void __launch_bounds__(PS - 2, ((OCC3 ? 768 : 512) / (PS - 2)) > 0 ? ((OCC3 ? 768 : 512) / (PS - 2)) : 1)
+__global__ void __launch_bounds__(PS - 2, band2_min_blocks<PS, OCC3>())
 warp_bwd_band2_kernel(const float *g, const float *img, const float *disp,
                       float *__restrict__ g_img, float *__restrict__ g_disp, int H, int W, int R,
                       float halfW, float tscale, float halfH, int pf) {
@@ -62,8 +72,8 @@ warp_bwd_band2_kernel(const float *g, const float *img, const float *disp,
     constexpr int ABUF = NCT * ACH;           // one accumulator buffer
     constexpr int VW = NCT == 3 ? 4 : NCT;    // floats per difference cell
     constexpr int DBUF = 4 * PS * VW * 4;     // one difference row: float dvr[4][PS][VW] (cell p = k + 4)
-    constexpr int NW = (PS - 2) / 32;         // warps per block (upper bound): 2, 4, 8, 16
-    constexpr int NWP = NW < 4 ? 4 : NW;      // padded to whole float4s
+    constexpr int NW = (PS - 2) / 32;         // warps per block (upper bound): 2, 4, 8, 10, 16
+    constexpr int NWP = NW <= 4 ? 4 : NW <= 8 ? 8 : 16;   // padded to a power of two (whole float4s; the butterfly below)
     extern __shared__ __align__(16) unsigned char smem_raw[];   // acc[2] | dvr[2]
     __shared__ __align__(16) float s_sum[2][NWP];       // per-warp sums of |g| of a row (all channels)
     __shared__ __align__(16) unsigned s_max[2][NWP];    // per-warp maximum over threads of the thread's sum (bits)
@@ -579,7 +589,7 @@ int warp_bwd_band2_f32(const float *g, const float *img, const float *disp, floa
         return border ? launch_band2<PSV, true, false>(g, img, disp, g_img, g_disp, B, C, H, W, s)                         \
                       : launch_band2<PSV, false, false>(g, img, disp, g_img, g_disp, B, C, H, W, s);                       \
     }
-    DSSMD_BAND2(66) DSSMD_BAND2(130) DSSMD_BAND2(258) DSSMD_BAND2(514)
+    DSSMD_BAND2(66) DSSMD_BAND2(130) DSSMD_BAND2(258) DSSMD_BAND2(322) DSSMD_BAND2(514)
 #undef DSSMD_BAND2
     return -1;
 }
