@@ -39,9 +39,7 @@ constexpr int kWideMaxStages = 8;
 
 struct WideParams {
     float *gL, *gR;
-    const float *L, *R, *g;   // the tensors behind the tensor maps (L2 prefetch before griddepcontrol.wait)
-    long long gbs;            // elements between two images of g
-    int pf;                   // items of a block prefetched that way (> 0: by lines, < 0: by TMA prefetch); 0 = none
+    int pf;                   // items of a block whose boxes are prefetched towards the L2 before griddepcontrol.wait; 0 = none
     int C, H, W, D;
     int TX, XT;     // x tile in pixels (multiple of 4, <= 128), tiles per row
     int CB;         // channels per item = NWG * CPW
@@ -109,44 +107,9 @@ corr_bwd_wide_kernel(const WideParams p, const __grid_constant__ CUtensorMap map
     }
     __syncthreads();
     pdl_launch_dependents();  // the next kernel on the stream may start its ramp
-    if (p.pf != 0) {
-        // the boxes of this block's first items towards the L2 while the previous kernel drains (common.cuh: prefetch_l2);
-        // pf > 0: as 128-byte lines by all threads, pf < 0: as TMA prefetches of the same boxes by one thread
-        const int np = nitems < abs(p.pf) ? nitems : abs(p.pf);
-        if (p.pf < 0 && tid == (int)blockDim.x - 1) { tma_prefetch_desc(&mapL); tma_prefetch_desc(&mapR); tma_prefetch_desc(&mapG); }
-        const int nl = ((p.WP * 4) >> 7) + 2;   // 128-byte lines one operand row of an item can touch
-        const size_t HWp = (size_t)p.H * p.W;
-        for (int k = 0; k < np; ++k) {
-            const int it = i0 + k, cb = it % p.NCB, grp = it / p.NCB, xt = grp % p.XT, row = grp / p.XT;
-            const int b = row / p.H, y = row - b * p.H;
-            if (p.pf < 0) {
-                if (tid == (int)blockDim.x - 1) {
-                    tma_prefetch_4d(&mapR, xt * p.TX - kWD, y, cb * p.CB, b);
-                    tma_prefetch_4d(&mapL, xt * p.TX, y, cb * p.CB, b);
-                    if (k == 0 || cb == 0) tma_prefetch_4d(&mapG, xt * p.TX, y, 0, b);
-                }
-                continue;
-            }
-            const int xlo = (xt * p.TX - kWD > 0) ? xt * p.TX - kWD : 0;
-            const int xhi = (xt * p.TX + p.TX + kWD < p.W) ? xt * p.TX + p.TX + kWD : p.W;
-            const int nrow = 2 * p.CB + ((k == 0 || cb == 0) ? p.D : 0);   // L and R channel rows, and the g rows of a new group
-            for (int idx = tid; idx < nrow * nl; idx += (int)blockDim.x) {
-                const int j = idx % nl, r = idx / nl;
-                const float *rowp;
-                if (r < 2 * p.CB) {
-                    const int c = cb * p.CB + (r >> 1);
-                    if (c >= p.C) continue;
-                    rowp = ((r & 1) ? p.R : p.L) + ((size_t)b * p.C + c) * HWp + (size_t)y * p.W;
-                } else {
-                    rowp = p.g + (size_t)b * p.gbs + (size_t)(r - 2 * p.CB) * HWp + (size_t)y * p.W;
-                }
-                const uintptr_t a = (reinterpret_cast<uintptr_t>(rowp + xlo) & ~(uintptr_t)127) + (uintptr_t)j * 128;
-                if (a < reinterpret_cast<uintptr_t>(rowp + xhi)) prefetch_l2(reinterpret_cast<const void *>(a));
-            }
-        }
-    }
-    pdl_wait();               // no load or store above
 
+    // everything that does not touch global memory comes BEFORE griddepcontrol.wait: launched behind another kernel the block does it
+    // while that kernel drains
     // first item of this block: channel block, x tile, row
     const int cb0 = i0 % p.NCB, grp0 = i0 / p.NCB;
     const int xt0 = grp0 % p.XT, row0 = grp0 / p.XT;
@@ -171,10 +134,6 @@ corr_bwd_wide_kernel(const WideParams p, const __grid_constant__ CUtensorMap map
         tma_load_4d(dst + op_stride, &mapL, X0, y, cb * p.CB, b, bar);   // gR: L[x' + d], right halo
         if (with_g) tma_load_4d(sbase + g_base + (uint32_t)(gn & 1) * g_stride, &mapG, X0, y, 0, b, bar);
     };
-    if (tid == 0) {
-        for (int k = 0; k < p.S - 1; ++k)
-            if (k < nitems) issue();
-    }
 
     // this warp's gradient and channel group; this lane's pixels
     const int mode = warp >= NWG ? 1 : 0;
@@ -187,6 +146,27 @@ corr_bwd_wide_kernel(const WideParams p, const __grid_constant__ CUtensorMap map
     // (gL: the box starts 24 pixels left of the tile, the window covers x - 24 .. x + 3; gR: x' .. x' + 27)
     const uint32_t wp4 = (uint32_t)p.WP * 4u;
     const uint32_t wbase = (uint32_t)mode * op_stride + (uint32_t)(cgw * CPW) * wp4 + (uint32_t)(lane_on ? xl : 0) * 4u;
+
+    if (p.pf != 0 && tid == (int)blockDim.x - 1) {
+        // the boxes of this block's first item(s) towards the L2 while the previous kernel drains (common.cuh: prefetch_l2)
+        tma_prefetch_desc(&mapL); tma_prefetch_desc(&mapR); tma_prefetch_desc(&mapG);
+        int kcb = cb0, kxt = xt0, ky = y0, kb = b0;
+        const int np = nitems < p.pf ? nitems : p.pf;
+        for (int k = 0; k < np; ++k) {
+            tma_prefetch_4d(&mapR, kxt * p.TX - kWD, ky, kcb * p.CB, kb);
+            tma_prefetch_4d(&mapL, kxt * p.TX, ky, kcb * p.CB, kb);
+            if (k == 0 || kcb == 0) tma_prefetch_4d(&mapG, kxt * p.TX, ky, 0, kb);
+            if (++kcb == p.NCB) {
+                kcb = 0;
+                if (++kxt == p.XT) { kxt = 0; if (++ky == p.H) { ky = 0; ++kb; } }
+            }
+        }
+    }
+    pdl_wait();               // no load or store above
+    if (tid == 0) {
+        for (int k = 0; k < p.S - 1; ++k)
+            if (k < nitems) issue();
+    }
 
     float gv[kWD][PX];
     int s = 0, cb = cb0, gn = 0, xt = xt0, b = b0, y = y0;   // consumer state: the item being computed
@@ -306,7 +286,7 @@ int corr_bwd_wide_f32(const void *g, const void *L, const void *R, void *gL, voi
     if ((gbs * 4) % 16 != 0 || (long long)B * H * 64 >= (1LL << 30)) return -1;
     WideParams p{};
     p.gL = (float *)gL; p.gR = (float *)gR;
-    p.L = (const float *)L; p.R = (const float *)R; p.g = (const float *)g; p.gbs = gbs; p.pf = pdl_prefetch(-1);
+    p.pf = pdl_prefetch(1);
     p.C = C; p.H = H; p.W = W; p.D = D;
     p.invC = 1.0f / (float)C;
     p.XT = ceil_div(W, 128);

@@ -25,8 +25,7 @@ namespace {
 
 struct FwdRegParams {
     void *out;
-    const void *L, *R;  // the tensors behind the two tensor maps (L2 prefetch before griddepcontrol.wait)
-    int pf;             // items of a block prefetched that way (> 0: by lines, < 0: by TMA prefetch); 0 = none
+    int pf;             // items of a block whose boxes are prefetched towards the L2 before griddepcontrol.wait; 0 = none
     long long OBS;  // elements between two images of `out`
     int C, H, W, D;
     int NH;         // lanes per pixel group (power of two), D <= 12*NH
@@ -65,48 +64,28 @@ __global__ void __launch_bounds__(512) corr_fwd_reg_kernel(const FwdRegParams p,
     }
     __syncthreads();
     pdl_launch_dependents();  // the next kernel on the stream may start its ramp
-    if (p.pf != 0) {
-        // the boxes of this block's first items towards the L2 while the previous kernel drains (common.cuh: prefetch_l2);
-        // pf > 0: as 128-byte lines by all threads, pf < 0: as TMA prefetches of the same boxes by one thread
-        const int np = (i1 - i0 < abs(p.pf)) ? i1 - i0 : abs(p.pf);
-        const int nl = ((p.WP * (int)sizeof(T)) >> 7) + 2;   // 128-byte lines a staged row can touch
-        if (p.pf < 0 && tid == (int)blockDim.x - 1) { tma_prefetch_desc(&mapL); tma_prefetch_desc(&mapR); }
-        for (int k = 0; k < np; ++k) {
-            const int it = i0 + k, cb = it % p.NCB, gx = it / p.NCB, xt = gx % p.XT, row = gx / p.XT;
-            const int b = row / p.H, y = row - b * p.H;
-            if (p.pf < 0) {
-                if (tid == (int)blockDim.x - 1) {
-                    tma_prefetch_4d(&mapL, xt * p.TX, y, cb * p.CB, b);
-                    tma_prefetch_4d(&mapR, xt * p.TX - p.HALO, y, cb * p.CB, b);
-                }
-                continue;
-            }
-            const int xlo = (xt * p.TX - p.HALO > 0) ? xt * p.TX - p.HALO : 0;
-            const int xhi = (xt * p.TX + p.TX < p.W) ? xt * p.TX + p.TX : p.W;
-            for (int idx = tid; idx < 2 * p.CB * nl; idx += (int)blockDim.x) {
-                const int j = idx % nl, r = idx / nl, c = cb * p.CB + (r >> 1);
-                if (c >= p.C) continue;
-                const char *rowp = reinterpret_cast<const char *>((r & 1) ? p.R : p.L) + (((size_t)b * p.C + c) * p.H + y) * p.W * sizeof(T);
-                const uintptr_t a = (reinterpret_cast<uintptr_t>(rowp + (size_t)xlo * sizeof(T)) & ~(uintptr_t)127) + (uintptr_t)j * 128;
-                if (a < reinterpret_cast<uintptr_t>(rowp + (size_t)xhi * sizeof(T))) prefetch_l2(reinterpret_cast<const void *>(a));
-            }
-        }
-    }
-    pdl_wait();               // no load or store above
 
-    auto issue = [&](int it, int s) {  // one thread
-        const int cb = it % p.NCB, gx = it / p.NCB;
-        const int xt = gx % p.XT, row = gx / p.XT;
-        const int b = row / p.H, y = row - b * p.H;
+    // Everything that does not touch global memory comes BEFORE griddepcontrol.wait: launched behind another kernel the block
+    // does it while that kernel drains (ncu: ~650 instructions per warp of set-up, a quarter of what a warp executes here).
+    // First group of this block (a block owns whole groups, so its first item is channel block 0); the loop below keeps
+    // (channel block, x tile, row, image) as counters: the divisions of an item index by run-time values cost ~25 instructions
+    // each, several per item and warp.
+    const int xt0 = g0 % p.XT, row0 = g0 / p.XT;
+    const int b0 = row0 / p.H, y0 = row0 - b0 * p.H;
+    int icb = 0, ixt = xt0, iy = y0, ib = b0;   // producer: the next item to request
+    auto issue = [&](int s) {  // one thread; requests the next item into stage s and advances
         const uint32_t bar = smem_u32(&s_bar[s]);
         const uint32_t dst = smem_u32(smem_raw) + (uint32_t)s * p.stage_bytes;
         fence_proxy_async();  // the stage was read / written through the generic proxy before the block barrier
         mbar_arrive_expect_tx(bar, p.l_bytes + p.r_bytes);
-        const int X0 = xt * p.TX;
-        tma_load_4d(dst, &mapL, X0, y, cb * p.CB, b, bar);
-        tma_load_4d(dst + l_stride, &mapR, X0 - p.HALO, y, cb * p.CB, b, bar);
+        const int X0 = ixt * p.TX;
+        tma_load_4d(dst, &mapL, X0, iy, icb * p.CB, ib, bar);
+        tma_load_4d(dst + l_stride, &mapR, X0 - p.HALO, iy, icb * p.CB, ib, bar);
+        if (++icb == p.NCB) {
+            icb = 0;
+            if (++ixt == p.XT) { ixt = 0; if (++iy == p.H) { iy = 0; ++ib; } }
+        }
     };
-    if (tid == 0) issue(i0, 0);
 
     // this lane's pixels (inside the x tile) and disparity part
     const int wseg = warp % p.WPR, cgw = warp / p.WPR;
@@ -115,12 +94,29 @@ __global__ void __launch_bounds__(512) corr_fwd_reg_kernel(const FwdRegParams p,
     const int woff = xl + p.HALO - kDP * (h + 1);           // window start inside a staged R row
     const size_t HW = (size_t)p.H * p.W;
 
+    if (p.pf != 0 && tid == (int)blockDim.x - 1) {
+        // the boxes of this block's first item(s) towards the L2 while the previous kernel drains (common.cuh: prefetch_l2)
+        tma_prefetch_desc(&mapL); tma_prefetch_desc(&mapR);
+        int kcb = 0, kxt = xt0, ky = y0, kb = b0;
+        const int np = (i1 - i0 < p.pf) ? i1 - i0 : p.pf;
+        for (int k = 0; k < np; ++k) {
+            tma_prefetch_4d(&mapL, kxt * p.TX, ky, kcb * p.CB, kb);
+            tma_prefetch_4d(&mapR, kxt * p.TX - p.HALO, ky, kcb * p.CB, kb);
+            if (++kcb == p.NCB) {
+                kcb = 0;
+                if (++kxt == p.XT) { kxt = 0; if (++ky == p.H) { ky = 0; ++kb; } }
+            }
+        }
+    }
+    pdl_wait();               // no load or store above
+    if (tid == 0) issue(0);
+
     float acc[kDP][PX];
+    int cb = 0, xt = xt0, y = y0, b = b0;   // consumer: the item being computed
     for (int it = i0; it < i1; ++it) {
         const int s = (it - i0) & 1;
         const uint32_t ph = ((it - i0) >> 1) & 1u;
-        if (tid == 0 && it + 1 < i1) issue(it + 1, s ^ 1);  // stage s^1 was released by the barrier ending item it-1
-        const int cb = it % p.NCB, gx = it / p.NCB;
+        if (tid == 0 && it + 1 < i1) issue(s ^ 1);  // stage s^1 was released by the barrier ending item it-1
         unsigned char *stage = smem_raw + (size_t)s * p.stage_bytes;
         const T *lt = reinterpret_cast<const T *>(stage);
         const T *rt = reinterpret_cast<const T *>(stage + l_stride);
@@ -159,8 +155,6 @@ __global__ void __launch_bounds__(512) corr_fwd_reg_kernel(const FwdRegParams p,
 
         if (cb == p.NCB - 1) {
             // all channels of this (row, x tile) are in: combine the CGW partial sums and write the 12 x 4 outputs
-            const int xt = gx % p.XT, row = gx / p.XT;
-            const int b = row / p.H, y = row - b * p.H;
             const int x = xt * p.TX + xl;
             T *o = reinterpret_cast<T *>(p.out) + (size_t)b * p.OBS + (size_t)y * p.W + x;
             if (p.CGW == 1) {
@@ -200,6 +194,10 @@ __global__ void __launch_bounds__(512) corr_fwd_reg_kernel(const FwdRegParams p,
             }
         }
         __syncthreads();  // everyone is done with stage s
+        if (++cb == p.NCB) {
+            cb = 0;
+            if (++xt == p.XT) { xt = 0; if (++y == p.H) { y = 0; ++b; } }
+        }
     }
 }
 
@@ -230,14 +228,15 @@ int launch_fwd_reg_cpw(FwdRegParams p, const CUtensorMap &mapL, const CUtensorMa
     return check_launch("corr_fwd(reg)");
 }
 
-// channels per warp and item as a compile-time constant where it is 8, 4 or 2 (fp32 model shapes: 32 channels per item over 4
+// channels per warp and item as a compile-time constant where it is 8 or 4 (fp32 model shapes: 32 channels per item over 4
 // channel groups); 0 = run-time loop
 template <typename T, int LOGNH>
 int launch_fwd_reg(FwdRegParams p, const CUtensorMap &mapL, const CUtensorMap &mapR, int threads, size_t smem, cudaStream_t stream) {
-    if (sizeof(T) == 4 && env_int_fwd("DSSMD_CORR_FWD_UNROLLED", 1) != 0) {
-        if (p.CB == 8 * p.CGW) return launch_fwd_reg_cpw<T, LOGNH, 8>(p, mapL, mapR, threads, smem, stream);
-        if (p.CB == 4 * p.CGW) return launch_fwd_reg_cpw<T, LOGNH, 4>(p, mapL, mapR, threads, smem, stream);
-        if (p.CB == 2 * p.CGW) return launch_fwd_reg_cpw<T, LOGNH, 2>(p, mapL, mapR, threads, smem, stream);
+    if constexpr (sizeof(T) == 4) {
+        if (env_int_fwd("DSSMD_CORR_FWD_UNROLLED", 1) != 0) {
+            if (p.CB == 8 * p.CGW) return launch_fwd_reg_cpw<T, LOGNH, 8>(p, mapL, mapR, threads, smem, stream);
+            if (p.CB == 4 * p.CGW) return launch_fwd_reg_cpw<T, LOGNH, 4>(p, mapL, mapR, threads, smem, stream);
+        }
     }
     return launch_fwd_reg_cpw<T, LOGNH, 0>(p, mapL, mapR, threads, smem, stream);
 }
@@ -251,7 +250,7 @@ int corr_fwd_reg_typed(const void *L, const void *R, void *out, int B, int C, in
     if ((long long)B * H * 64 >= (1LL << 31)) return -1;
     FwdRegParams p{};
     p.out = out; p.OBS = obs;
-    p.L = L; p.R = R; p.pf = pdl_prefetch(1);
+    p.pf = pdl_prefetch(1);
     p.C = C; p.H = H; p.W = W; p.D = D;
     p.invC = 1.0f / (float)C;
     int nh = 1, lognh = 0;
