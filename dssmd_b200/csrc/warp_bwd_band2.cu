@@ -21,6 +21,10 @@
 //     or NaN reaches exactly the cells ATen's scatter would reach (the finite cells of such a row are summed in arrival order).
 // Error bound of the fast path: a cell that receives n taps differs from the exact sum by at most n * 2^-31 * 2 * S, S the
 // row's sum of |g| over all channels (the scale is the largest power of two with S * scale <= 2^30); exact path: 2^-19 of that.
+// Measured and left out (round 2): the float -> fixed-point conversions as fma(g, w, 1.5 * 2^23) - bits(1.5 * 2^23) instead of FMUL + F2I
+// for rows whose largest element allows it.  F2I.NTZ does run at only 15.8 conversions / clk / SM (scripts/micro/f2i_rate.cu; 55 for
+// the FFMA + IADD pair) and ncu shows the XU pipe as the busiest one of this kernel, yet the kernel did not get faster (576x960 x4
+// 28.9 -> 29.2 us, KITTI 97.5 -> 100.9): the conversions are not what the warps wait for.
 // Upstream: autograd of utils/disparity_warper.py:83-106 (aten::grid_sampler_2d_backward + the coordinate chain).
 #include "warp_lean.cuh"
 
