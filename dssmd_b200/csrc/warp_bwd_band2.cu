@@ -266,6 +266,9 @@ warp_bwd_band2_kernel(const float *g, const float *img, const float *disp,
     // row y - 1.  A row that was not scattered (beyond y_real) reads zeros with zero weights.
     auto read_out = [&](int y, auto slow_tag) {
         constexpr bool SLOW = decltype(slow_tag)::value;
+        // read and clear a cell with ONE shared-memory operation (atom.exch) instead of a load and a store: the shared-memory pipe is
+        // this kernel's busiest unit (ncu: 58 %); 576x960 x4 28.9 -> 28.4 us, 384x1280 x16 97.5 -> 96.4 us
+        constexpr bool XCHG = true;
         const float4 vw = s_vw[y - ys];
         const uint32_t ra = 4u * (uint32_t)tid + 4u + (uint32_t)((y & 1) * ABUF);   // slot tid + 1 of planes 0..3
         const int r_out = y - 1;
@@ -287,8 +290,13 @@ warp_bwd_band2_kernel(const float *g, const float *img, const float *disp,
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint32_t a = ra + (uint32_t)(c * ACH + j * P * 4);
-                const int v = ldsi_at(smem_raw, a);
-                stsi_at(smem_raw, a, 0);
+                int v;
+                if (XCHG) {
+                    asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(v) : "r"(abase + a), "r"(0) : "memory");
+                } else {
+                    v = ldsi_at(smem_raw, a);
+                    stsi_at(smem_raw, a, 0);
+                }
                 if (SLOW) {
                     const float cur = __int_as_float(v);
                     o[j] = on0 ? fmaf(wa, cur, pendA[c][j]) : pendA[c][j];
