@@ -44,8 +44,25 @@ __device__ __forceinline__ void mma1688(float (&c)[4], const uint32_t (&a)[4], u
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// NT = 8-column tiles per warp (8 * NT >= HALO + 16)
-template <int NT>
+// two bf16 in one register, `first` in the low half (the lower k index of a fragment pair)
+__device__ __forceinline__ uint32_t pack_bf16(float first, float second) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(second), "f"(first));
+    return r;
+}
+__device__ __forceinline__ void mma16816_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// NT = 8-column tiles per warp (8 * NT >= HALO + 16).
+// BX: the two CROSS terms on the bf16 instruction.  hi * lo and lo * hi are 2^-11 of the product, so their operands need only 8
+// significant bits for the same 2^-20 relative error that dropping lo * lo already allows: bf16(hi) x bf16(lo) + bf16(lo) x bf16(hi) on
+// mma.m16n8k16.bf16 -- ONE instruction per 16 channels and term where tf32 needs two k8 steps.  Per 16 channels and 8-column tile
+// 2 tf32 + 2 bf16 MMAs instead of 6 tf32 (the kernel is bound by the tensor pipe of this instruction family).  The contraction index
+// may be permuted freely as long as A and B agree: bf16 slot pair (2 tq, 2 tq + 1) takes the lane's tf32 elements (tq, tq + 4) of the first
+// k8 step, pair (2 tq + 8, 2 tq + 9) those of the second, for both operands.
+template <int NT, bool BX>
 __global__ void __launch_bounds__(kMaxWarps * 32) corr_fwd_mma32_kernel(const Mma32Params p, const __grid_constant__ CUtensorMap mapL,
                                                                         const __grid_constant__ CUtensorMap mapR) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -100,6 +117,49 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_fwd_mma32_kernel(const Mm
         mbar_wait(smem_u32(&s_bar[s]), (uint32_t)((ck >> 1) & 1));
         const float *Ls = reinterpret_cast<const float *>(smem + (size_t)s * stage_bytes);
         const float *Rs = reinterpret_cast<const float *>(smem + (size_t)s * stage_bytes + l_bytes);
+        if constexpr (BX) {
+            static_assert(kCK == 16, "one bf16 k16 step per stage");
+            uint32_t ah[2][4], ahb[4], alb[4];
+            {
+                float av[2][4], lo[2][4];
+#pragma unroll
+                for (int k8 = 0; k8 < 2; ++k8) {
+                    const float *la = Ls + k8 * 8 * p.LW + a_idx;
+                    av[k8][0] = la[0]; av[k8][1] = la[8]; av[k8][2] = la[4 * p.LW]; av[k8][3] = la[4 * p.LW + 8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(ah[k8][i]) : "f"(av[k8][i]));
+                        lo[k8][i] = av[k8][i] - __uint_as_float(ah[k8][i]);
+                    }
+                }
+                // rows g (elements 0, 2) and g + 8 (elements 1, 3); k pairs (tq, tq + 4) of each k8 step
+                ahb[0] = pack_bf16(__uint_as_float(ah[0][0]), __uint_as_float(ah[0][2]));
+                ahb[1] = pack_bf16(__uint_as_float(ah[0][1]), __uint_as_float(ah[0][3]));
+                ahb[2] = pack_bf16(__uint_as_float(ah[1][0]), __uint_as_float(ah[1][2]));
+                ahb[3] = pack_bf16(__uint_as_float(ah[1][1]), __uint_as_float(ah[1][3]));
+                alb[0] = pack_bf16(lo[0][0], lo[0][2]);
+                alb[1] = pack_bf16(lo[0][1], lo[0][3]);
+                alb[2] = pack_bf16(lo[1][0], lo[1][2]);
+                alb[3] = pack_bf16(lo[1][1], lo[1][3]);
+            }
+            const float *rb = Rs + b_idx;
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                const float b00 = rb[8 * n], b01 = rb[4 * p.RW + 8 * n], b10 = rb[8 * p.RW + 8 * n], b11 = rb[12 * p.RW + 8 * n];
+                uint32_t h00, h01, h10, h11;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h00) : "f"(b00));
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h01) : "f"(b01));
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h10) : "f"(b10));
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h11) : "f"(b11));
+                const uint32_t bhb0 = pack_bf16(__uint_as_float(h00), __uint_as_float(h01)), bhb1 = pack_bf16(__uint_as_float(h10), __uint_as_float(h11));
+                const uint32_t blb0 = pack_bf16(b00 - __uint_as_float(h00), b01 - __uint_as_float(h01));
+                const uint32_t blb1 = pack_bf16(b10 - __uint_as_float(h10), b11 - __uint_as_float(h11));
+                mma16816_bf16(acc[n], alb, bhb0, bhb1);   // small terms first
+                mma16816_bf16(acc[n], ahb, blb0, blb1);
+                mma1688(acc[n], ah[0], h00, h01);
+                mma1688(acc[n], ah[1], h10, h11);
+            }
+        } else {
 #pragma unroll
         for (int k8 = 0; k8 < kCK / 8; ++k8) {
             const float *la = Ls + k8 * 8 * p.LW + a_idx;
@@ -118,6 +178,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_fwd_mma32_kernel(const Mm
                 mma1688(acc[n], ah, bl0, bl1);
                 mma1688(acc[n], ah, bh0, bh1);
             }
+        }
         }
         __syncthreads();   // stage s may be refilled by the next iteration's TMA
     }
@@ -147,9 +208,9 @@ int env_int_m32(const char *name, int dflt) {
     return (v && *v) ? std::atoi(v) : dflt;
 }
 
-template <int NT>
-int launch_nt(const Mma32Params &p, const CUtensorMap &mapL, const CUtensorMap &mapR, int grid, int threads, size_t smem, cudaStream_t stream) {
-    auto kern = corr_fwd_mma32_kernel<NT>;
+template <int NT, bool BX>
+int launch_nt_bx(const Mma32Params &p, const CUtensorMap &mapL, const CUtensorMap &mapR, int grid, int threads, size_t smem, cudaStream_t stream) {
+    auto kern = corr_fwd_mma32_kernel<NT, BX>;
     {
         const cudaError_t e = kernel_smem_optin(kern, smem);
         if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_fwd(mma32): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
@@ -157,6 +218,12 @@ int launch_nt(const Mma32Params &p, const CUtensorMap &mapL, const CUtensorMap &
     const cudaError_t le = launch_pdl(kern, dim3((unsigned)grid), dim3((unsigned)threads), smem, stream, p, mapL, mapR);
     if (le != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_fwd(mma32): launch failed: %s", cudaGetErrorString(le));
     return check_launch("corr_fwd(mma32)");
+}
+
+template <int NT>
+int launch_nt(const Mma32Params &p, const CUtensorMap &mapL, const CUtensorMap &mapR, int grid, int threads, size_t smem, cudaStream_t stream) {
+    if (env_int_m32("DSSMD_MMA32_BF16X", 1) != 0) return launch_nt_bx<NT, true>(p, mapL, mapR, grid, threads, smem, stream);
+    return launch_nt_bx<NT, false>(p, mapL, mapR, grid, threads, smem, stream);
 }
 
 }  // namespace
