@@ -34,6 +34,12 @@ struct BwdMma32Params {
     int pf;          // first stage's boxes prefetched towards the L2 before griddepcontrol.wait (common.cuh: prefetch_l2)
 };
 
+static inline bool bwd_mma32_bf16x() {   // DSSMD_MMA32_BF16X=0 (tuning): all three products on tf32
+    if (!tuning_enabled()) return true;
+    const char *v = std::getenv("DSSMD_MMA32_BF16X");
+    return !(v && v[0] == '0');
+}
+
 __device__ __forceinline__ void split_tf32b(float v, uint32_t &hi, uint32_t &lo) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
     const float r = v - __uint_as_float(hi);
@@ -45,8 +51,23 @@ __device__ __forceinline__ void mma1688b(float (&c)[4], const uint32_t (&a)[4], 
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// NK = k8 steps (8 * NK >= HALO + 16)
-template <int MODE, int NK>
+// two bf16 in one register, `first` in the low half (the lower k index of a fragment pair)
+__device__ __forceinline__ uint32_t pack_bf16b(float first, float second) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(second), "f"(first));
+    return r;
+}
+__device__ __forceinline__ void mma16816_bf16b(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// NK = k8 steps (8 * NK >= HALO + 16).
+// BX: the two cross terms (hi x lo, lo x hi) of a PAIR of k8 steps on one bf16 m16n8k16 MMA each, as in corr_fwd_mma32.cu (the
+// operands of a term that is 2^-11 of the product need 8 significant bits; the contraction index -- here the band position --
+// is permuted the same way for A and G^T): 2 tf32 + 2 bf16 MMAs per pair and pixel tile instead of 6 tf32; an odd last step
+// keeps its three tf32 products.
+template <int MODE, int NK, bool BX>
 __global__ void __launch_bounds__(kMaxWarps * 32) corr_bwd_mma32_kernel(const BwdMma32Params p, const __grid_constant__ CUtensorMap mapIn,
                                                                         const __grid_constant__ CUtensorMap mapG) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -89,6 +110,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_bwd_mma32_kernel(const Bw
     const int g8 = lane >> 2, tq = lane & 3;
     const int wx = warp * 16;
     uint32_t gh[NK][2][2], gl[NK][2][2];     // G^T "col" fragments (k = tq / tq + 4, pixel 8 t + g8) of every k8 step, hi and lo
+    constexpr int NP = BX ? NK / 2 : 0;      // pairs of k8 steps whose cross terms go through bf16
+    uint32_t ghb[NP > 0 ? NP : 1][2][2], glb[NP > 0 ? NP : 1][2][2];   // ... packed: [pair][pixel tile][step of the pair]
     const int a_idx = g8 * p.RW + wx + tq;   // A fragment: (channel g8 / g8 + 8, position tq / tq + 4) of each k8 step
     float *const ob = p.out + (size_t)b * p.C * HW + (size_t)y * p.W + X0 + wx + 2 * tq;
     const bool st0 = X0 + wx + 2 * tq < p.W, st1 = X0 + wx + 8 + 2 * tq < p.W;   // W % 4 == 0 and even offsets: a pixel pair is in or out together
@@ -111,6 +134,18 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_bwd_mma32_kernel(const Bw
                         const float v = (d >= 0 && d < p.D) ? gt[d * p.GW + xc] : 0.f;
                         split_tf32b(v, gh[q][t][e], gl[q][t][e]);
                     }
+            if constexpr (BX) {
+#pragma unroll
+                for (int pq = 0; pq < NP; ++pq)
+#pragma unroll
+                    for (int t = 0; t < 2; ++t)
+#pragma unroll
+                        for (int st = 0; st < 2; ++st) {
+                            const int q = 2 * pq + st;
+                            ghb[pq][t][st] = pack_bf16b(__uint_as_float(gh[q][t][0]), __uint_as_float(gh[q][t][1]));
+                            glb[pq][t][st] = pack_bf16b(__uint_as_float(gl[q][t][0]), __uint_as_float(gl[q][t][1]));
+                        }
+            }
         }
         const float *Rs = reinterpret_cast<const float *>(smem + g_pad + (size_t)s * stage_bytes);
         const int c0 = ck * kCK;
@@ -122,8 +157,40 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_bwd_mma32_kernel(const Bw
 #pragma unroll
                 for (int k = 0; k < 4; ++k) acc[t][k] = 0.f;
             const float *ra = Rs + mt * 16 * p.RW + a_idx;
+            if constexpr (BX) {
 #pragma unroll
-            for (int q = 0; q < NK; ++q) {
+                for (int pq = 0; pq < NP; ++pq) {
+                    uint32_t ah[2][4], ahb[4], alb[4];
+                    float lo[2][4];
+#pragma unroll
+                    for (int st = 0; st < 2; ++st) {
+                        const int q = 2 * pq + st;
+                        const float av[4] = {ra[8 * q], ra[8 * p.RW + 8 * q], ra[8 * q + 4], ra[8 * p.RW + 8 * q + 4]};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(ah[st][i]) : "f"(av[i]));
+                            lo[st][i] = av[i] - __uint_as_float(ah[st][i]);
+                        }
+                    }
+                    ahb[0] = pack_bf16b(__uint_as_float(ah[0][0]), __uint_as_float(ah[0][2]));
+                    ahb[1] = pack_bf16b(__uint_as_float(ah[0][1]), __uint_as_float(ah[0][3]));
+                    ahb[2] = pack_bf16b(__uint_as_float(ah[1][0]), __uint_as_float(ah[1][2]));
+                    ahb[3] = pack_bf16b(__uint_as_float(ah[1][1]), __uint_as_float(ah[1][3]));
+                    alb[0] = pack_bf16b(lo[0][0], lo[0][2]);
+                    alb[1] = pack_bf16b(lo[0][1], lo[0][3]);
+                    alb[2] = pack_bf16b(lo[1][0], lo[1][2]);
+                    alb[3] = pack_bf16b(lo[1][1], lo[1][3]);
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        mma16816_bf16b(acc[t], alb, ghb[pq][t][0], ghb[pq][t][1]);     // small terms first
+                        mma16816_bf16b(acc[t], ahb, glb[pq][t][0], glb[pq][t][1]);
+                        mma1688b(acc[t], ah[0], gh[2 * pq][t][0], gh[2 * pq][t][1]);
+                        mma1688b(acc[t], ah[1], gh[2 * pq + 1][t][0], gh[2 * pq + 1][t][1]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = BX ? 2 * NP : 0; q < NK; ++q) {
                 uint32_t ah[4], al[4];
                 split_tf32b(ra[8 * q], ah[0], al[0]);
                 split_tf32b(ra[8 * p.RW + 8 * q], ah[1], al[1]);
@@ -157,9 +224,9 @@ int env_int_bm32(const char *name, int dflt) {
     return (v && *v) ? std::atoi(v) : dflt;
 }
 
-template <int MODE, int NK>
-int launch_bnk(const BwdMma32Params &p, const CUtensorMap &mapIn, const CUtensorMap &mapG, int grid, int threads, size_t smem, cudaStream_t stream) {
-    auto kern = corr_bwd_mma32_kernel<MODE, NK>;
+template <int MODE, int NK, bool BX>
+int launch_bnk_bx(const BwdMma32Params &p, const CUtensorMap &mapIn, const CUtensorMap &mapG, int grid, int threads, size_t smem, cudaStream_t stream) {
+    auto kern = corr_bwd_mma32_kernel<MODE, NK, BX>;
     {
         const cudaError_t e = kernel_smem_optin(kern, smem);
         if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_bwd(mma32): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
@@ -167,6 +234,12 @@ int launch_bnk(const BwdMma32Params &p, const CUtensorMap &mapIn, const CUtensor
     const cudaError_t le = launch_pdl(kern, dim3((unsigned)grid), dim3((unsigned)threads), smem, stream, p, mapIn, mapG);
     if (le != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_bwd(mma32): launch failed: %s", cudaGetErrorString(le));
     return check_launch(MODE == 0 ? "corr_bwd(gL, mma32)" : "corr_bwd(gR, mma32)");
+}
+
+template <int MODE, int NK>
+int launch_bnk(const BwdMma32Params &p, const CUtensorMap &mapIn, const CUtensorMap &mapG, int grid, int threads, size_t smem, cudaStream_t stream) {
+    if (bwd_mma32_bf16x()) return launch_bnk_bx<MODE, NK, true>(p, mapIn, mapG, grid, threads, smem, stream);
+    return launch_bnk_bx<MODE, NK, false>(p, mapIn, mapG, grid, threads, smem, stream);
 }
 
 template <int MODE>
