@@ -51,6 +51,13 @@ __device__ __forceinline__ void mma1688b(float (&c)[4], const uint32_t (&a)[4], 
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// hi = v rounded to tf32 (nearest, ties away), lo = v - hi: the two integer operations of cvt.rna.tf32.f32 without its compare and
+// select for inf / NaN (see corr_fwd_mma32.cu: a NaN still reaches the accumulator through lo)
+__device__ __forceinline__ void split_rnb(float v, uint32_t &hi, float &lo) {
+    hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
+    lo = v - __uint_as_float(hi);
+}
+
 // two bf16 in one register, `first` in the low half (the lower k index of a fragment pair)
 __device__ __forceinline__ uint32_t pack_bf16b(float first, float second) {
     uint32_t r;
@@ -167,10 +174,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_bwd_mma32_kernel(const Bw
                         const int q = 2 * pq + st;
                         const float av[4] = {ra[8 * q], ra[8 * p.RW + 8 * q], ra[8 * q + 4], ra[8 * p.RW + 8 * q + 4]};
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(ah[st][i]) : "f"(av[i]));
-                            lo[st][i] = av[i] - __uint_as_float(ah[st][i]);
-                        }
+                        for (int i = 0; i < 4; ++i) split_rnb(av[i], ah[st][i], lo[st][i]);
                     }
                     ahb[0] = pack_bf16b(__uint_as_float(ah[0][0]), __uint_as_float(ah[0][2]));
                     ahb[1] = pack_bf16b(__uint_as_float(ah[0][1]), __uint_as_float(ah[0][3]));

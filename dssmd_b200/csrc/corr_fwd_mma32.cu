@@ -44,6 +44,16 @@ __device__ __forceinline__ void mma1688(float (&c)[4], const uint32_t (&a)[4], u
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// hi = v rounded to tf32 (nearest, ties away: the bit pattern plus half an ulp of tf32, low 13 bits cleared), lo = v - hi (exact).
+// cvt.rna.tf32.f32 compiles to these two integer operations PLUS a compare and a select that keep inf / NaN patterns unchanged
+// (4 ALU instructions per element; ncu: the ALU pipe was the busiest unit of this kernel at 53 %).  Not needed here: an inf
+// keeps its pattern anyway, and a NaN whose payload overflows still gives lo = NaN, which reaches the accumulator through the
+// cross terms like it did before.
+__device__ __forceinline__ void split_rn(float v, uint32_t &hi, float &lo) {
+    hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
+    lo = v - __uint_as_float(hi);
+}
+
 // two bf16 in one register, `first` in the low half (the lower k index of a fragment pair)
 __device__ __forceinline__ uint32_t pack_bf16(float first, float second) {
     uint32_t r;
@@ -118,46 +128,45 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_fwd_mma32_kernel(const Mm
         const float *Ls = reinterpret_cast<const float *>(smem + (size_t)s * stage_bytes);
         const float *Rs = reinterpret_cast<const float *>(smem + (size_t)s * stage_bytes + l_bytes);
         if constexpr (BX) {
-            static_assert(kCK == 16, "one bf16 k16 step per stage");
-            uint32_t ah[2][4], ahb[4], alb[4];
-            {
-                float av[2][4], lo[2][4];
 #pragma unroll
-                for (int k8 = 0; k8 < 2; ++k8) {
-                    const float *la = Ls + k8 * 8 * p.LW + a_idx;
-                    av[k8][0] = la[0]; av[k8][1] = la[8]; av[k8][2] = la[4 * p.LW]; av[k8][3] = la[4 * p.LW + 8];
+            for (int k16 = 0; k16 < kCK / 16; ++k16) {
+                uint32_t ah[2][4], ahb[4], alb[4];
+                {
+                    float lo[2][4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(ah[k8][i]) : "f"(av[k8][i]));
-                        lo[k8][i] = av[k8][i] - __uint_as_float(ah[k8][i]);
+                    for (int k8 = 0; k8 < 2; ++k8) {
+                        const float *la = Ls + (k16 * 16 + k8 * 8) * p.LW + a_idx;
+                        split_rn(la[0], ah[k8][0], lo[k8][0]);
+                        split_rn(la[8], ah[k8][1], lo[k8][1]);
+                        split_rn(la[4 * p.LW], ah[k8][2], lo[k8][2]);
+                        split_rn(la[4 * p.LW + 8], ah[k8][3], lo[k8][3]);
                     }
+                    // rows g (elements 0, 2) and g + 8 (elements 1, 3); k pairs (tq, tq + 4) of each k8 step
+                    ahb[0] = pack_bf16(__uint_as_float(ah[0][0]), __uint_as_float(ah[0][2]));
+                    ahb[1] = pack_bf16(__uint_as_float(ah[0][1]), __uint_as_float(ah[0][3]));
+                    ahb[2] = pack_bf16(__uint_as_float(ah[1][0]), __uint_as_float(ah[1][2]));
+                    ahb[3] = pack_bf16(__uint_as_float(ah[1][1]), __uint_as_float(ah[1][3]));
+                    alb[0] = pack_bf16(lo[0][0], lo[0][2]);
+                    alb[1] = pack_bf16(lo[0][1], lo[0][3]);
+                    alb[2] = pack_bf16(lo[1][0], lo[1][2]);
+                    alb[3] = pack_bf16(lo[1][1], lo[1][3]);
                 }
-                // rows g (elements 0, 2) and g + 8 (elements 1, 3); k pairs (tq, tq + 4) of each k8 step
-                ahb[0] = pack_bf16(__uint_as_float(ah[0][0]), __uint_as_float(ah[0][2]));
-                ahb[1] = pack_bf16(__uint_as_float(ah[0][1]), __uint_as_float(ah[0][3]));
-                ahb[2] = pack_bf16(__uint_as_float(ah[1][0]), __uint_as_float(ah[1][2]));
-                ahb[3] = pack_bf16(__uint_as_float(ah[1][1]), __uint_as_float(ah[1][3]));
-                alb[0] = pack_bf16(lo[0][0], lo[0][2]);
-                alb[1] = pack_bf16(lo[0][1], lo[0][3]);
-                alb[2] = pack_bf16(lo[1][0], lo[1][2]);
-                alb[3] = pack_bf16(lo[1][1], lo[1][3]);
-            }
-            const float *rb = Rs + b_idx;
+                const float *rb = Rs + k16 * 16 * p.RW + b_idx;
 #pragma unroll
-            for (int n = 0; n < NT; ++n) {
-                const float b00 = rb[8 * n], b01 = rb[4 * p.RW + 8 * n], b10 = rb[8 * p.RW + 8 * n], b11 = rb[12 * p.RW + 8 * n];
-                uint32_t h00, h01, h10, h11;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h00) : "f"(b00));
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h01) : "f"(b01));
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h10) : "f"(b10));
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h11) : "f"(b11));
-                const uint32_t bhb0 = pack_bf16(__uint_as_float(h00), __uint_as_float(h01)), bhb1 = pack_bf16(__uint_as_float(h10), __uint_as_float(h11));
-                const uint32_t blb0 = pack_bf16(b00 - __uint_as_float(h00), b01 - __uint_as_float(h01));
-                const uint32_t blb1 = pack_bf16(b10 - __uint_as_float(h10), b11 - __uint_as_float(h11));
-                mma16816_bf16(acc[n], alb, bhb0, bhb1);   // small terms first
-                mma16816_bf16(acc[n], ahb, blb0, blb1);
-                mma1688(acc[n], ah[0], h00, h01);
-                mma1688(acc[n], ah[1], h10, h11);
+                for (int n = 0; n < NT; ++n) {
+                    uint32_t h00, h01, h10, h11;
+                    float l00, l01, l10, l11;
+                    split_rn(rb[8 * n], h00, l00);
+                    split_rn(rb[4 * p.RW + 8 * n], h01, l01);
+                    split_rn(rb[8 * p.RW + 8 * n], h10, l10);
+                    split_rn(rb[12 * p.RW + 8 * n], h11, l11);
+                    const uint32_t bhb0 = pack_bf16(__uint_as_float(h00), __uint_as_float(h01)), bhb1 = pack_bf16(__uint_as_float(h10), __uint_as_float(h11));
+                    const uint32_t blb0 = pack_bf16(l00, l01), blb1 = pack_bf16(l10, l11);
+                    mma16816_bf16(acc[n], alb, bhb0, bhb1);   // small terms first
+                    mma16816_bf16(acc[n], ahb, blb0, blb1);
+                    mma1688(acc[n], ah[0], h00, h01);
+                    mma1688(acc[n], ah[1], h10, h11);
+                }
             }
         } else {
 #pragma unroll
