@@ -196,10 +196,20 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_bwd_mma32_kernel(const Bw
 #pragma unroll
             for (int q = BX ? 2 * NP : 0; q < NK; ++q) {
                 uint32_t ah[4], al[4];
-                split_tf32b(ra[8 * q], ah[0], al[0]);
-                split_tf32b(ra[8 * p.RW + 8 * q], ah[1], al[1]);
-                split_tf32b(ra[8 * q + 4], ah[2], al[2]);
-                split_tf32b(ra[8 * p.RW + 8 * q + 4], ah[3], al[3]);
+                if constexpr (BX) {   // the cheap split; lo truncated to tf32 (2^-21 of the product)
+                    const float av[4] = {ra[8 * q], ra[8 * p.RW + 8 * q], ra[8 * q + 4], ra[8 * p.RW + 8 * q + 4]};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float lo;
+                        split_rnb(av[i], ah[i], lo);
+                        al[i] = __float_as_uint(lo) & 0xffffe000u;
+                    }
+                } else {
+                    split_tf32b(ra[8 * q], ah[0], al[0]);
+                    split_tf32b(ra[8 * p.RW + 8 * q], ah[1], al[1]);
+                    split_tf32b(ra[8 * q + 4], ah[2], al[2]);
+                    split_tf32b(ra[8 * p.RW + 8 * q + 4], ah[3], al[3]);
+                }
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                     mma1688b(acc[t], al, gh[q][t][0], gh[q][t][1]);     // small terms first
