@@ -601,7 +601,14 @@ int warp_bwd_band2_f32(const float *g, const float *img, const float *disp, floa
         return border ? launch_band2<PSV, true, false>(g, img, disp, g_img, g_disp, B, C, H, W, s)                         \
                       : launch_band2<PSV, false, false>(g, img, disp, g_img, g_disp, B, C, H, W, s);                       \
     }
-    DSSMD_BAND2(66) DSSMD_BAND2(130) DSSMD_BAND2(258) DSSMD_BAND2(322) DSSMD_BAND2(514)
+    // the 320-thread instance (two blocks per SM at 96 registers) only pays when there are blocks to fill the second slot: measured at
+    // 384x1280 over the batch size (scripts/kitti_warp_b_sweep.py), 512- / 320-thread instance: B = 1 13.1 / 17.2 us, B = 2 18.0 / 21.4,
+    // B = 4 29.6 / 30.2, B = 6 41.4 / 39.4, B = 8 54.9 / 51.3, B = 16 109.6 / 96.6
+    const int w320 = env_int_lean("DSSMD_WARP_BWD_BAND_W320", -1);
+    const bool use320 = w320 >= 0 ? w320 != 0 : (long)B * H >= 2048;
+    DSSMD_BAND2(66) DSSMD_BAND2(130) DSSMD_BAND2(258)
+    if (use320) { DSSMD_BAND2(322) }
+    DSSMD_BAND2(514)
 #undef DSSMD_BAND2
     return -1;
 }
