@@ -1440,6 +1440,47 @@ def test_corr_fwd_mma32(ops, oracle, shape, relu, monkeypatch, capfd):
     assert torch.equal(ops.build_corr_cat(head, L, R, D), torch.cat((head, out), dim=1))
 
 
+@pytest.mark.parametrize("bx", ["1", "0"])
+def test_corr_mma32_cross_terms_on_bf16(ops, oracle, bx, monkeypatch, capfd):
+    """The default mma.sync fp32 kernels compute hi * hi on tf32 and the two cross terms (hi * lo, lo * hi) on bf16 MMAs
+    (DSSMD_MMA32_BF16X=0: all three on tf32).  Both must meet the fp32 bar on channels whose scales differ by six decades
+    (the split is per element, so no channel may drown another), forward and both gradients."""
+    B, C, H, W, D = 1, 64, 3, 160, 41
+    sc = torch.logspace(-3, 3, C, device="cuda").view(1, C, 1, 1)
+    L0, R0 = feat((B, C, H, W), 61, False) * sc, feat((B, C, H, W), 62, False) / sc
+    g = feat((B, D, H, W), 63, False)
+    monkeypatch.setenv("DSSMD_MMA32_BF16X", bx)
+    monkeypatch.setenv("DSSMD_CORR_FWD_VARIANT", "3")
+    monkeypatch.setenv("DSSMD_CORR_BWD_VARIANT", "3")
+    monkeypatch.setenv("DSSMD_CORR_DEBUG", "1")
+    L, R = L0.clone().requires_grad_(True), R0.clone().requires_grad_(True)
+    out = ops.build_corr(L, R, D)
+    out.backward(g)
+    torch.cuda.synchronize()
+    err = capfd.readouterr().err
+    assert "corr_fwd mma32 cfg" in err and err.count("corr_bwd mma32 cfg") == 2, err
+    assert rel_err(out.detach().cpu().numpy(), oracle.corr_fwd(L0.cpu().numpy(), R0.cpu().numpy(), D)) <= TOL_F32
+    gL, gR = oracle.corr_bwd(g.cpu().numpy(), L0.cpu().numpy(), R0.cpu().numpy())
+    assert rel_err(L.grad.cpu().numpy(), gL) <= TOL_F32
+    assert rel_err(R.grad.cpu().numpy(), gR) <= TOL_F32
+
+
+@pytest.mark.parametrize("bad", [float("nan"), float("inf")])
+def test_corr_mma32_nonfinite_inputs_stay_local(ops, bad, monkeypatch):
+    """The tf32 split of the tensor-core kernels has no special case for inf / NaN: a non-finite feature must still make exactly the
+    outputs that read it non-finite (through lo = v - hi) and leave every other output finite."""
+    B, C, H, W, D = 1, 32, 4, 160, 24
+    L, R = feat((B, C, H, W), 71, True), feat((B, C, H, W), 72, True)
+    L[0, 5, 2, 77] = bad
+    monkeypatch.setenv("DSSMD_CORR_FWD_VARIANT", "3")
+    out = ops.build_corr(L, R, D)
+    torch.cuda.synchronize()
+    nf = ~torch.isfinite(out)
+    expect = torch.zeros_like(nf)
+    expect[0, :, 2, 77] = True           # out[d, y, x] reads L[c, y, x] for every d <= x
+    assert bool((nf == expect).all())
+
+
 WIDE_SHAPES = [
     (4, 128, 3, 120, 24),    # cfg5 rows: one tile of 120 pixels, two rows per block
     (1, 128, 40, 80, 24),    # cfg1 / cfg3 model shape (20 of 32 lanes)
