@@ -74,8 +74,10 @@ __device__ __forceinline__ void mma16816_bf16b(float (&c)[4], const uint32_t (&a
 // operands of a term that is 2^-11 of the product need 8 significant bits; the contraction index -- here the band position --
 // is permuted the same way for A and G^T): 2 tf32 + 2 bf16 MMAs per pair and pixel tile instead of 6 tf32; an odd last step
 // keeps its three tf32 products.
-template <int MODE, int NK, bool BX>
-__global__ void __launch_bounds__(kMaxWarps * 32) corr_bwd_mma32_kernel(const BwdMma32Params p, const __grid_constant__ CUtensorMap mapIn,
+// TB: the most threads a block may have.  Blocks of up to five warps (rows tiled in 80 pixels: cfg2, KITTI, the 320x640 crops) ask for
+// four resident blocks (96 registers instead of ~125 and three blocks: cfg2 backward 116.0 -> 114.2 us, KITTI 60.5 -> 59.1 us)
+template <int MODE, int NK, bool BX, int TB>
+__global__ void __launch_bounds__(TB, TB <= 160 ? 4 : 2) corr_bwd_mma32_kernel(const BwdMma32Params p, const __grid_constant__ CUtensorMap mapIn,
                                                                         const __grid_constant__ CUtensorMap mapG) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long s_bar[2];
@@ -238,9 +240,9 @@ int env_int_bm32(const char *name, int dflt) {
     return (v && *v) ? std::atoi(v) : dflt;
 }
 
-template <int MODE, int NK, bool BX>
-int launch_bnk_bx(const BwdMma32Params &p, const CUtensorMap &mapIn, const CUtensorMap &mapG, int grid, int threads, size_t smem, cudaStream_t stream) {
-    auto kern = corr_bwd_mma32_kernel<MODE, NK, BX>;
+template <int MODE, int NK, bool BX, int TB>
+int launch_bnk_tb(const BwdMma32Params &p, const CUtensorMap &mapIn, const CUtensorMap &mapG, int grid, int threads, size_t smem, cudaStream_t stream) {
+    auto kern = corr_bwd_mma32_kernel<MODE, NK, BX, TB>;
     {
         const cudaError_t e = kernel_smem_optin(kern, smem);
         if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_bwd(mma32): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
@@ -252,8 +254,13 @@ int launch_bnk_bx(const BwdMma32Params &p, const CUtensorMap &mapIn, const CUten
 
 template <int MODE, int NK>
 int launch_bnk(const BwdMma32Params &p, const CUtensorMap &mapIn, const CUtensorMap &mapG, int grid, int threads, size_t smem, cudaStream_t stream) {
-    if (bwd_mma32_bf16x()) return launch_bnk_bx<MODE, NK, true>(p, mapIn, mapG, grid, threads, smem, stream);
-    return launch_bnk_bx<MODE, NK, false>(p, mapIn, mapG, grid, threads, smem, stream);
+    if (bwd_mma32_bf16x()) {
+        if constexpr (NK <= 8) {   // beyond that the 96-register build spills
+            if (threads <= 160) return launch_bnk_tb<MODE, NK, true, 160>(p, mapIn, mapG, grid, threads, smem, stream);
+        }
+        return launch_bnk_tb<MODE, NK, true, kMaxWarps * 32>(p, mapIn, mapG, grid, threads, smem, stream);
+    }
+    return launch_bnk_tb<MODE, NK, false, kMaxWarps * 32>(p, mapIn, mapG, grid, threads, smem, stream);
 }
 
 template <int MODE>
