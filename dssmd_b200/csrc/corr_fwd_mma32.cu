@@ -21,26 +21,6 @@ namespace {
 
 constexpr int kCK = 16;          // channels per stage (two k8 steps; 32 is slower at three of the four bench shapes)
 constexpr int kMaxWarps = 8;     // 128 pixels per block
-constexpr int kM32MaxStages = 8;
-
-// bounded mbarrier wait that the compiler does not unroll into 64 copies (a protocol bug traps instead of hanging the GPU)
-__device__ __forceinline__ bool mbar_try_m(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    return done != 0;
-}
-__device__ __noinline__ void mbar_wait_slow_m(uint32_t bar, uint32_t parity) {
-    for (int spin = 0; spin < (1 << 26); ++spin)
-        if (mbar_try_m(bar, parity)) return;
-    __trap();
-}
-__device__ __forceinline__ void mbar_wait_m(uint32_t bar, uint32_t parity) {
-    if (!mbar_try_m(bar, parity)) mbar_wait_slow_m(bar, parity);
-}
 
 struct Mma32Params {
     float *out;
@@ -51,7 +31,6 @@ struct Mma32Params {
     int LW, RW;      // staged row widths in floats (= box widths, 8 mod 32)
     float invC;
     int pf;          // first stage's boxes prefetched towards the L2 before griddepcontrol.wait (common.cuh: prefetch_l2)
-    int S;           // RING kernels: stages of the ring (3 .. kM32MaxStages)
 };
 
 __device__ __forceinline__ void split_tf32(float v, uint32_t &hi, uint32_t &lo) {
@@ -93,16 +72,12 @@ __device__ __forceinline__ void mma16816_bf16(float (&c)[4], const uint32_t (&a)
 // 2 tf32 + 2 bf16 MMAs instead of 6 tf32 (the kernel is bound by the tensor pipe of this instruction family).  The contraction index
 // may be permuted freely as long as A and B agree: bf16 slot pair (2 tq, 2 tq + 1) takes the lane's tf32 elements (tq, tq + 4) of the first
 // k8 step, pair (2 tq + 8, 2 tq + 9) those of the second, for both operands.
-// RING: the warps are decoupled -- p.S stages with a full (TMA) and an empty (one arrival per warp) mbarrier each instead of two stages
-// and a block barrier per stage.  It pays where a block's eight or so stages are a chain of memory round trips with little to overlap
-// them (few, short rows: the 576x960 and 320x640 model shapes); on the large problems the two-stage kernel is faster (more resident blocks).
-template <int NT, bool BX, bool RING>
+template <int NT, bool BX>
 __global__ void __launch_bounds__(kMaxWarps * 32) corr_fwd_mma32_kernel(const Mma32Params p, const __grid_constant__ CUtensorMap mapL,
                                                                         const __grid_constant__ CUtensorMap mapR) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ __align__(8) unsigned long long s_bar[RING ? kM32MaxStages : 2], s_empty[RING ? kM32MaxStages : 1];
+    __shared__ __align__(8) unsigned long long s_bar[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int S = RING ? p.S : 2;
     const int row = blockIdx.x / p.XT, xt = blockIdx.x - row * p.XT;
     const int b = row / p.H, y = row - b * p.H;
     const int X0 = xt * p.TX;
@@ -115,16 +90,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_fwd_mma32_kernel(const Mm
     auto issue = [&](int c0, int s) {   // one thread
         const uint32_t ls = sbase + (uint32_t)s * stage_bytes, rs = ls + l_bytes;
         const uint32_t bar = smem_u32(&s_bar[s]);
-        if (!RING) fence_proxy_async();   // the stage was read through the generic proxy before the block barrier
+        fence_proxy_async();   // the stage was read through the generic proxy before the block barrier
         mbar_arrive_expect_tx(bar, stage_bytes);
         tma_load_4d(ls, &mapL, X0, y, c0, b, bar);
         tma_load_4d(rs, &mapR, X0 - p.HALO, y, c0, b, bar);
     };
     if (tid == 0) {
-        for (int k = 0; k < S; ++k) {
-            mbar_init(smem_u32(&s_bar[k]), 1);
-            if (RING) mbar_init(smem_u32(&s_empty[k]), (int)(blockDim.x >> 5));
-        }
+        mbar_init(smem_u32(&s_bar[0]), 1);
+        mbar_init(smem_u32(&s_bar[1]), 1);
         fence_proxy_async();
     }
     __syncthreads();
@@ -135,10 +108,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_fwd_mma32_kernel(const Mm
         tma_prefetch_4d(&mapR, X0 - p.HALO, y, 0, b);
     }
     pdl_wait();            // no load or store above
-    if (tid == 0) {
-        if (RING) { for (int k = 0; k < S - 1 && k < nck; ++k) issue(k * kCK, k); }
-        else issue(0, 0);
-    }
+    if (tid == 0) issue(0, 0);
 
     float acc[NT][4];
 #pragma unroll
@@ -151,23 +121,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_fwd_mma32_kernel(const Mm
     // fragment elements of this lane: A (pixel g / g + 8, channel tq / tq + 4), B (channel tq / tq + 4, column g of each tile)
     const int a_idx = tq * p.LW + wx + g, b_idx = tq * p.RW + wx + g;
 
-    int rs = 0;            // RING: stage of the current chunk and parity of its pass
-    uint32_t rph = 0;
     for (int ck = 0; ck < nck; ++ck) {
-        const int s = RING ? rs : ck & 1;
-        if (RING) {
-            if (tid == 0 && ck + S - 1 < nck) {
-                // chunk ck + S - 1 goes into the stage of chunk ck - 1, once every warp has released it
-                const int sp = s == 0 ? S - 1 : s - 1;
-                if (ck > 0) mbar_wait_m(smem_u32(&s_empty[sp]), s == 0 ? rph ^ 1u : rph);
-                issue((ck + S - 1) * kCK, sp);
-            }
-            __syncwarp();
-            mbar_wait_m(smem_u32(&s_bar[s]), rph);
-        } else {
-            if (tid == 0 && ck + 1 < nck) issue((ck + 1) * kCK, s ^ 1);   // stage s^1 was released by the barrier ending iteration ck-1
-            mbar_wait(smem_u32(&s_bar[s]), (uint32_t)((ck >> 1) & 1));
-        }
+        const int s = ck & 1;
+        if (tid == 0 && ck + 1 < nck) issue((ck + 1) * kCK, s ^ 1);   // stage s^1 was released by the barrier ending iteration ck-1
+        mbar_wait(smem_u32(&s_bar[s]), (uint32_t)((ck >> 1) & 1));
         const float *Ls = reinterpret_cast<const float *>(smem + (size_t)s * stage_bytes);
         const float *Rs = reinterpret_cast<const float *>(smem + (size_t)s * stage_bytes + l_bytes);
         if constexpr (BX) {
@@ -232,15 +189,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32) corr_fwd_mma32_kernel(const Mm
             }
         }
         }
-        if (RING) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&s_empty[s]));   // this warp is done with stage s
-            if (++rs == S) { rs = 0; rph ^= 1u; }
-        } else {
-            __syncthreads();   // stage s may be refilled by the next iteration's TMA
-        }
+        __syncthreads();   // stage s may be refilled by the next iteration's TMA
     }
-    if (RING) __syncthreads();   // the staging tiles below lie over the stages: every warp must have left the channel loop
 
     // ---- epilogue: band of the accumulator -> per-warp staging tile [D][17] -> 64-byte row segments ------------------------
     float *so = reinterpret_cast<float *>(smem) + (size_t)warp * p.D * 17;
@@ -267,9 +217,9 @@ int env_int_m32(const char *name, int dflt) {
     return (v && *v) ? std::atoi(v) : dflt;
 }
 
-template <int NT, bool BX, bool RING = false>
+template <int NT, bool BX>
 int launch_nt_bx(const Mma32Params &p, const CUtensorMap &mapL, const CUtensorMap &mapR, int grid, int threads, size_t smem, cudaStream_t stream) {
-    auto kern = corr_fwd_mma32_kernel<NT, BX, RING>;
+    auto kern = corr_fwd_mma32_kernel<NT, BX>;
     {
         const cudaError_t e = kernel_smem_optin(kern, smem);
         if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_fwd(mma32): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
@@ -281,10 +231,7 @@ int launch_nt_bx(const Mma32Params &p, const CUtensorMap &mapL, const CUtensorMa
 
 template <int NT>
 int launch_nt(const Mma32Params &p, const CUtensorMap &mapL, const CUtensorMap &mapR, int grid, int threads, size_t smem, cudaStream_t stream) {
-    if (env_int_m32("DSSMD_MMA32_BF16X", 1) != 0) {
-        if (p.S >= 3) return launch_nt_bx<NT, true, true>(p, mapL, mapR, grid, threads, smem, stream);
-        return launch_nt_bx<NT, true>(p, mapL, mapR, grid, threads, smem, stream);
-    }
+    if (env_int_m32("DSSMD_MMA32_BF16X", 1) != 0) return launch_nt_bx<NT, true>(p, mapL, mapR, grid, threads, smem, stream);
     return launch_nt_bx<NT, false>(p, mapL, mapR, grid, threads, smem, stream);
 }
 
@@ -312,14 +259,7 @@ int corr_fwd_mma32(const void *L, const void *R, void *out, int B, int C, int H,
     p.LW = w8mod32(p.TX);
     p.RW = w8mod32(p.TX + 8 * nt - 16);
     if (p.LW > 256 || p.RW > 256) return -1;
-    // ring of stages (decoupled warps) for small problems; DSSMD_MMA32_STAGES forces a depth (2 = the two-stage kernel)
-    const long long tiles16 = (long long)B * H * ceil_div(W, 16);
-    int S = env_int_m32("DSSMD_MMA32_STAGES", tiles16 < 4000 ? 4 : 2);
-    if (S > kM32MaxStages) S = kM32MaxStages;
-    if (S > ceil_div(C, kCK)) S = ceil_div(C, kCK);
-    if (S < 3) S = 2;
-    p.S = S;
-    size_t smem = (size_t)S * (size_t)kCK * (size_t)(p.LW + p.RW) * 4;
+    size_t smem = 2 * (size_t)kCK * (size_t)(p.LW + p.RW) * 4;
     const size_t epi = (size_t)warps * D * 17 * sizeof(float);
     if (epi > smem) smem = epi;
     if (smem > 200 * 1024) return -1;
