@@ -619,10 +619,12 @@ int launch_typed(const void *L, const void *R, void *out, int B, int C, int H, i
         // 3 = mma.sync with 3xTF32 splitting.  Unset: taken where it measured faster than the other fp32 kernels -- rows that fill the
         // register-blocked kernel's 128-pixel tiles badly (W = 80: 12.9 vs 18.5 us at 320x640 / 8) and problems of several thousand
         // 16-pixel warp tiles (cfg2 73.8 vs 86.2 us on tcgen05, KITTI 35.6 vs 41.6 us); the register-blocked kernel keeps the small
-        // well-fitting shapes (cfg5, W = 120: 12.9 vs 14.4 us)
+        // well-fitting shapes with few disparities.  Since the cross terms of the split run on bf16 MMAs and a stage holds 32 channels
+        // (corr_fwd_mma32.cu) it also wins at the 576x960 model shape with D = 24 (10.3 vs 10.7 - 10.9 us; D = 12: 9.2 vs 8.9,
+        // D = 5: 10.0 vs 8.9 -- scripts/cfg5_fwd_variants.py): D >= 20 goes there as well
         const long warp_tiles = (long)B * H * ceil_div(W, 16);
         const bool fills_reg_tiles = (double)W >= 0.75 * (double)(ceil_div(W, 128) * 128);
-        if (variant == 3 || (variant < 0 && (!fills_reg_tiles || warp_tiles >= 3500))) {
+        if (variant == 3 || (variant < 0 && (!fills_reg_tiles || warp_tiles >= 3500 || (D >= 20 && C >= 32)))) {
             const int rc = corr_fwd_mma32(L, R, out, B, C, H, W, D, obs, stream);
             if (rc >= 0) return rc;
         }

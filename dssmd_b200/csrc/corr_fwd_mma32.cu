@@ -19,7 +19,7 @@ namespace dssmd {
 
 namespace {
 
-constexpr int kCK = 16;          // channels per stage (two k8 steps; 32 is slower at three of the four bench shapes)
+// channels per stage: a kernel template parameter CK, 16 or 32 (chosen by corr_fwd_mma32 below)
 constexpr int kMaxWarps = 8;     // 128 pixels per block
 
 struct Mma32Params {
@@ -30,6 +30,7 @@ struct Mma32Params {
     int TX, XT;      // pixels per block tile (multiple of 16), tiles per row
     int LW, RW;      // staged row widths in floats (= box widths, 8 mod 32)
     float invC;
+    int CK;          // channels per stage (16 or 32)
     int pf;          // first stage's boxes prefetched towards the L2 before griddepcontrol.wait (common.cuh: prefetch_l2)
 };
 
@@ -72,7 +73,7 @@ __device__ __forceinline__ void mma16816_bf16(float (&c)[4], const uint32_t (&a)
 // 2 tf32 + 2 bf16 MMAs instead of 6 tf32 (the kernel is bound by the tensor pipe of this instruction family).  The contraction index
 // may be permuted freely as long as A and B agree: bf16 slot pair (2 tq, 2 tq + 1) takes the lane's tf32 elements (tq, tq + 4) of the first
 // k8 step, pair (2 tq + 8, 2 tq + 9) those of the second, for both operands.
-template <int NT, bool BX>
+template <int NT, bool BX, int kCK>
 __global__ void __launch_bounds__(kMaxWarps * 32) corr_fwd_mma32_kernel(const Mma32Params p, const __grid_constant__ CUtensorMap mapL,
                                                                         const __grid_constant__ CUtensorMap mapR) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -217,9 +218,9 @@ int env_int_m32(const char *name, int dflt) {
     return (v && *v) ? std::atoi(v) : dflt;
 }
 
-template <int NT, bool BX>
+template <int NT, bool BX, int CK>
 int launch_nt_bx(const Mma32Params &p, const CUtensorMap &mapL, const CUtensorMap &mapR, int grid, int threads, size_t smem, cudaStream_t stream) {
-    auto kern = corr_fwd_mma32_kernel<NT, BX>;
+    auto kern = corr_fwd_mma32_kernel<NT, BX, CK>;
     {
         const cudaError_t e = kernel_smem_optin(kern, smem);
         if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_fwd(mma32): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
@@ -231,8 +232,11 @@ int launch_nt_bx(const Mma32Params &p, const CUtensorMap &mapL, const CUtensorMa
 
 template <int NT>
 int launch_nt(const Mma32Params &p, const CUtensorMap &mapL, const CUtensorMap &mapR, int grid, int threads, size_t smem, cudaStream_t stream) {
-    if (env_int_m32("DSSMD_MMA32_BF16X", 1) != 0) return launch_nt_bx<NT, true>(p, mapL, mapR, grid, threads, smem, stream);
-    return launch_nt_bx<NT, false>(p, mapL, mapR, grid, threads, smem, stream);
+    if (env_int_m32("DSSMD_MMA32_BF16X", 1) != 0) {
+        if (p.CK == 32) return launch_nt_bx<NT, true, 32>(p, mapL, mapR, grid, threads, smem, stream);
+        return launch_nt_bx<NT, true, 16>(p, mapL, mapR, grid, threads, smem, stream);
+    }
+    return launch_nt_bx<NT, false, 16>(p, mapL, mapR, grid, threads, smem, stream);
 }
 
 }  // namespace
@@ -259,6 +263,18 @@ int corr_fwd_mma32(const void *L, const void *R, void *out, int B, int C, int H,
     p.LW = w8mod32(p.TX);
     p.RW = w8mod32(p.TX + 8 * nt - 16);
     if (p.LW > 256 || p.RW > 256) return -1;
+    // channels per stage: 32 (half the TMA operations and block barriers) while two such stages leave room for four blocks per SM,
+    // else 16.  Measured, 16 / 32: cfg5 shape 12.4 / 10.8 us, KITTI x16 29.6 / 29.0, 320x640 12.1 / 11.7, cfg2 (61 KB of stages with 32)
+    // 54.6 / 57.8.  DSSMD_MMA32_CK forces one.
+    int kCK = env_int_m32("DSSMD_MMA32_CK", 0);
+    if (kCK != 16 && kCK != 32) {
+        const size_t smem32 = 2 * (size_t)32 * (size_t)(p.LW + p.RW) * 4;
+        const long long slots = smem32 <= 200 * 1024 ? (long long)sm_count() * (long long)((220 * 1024) / smem32) : 0;
+        // ... or while every block of the problem is resident anyway (the 576x960 model shape: 288 blocks of 78 KB)
+        kCK = (C >= 32 && (smem32 <= 56 * 1024 || (long long)B * H * p.XT <= slots)) ? 32 : 16;
+    }
+    if (env_int_m32("DSSMD_MMA32_BF16X", 1) == 0) kCK = 16;
+    p.CK = kCK;
     size_t smem = 2 * (size_t)kCK * (size_t)(p.LW + p.RW) * 4;
     const size_t epi = (size_t)warps * D * 17 * sizeof(float);
     if (epi > smem) smem = epi;
