@@ -27,6 +27,8 @@ namespace dssmd {
 int corr_bwd_reg(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, long long gbs, int dtype, cudaStream_t stream);
 // corr_bwd_mma32.cu: fp32 on mma.sync with 3xTF32 splitting; -1 = shape not eligible
 int corr_bwd_mma32(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, long long gbs, cudaStream_t stream);
+// ... both gradients in one launch (grid.y = gradient); -1 = not eligible
+int corr_bwd_mma32_both(const void *g, const void *L, const void *R, void *gL, void *gR, int B, int C, int H, int W, int D, long long gbs, cudaStream_t stream);
 // corr_bwd_fused.cu: both gradients of an fp32 correlation in one launch; -1 = not eligible
 int corr_bwd_fused_f32(const void *g, const void *L, const void *R, void *gL, void *gR, int B, int C, int H, int W, int D, long long gbs,
                        cudaStream_t stream);
@@ -425,6 +427,13 @@ int launch_typed(const void *g, const void *L, const void *R, void *gL, void *gR
             if (rc >= 0) return rc;
             rc = corr_bwd_fused_f32(g, L, R, gL, gR, B, C, H, W, D, gbs, stream);
             if (rc >= 0) return rc;
+            // where both gradients would take the mma.sync kernel (launch_mode's rule): one launch for the two
+            const long warp_tiles = (long)B * H * ceil_div(W, 16);
+            const bool fills_reg_tiles = (double)W >= 0.75 * (double)(ceil_div(W, 128) * 128);
+            if (!fills_reg_tiles || warp_tiles >= 4000) {
+                rc = corr_bwd_mma32_both(g, L, R, gL, gR, B, C, H, W, D, gbs, stream);
+                if (rc >= 0) return rc;
+            }
         }
     }
     if (gL) {

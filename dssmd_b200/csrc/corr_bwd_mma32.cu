@@ -76,9 +76,8 @@ __device__ __forceinline__ void mma16816_bf16b(float (&c)[4], const uint32_t (&a
 // keeps its three tf32 products.
 // TB: the most threads a block may have.  Blocks of up to five warps (rows tiled in 80 pixels: cfg2, KITTI, the 320x640 crops) ask for
 // four resident blocks (96 registers instead of ~125 and three blocks: cfg2 backward 116.0 -> 114.2 us, KITTI 60.5 -> 59.1 us)
-template <int MODE, int NK, bool BX, int TB>
-__global__ void __launch_bounds__(TB, TB <= 160 ? 4 : 2) corr_bwd_mma32_kernel(const BwdMma32Params p, const __grid_constant__ CUtensorMap mapIn,
-                                                                        const __grid_constant__ CUtensorMap mapG) {
+template <int MODE, int NK, bool BX>
+__device__ __forceinline__ void corr_bwd_mma32_body(const BwdMma32Params &p, const CUtensorMap &mapIn, const CUtensorMap &mapG) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long s_bar[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -234,6 +233,22 @@ __global__ void __launch_bounds__(TB, TB <= 160 ? 4 : 2) corr_bwd_mma32_kernel(c
     }
 }
 
+template <int MODE, int NK, bool BX, int TB>
+__global__ void __launch_bounds__(TB, TB <= 160 ? 4 : 2) corr_bwd_mma32_kernel(const BwdMma32Params p, const __grid_constant__ CUtensorMap mapIn,
+                                                                        const __grid_constant__ CUtensorMap mapG) {
+    corr_bwd_mma32_body<MODE, NK, BX>(p, mapIn, mapG);
+}
+
+// both gradients in ONE launch: blockIdx.y = 0 computes gL (operand R), 1 computes gR (operand L); the two halves of the grid share the
+// launch ramp and drain, and the second gradient's blocks fill the SMs the first one's last wave leaves idle
+template <int NK, int TB>
+__global__ void __launch_bounds__(TB, TB <= 160 ? 4 : 2) corr_bwd_mma32_both_kernel(const BwdMma32Params p0, const BwdMma32Params p1,
+                                                                             const __grid_constant__ CUtensorMap mapIn0, const __grid_constant__ CUtensorMap mapG0,
+                                                                             const __grid_constant__ CUtensorMap mapIn1, const __grid_constant__ CUtensorMap mapG1) {
+    if (blockIdx.y == 0) corr_bwd_mma32_body<0, NK, true>(p0, mapIn0, mapG0);
+    else corr_bwd_mma32_body<1, NK, true>(p1, mapIn1, mapG1);
+}
+
 int env_int_bm32(const char *name, int dflt) {
     if (!tuning_enabled()) return dflt;
     const char *v = std::getenv(name);
@@ -263,19 +278,29 @@ int launch_bnk(const BwdMma32Params &p, const CUtensorMap &mapIn, const CUtensor
     return launch_bnk_tb<MODE, NK, false, kMaxWarps * 32>(p, mapIn, mapG, grid, threads, smem, stream);
 }
 
+struct BwdPlan {
+    BwdMma32Params p;
+    CUtensorMap mapIn, mapG;
+    int nk, warps;
+    long long blocks;
+    size_t smem;
+};
+
+// parameters, tensor maps and launch geometry of one gradient; false = shape not eligible
 template <int MODE>
-int corr_bwd_mma32_mode(const void *g, const void *in, void *out, int B, int C, int H, int W, int D, long long gbs, cudaStream_t stream) {
-    if (W % 4 != 0 || D > 81 || C < 8) return -1;
-    if (((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(in)) & 15) != 0 || (gbs % 4) != 0) return -1;
-    if ((reinterpret_cast<uintptr_t>(out) & 7) != 0) return -1;   // 8-byte stores
-    BwdMma32Params p{};
+bool plan_bwd_mma32(BwdPlan &pl, const void *g, const void *in, void *out, int B, int C, int H, int W, int D, long long gbs) {
+    if (W % 4 != 0 || D > 81 || C < 8) return false;
+    if (((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(in)) & 15) != 0 || (gbs % 4) != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(out) & 7) != 0) return false;   // 8-byte stores
+    BwdMma32Params &p = pl.p;
+    p = BwdMma32Params{};
     p.out = static_cast<float *>(out);
     p.pf = pdl_prefetch(1);
     p.C = C; p.H = H; p.W = W; p.D = D;
     p.invC = 1.0f / (float)C;
     p.HALO = round_up(D - 1, 4);
     const int nk = ceil_div(p.HALO + 16, 8);
-    if (nk < 2 || nk > 12) return -1;
+    if (nk < 2 || nk > 12) return false;
     int warps = ceil_div(W, 16);
     int maxw = env_int_bm32("DSSMD_MMA32_MAXW", kMaxWarps);
     if (maxw < 1 || maxw > kMaxWarps) maxw = kMaxWarps;
@@ -285,33 +310,72 @@ int corr_bwd_mma32_mode(const void *g, const void *in, void *out, int B, int C, 
     const int need = p.TX + 8 * nk - 16;                  // operand positions a block touches
     p.RW = ((need + 27) / 32) * 32 + 4;                   // smallest value >= need that is 4 (mod 32)
     p.GW = MODE == 0 ? p.TX : round_up(need, 4);
-    if (p.RW > 256 || p.GW > 256) return -1;
-    const size_t smem = (((size_t)D * p.GW * 4 + 127) & ~(size_t)127) + 2 * (size_t)kCK * p.RW * 4;
-    if (smem > 200 * 1024) return -1;
-    const long long blocks = (long long)B * H * p.XT;
-    if (blocks >= (1LL << 31)) return -1;
-    CUtensorMap mapIn, mapG;
+    if (p.RW > 256 || p.GW > 256) return false;
+    pl.smem = (((size_t)D * p.GW * 4 + 127) & ~(size_t)127) + 2 * (size_t)kCK * p.RW * 4;
+    if (pl.smem > 200 * 1024) return false;
+    pl.blocks = (long long)B * H * p.XT;
+    if (pl.blocks >= (1LL << 31)) return false;
     const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
     const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)C * H * W * 4};
     const cuuint32_t box[4] = {(cuuint32_t)p.RW, 1, (cuuint32_t)kCK, 1};
     const cuuint64_t gdims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
     const cuuint64_t gstrides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)gbs * 4};
     const cuuint32_t gbox[4] = {(cuuint32_t)p.GW, 1, (cuuint32_t)D, 1};
-    if (!make_tmap_f32(&mapIn, in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE) ||
-        !make_tmap_f32(&mapG, g, 4, gdims, gstrides, gbox, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
+    if (!make_tmap_f32(&pl.mapIn, in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE) ||
+        !make_tmap_f32(&pl.mapG, g, 4, gdims, gstrides, gbox, CU_TENSOR_MAP_SWIZZLE_NONE)) return false;
+    pl.nk = nk; pl.warps = warps;
     if (env_int_bm32("DSSMD_CORR_DEBUG", 0))
         fprintf(stderr, "corr_bwd mma32 cfg: mode=%d NK=%d HALO=%d TX=%d XT=%d RW=%d GW=%d warps=%d grid=%lld smem=%zu\n", MODE, nk, p.HALO, p.TX, p.XT,
-                p.RW, p.GW, warps, blocks, smem);
-#define DSSMD_BNK_CASE(n) case n: return launch_bnk<MODE, n>(p, mapIn, mapG, (int)blocks, warps * 32, smem, stream);
-    switch (nk) {
+                p.RW, p.GW, warps, pl.blocks, pl.smem);
+    return true;
+}
+
+template <int MODE>
+int corr_bwd_mma32_mode(const void *g, const void *in, void *out, int B, int C, int H, int W, int D, long long gbs, cudaStream_t stream) {
+    BwdPlan pl;
+    if (!plan_bwd_mma32<MODE>(pl, g, in, out, B, C, H, W, D, gbs)) return -1;
+#define DSSMD_BNK_CASE(n) case n: return launch_bnk<MODE, n>(pl.p, pl.mapIn, pl.mapG, (int)pl.blocks, pl.warps * 32, pl.smem, stream);
+    switch (pl.nk) {
         DSSMD_BNK_CASE(2) DSSMD_BNK_CASE(3) DSSMD_BNK_CASE(4) DSSMD_BNK_CASE(5) DSSMD_BNK_CASE(6) DSSMD_BNK_CASE(7)
         DSSMD_BNK_CASE(8) DSSMD_BNK_CASE(9) DSSMD_BNK_CASE(10) DSSMD_BNK_CASE(11)
-        default: return launch_bnk<MODE, 12>(p, mapIn, mapG, (int)blocks, warps * 32, smem, stream);
+        default: return launch_bnk<MODE, 12>(pl.p, pl.mapIn, pl.mapG, (int)pl.blocks, pl.warps * 32, pl.smem, stream);
     }
 #undef DSSMD_BNK_CASE
 }
 
+template <int NK, int TB>
+int launch_both(const BwdPlan &a, const BwdPlan &b, cudaStream_t stream) {
+    auto kern = corr_bwd_mma32_both_kernel<NK, TB>;
+    const size_t smem = a.smem > b.smem ? a.smem : b.smem;
+    {
+        const cudaError_t e = kernel_smem_optin(kern, smem);
+        if (e != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_bwd(mma32, both): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+    }
+    const cudaError_t le = launch_pdl(kern, dim3((unsigned)a.blocks, 2u), dim3((unsigned)(a.warps * 32)), smem, stream, a.p, b.p, a.mapIn, a.mapG, b.mapIn, b.mapG);
+    if (le != cudaSuccess) return fail(DSSMD_ERR_CUDA, "corr_bwd(mma32, both): launch failed: %s", cudaGetErrorString(le));
+    return check_launch("corr_bwd(gL + gR, mma32)");
+}
+
 }  // namespace
+
+// Both gradients in one launch (grid.y = gradient).  Blocks of up to five warps and NK <= 8 (the 96-register build): the shapes the
+// per-gradient kernels are taken for by default.  -1 = not eligible (the caller issues one launch per gradient).
+int corr_bwd_mma32_both(const void *g, const void *L, const void *R, void *gL, void *gR, int B, int C, int H, int W, int D, long long gbs, cudaStream_t stream) {
+    if (!bwd_mma32_bf16x() || env_int_bm32("DSSMD_MMA32_BOTH", 1) == 0) return -1;
+    BwdPlan a, b;
+    if (!plan_bwd_mma32<0>(a, g, R, gL, B, C, H, W, D, gbs) || !plan_bwd_mma32<1>(b, g, L, gR, B, C, H, W, D, gbs)) return -1;
+    if (a.nk != b.nk || a.warps != b.warps || a.blocks != b.blocks || a.warps * 32 > 160 || a.nk > 8 || a.blocks > 65535LL * 32768) return -1;
+    if (env_int_bm32("DSSMD_CORR_DEBUG", 0)) fprintf(stderr, "corr_bwd mma32 both cfg: one launch, grid=(%lld,2)\n", a.blocks);
+    switch (a.nk) {
+        case 2: return launch_both<2, 160>(a, b, stream);
+        case 3: return launch_both<3, 160>(a, b, stream);
+        case 4: return launch_both<4, 160>(a, b, stream);
+        case 5: return launch_both<5, 160>(a, b, stream);
+        case 6: return launch_both<6, 160>(a, b, stream);
+        case 7: return launch_both<7, 160>(a, b, stream);
+        default: return launch_both<8, 160>(a, b, stream);
+    }
+}
 
 // fp32 tensors.  mode 0: out = gL, in = R;  mode 1: out = gR, in = L.  -1 = not eligible (caller falls back).
 int corr_bwd_mma32(const void *g, const void *in, void *out, int mode, int B, int C, int H, int W, int D, long long gbs, cudaStream_t stream) {

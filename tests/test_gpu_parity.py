@@ -1089,9 +1089,9 @@ print("done")
     assert sec["cfg5"] == ["corr_fwd mma32", "corr_bwd wide"], sec
     assert sec["cfg5_d12"][0] == "corr_fwd reg", sec
     assert sec["cfg3"] == ["corr_fwd mma32", "corr_bwd wide"], sec
-    # C256 80x160 D41 and KITTI feature maps: the fp32 mma.sync (3xTF32) kernels, one launch per gradient
+    # C256 80x160 D41 and KITTI feature maps: the fp32 mma.sync (3xTF32) kernels, both gradients planned and issued as ONE launch
     for k in ("cfg2", "cfg4"):
-        assert sec[k] == ["corr_fwd mma32", "corr_bwd mma32", "corr_bwd mma32"], (k, sec)
+        assert sec[k] == ["corr_fwd mma32", "corr_bwd mma32", "corr_bwd mma32", "corr_bwd mma32 both"], (k, sec)
     # image-sized warps: lean forward, one-pass band backward (rewritten kernel)
     for k in ("cfg5w", "cfg3w", "cfg4w"):
         assert sec[k] == ["warp_fwd lean", "warp_bwd band2"], (k, sec)
