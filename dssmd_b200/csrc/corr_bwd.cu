@@ -423,14 +423,24 @@ int launch_typed(const void *g, const void *L, const void *R, void *gL, void *gR
         // both gradients wanted (the autograd case): one fused launch where the shape is eligible (corr_bwd_fused.cu).  A forced
         // per-gradient variant (DSSMD_CORR_BWD_VARIANT) keeps the two-launch path; DSSMD_CORR_BWD_FUSED=0 disables the fusion.
         if (gL && gR && env_int("DSSMD_CORR_BWD_VARIANT", -1) < 0) {
-            int rc = corr_bwd_wide_f32(g, L, R, gL, gR, B, C, H, W, D, gbs, stream);
+            // Where both gradients would take the mma.sync kernel (launch_mode's rule) they are issued as ONE launch.  Rows that fill
+            // the FFMA kernels' 128-pixel lane tiles badly (W = 80, 160) go there FIRST: measured over the batch size
+            // (scripts/corr_bwd_b_sweep.py), wide FFMA kernel / one-launch mma.sync: 48x160 B = 1 9.4 / 8.3 us, B = 4 24.4 / 17.6,
+            // B = 16 58.6 (two mma.sync launches) / 53.2; 40x80 B = 1 6.2 / 5.9, B = 8 20.0 / 15.8, B = 16 36.3 / 25.2; 72x120 (fills
+            // its tile) B = 4 18.3 / 19.0, B = 8 33.2 / 35.9: the wide kernel keeps it.  DSSMD_CORR_BWD_WIDE=2 forces the wide kernel.
+            const long warp_tiles = (long)B * H * ceil_div(W, 16);
+            const bool fills_reg_tiles = (double)W >= 0.75 * (double)(ceil_div(W, 128) * 128);
+            const int both = env_int("DSSMD_MMA32_BOTH", 1);
+            int rc = -1;
+            if (!fills_reg_tiles && both != 0 && env_int("DSSMD_CORR_BWD_WIDE", 1) < 2) {
+                rc = corr_bwd_mma32_both(g, L, R, gL, gR, B, C, H, W, D, gbs, stream);
+                if (rc >= 0) return rc;
+            }
+            rc = corr_bwd_wide_f32(g, L, R, gL, gR, B, C, H, W, D, gbs, stream);
             if (rc >= 0) return rc;
             rc = corr_bwd_fused_f32(g, L, R, gL, gR, B, C, H, W, D, gbs, stream);
             if (rc >= 0) return rc;
-            // where both gradients would take the mma.sync kernel (launch_mode's rule): one launch for the two
-            const long warp_tiles = (long)B * H * ceil_div(W, 16);
-            const bool fills_reg_tiles = (double)W >= 0.75 * (double)(ceil_div(W, 128) * 128);
-            if (!fills_reg_tiles || warp_tiles >= 4000) {
+            if (!fills_reg_tiles || warp_tiles >= 4000 || both == 2) {
                 rc = corr_bwd_mma32_both(g, L, R, gL, gR, B, C, H, W, D, gbs, stream);
                 if (rc >= 0) return rc;
             }

@@ -324,16 +324,20 @@ bool plan_bwd_mma32(BwdPlan &pl, const void *g, const void *in, void *out, int B
     if (!make_tmap_f32(&pl.mapIn, in, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE) ||
         !make_tmap_f32(&pl.mapG, g, 4, gdims, gstrides, gbox, CU_TENSOR_MAP_SWIZZLE_NONE)) return false;
     pl.nk = nk; pl.warps = warps;
-    if (env_int_bm32("DSSMD_CORR_DEBUG", 0))
-        fprintf(stderr, "corr_bwd mma32 cfg: mode=%d NK=%d HALO=%d TX=%d XT=%d RW=%d GW=%d warps=%d grid=%lld smem=%zu\n", MODE, nk, p.HALO, p.TX, p.XT,
-                p.RW, p.GW, warps, pl.blocks, pl.smem);
     return true;
+}
+
+void debug_plan(const BwdPlan &pl, int mode) {
+    if (env_int_bm32("DSSMD_CORR_DEBUG", 0))
+        fprintf(stderr, "corr_bwd mma32 cfg: mode=%d NK=%d HALO=%d TX=%d XT=%d RW=%d GW=%d warps=%d grid=%lld smem=%zu\n", mode, pl.nk, pl.p.HALO, pl.p.TX,
+                pl.p.XT, pl.p.RW, pl.p.GW, pl.warps, pl.blocks, pl.smem);
 }
 
 template <int MODE>
 int corr_bwd_mma32_mode(const void *g, const void *in, void *out, int B, int C, int H, int W, int D, long long gbs, cudaStream_t stream) {
     BwdPlan pl;
     if (!plan_bwd_mma32<MODE>(pl, g, in, out, B, C, H, W, D, gbs)) return -1;
+    debug_plan(pl, MODE);
 #define DSSMD_BNK_CASE(n) case n: return launch_bnk<MODE, n>(pl.p, pl.mapIn, pl.mapG, (int)pl.blocks, pl.warps * 32, pl.smem, stream);
     switch (pl.nk) {
         DSSMD_BNK_CASE(2) DSSMD_BNK_CASE(3) DSSMD_BNK_CASE(4) DSSMD_BNK_CASE(5) DSSMD_BNK_CASE(6) DSSMD_BNK_CASE(7)
@@ -364,17 +368,15 @@ int corr_bwd_mma32_both(const void *g, const void *L, const void *R, void *gL, v
     if (!bwd_mma32_bf16x() || env_int_bm32("DSSMD_MMA32_BOTH", 1) == 0) return -1;
     BwdPlan a, b;
     if (!plan_bwd_mma32<0>(a, g, R, gL, B, C, H, W, D, gbs) || !plan_bwd_mma32<1>(b, g, L, gR, B, C, H, W, D, gbs)) return -1;
-    if (a.nk != b.nk || a.warps != b.warps || a.blocks != b.blocks || a.warps * 32 > 160 || a.nk > 8 || a.blocks > 65535LL * 32768) return -1;
+    if (a.nk != b.nk || a.warps != b.warps || a.blocks != b.blocks || a.nk > 8) return -1;
+    debug_plan(a, 0); debug_plan(b, 1);
     if (env_int_bm32("DSSMD_CORR_DEBUG", 0)) fprintf(stderr, "corr_bwd mma32 both cfg: one launch, grid=(%lld,2)\n", a.blocks);
+#define DSSMD_BOTH_CASE(n) case n: return a.warps * 32 <= 160 ? launch_both<n, 160>(a, b, stream) : launch_both<n, kMaxWarps * 32>(a, b, stream);
     switch (a.nk) {
-        case 2: return launch_both<2, 160>(a, b, stream);
-        case 3: return launch_both<3, 160>(a, b, stream);
-        case 4: return launch_both<4, 160>(a, b, stream);
-        case 5: return launch_both<5, 160>(a, b, stream);
-        case 6: return launch_both<6, 160>(a, b, stream);
-        case 7: return launch_both<7, 160>(a, b, stream);
-        default: return launch_both<8, 160>(a, b, stream);
+        DSSMD_BOTH_CASE(2) DSSMD_BOTH_CASE(3) DSSMD_BOTH_CASE(4) DSSMD_BOTH_CASE(5) DSSMD_BOTH_CASE(6) DSSMD_BOTH_CASE(7)
+        default: return a.warps * 32 <= 160 ? launch_both<8, 160>(a, b, stream) : launch_both<8, kMaxWarps * 32>(a, b, stream);
     }
+#undef DSSMD_BOTH_CASE
 }
 
 // fp32 tensors.  mode 0: out = gL, in = R;  mode 1: out = gR, in = L.  -1 = not eligible (caller falls back).

@@ -1085,10 +1085,10 @@ print("done")
     assert "not eligible" not in r.stderr, r.stderr[-3000:]
     # the model shape of the headline config: the mma.sync forward (D = 24; the register-blocked FFMA kernel keeps D < 20), ONE
     # backward launch for both gradients (the D <= 24 kernel with a lane owning all disparities of its pixels); 320x640 feature
-    # maps (W = 80): the same backward
+    # maps (W = 80, 62 % of a 128-pixel lane tile): the mma.sync kernels, both gradients in ONE launch
     assert sec["cfg5"] == ["corr_fwd mma32", "corr_bwd wide"], sec
     assert sec["cfg5_d12"][0] == "corr_fwd reg", sec
-    assert sec["cfg3"] == ["corr_fwd mma32", "corr_bwd wide"], sec
+    assert sec["cfg3"] == ["corr_fwd mma32", "corr_bwd mma32", "corr_bwd mma32", "corr_bwd mma32 both"], sec
     # C256 80x160 D41 and KITTI feature maps: the fp32 mma.sync (3xTF32) kernels, both gradients planned and issued as ONE launch
     for k in ("cfg2", "cfg4"):
         assert sec[k] == ["corr_fwd mma32", "corr_bwd mma32", "corr_bwd mma32", "corr_bwd mma32 both"], (k, sec)
