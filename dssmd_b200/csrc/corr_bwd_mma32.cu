@@ -20,7 +20,8 @@ namespace dssmd {
 
 namespace {
 
-constexpr int kCK = 32;          // channels per stage (two 16-channel M tiles)
+constexpr int kCK = 32;          // channels per stage (two 16-channel M tiles); 16 / 64 measured slower with the one-launch kernel
+                                 // (cfg2 112 / 133 us against 105.6, 320x640 18.5 / 19.6 against 16.2: profiles/r04as_bwd_mma32_ck.log)
 constexpr int kMaxWarps = 8;     // 128 pixels per block
 
 struct BwdMma32Params {
